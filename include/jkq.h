@@ -1,0 +1,140 @@
+/* jkq.h -- C ABI of the B200-native QMDD engine (libjkq_b200.so).
+ *
+ * This is the boundary the reference crosses with a subprocess pipe:
+ *   qiskit_jku_provider/qasm_simulator_jku.py:82-97  JKUSimulatorWrapper.run()  argv + QASM on stdin,
+ *                                                   JSON on stdout
+ *   src/main.cpp:75-150                              srand, QMDDinit, QASMsimulator, Simulate(shots)
+ * Each entry point names the reference routine it replaces.  Plain pointers and sizes only; the
+ * caller owns every output buffer; a handle owns all device memory and is bound to one CUDA device.
+ * A handle is not thread-safe; distinct handles may be used from distinct threads.
+ * Every function returns 0 on success or a JKQ_E_* code; jkq_last_error() gives the text.
+ * There is no CPU path: jkq_create fails when no CUDA device is usable.
+ */
+#ifndef JKQ_H
+#define JKQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jkq_handle jkq_handle;
+
+enum {
+  JKQ_E_OK = 0,
+  JKQ_E_NODE_FULL = 1,   /* node arena exhausted even after a collection */
+  JKQ_E_UTAB_FULL = 2,
+  JKQ_E_VALUE_FULL = 3,  /* complex-value table exhausted */
+  JKQ_E_ITEM_FULL = 4,   /* frontier pool exhausted */
+  JKQ_E_DTAB_FULL = 5,
+  JKQ_E_PEND_FULL = 6,
+  JKQ_E_BARRIER_TIMEOUT = 7,
+  JKQ_E_ZERO_STATE = 8,  /* "numerical instabilities led to a 0-vector", Simulator.cpp:158-161 */
+  JKQ_E_INTERNAL = 9,
+  JKQ_E_CUDA = 100,      /* CUDA runtime error or no device */
+  JKQ_E_ARGUMENT = 101,
+  JKQ_E_STATE = 102,     /* call made in the wrong order */
+  JKQ_E_CAPACITY = 103   /* caller buffer too small */
+};
+
+/* One configuration struct at handle creation replaces the reference's compile-time limits and CLI
+ * flags (QMDDpackage.h:35-57 MAXN/NBUCKET/GCLIMIT1, QMDDcomplexD.cpp:336 Ctol, main.cpp:108-113
+ * --precision).  Zero in any field selects the default. */
+typedef struct {
+  int32_t device;           /* CUDA ordinal                                   default 0       */
+  int32_t force_mode;       /* 0 auto, 1 single-CTA path only, 2 grid path only               */
+  double tolerance;         /* complex-table tolerance Ctol                   default 1e-10   */
+  uint32_t node_capacity;   /* nodes per arena (power of two)                 default 1<<22   */
+  uint32_t value_capacity;  /* distinct reals (power of two)                  default 1<<20   */
+  uint32_t item_capacity;   /* frontier work items (power of two)             default = nodes */
+  uint32_t cta_threads;     /* threads of the single-CTA path                 default 256     */
+  uint32_t cta_item_limit;  /* frontier size that escalates to the grid path  default 4096    */
+  uint32_t gc_min;          /* never collect below this many allocated nodes  default 1<<15   */
+  uint32_t grid_blocks_per_sm; /* grid path CTAs per SM                       default 2       */
+  uint32_t reserved;
+} jkq_config;
+
+enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER = 3 };
+
+/* One operation of a circuit.
+ *  GATE      2x2 matrix m (row major, re/im pairs) on `target`, applied where every qubit in ctrl_pos
+ *            is 1 and every qubit in ctrl_neg is 0 -- the general form QMDDmvlgate builds
+ *            (QMDDpackage.cpp:1746-1828); U and CX of the reference front end
+ *            (QASMsimulator.cpp:281-357) are the cases {no control} and {m = X, one positive control}.
+ *  SNAPSHOT  record the full state vector in slot `arg` (QASMsimulator.cpp:973-1037).
+ *  MEASURE   qubit `target` -> classical bit `arg`; counts are sampled from the final state
+ *            (QASMsimulator.cpp:487-500).
+ *  BARRIER   no-op (QASMsimulator.cpp:944-949). */
+typedef struct {
+  uint32_t kind;
+  uint32_t target;
+  uint64_t ctrl_pos;
+  uint64_t ctrl_neg;
+  double m[8];
+  uint32_t arg;
+  uint32_t reserved;
+} jkq_op;
+
+typedef struct {
+  uint64_t gates;            /* ApplyGate calls (Simulator.cpp:466)                            */
+  uint64_t items;            /* frontier pairs processed (the reference's CTlook, :993)        */
+  uint64_t nodes_created;    /* unique-table inserts (UTlookups - UTmatch, :708,730)           */
+  uint64_t value_inserts;    /* reals appended to the value table                              */
+  uint64_t gc_runs;
+  uint64_t gc_nodes_copied;
+  uint64_t retry_rounds;     /* serial value-insert sections                                   */
+  uint64_t max_frontier;     /* largest per-gate item count                                    */
+  uint64_t live_nodes;       /* after the last collection                                      */
+  uint64_t live_values;
+  uint64_t cta_launches, grid_launches, sample_launches;
+  double apply_ms;           /* CUDA-event time of the apply kernels of the last run           */
+  double sample_ms;          /* ... of build_sampling + sample + histogram compaction          */
+  double sample_kernel_ms;   /* ... of the sampling kernel alone                               */
+  double norm;               /* squared norm of the final state                                */
+  uint64_t distinct_outcomes;
+} jkq_stats;
+
+/* sampling record exported for multi-GPU shot sharding (16 bytes) */
+typedef struct {
+  uint32_t c0, c1;
+  double q0;
+} jkq_snode;
+
+int jkq_create(jkq_handle **out, const jkq_config *cfg);              /* replaces QMDDinit, QMDDpackage.cpp:1248 */
+void jkq_destroy(jkq_handle *h);
+const char *jkq_last_error(const jkq_handle *h);
+
+int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *ops, size_t n_ops);
+int jkq_set_option(jkq_handle *h, const char *name, int64_t value);   /* "level_log" = 1: per-gate live counts */
+
+/* apply every op of the loaded circuit to |0..0> (Simulator::AddVariables + ApplyGate per gate) */
+int jkq_apply(jkq_handle *h);
+/* AssignProbs + MeasureAll x shots (Simulator.cpp:127-224): shots [shot_offset, shot_offset+shots) of
+ * the Philox stream `seed`; accumulate = 0 clears the histogram first */
+int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offset, int accumulate);
+/* jkq_apply + jkq_sample(shots, seed, 0, 0): what `jku_simulator --shots --seed` does */
+int jkq_run(jkq_handle *h, uint64_t shots, uint64_t seed);
+
+int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, size_t cap, size_t *n);
+int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, size_t cap_amplitudes);
+int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count, double *re_im); /* GetElementOfVector */
+int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n);              /* Active[v] */
+int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_written);
+int jkq_get_stats(jkq_handle *h, jkq_stats *out);
+
+/* multi-GPU shot sharding: export the level-ordered sampling DD, import it on another handle */
+int jkq_dd_export(jkq_handle *h, jkq_snode *host_nodes, size_t cap, uint32_t *n_nodes, uint32_t *root);
+int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *host_nodes, uint32_t n_nodes, uint32_t root,
+                  const uint8_t *clbit_of_level);
+int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n);
+
+/* GPU-measured roofline denominators: uniform random 32-byte sector reads and 64-bit atomicCAS over
+ * a `bytes`-sized buffer; returns giga-operations per second */
+int jkq_random_sector_bench(jkq_handle *h, uint64_t bytes, int iters, double *gsectors_per_s, double *gcas_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

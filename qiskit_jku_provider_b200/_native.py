@@ -1,0 +1,74 @@
+"""ctypes binding of libjkq_b200.so (include/jkq.h).  No CPU fallback: a missing library or a
+missing GPU raises."""
+
+import ctypes as C
+import os
+
+from ._build import LIB
+
+_lib = None
+
+
+class JkqConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("force_mode", C.c_int32), ("tolerance", C.c_double),
+                ("node_capacity", C.c_uint32), ("value_capacity", C.c_uint32), ("item_capacity", C.c_uint32),
+                ("cta_threads", C.c_uint32), ("cta_item_limit", C.c_uint32), ("gc_min", C.c_uint32),
+                ("grid_blocks_per_sm", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class JkqOp(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("target", C.c_uint32), ("ctrl_pos", C.c_uint64), ("ctrl_neg", C.c_uint64),
+                ("m", C.c_double * 8), ("arg", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class JkqStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in (
+        "gates", "items", "nodes_created", "value_inserts", "gc_runs", "gc_nodes_copied", "retry_rounds",
+        "max_frontier", "live_nodes", "live_values", "cta_launches", "grid_launches", "sample_launches")] + [
+        ("apply_ms", C.c_double), ("sample_ms", C.c_double), ("sample_kernel_ms", C.c_double), ("norm", C.c_double),
+        ("distinct_outcomes", C.c_uint64)]
+
+
+class JkqSNode(C.Structure):
+    _fields_ = [("c0", C.c_uint32), ("c1", C.c_uint32), ("q0", C.c_double)]
+
+
+# every symbol include/jkq.h declares: (name, restype, argtypes)
+_H = C.c_void_p
+SYMBOLS = [
+    ("jkq_create", C.c_int, [C.POINTER(_H), C.POINTER(JkqConfig)]),
+    ("jkq_destroy", None, [_H]),
+    ("jkq_last_error", C.c_char_p, [_H]),
+    ("jkq_load_circuit", C.c_int, [_H, C.c_uint32, C.POINTER(JkqOp), C.c_size_t]),
+    ("jkq_set_option", C.c_int, [_H, C.c_char_p, C.c_int64]),
+    ("jkq_apply", C.c_int, [_H]),
+    ("jkq_sample", C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
+    ("jkq_run", C.c_int, [_H, C.c_uint64, C.c_uint64]),
+    ("jkq_get_counts", C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("jkq_get_statevector", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.c_size_t]),
+    ("jkq_get_amplitudes", C.c_int, [_H, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
+    ("jkq_get_level_counts", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t]),
+    ("jkq_get_level_log", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("jkq_get_stats", C.c_int, [_H, C.POINTER(JkqStats)]),
+    ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("jkq_dd_import", C.c_int, [_H, C.c_uint32, C.POINTER(JkqSNode), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
+    ("jkq_get_measure_map", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_size_t]),
+    ("jkq_random_sector_bench", C.c_int, [_H, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+]
+
+
+def load():
+    """dlopen the in-tree library and bind every symbol; raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the engine is CUDA only, there is no CPU fallback)" % LIB)
+    lib = C.CDLL(LIB)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

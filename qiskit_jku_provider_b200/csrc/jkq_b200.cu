@@ -1,0 +1,743 @@
+// libjkq_b200.so -- kernels and the C ABI (include/jkq.h) of the B200-native QMDD engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/jkq.h"
+#include "jkq_apply.cuh"
+#include "jkq_sample.cuh"
+
+// =============================================================================== kernels
+template <int MODE> __device__ __forceinline__ Ctx make_ctx(JEng *E) {
+  Ctx c;
+  c.E = E;
+  c.phase = 0;
+  c.ltid = threadIdx.x;
+  c.lnth = blockDim.x;
+  if (MODE == MODE_CTA) { c.tid = threadIdx.x; c.nth = blockDim.x; c.block0 = 1; }
+  else { c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x; c.block0 = blockIdx.x == 0; }
+  return c;
+}
+
+template <int MODE> __global__ void __launch_bounds__(256) k_init(JEng *E) {
+  Ctx c = make_ctx<MODE>(E);
+  init_state<MODE>(c);
+}
+
+// Persistent circuit kernel: all gates of a segment in one launch, no host round trip per gate.
+template <int MODE> __global__ void __launch_bounds__(256) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
+  Ctx c = make_ctx<MODE>(E);
+  run_gates<MODE>(c, gates, n_gates);
+}
+
+template <int MODE> __global__ void __launch_bounds__(256) k_build_sampling(JEng *E, JSNode *sn, double *prob) {
+  Ctx c = make_ctx<MODE>(E);
+  build_sampling<MODE>(c, sn, prob);
+}
+
+__global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *out) {
+  Ctx c;
+  c.E = E; c.phase = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
+  for (uint64_t i = c.tid; i < count; i += c.nth) {
+    double re, im;
+    amp_walk<MODE_GRID>(c, first + i, &re, &im);
+    out[i] = make_double2(re, im);
+  }
+}
+
+struct SampleParams {
+  uint8_t bitpos[JKQ_MAXQ];
+};
+
+#define JH_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define JH_SMEM 2048
+
+__device__ __forceinline__ void hist_global_add(unsigned long long *hk, unsigned long long *hc, uint32_t hmask, uint64_t key,
+                                                unsigned long long cnt, int *overflow) {
+  uint32_t h = (uint32_t)jmix(key) & hmask;
+  for (uint32_t probes = 0; probes <= hmask; probes++) {
+    unsigned long long old = hk[h];
+    if (old != key) {
+      if (old != JH_EMPTY) { h = (h + 1) & hmask; continue; }
+      old = atomicCAS(hk + h, JH_EMPTY, (unsigned long long)key);
+      if (old != JH_EMPTY && old != key) { h = (h + 1) & hmask; continue; }
+    }
+    atomicAdd(hc + h, cnt);
+    return;
+  }
+  *overflow = 1;
+}
+
+// MeasureAll x shots (Simulator.cpp:148-224, QASMsimulator.cpp:487-500): one thread per shot, n
+// dependent 16-byte loads through L1/L2, equal outcomes merged inside the warp (__match_any_sync),
+// then in a shared-memory hash, then in the HBM hash histogram.
+__global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, uint32_t root, int n, SampleParams sp, uint64_t seed,
+                                               uint64_t shot0, uint64_t nshots, unsigned long long *hk, unsigned long long *hc,
+                                               uint32_t hmask, int *overflow) {
+  __shared__ unsigned long long skeys[JH_SMEM];
+  __shared__ unsigned int scnts[JH_SMEM];
+  for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x) { skeys[i] = JH_EMPTY; scnts[i] = 0; }
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounded = (nshots + 31) & ~31ull;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < rounded; s += stride) {
+    const bool active = s < nshots;
+    uint64_t key = active ? sample_walk(sn, root, n, sp.bitpos, seed, shot0 + s) : JH_EMPTY;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (!active || lane != (uint32_t)(__ffs(peers) - 1)) continue;
+    uint32_t cnt = __popc(peers);
+    uint32_t h = (uint32_t)jmix(key) & (JH_SMEM - 1);
+    bool done = false;
+    for (int p = 0; p < 8 && !done; p++) {
+      unsigned long long old = skeys[h];
+      if (old != key) {
+        if (old == JH_EMPTY) old = atomicCAS(&skeys[h], JH_EMPTY, (unsigned long long)key);
+        if (old != JH_EMPTY && old != key) { h = (h + 1) & (JH_SMEM - 1); continue; }
+      }
+      atomicAdd(&scnts[h], cnt);
+      done = true;
+    }
+    if (!done) hist_global_add(hk, hc, hmask, key, cnt, overflow);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x)
+    if (skeys[i] != JH_EMPTY && scnts[i]) hist_global_add(hk, hc, hmask, skeys[i], scnts[i], overflow);
+}
+
+__global__ void k_hist_fill(unsigned long long *hk, unsigned long long *hc, uint64_t slots) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    hk[i] = JH_EMPTY;
+    hc[i] = 0;
+  }
+}
+
+__global__ void k_hist_compact(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, unsigned long long *ok,
+                               unsigned long long *oc, unsigned long long *n_out, uint64_t cap) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (hk[i] != JH_EMPTY) {
+      unsigned long long p = atomicAdd(n_out, 1ull);
+      if (p < cap) { ok[p] = hk[i]; oc[p] = hc[i]; }
+    }
+  }
+}
+
+// Roofline denominators measured on the device in use: uniform random 32-byte sector reads
+// (ld.global.cg, one sector per load) and random 64-bit atomicCAS.
+__global__ void k_random_sector(const uint4 *buf, uint64_t n_sectors2, int per_thread, uint64_t seed, unsigned long long *sink) {
+  uint64_t x = jmix(seed + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  uint32_t acc = 0;
+  for (int i = 0; i < per_thread; i++) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    uint64_t idx = (x >> 20) % n_sectors2;
+    uint4 v = __ldcg(buf + idx * 2);  // 16 bytes out of a distinct 32-byte sector
+    acc += v.x ^ v.w;
+  }
+  if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+__global__ void k_random_cas(unsigned long long *buf, uint64_t n_words, int per_thread, uint64_t seed) {
+  uint64_t x = jmix(seed + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  for (int i = 0; i < per_thread; i++) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    uint64_t idx = (x >> 20) % n_words;
+    atomicCAS(buf + idx, 0ull, x | 1ull);
+  }
+}
+
+// =============================================================================== host side
+struct jkq_handle {
+  jkq_config cfg;
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string err;
+  JEng host;       // host mirror of the control block
+  JEng *dev = nullptr;
+  JSNode *snodes = nullptr;
+  double *prob = nullptr;
+  uint32_t *lvl_log = nullptr;
+  JGate *gates_dev = nullptr;
+  std::vector<jkq_op> ops;
+  std::vector<JGate> gates;         // GATE ops only
+  std::vector<int> gate_of_op;      // ops index -> number of gates before it
+  uint32_t n = 0;
+  bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
+  SampleParams sp;
+  uint32_t dd_root = 0, dd_nodes = 0;
+  std::map<uint32_t, double2 *> snapshots;  // slot -> device buffer of 2^n amplitudes
+  // histogram
+  unsigned long long *hk = nullptr, *hc = nullptr, *ok = nullptr, *oc = nullptr, *n_out = nullptr;
+  int *overflow = nullptr;
+  uint64_t hslots = 0, out_cap = 0;
+  bool hist_valid = false;
+  jkq_stats stats;
+  int grid_blocks = 0;
+};
+
+static int fail(jkq_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(h, JKQ_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static uint32_t pow2_at_least(uint64_t v, uint32_t lo) {
+  uint32_t p = lo;
+  while (p < v && p < 0x80000000u) p <<= 1;
+  return p;
+}
+static const char *status_text(int s) {
+  switch (s) {
+    case JKQ_ERR_NODE_FULL: return "node arena full (raise jkq_config.node_capacity)";
+    case JKQ_ERR_UTAB_FULL: return "unique table full";
+    case JKQ_ERR_VAL_FULL: return "complex-value table full (raise jkq_config.value_capacity)";
+    case JKQ_ERR_ITEM_FULL: return "frontier pool full (raise jkq_config.item_capacity)";
+    case JKQ_ERR_DTAB_FULL: return "frontier de-dup table full";
+    case JKQ_ERR_PEND_FULL: return "pending-value buffer full";
+    case JKQ_ERR_BARRIER_TIMEOUT: return "grid barrier timeout";
+    case JKQ_ERR_ZERO_STATE: return "numerical instabilities led to a 0-vector";
+    default: return "internal error";
+  }
+}
+
+extern "C" const char *jkq_last_error(const jkq_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+static void free_hist(jkq_handle *h) {
+  cudaFree(h->hk); cudaFree(h->hc); cudaFree(h->ok); cudaFree(h->oc);
+  h->hk = h->hc = h->ok = h->oc = nullptr;
+  h->hslots = 0; h->out_cap = 0; h->hist_valid = false;
+}
+static void free_snapshots(jkq_handle *h) {
+  for (auto &kv : h->snapshots) cudaFree(kv.second);
+  h->snapshots.clear();
+}
+
+extern "C" void jkq_destroy(jkq_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  JEng &E = h->host;
+  cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
+  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.fwd); cudaFree(E.vfwd);
+  cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
+  cudaFree(h->n_out); cudaFree(h->overflow);
+  free_hist(h);
+  free_snapshots(h);
+  if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
+  if (!out) return JKQ_E_ARGUMENT;
+  *out = nullptr;
+  jkq_handle *h = new jkq_handle();
+  jkq_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  if (cfg_in) cfg = *cfg_in;
+  if (cfg.tolerance <= 0) cfg.tolerance = 1e-10;
+  cfg.node_capacity = pow2_at_least(cfg.node_capacity ? cfg.node_capacity : (1u << 22), 1u << 10);
+  cfg.value_capacity = pow2_at_least(cfg.value_capacity ? cfg.value_capacity : (1u << 20), 1u << 10);
+  cfg.item_capacity = pow2_at_least(cfg.item_capacity ? cfg.item_capacity : cfg.node_capacity, 1u << 10);
+  if (!cfg.cta_threads) cfg.cta_threads = 256;
+  if (cfg.cta_threads > 256) cfg.cta_threads = 256;
+  cfg.cta_threads = (cfg.cta_threads + 31) & ~31u;
+  if (!cfg.cta_item_limit) cfg.cta_item_limit = 4096;
+  if (!cfg.gc_min) cfg.gc_min = 1u << 15;
+  if (!cfg.grid_blocks_per_sm) cfg.grid_blocks_per_sm = 2;
+  h->cfg = cfg;
+  h->device = cfg.device;
+  memset(&h->stats, 0, sizeof(h->stats));
+  memset(&h->host, 0, sizeof(h->host));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || cfg.device >= ndev) {
+    // no CPU fallback: the product path is CUDA only
+    fprintf(stderr, "jkq_create: no usable CUDA device (%s)\n", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    delete h;
+    return JKQ_E_CUDA;
+  }
+  *out = h;  // from here on the caller can read jkq_last_error and must jkq_destroy
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
+  JEng &E = h->host;
+  E.tol = cfg.tolerance;
+  E.node_cap = cfg.node_capacity; E.utab_mask = cfg.node_capacity * 2 - 1;
+  E.val_cap = cfg.value_capacity; E.vtab_mask = cfg.value_capacity * 4 - 1;
+  E.pend_cap = cfg.value_capacity;
+  E.item_cap = cfg.item_capacity; E.dtab_mask = cfg.item_capacity * 2 - 1;
+  E.cta_item_limit = cfg.cta_item_limit; E.gc_min = cfg.gc_min;
+  CU(cudaMalloc(&E.nodes, (size_t)E.node_cap * sizeof(JNode)));
+  CU(cudaMalloc(&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)));
+  CU(cudaMalloc(&E.utab, ((size_t)E.utab_mask + 1) * 4));
+  CU(cudaMalloc(&E.vals, (size_t)E.val_cap * 8));
+  CU(cudaMalloc(&E.vals_alt, (size_t)E.val_cap * 8));
+  CU(cudaMalloc(&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)));
+  CU(cudaMalloc(&E.pend, (size_t)E.pend_cap * 8));
+  CU(cudaMalloc(&E.items, (size_t)E.item_cap * sizeof(JItem)));
+  CU(cudaMalloc(&E.dtab, ((size_t)E.dtab_mask + 1) * 8));
+  CU(cudaMalloc(&E.fwd, (size_t)E.node_cap * 4));
+  CU(cudaMalloc(&E.vfwd, (size_t)E.val_cap * 4));
+  CU(cudaMalloc(&h->dev, sizeof(JEng)));
+  CU(cudaMalloc(&h->snodes, (size_t)E.node_cap * sizeof(JSNode)));
+  CU(cudaMalloc(&h->prob, (size_t)E.node_cap * 8));
+  CU(cudaMalloc(&h->n_out, 8));
+  CU(cudaMalloc(&h->overflow, 4));
+  // cooperative grid size: every CTA must be resident
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID>, 256, 0));
+  if (per_sm < 1) return fail(h, JKQ_E_CUDA, "grid kernel does not fit on an SM");
+  if ((uint32_t)per_sm > cfg.grid_blocks_per_sm) per_sm = (int)cfg.grid_blocks_per_sm;
+  h->grid_blocks = per_sm * h->sm_count;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
+  if (!h || !name) return JKQ_E_ARGUMENT;
+  if (!strcmp(name, "level_log")) { h->level_log = value != 0; return JKQ_E_OK; }
+  if (!strcmp(name, "force_mode")) { h->cfg.force_mode = (int)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_item_limit")) { h->cfg.cta_item_limit = (uint32_t)value; h->host.cta_item_limit = (uint32_t)value; return JKQ_E_OK; }
+  return fail(h, JKQ_E_ARGUMENT, "unknown option %s", name);
+}
+
+extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *ops, size_t n_ops) {
+  if (!h) return JKQ_E_ARGUMENT;
+  if (n_qubits < 1 || n_qubits > JKQ_MAXQ) return fail(h, JKQ_E_ARGUMENT, "n_qubits must be 1..%d", JKQ_MAXQ);
+  if (n_ops && !ops) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  h->n = n_qubits;
+  h->ops.assign(ops, ops + n_ops);
+  h->gates.clear();
+  h->gate_of_op.clear();
+  bool any_measure = false;
+  for (int L = 0; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
+  const uint64_t qmask = n_qubits == 64 ? ~0ull : ((1ull << n_qubits) - 1);
+  for (size_t i = 0; i < n_ops; i++) {
+    const jkq_op &o = ops[i];
+    h->gate_of_op.push_back((int)h->gates.size());
+    if (o.kind == JKQ_OP_GATE) {
+      if (o.target >= n_qubits || ((o.ctrl_pos | o.ctrl_neg) & ~qmask) || ((o.ctrl_pos | o.ctrl_neg) >> o.target & 1) ||
+          (o.ctrl_pos & o.ctrl_neg))
+        return fail(h, JKQ_E_ARGUMENT, "op %zu: bad target/control qubits", i);
+      JGate g;
+      memset(&g, 0, sizeof(g));
+      memcpy(g.m, o.m, sizeof(g.m));
+      g.target = (int)(n_qubits - 1 - o.target);  // qubit q -> level n-1-q, QASMsimulator.cpp:300
+      g.low = g.top = g.target;
+      g.role[g.target] = JR_TARGET;
+      for (uint32_t q = 0; q < n_qubits; q++) {
+        int L = (int)(n_qubits - 1 - q);
+        if (o.ctrl_pos >> q & 1) g.role[L] = JR_CPOS;
+        else if (o.ctrl_neg >> q & 1) g.role[L] = JR_CNEG;
+        else continue;
+        if (L < g.low) g.low = L;
+        if (L > g.top) g.top = L;
+      }
+      h->gates.push_back(g);
+    } else if (o.kind == JKQ_OP_MEASURE) {
+      if (o.target >= n_qubits || o.arg >= 64) return fail(h, JKQ_E_ARGUMENT, "op %zu: bad measure", i);
+      h->sp.bitpos[n_qubits - 1 - o.target] = (uint8_t)o.arg;
+      any_measure = true;
+    } else if (o.kind != JKQ_OP_SNAPSHOT && o.kind != JKQ_OP_BARRIER) {
+      return fail(h, JKQ_E_ARGUMENT, "op %zu: unknown kind %u", i, o.kind);
+    }
+  }
+  if (!any_measure)  // engine-level default: every qubit, key bit q = qubit q
+    for (uint32_t q = 0; q < n_qubits && q < 64; q++) h->sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
+  cudaFree(h->gates_dev);
+  h->gates_dev = nullptr;
+  if (!h->gates.empty()) {
+    CU(cudaMalloc(&h->gates_dev, h->gates.size() * sizeof(JGate)));
+    CU(cudaMemcpyAsync(h->gates_dev, h->gates.data(), h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  }
+  h->loaded = true; h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
+  return JKQ_E_OK;
+}
+
+static int pull_state(jkq_handle *h) {
+  CU(cudaMemcpyAsync(&h->host, h->dev, sizeof(JEng), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
+// the grid barrier's counter and flag ring must start clean at every cooperative launch
+static int reset_barrier(jkq_handle *h) {
+  CU(cudaMemsetAsync(&h->dev->bar_count, 0, sizeof(unsigned int), h->stream));
+  CU(cudaMemsetAsync(&h->dev->bar_flags[0], 0, 3 * sizeof(unsigned int), h->stream));
+  return JKQ_E_OK;
+}
+
+static int launch_gates(jkq_handle *h, bool grid, int upto) {
+  if (grid) {
+    int rb = reset_barrier(h);
+    if (rb) return rb;
+    JEng *E = h->dev;
+    const JGate *g = h->gates_dev;
+    void *args[] = {&E, &g, &upto};
+    CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
+    h->stats.grid_launches++;
+  } else {
+    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, 0, h->stream>>>(h->dev, h->gates_dev, upto);
+    CU(cudaGetLastError());
+    h->stats.cta_launches++;
+  }
+  return JKQ_E_OK;
+}
+
+// run gates [host.next_gate, upto): single-CTA path until a frontier outgrows it, then the grid path
+static int run_segment(jkq_handle *h, int upto) {
+  bool grid = h->cfg.force_mode == 2;
+  for (;;) {
+    int rc = launch_gates(h, grid, upto);
+    if (rc) return rc;
+    rc = pull_state(h);
+    if (rc) return rc;
+    if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
+    if (h->host.next_gate >= upto) return JKQ_E_OK;
+    if (h->host.want_grid && !grid) {
+      if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: frontier exceeds cta_item_limit and force_mode=1", h->host.next_gate);
+      grid = true;
+      h->host.want_grid = 0;
+      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      continue;
+    }
+    return fail(h, JKQ_E_INTERNAL, "gate kernel stopped at gate %d of %d without a reason", h->host.next_gate, upto);
+  }
+}
+
+extern "C" int jkq_apply(jkq_handle *h) {
+  if (!h) return JKQ_E_ARGUMENT;
+  if (!h->loaded) return fail(h, JKQ_E_STATE, "jkq_apply before jkq_load_circuit");
+  CU(cudaSetDevice(h->device));
+  free_snapshots(h);
+  h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
+  JEng &E = h->host;
+  E.n = h->n;
+  cudaFree(h->lvl_log);
+  h->lvl_log = nullptr;
+  if (h->level_log && !h->gates.empty()) {
+    CU(cudaMalloc(&h->lvl_log, h->gates.size() * h->n * 4));
+    CU(cudaMemsetAsync(h->lvl_log, 0, h->gates.size() * h->n * 4, h->stream));
+  }
+  E.lvl_log = h->lvl_log;
+  E.status = 0; E.next_gate = 0; E.want_grid = 0;
+  E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  CU(cudaMemcpyAsync(h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice, h->stream));
+  {
+    JEng *Ed = h->dev;
+    void *args[] = {&Ed};
+    CU(cudaLaunchCooperativeKernel((void *)k_init<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
+  }
+  const uint64_t cta0 = h->stats.cta_launches, grid0 = h->stats.grid_launches;
+  size_t i = 0;
+  while (i < h->ops.size()) {
+    if (h->ops[i].kind == JKQ_OP_GATE) {
+      size_t j = i;
+      while (j < h->ops.size() && h->ops[j].kind != JKQ_OP_SNAPSHOT) j++;
+      int upto = j < h->ops.size() ? h->gate_of_op[j] : (int)h->gates.size();
+      int rc = run_segment(h, upto);
+      if (rc) return rc;
+      i = j;
+    } else if (h->ops[i].kind == JKQ_OP_SNAPSHOT) {
+      if (h->n > 30) return fail(h, JKQ_E_CAPACITY, "state-vector snapshot needs 2^%u amplitudes", h->n);
+      double2 *buf = nullptr;
+      uint64_t len = 1ull << h->n;
+      CU(cudaMalloc(&buf, len * sizeof(double2)));
+      auto it = h->snapshots.find(h->ops[i].arg);
+      if (it != h->snapshots.end()) { cudaFree(it->second); h->snapshots.erase(it); }
+      h->snapshots[h->ops[i].arg] = buf;
+      int blocks = (int)((len + 255) / 256);
+      if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+      k_amplitudes<<<blocks, 256, 0, h->stream>>>(h->dev, 0, len, buf);
+      CU(cudaGetLastError());
+      i++;
+    } else {
+      i++;
+    }
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  int rc = pull_state(h);
+  if (rc) return rc;
+  if (h->host.status) return fail(h, h->host.status, "%s", status_text(h->host.status));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.apply_ms = ms;
+  (void)cta0; (void)grid0;
+  h->applied = true;
+  return JKQ_E_OK;
+}
+
+static int ensure_sampling(jkq_handle *h) {
+  if (h->sampling_ready) return JKQ_E_OK;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply or jkq_dd_import first");
+  // level-ordered compaction + bottom-up probabilities; grid path only for big DDs
+  bool grid = h->cfg.force_mode == 2 || (h->cfg.force_mode != 1 && h->host.node_count > 65536);
+  JEng *E = h->dev;
+  JSNode *sn = h->snodes;
+  double *pr = h->prob;
+  if (grid) {
+    int rb = reset_barrier(h);
+    if (rb) return rb;
+    void *args[] = {&E, &sn, &pr};
+    CU(cudaLaunchCooperativeKernel((void *)k_build_sampling<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
+  } else {
+    k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, 0, h->stream>>>(E, sn, pr);
+    CU(cudaGetLastError());
+  }
+  int rc = pull_state(h);
+  if (rc) return rc;
+  if (h->host.status) return fail(h, h->host.status, "build_sampling: %s", status_text(h->host.status));
+  h->dd_root = h->host.root;
+  h->dd_nodes = h->host.node_count;
+  h->stats.norm = h->host.norm;
+  h->sampling_ready = true;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offset, int accumulate) {
+  if (!h) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev2, h->stream));
+  if (!h->imported) {
+    int rc = ensure_sampling(h);
+    if (rc) return rc;
+  }
+  if (fabs(h->stats.norm - 1.0) > 0.01 && !h->imported)  // the reference only warns, Simulator.cpp:157-163
+    fprintf(stderr, "WARNING in measurement: numerical instability occurred during simulation: |alpha|^2 + |beta|^2 = %g, but should be 1!\n",
+            h->stats.norm);
+  int measured = 0;
+  for (uint32_t L = 0; L < h->n; L++) measured += h->sp.bitpos[L] < 64;
+  uint64_t need = shots < (1ull << 40) ? shots : (1ull << 40);
+  if (measured < 40 && (1ull << measured) < need) need = 1ull << measured;
+  uint64_t slots = pow2_at_least(need * 2, 1u << 12);
+  if (!accumulate || !h->hist_valid || slots > h->hslots) {
+    if (accumulate && h->hist_valid) return fail(h, JKQ_E_STATE, "accumulating histogram would need to grow; sample the largest batch first");
+    if (slots > h->hslots) {
+      free_hist(h);
+      CU(cudaMalloc(&h->hk, slots * 8));
+      CU(cudaMalloc(&h->hc, slots * 8));
+      h->hslots = slots;
+    }
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
+    h->hist_valid = true;
+  }
+  if (shots) {
+    uint64_t want = (shots + 255) / 256;
+    int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
+    CU(cudaEventRecord(h->ev3, h->stream));
+    k_sample<<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hk, h->hc,
+                                            (uint32_t)(h->hslots - 1), h->overflow);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, h->stream));
+    h->stats.sample_launches++;
+  }
+  int ovf = 0;
+  CU(cudaMemcpyAsync(&ovf, h->overflow, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (ovf) return fail(h, JKQ_E_CAPACITY, "count histogram overflow");
+  if (shots) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev3, h->ev1));
+    h->stats.sample_kernel_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev1));
+    h->stats.sample_ms = ms;
+  }
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_run(jkq_handle *h, uint64_t shots, uint64_t seed) {
+  int rc = jkq_apply(h);
+  if (rc) return rc;
+  return jkq_sample(h, shots, seed, 0, 0);
+}
+
+extern "C" int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, size_t cap, size_t *n) {
+  if (!h || !n) return JKQ_E_ARGUMENT;
+  if (!h->hist_valid) return fail(h, JKQ_E_STATE, "no histogram: call jkq_sample first");
+  CU(cudaSetDevice(h->device));
+  uint64_t want = cap ? cap : 1;
+  if (want > h->out_cap) {
+    cudaFree(h->ok); cudaFree(h->oc);
+    h->ok = h->oc = nullptr;
+    CU(cudaMalloc(&h->ok, want * 8));
+    CU(cudaMalloc(&h->oc, want * 8));
+    h->out_cap = want;
+  }
+  CU(cudaMemsetAsync(h->n_out, 0, 8, h->stream));
+  k_hist_compact<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, h->ok, h->oc, h->n_out, cap);
+  CU(cudaGetLastError());
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, h->n_out, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *n = (size_t)cnt;
+  h->stats.distinct_outcomes = cnt;
+  if (cnt > cap) return keys ? fail(h, JKQ_E_CAPACITY, "%llu distinct outcomes, buffer holds %zu", cnt, cap) : JKQ_E_OK;
+  if (cnt && keys && counts) {
+    CU(cudaMemcpyAsync(keys, h->ok, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(counts, h->oc, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count, double *re_im) {
+  if (!h || (count && !re_im)) return JKQ_E_ARGUMENT;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  if (h->n < 64 && first + count > (1ull << h->n)) return fail(h, JKQ_E_ARGUMENT, "amplitude range exceeds 2^n");
+  if (!count) return JKQ_E_OK;
+  CU(cudaSetDevice(h->device));
+  double2 *buf = nullptr;
+  CU(cudaMalloc(&buf, count * sizeof(double2)));
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+  k_amplitudes<<<blocks, 256, 0, h->stream>>>(h->dev, first, count, buf);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(re_im, buf, count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "amplitudes: %s", cudaGetErrorString(e));
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, size_t cap_amplitudes) {
+  if (!h || !re_im) return JKQ_E_ARGUMENT;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  uint64_t len = 1ull << h->n;
+  if (cap_amplitudes < len) return fail(h, JKQ_E_CAPACITY, "need room for %llu amplitudes", (unsigned long long)len);
+  if (slot == 0xFFFFFFFFu) return jkq_get_amplitudes(h, 0, len, re_im);
+  auto it = h->snapshots.find(slot);
+  if (it == h->snapshots.end()) return fail(h, JKQ_E_ARGUMENT, "no snapshot in slot %u", slot);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(re_im, it->second, len * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n) {
+  if (!h || !per_level) return JKQ_E_ARGUMENT;
+  if (n < h->n) return fail(h, JKQ_E_CAPACITY, "need %u entries", h->n);
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_sampling(h);  // runs the collector: lvl_cnt = live nodes per level
+  if (rc) return rc;
+  for (uint32_t L = 0; L < h->n; L++) per_level[L] = h->host.lvl_cnt[L];
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_written) {
+  if (!h || !out || !n_written) return JKQ_E_ARGUMENT;
+  if (!h->applied || !h->lvl_log) return fail(h, JKQ_E_STATE, "level log not recorded (set option level_log=1 before jkq_apply)");
+  size_t total = h->gates.size() * h->n;
+  if (cap < total) return fail(h, JKQ_E_CAPACITY, "need %zu entries", total);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, h->lvl_log, total * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *n_written = total;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
+  if (!h || !out) return JKQ_E_ARGUMENT;
+  const JEng &E = h->host;
+  h->stats.gates = E.st_gates; h->stats.items = E.st_items; h->stats.nodes_created = E.st_nodes_created;
+  h->stats.value_inserts = E.st_val_inserts; h->stats.gc_runs = E.st_gc_runs; h->stats.gc_nodes_copied = E.st_gc_nodes_copied;
+  h->stats.retry_rounds = E.st_retry_rounds; h->stats.max_frontier = E.st_max_frontier;
+  h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;
+  *out = h->stats;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_dd_export(jkq_handle *h, jkq_snode *host_nodes, size_t cap, uint32_t *n_nodes, uint32_t *root) {
+  if (!h || !n_nodes || !root) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  if (!h->imported) {
+    int rc = ensure_sampling(h);
+    if (rc) return rc;
+  }
+  *n_nodes = h->dd_nodes;
+  *root = h->dd_root;
+  if (!host_nodes) return JKQ_E_OK;
+  if (cap < h->dd_nodes) return fail(h, JKQ_E_CAPACITY, "need room for %u nodes", h->dd_nodes);
+  CU(cudaMemcpyAsync(host_nodes, h->snodes, (size_t)h->dd_nodes * sizeof(JSNode), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *host_nodes, uint32_t n_nodes, uint32_t root,
+                             const uint8_t *clbit_of_level) {
+  if (!h || !host_nodes || !clbit_of_level) return JKQ_E_ARGUMENT;
+  if (n_qubits < 1 || n_qubits > JKQ_MAXQ || n_nodes > h->host.node_cap || root >= n_nodes) return fail(h, JKQ_E_ARGUMENT, "bad DD");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->snodes, host_nodes, (size_t)n_nodes * sizeof(JSNode), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n = n_qubits; h->dd_root = root; h->dd_nodes = n_nodes;
+  memcpy(h->sp.bitpos, clbit_of_level, n_qubits);
+  for (uint32_t L = n_qubits; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
+  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false;
+  h->stats.norm = 1.0;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n) {
+  if (!h || !clbit_of_level || n < h->n) return JKQ_E_ARGUMENT;
+  memcpy(clbit_of_level, h->sp.bitpos, h->n);
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_random_sector_bench(jkq_handle *h, uint64_t bytes, int iters, double *gsectors_per_s, double *gcas_per_s) {
+  if (!h || !gsectors_per_s || !gcas_per_s) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  if (bytes < (1ull << 20)) bytes = 1ull << 20;
+  if (iters < 1) iters = 1;
+  uint4 *buf = nullptr;
+  unsigned long long *sink = nullptr;
+  CU(cudaMalloc(&buf, bytes));
+  CU(cudaMalloc(&sink, 8));
+  CU(cudaMemsetAsync(buf, 0, bytes, h->stream));
+  CU(cudaMemsetAsync(sink, 0, 8, h->stream));
+  const int blocks = h->sm_count * 8, threads = 256, per_thread = 256;
+  const double ops = (double)blocks * threads * per_thread;
+  float best_rd = 1e30f, best_cas = 1e30f;
+  for (int it = 0; it < iters + 1; it++) {
+    CU(cudaEventRecord(h->ev2, h->stream));
+    k_random_sector<<<blocks, threads, 0, h->stream>>>(buf, bytes / 32, per_thread, 0x1234 + it, sink);
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    if (it > 0 && ms < best_rd) best_rd = ms;
+  }
+  for (int it = 0; it < iters + 1; it++) {
+    CU(cudaMemsetAsync(buf, 0, bytes, h->stream));
+    CU(cudaEventRecord(h->ev2, h->stream));
+    k_random_cas<<<blocks, threads, 0, h->stream>>>((unsigned long long *)buf, bytes / 8, per_thread, 0x9876 + it);
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    if (it > 0 && ms < best_cas) best_cas = ms;
+  }
+  cudaFree(buf); cudaFree(sink);
+  *gsectors_per_s = ops / (best_rd * 1e-3) * 1e-9;
+  *gcas_per_s = ops / (best_cas * 1e-3) * 1e-9;
+  return JKQ_E_OK;
+}

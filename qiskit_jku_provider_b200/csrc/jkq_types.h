@@ -1,0 +1,147 @@
+// Plain data layouts shared by the CUDA kernels and the host side of the C-ABI library.
+//
+// Everything the engine keeps lives in HBM behind one `JEng` control block:
+//   * node arena      16-byte records, bump-allocated by atomicAdd, two semi-spaces for the
+//                     copying collector (replaces QMDDnode/QMDDgetNode, QMDDpackage.h:90-100,
+//                     QMDDpackage.cpp:833-860; a state-vector node only needs e[0], e[2] and, after
+//                     NormC normalisation, ONE free weight);
+//   * unique table    open addressing over 32-bit node ids (replaces Unique[MAXN][NBUCKET],
+//                     QMDDpackage.h:235, QMDDutLookup QMDDpackage.cpp:693-763);
+//   * value table     tolerance-bucketed reals, 16-byte slots (replaces Ctable/Ctable2/Cmag,
+//                     QMDDcomplexD.cpp:45,372-466);
+//   * frontier pool   80-byte work items + generation-tagged de-dup table (replaces the recursion
+//                     of QMDDmultiply2/QMDDadd and their compute tables, QMDDpackage.cpp:986-1072,
+//                     1319-1517).
+#ifndef JKQ_TYPES_H
+#define JKQ_TYPES_H
+#include <stdint.h>
+
+#define JKQ_MAXQ 64
+
+// complex weight id: (R<<32)|I, each half = sign bit + 31-bit index into the value table
+// (same encoding as the reference, QMDDcomplex.h:129-131, QMDDcomplexD.cpp:75-83)
+#define JW_ZERO 0x0ull
+#define JW_ONE 0x0000000100000000ull
+#define JW_MONE 0x8000000100000000ull
+
+typedef struct __attribute__((aligned(16))) {
+  uint32_t c0;  // child 0 node id | (norm flag << 31).  flag = index of the child whose weight is ONE
+  uint32_t c1;  // child 1 node id
+  uint64_t w;   // weight id of the OTHER child (may be JW_ZERO -> that child is the terminal 0)
+} JNode;
+
+typedef struct __attribute__((aligned(16))) {
+  double value;    // non-negative real
+  uint32_t id1;    // value index + 1 (0 = empty slot)
+  uint32_t keylo;  // low 32 bits of the bucket number floor(value / tol)
+} JVSlot;
+
+// work-item kinds
+#define JK_M 1u  // gate x node, at or above the target level
+#define JK_F 2u  // fused  P*(wa*A + wb*B) + (I-P)*(wc*C)   below the target, controls remaining
+#define JK_S 3u  // plain sum  A + wb*B                      (the reference's QMDDadd pair)
+// child-slot kinds
+#define JC_ZERO 0u
+#define JC_PASS 1u  // finished edge (node id, weight)
+#define JC_REF 2u   // result of another work item one level down, times a factor
+// item states
+#define JS_NEW 0u
+#define JS_RETRY 1u
+#define JS_DONE 2u
+#define JS_DEAD 3u
+
+typedef struct __attribute__((aligned(16))) {
+  uint32_t a, b;        // operand node ids (0 = absent)
+  uint64_t wa, wb, wc;  // normalised operand weights (kind dependent)
+  uint64_t chw[2];      // child-slot weight: factor (REF) or edge weight (PASS)
+  uint64_t rw;          // result edge weight
+  uint32_t ch[2];       // child-slot target: item index (REF) or node id (PASS)
+  uint32_t rnode;       // result edge node
+  uint32_t tag;         // kind | sel << 4
+  uint8_t chk[2];       // child-slot kinds
+  uint8_t state;
+  uint8_t pad0;
+  uint32_t pad1;
+} JItem;  // 80 bytes
+
+// level roles of a gate (bottom variable = level 0; qubit q lives on level n-1-q,
+// reference QASMsimulator.cpp:300)
+#define JR_IDLE 0
+#define JR_CPOS 1
+#define JR_CNEG 2
+#define JR_TARGET 3
+
+typedef struct {
+  double m[8];  // 2x2 matrix, row major, (re, im) pairs -- FP64 entries from the host
+  int32_t target;  // level
+  int32_t low;     // lowest level carrying a control or the target
+  int32_t top;     // highest such level
+  int32_t pad;
+  uint8_t role[JKQ_MAXQ];
+} JGate;
+
+// sampling record: one per node, level-ordered arena
+typedef struct __attribute__((aligned(16))) {
+  uint32_t c0, c1;
+  double q0;  // probability of taking child 0
+} JSNode;
+
+typedef struct {
+  // ---- configuration (host-written before launch) ----
+  uint32_t n;
+  uint32_t node_cap, utab_mask, val_cap, vtab_mask, pend_cap, item_cap, dtab_mask;
+  uint32_t cta_item_limit;  // CTA mode bails out to grid mode above this frontier size
+  uint32_t gc_min;          // never collect below this many allocated nodes
+  double tol;
+  // ---- arrays ----
+  JNode *nodes, *nodes_alt;
+  uint32_t *utab;
+  double *vals, *vals_alt;
+  JVSlot *vtab;
+  double *pend;
+  JItem *items;
+  unsigned long long *dtab;
+  uint32_t *fwd;      // node_cap entries: forwarding ids for the collector
+  uint32_t *vfwd;     // val_cap entries: value id remap for the collector
+  uint32_t *lvl_log;  // optional [gate][level] live-node counts
+  // ---- mutable state ----
+  uint32_t node_count;  // next free node id (id 0 = terminal)
+  uint32_t val_count;
+  uint32_t item_count;
+  uint32_t pend_n[2];
+  uint32_t gen;  // de-dup table generation (one per gate attempt)
+  uint32_t root;
+  uint64_t rootw;
+  uint64_t cur_u[4];  // canonical ids of the current gate's matrix (device-written at gate setup)
+  uint32_t gc_limit;
+  uint32_t gc_count;   // collector cursor
+  double norm;        // squared norm of the state at the last finalisation
+  uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L+1], lvl_off[L]) ... see gc
+  uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection
+  // ---- status ----
+  int32_t status;       // 0 ok, >0 error code
+  int32_t next_gate;    // first gate not yet applied
+  int32_t want_grid;    // CTA mode asked for the grid path
+  int32_t pad_s;
+  // ---- counters ----
+  unsigned long long st_items, st_nodes_created, st_val_inserts, st_gc_runs, st_retry_rounds,
+      st_ut_probes, st_dt_probes, st_vt_probes, st_max_frontier, st_gates, st_gc_nodes_copied;
+  // ---- grid barrier ----
+  unsigned int bar_count;
+  unsigned int bar_gen;
+  unsigned int bar_flags[3];
+} JEng;
+
+// error codes (JEng.status, also returned by the C-ABI)
+#define JKQ_OK 0
+#define JKQ_ERR_NODE_FULL 1
+#define JKQ_ERR_UTAB_FULL 2
+#define JKQ_ERR_VAL_FULL 3
+#define JKQ_ERR_ITEM_FULL 4
+#define JKQ_ERR_DTAB_FULL 5
+#define JKQ_ERR_PEND_FULL 6
+#define JKQ_ERR_BARRIER_TIMEOUT 7
+#define JKQ_ERR_ZERO_STATE 8
+#define JKQ_ERR_INTERNAL 9
+
+#endif

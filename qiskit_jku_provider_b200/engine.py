@@ -1,0 +1,185 @@
+"""Thin Python wrapper over one ``jkq_handle`` of libjkq_b200.so (include/jkq.h)."""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .jkusimulatorerror import JKUSimulatorError
+
+OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER = 0, 1, 2, 3
+FINAL_SLOT = 0xFFFFFFFF
+
+SNODE_DTYPE = np.dtype([("c0", "<u4"), ("c1", "<u4"), ("q0", "<f8")])
+
+
+def gate_op(target, matrix, controls=()):
+    """jkq_op for a 2x2 ``matrix`` (nested sequence of complex) on ``target``; controls = ((qubit, value), ...)."""
+    op = _native.JkqOp()
+    op.kind = OP_GATE
+    op.target = int(target)
+    pos = neg = 0
+    for q, v in controls:
+        if v:
+            pos |= 1 << int(q)
+        else:
+            neg |= 1 << int(q)
+    op.ctrl_pos, op.ctrl_neg = pos, neg
+    k = 0
+    for i in range(2):
+        for j in range(2):
+            z = complex(matrix[i][j])
+            op.m[k], op.m[k + 1] = z.real, z.imag
+            k += 2
+    return op
+
+
+def simple_op(kind, target=0, arg=0):
+    op = _native.JkqOp()
+    op.kind, op.target, op.arg = kind, int(target), int(arg)
+    return op
+
+
+class Engine:
+    """One engine instance bound to one CUDA device.  Not thread-safe."""
+
+    def __init__(self, device=0, **cfg):
+        self._lib = _native.load()
+        c = _native.JkqConfig()
+        c.device = int(device)
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise TypeError("unknown engine option %r" % k)
+            setattr(c, k, v)
+        self._h = C.c_void_p()
+        rc = self._lib.jkq_create(C.byref(self._h), C.byref(c))
+        if rc != 0:
+            msg = self._lib.jkq_last_error(self._h).decode() if self._h else "no usable CUDA device"
+            if self._h:
+                self._lib.jkq_destroy(self._h)
+                self._h = None
+            raise JKUSimulatorError("jkq_create failed (%d): %s" % (rc, msg))
+        self.n = 0
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.jkq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise JKUSimulatorError("jkq error %d: %s" % (rc, self._lib.jkq_last_error(self._h).decode()))
+
+    # -- circuit ----------------------------------------------------------------------------
+    def load_ops(self, n_qubits, ops):
+        arr = (_native.JkqOp * max(1, len(ops)))(*ops)
+        self._check(self._lib.jkq_load_circuit(self._h, int(n_qubits), arr, len(ops)))
+        self.n = int(n_qubits)
+
+    def load(self, circuit, measure=None, final_snapshot=False):
+        """``circuit``: circuits.Circuit; ``measure``: {qubit: clbit} (None = all qubits, bit q = qubit q)."""
+        ops = [gate_op(op.target, op.matrix(), op.controls) for op in circuit.ops]
+        if final_snapshot:
+            ops.append(simple_op(OP_SNAPSHOT, 0, 0))
+        for q, cbit in (measure or {}).items():
+            ops.append(simple_op(OP_MEASURE, q, cbit))
+        self.load_ops(circuit.n, ops)
+
+    def set_option(self, name, value):
+        self._check(self._lib.jkq_set_option(self._h, name.encode(), int(value)))
+
+    # -- execution --------------------------------------------------------------------------
+    def apply(self):
+        self._check(self._lib.jkq_apply(self._h))
+
+    def sample(self, shots, seed=1, shot_offset=0, accumulate=False):
+        self._check(self._lib.jkq_sample(self._h, int(shots), int(seed), int(shot_offset), int(bool(accumulate))))
+
+    def run(self, shots, seed=1):
+        self._check(self._lib.jkq_run(self._h, int(shots), int(seed)))
+
+    # -- results ----------------------------------------------------------------------------
+    def counts_arrays(self):
+        n = C.c_size_t(0)
+        self._check(self._lib.jkq_get_counts(self._h, None, None, 0, C.byref(n)))
+        k = np.zeros(max(1, n.value), dtype=np.uint64)
+        v = np.zeros(max(1, n.value), dtype=np.uint64)
+        self._check(self._lib.jkq_get_counts(self._h, k.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                             v.ctypes.data_as(C.POINTER(C.c_uint64)), k.size, C.byref(n)))
+        return k[:n.value], v[:n.value]
+
+    def counts(self):
+        """{outcome as int (bit c = classical bit c): count}"""
+        k, v = self.counts_arrays()
+        return {int(a): int(b) for a, b in zip(k, v)}
+
+    def counts_bitstrings(self, width=None):
+        """{string with character i = bit i: count} -- the layout the reference engine prints
+        (QASMsimulator.cpp:491-494)."""
+        width = width or self.n
+        return {"".join("1" if (k >> i) & 1 else "0" for i in range(width)): v for k, v in self.counts().items()}
+
+    def statevector(self, slot=FINAL_SLOT):
+        out = np.zeros(2 << self.n, dtype=np.float64)
+        self._check(self._lib.jkq_get_statevector(self._h, int(slot), out.ctypes.data_as(C.POINTER(C.c_double)), 1 << self.n))
+        return out.view(np.complex128)
+
+    def amplitudes(self, first, count):
+        out = np.zeros(2 * max(1, count), dtype=np.float64)
+        self._check(self._lib.jkq_get_amplitudes(self._h, int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.view(np.complex128)[:count]
+
+    def level_counts(self):
+        out = np.zeros(self.n, dtype=np.uint32)
+        self._check(self._lib.jkq_get_level_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), self.n))
+        return [int(x) for x in out]
+
+    def level_log(self, n_gates):
+        out = np.zeros(max(1, n_gates * self.n), dtype=np.uint32)
+        w = C.c_size_t(0)
+        self._check(self._lib.jkq_get_level_log(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size, C.byref(w)))
+        return out[:w.value].reshape(n_gates, self.n).tolist()
+
+    def stats(self):
+        s = _native.JkqStats()
+        self._check(self._lib.jkq_get_stats(self._h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in s._fields_}
+
+    # -- multi-GPU plumbing -----------------------------------------------------------------
+    def dd_export(self):
+        n, root = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.jkq_dd_export(self._h, None, 0, C.byref(n), C.byref(root)))
+        arr = np.zeros(n.value, dtype=SNODE_DTYPE)
+        self._check(self._lib.jkq_dd_export(self._h, arr.ctypes.data_as(C.POINTER(_native.JkqSNode)), arr.size,
+                                            C.byref(n), C.byref(root)))
+        return arr, int(root.value)
+
+    def measure_map(self):
+        out = np.zeros(max(1, self.n), dtype=np.uint8)
+        self._check(self._lib.jkq_get_measure_map(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size))
+        return out[:self.n]
+
+    def dd_import(self, n_qubits, nodes, root, clbit_of_level):
+        nodes = np.ascontiguousarray(nodes, dtype=SNODE_DTYPE)
+        m = np.ascontiguousarray(clbit_of_level, dtype=np.uint8)
+        self._check(self._lib.jkq_dd_import(self._h, int(n_qubits), nodes.ctypes.data_as(C.POINTER(_native.JkqSNode)),
+                                            nodes.size, int(root), m.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self.n = int(n_qubits)
+
+    def random_sector_bench(self, nbytes=1 << 32, iters=3):
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._lib.jkq_random_sector_bench(self._h, int(nbytes), int(iters), C.byref(a), C.byref(b)))
+        return {"gsectors_per_s": a.value, "random_sector_gbs": a.value * 32.0, "gcas_per_s": b.value}
