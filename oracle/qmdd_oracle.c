@@ -36,6 +36,7 @@ typedef uint64_t cw;
 #define C_MONE 0x8000000100000000ull
 
 static double Ctol = 1e-10; /* QMDDcomplexD.cpp:336 */
+static int tie_rule = 0;    /* --tie-tol: NOT the reference's rule (see normalize) */
 static double *cval;        /* index -> value          (Ctable)  */
 static uint8_t *calive;     /* erased by cleanCtable?            */
 static uint32_t Ctentries, ccap;
@@ -277,7 +278,11 @@ static Edge normalize(Edge e) {
   for (int i = 0; i < 4; i++) {
     if (n->e[i].p == NULLP || n->e[i].w == C_ZERO) continue;
     double m = c_mag2(n->e[i].w);
-    if (max == -1 || m > best) { best = m; max = i; } /* strict >, first index wins ties (:565) */
+    /* strict >, first index wins ties (:565).  With --tie-tol (study instrument, off by default) two
+     * magnitudes closer than the snapping error of their canonical parts count as a tie, which is
+     * what the CUDA engine does (DESIGN.md "normalisation ties"). */
+    double slack = tie_rule ? 4.0 * Ctol * sqrt(m > best ? m : best) : 0.0;
+    if (max == -1 || m > best + slack) { best = m; max = i; }
   }
   if (max == -1) { e.w = C_ZERO; return e; }
   if (n->e[max].w == C_ONE) return e;
@@ -776,13 +781,14 @@ static int hent_cmp(const void *a, const void *b) {
 
 int main(int argc, char **argv) {
   const char *circuit = NULL;
-  long shots = 0, amp_limit = 0;
+  long shots = 0, amp_limit = 0, shot_offset = 0;
   int levels = 0, amps = 0, use_philox = 1, dump_ctable = 0;
   uint64_t seed = 1;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--circuit") && i + 1 < argc) circuit = argv[++i];
     else if (!strcmp(argv[i], "--shots") && i + 1 < argc) shots = atol(argv[++i]);
     else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], NULL, 10);
+    else if (!strcmp(argv[i], "--shot-offset") && i + 1 < argc) shot_offset = atol(argv[++i]);
     else if (!strcmp(argv[i], "--levels")) levels = 1;
     else if (!strcmp(argv[i], "--amps")) amps = 1;
     else if (!strcmp(argv[i], "--amp-limit") && i + 1 < argc) amp_limit = atol(argv[++i]);
@@ -790,6 +796,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--precision") && i + 1 < argc) Ctol = atof(argv[++i]);
     else if (!strcmp(argv[i], "--slab-ascending")) slab_descending = 0;
     else if (!strcmp(argv[i], "--dump-ctable")) dump_ctable = 1;
+    else if (!strcmp(argv[i], "--tie-tol")) tie_rule = 1;
   }
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
   if (!f) { fprintf(stderr, "usage: qmdd_oracle --circuit FILE [--shots N] [--seed S] [--levels] [--amps] [--rng rand|philox]\n"); return 2; }
@@ -903,7 +910,7 @@ int main(int argc, char **argv) {
     double p = AssignProbs(circ_e);
     if (fabs(p - 1) > 0.01) fprintf(stderr, "WARNING in measurement: |alpha|^2 + |beta|^2 = %g\n", p);
     HEnt *all = (HEnt *)malloc((size_t)shots * sizeof(HEnt));
-    for (long i = 0; i < shots; i++) { all[i].key = MeasureAll(use_philox, seed, (uint64_t)i); all[i].cnt = 1; }
+    for (long i = 0; i < shots; i++) { all[i].key = MeasureAll(use_philox, seed, (uint64_t)(shot_offset + i)); all[i].cnt = 1; }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     qsort(all, shots, sizeof(HEnt), hent_cmp);
     printf(",\n \"shots\": %ld,\n \"t_sample_s\": %.9g,\n \"norm\": %.17g,\n \"counts\": {", shots,

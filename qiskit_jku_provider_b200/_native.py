@@ -4,7 +4,7 @@ missing GPU raises."""
 import ctypes as C
 import os
 
-from ._build import LIB
+from ._build import LIB, build_native, stale
 
 _lib = None
 
@@ -62,6 +62,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if stale():  # sources newer than the library (or no library yet): rebuild when nvcc is around
+        try:
+            build_native()
+        except Exception:
+            pass
     if not os.path.exists(LIB):
         raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the engine is CUDA only, there is no CPU fallback)" % LIB)

@@ -33,6 +33,7 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
     JEng *E = c.E;
     const uint32_t slot = c.phase % 3u;
     if (threadIdx.x == 0) {
+      if (blockIdx.x < 1024) E->dbg_phase[blockIdx.x] = c.phase;
       if (r) atomicOr(&E->bar_flags[slot], r);
       unsigned int gen = *(volatile unsigned int *)&E->bar_gen;
       __threadfence();
@@ -45,7 +46,10 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
         long long t0 = clock64();
         while (*(volatile unsigned int *)&E->bar_gen == gen) {
           __nanosleep(64);
-          if (clock64() - t0 > 40000000000ll) { jset_error(E, JKQ_ERR_BARRIER_TIMEOUT); break; }
+          if (clock64() - t0 > 8000000000ll) {
+            if (atomicCAS(&E->status, 0, JKQ_ERR_BARRIER_TIMEOUT) == 0) E->dbg_timeout_block = blockIdx.x;
+            break;
+          }
         }
       }
       __threadfence();
@@ -70,7 +74,7 @@ template <int MODE> JD void serial_insert(Ctx &c) {
   JEng *E = c.E;
   const uint32_t par = (c.phase - 1) & 1u;  // the phase that produced the values ended at the last barrier
   if (c.block0) {
-    uint32_t n = ld_s<MODE>(&E->pend_n[par]);
+    uint32_t n = ld_s<MODE>(cnt_pend<MODE>(c, par));
     if (n > E->pend_cap) n = E->pend_cap;
     double *p = E->pend;
     if (n > 32) {  // bitonic sort by the whole CTA, padded with +inf
@@ -103,7 +107,7 @@ template <int MODE> JD void serial_insert(Ctx &c) {
         uint32_t idx;
         if (!real_find<MODE>(c, x, &idx)) real_insert_serial<MODE>(E, x);
       }
-      E->pend_n[par] = 0;
+      *cnt_pend<MODE>(c, par) = 0;
       E->st_retry_rounds++;
     }
   }
@@ -117,7 +121,7 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L, boo
   for (uint32_t round = 0;; round++) {
     uint32_t my = 0;
     for (uint32_t i = b + c.tid; i < e; i += c.nth) {
-      JItem *it = E->items + i;
+      JItem *it = c.items + i;
       uint32_t st = ld_s<MODE>(&it->state);
       if (st == JS_DEAD) continue;
       if (round > 0 && st != JS_RETRY) continue;
@@ -125,9 +129,11 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L, boo
       it->state = ok ? JS_DONE : JS_RETRY;
       if (!ok) my |= JF_RETRY;
     }
-    if (ld_r(&E->status) != 0) my |= JF_ERROR;
+    if (jhas_error<MODE>(c)) my |= JF_ERROR;
+    if (MODE == MODE_CTA && c.sh->want_grid) my |= JF_GRID;
     uint32_t flags = sync_or<MODE>(c, my);
     if (flags & JF_ERROR) return JF_ERROR;
+    if (flags & JF_GRID) return JF_GRID;
     if (!(flags & JF_RETRY)) return 0;
     serial_insert<MODE>(c);
   }
@@ -143,11 +149,13 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g) {
   if (c.block0 && c.ltid == 0) {
     for (int k = 0; k < 4; k++) E->cur_u[k] = cx_make_serial<MODE>(c, g.m[2 * k], g.m[2 * k + 1]);
     E->gen++;
-    JItem *it = E->items;
+    JItem *it = c.items;
     it->a = E->root; it->b = 0; it->wa = 0; it->wb = 0; it->wc = 0; it->tag = JK_M; it->state = JS_NEW;
-    E->item_count = 1;
+    *cnt_items<MODE>(c) = 1;
   }
-  if (sync_or<MODE>(c, ld_r(&E->status) ? JF_ERROR : 0) & JF_ERROR) return JF_ERROR;
+  if (MODE == MODE_CTA)
+    for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) c.sh->dtab[i] = 0;
+  if (sync_or<MODE>(c, jhas_error<MODE>(c) ? JF_ERROR : 0) & JF_ERROR) return JF_ERROR;
 
   uint32_t lb[JKQ_MAXQ + 1], le[JKQ_MAXQ + 1];  // items of level L: [lb[L], le[L])
   uint32_t b = 0, e = 1;
@@ -156,7 +164,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g) {
     lb[L] = b; le[L] = e; lowest = L;
     uint32_t f = run_level<MODE>(c, g, b, e, L, true);
     if (f) return f;
-    b = e; e = ld_s<MODE>(&E->item_count);  // children of level 0 are terminals, never items
+    b = e; e = rd_items<MODE>(c);  // children of level 0 are terminals, never items
     if (MODE == MODE_CTA && e - b > E->cta_item_limit) return JF_GRID;
   }
   for (int L = lowest; L < n; L++) {
@@ -164,7 +172,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g) {
     if (f) return f;
   }
   if (c.block0 && c.ltid == 0) {
-    const JItem *it = E->items;
+    const JItem *it = c.items;
     uint64_t rw = ld_s<MODE>(&it->rw), w = 0;
     uint32_t rn = ld_s<MODE>(&it->rnode);
     if (rw == JW_ONE) w = E->rootw;
@@ -173,14 +181,14 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g) {
       double ar = jre<MODE>(c, rw), ai = jim<MODE>(c, rw), br = jre<MODE>(c, E->rootw), bi = jim<MODE>(c, E->rootw);
       w = cx_make_serial<MODE>(c, JKQ_DSUB(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi)), JKQ_DADD(JKQ_DMUL(ar, bi), JKQ_DMUL(ai, br)));
     }
-    if (w == 0 || rn == 0) jset_error(E, JKQ_ERR_ZERO_STATE);
+    if (w == 0 || rn == 0) jset_error_c<MODE>(c, JKQ_ERR_ZERO_STATE);
     E->root = rn; E->rootw = w;
-    unsigned long long cnt = E->item_count;
+    unsigned long long cnt = rd_items<MODE>(c);
     E->st_items += cnt;
     if (cnt > E->st_max_frontier) E->st_max_frontier = cnt;
     E->st_gates++;
   }
-  if (sync_or<MODE>(c, ld_r(&E->status) ? JF_ERROR : 0) & JF_ERROR) return JF_ERROR;
+  if (sync_or<MODE>(c, jhas_error<MODE>(c) ? JF_ERROR : 0) & JF_ERROR) return JF_ERROR;
   return 0;
 }
 
@@ -194,11 +202,18 @@ template <int MODE> JD uint32_t gc_run(Ctx &c) {
   JEng *E = c.E;
   const int n = (int)E->n;
   uint32_t *list = (uint32_t *)E->items;  // list[new_id - 1] = old id
-  const uint32_t old_count = ld_s<MODE>(&E->node_count), old_vals = ld_s<MODE>(&E->val_count);
+  c.spare_node = 0;  // ids are renumbered: a spare id from before the collection is meaningless
+  const uint32_t old_count = rd_nodes<MODE>(c), old_vals = ld_s<MODE>(&E->val_count);
+  // the reals are only swept when the table outgrew its limit, like the reference's
+  // `Ctable.size() > complex_limit` (Simulator.cpp:488-498): dropping an unreferenced value changes
+  // which representative later values snap to
+  const bool clean_vals = old_vals > ld_s<MODE>(&E->val_gc_limit);
   for (uint32_t i = c.tid; i < old_count; i += c.nth) E->fwd[i] = 0;
-  for (uint32_t i = c.tid; i < old_vals; i += c.nth) E->vfwd[i] = 0;
   for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
-  for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) E->vtab[i].id1 = 0;
+  if (clean_vals) {
+    for (uint32_t i = c.tid; i < old_vals; i += c.nth) E->vfwd[i] = 0;
+    for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) E->vtab[i].id1 = 0;
+  }
   if (c.block0 && c.ltid == 0) {
     list[0] = E->root;
     E->gc_count = 1;
@@ -232,25 +247,32 @@ template <int MODE> JD uint32_t gc_run(Ctx &c) {
     nn.c1 = c1 ? ld_s<MODE>(E->fwd + c1) : 0;
     nn.w = nd.w;
     E->nodes_alt[i + 1] = nn;
-    E->vfwd[(uint32_t)(nd.w >> 32) & 0x7FFFFFFFu] = 1;
-    E->vfwd[(uint32_t)nd.w & 0x7FFFFFFFu] = 1;
+    if (clean_vals) {
+      E->vfwd[(uint32_t)(nd.w >> 32) & 0x7FFFFFFFu] = 1;
+      E->vfwd[(uint32_t)nd.w & 0x7FFFFFFFu] = 1;
+    }
   }
   sync_or<MODE>(c, 0);
-  if (c.block0 && c.ltid == 0) {  // compact the reals, keeping insertion order; constants stay
-    uint64_t rw = E->rootw;
-    E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu] = 1;
-    E->vfwd[(uint32_t)rw & 0x7FFFFFFFu] = 1;
-    uint32_t nv = 0;
-    for (uint32_t i = 0; i < old_vals; i++) {
-      if (i < 4 || ld_s<MODE>(E->vfwd + i)) {
-        E->vals_alt[nv] = ld_s<MODE>(E->vals + i);
-        E->vfwd[i] = nv++;
+  if (c.block0 && c.ltid == 0) {
+    if (clean_vals) {  // compact the reals, keeping insertion order; constants stay
+      uint64_t rw = E->rootw;
+      E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu] = 1;
+      E->vfwd[(uint32_t)rw & 0x7FFFFFFFu] = 1;
+      uint32_t nv = 0;
+      for (uint32_t i = 0; i < old_vals; i++) {
+        if (i < 4 || ld_s<MODE>(E->vfwd + i)) {
+          E->vals_alt[nv] = ld_s<MODE>(E->vals + i);
+          E->vfwd[i] = nv++;
+        }
       }
+      E->val_count = nv;
+      E->rootw = ((uint64_t)(((uint32_t)(rw >> 32) & 0x80000000u) | E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu]) << 32) |
+                 (((uint32_t)rw & 0x80000000u) | E->vfwd[(uint32_t)rw & 0x7FFFFFFFu]);
+      if (E->val_gc_limit < 2 * nv) E->val_gc_limit *= 2;  // Simulator.cpp:495-497
+      if (E->val_gc_limit > E->val_cap / 2) E->val_gc_limit = E->val_cap / 2;
     }
-    E->val_count = nv;
-    E->rootw = ((uint64_t)((uint32_t)(rw >> 32) & 0x80000000u | E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu]) << 32) |
-               ((uint32_t)rw & 0x80000000u | E->vfwd[(uint32_t)rw & 0x7FFFFFFFu]);
     E->root = 1;
+    *cnt_nodes<MODE>(c) = live + 1;
     E->node_count = live + 1;
     uint32_t lim = 4 * (live + 1);
     if (lim < E->gc_min) lim = E->gc_min;
@@ -258,23 +280,27 @@ template <int MODE> JD uint32_t gc_run(Ctx &c) {
     E->gc_limit = lim;
     E->st_gc_runs++;
     E->st_gc_nodes_copied += live;
-    if (live + 1 >= E->node_cap / 2) jset_error(E, JKQ_ERR_NODE_FULL);
+    if (live + 1 >= E->node_cap / 2) jset_error_c<MODE>(c, JKQ_ERR_NODE_FULL);
   }
   sync_or<MODE>(c, 0);
   const uint32_t nv = ld_s<MODE>(&E->val_count);
   // copy back with remapped weights, rebuild the unique table
   for (uint32_t i = c.tid; i < live; i += c.nth) {
     JNode nn = ld_s<MODE>(E->nodes_alt + i + 1);
-    uint32_t hr = (uint32_t)(nn.w >> 32), hi = (uint32_t)nn.w;
-    hr = (hr & 0x80000000u) | ld_s<MODE>(E->vfwd + (hr & 0x7FFFFFFFu));
-    hi = (hi & 0x80000000u) | ld_s<MODE>(E->vfwd + (hi & 0x7FFFFFFFu));
-    nn.w = ((uint64_t)hr << 32) | hi;
+    if (clean_vals) {
+      uint32_t hr = (uint32_t)(nn.w >> 32), hi = (uint32_t)nn.w;
+      hr = (hr & 0x80000000u) | ld_s<MODE>(E->vfwd + (hr & 0x7FFFFFFFu));
+      hi = (hi & 0x80000000u) | ld_s<MODE>(E->vfwd + (hi & 0x7FFFFFFFu));
+      nn.w = ((uint64_t)hr << 32) | hi;
+    }
     E->nodes[i + 1] = nn;
     uint32_t h = ut_hash(nn) & E->utab_mask;
     while (jatomic_cas(E->utab + h, 0u, i + 1) != 0) h = (h + 1) & E->utab_mask;
   }
+  if (MODE == MODE_CTA)  // node ids changed: drop the shared node cache
+    for (uint32_t i = c.ltid; i < JKQ_SNC_SLOTS; i += c.lnth) c.sh->ntag[i] = 0;
   // copy the reals back, rebuild the value table (distinct buckets: claim a slot, then fill it)
-  for (uint32_t i = c.tid; i < nv; i += c.nth) {
+  for (uint32_t i = c.tid; clean_vals && i < nv; i += c.nth) {
     double x = ld_s<MODE>(E->vals_alt + i);
     E->vals[i] = x;
     if (i == 0) continue;  // 0.0 is never hashed: real_find short-cuts x <= tol
@@ -284,7 +310,7 @@ template <int MODE> JD uint32_t gc_run(Ctx &c) {
     E->vtab[h].value = x;
     E->vtab[h].keylo = (uint32_t)k;
   }
-  return sync_or<MODE>(c, ld_r(&E->status) ? JF_ERROR : 0) & JF_ERROR;
+  return sync_or<MODE>(c, jhas_error<MODE>(c) ? JF_ERROR : 0) & JF_ERROR;
 }
 
 // ------------------------------------------------------------------------------------ init
@@ -323,6 +349,7 @@ template <int MODE> JD uint32_t init_state(Ctx &c) {
     }
     E->root = prev; E->rootw = JW_ONE;
     E->gc_limit = E->gc_min > E->node_cap / 2 ? E->node_cap / 2 : E->gc_min;
+    E->val_gc_limit = 10000 < E->val_cap / 2 ? 10000 : E->val_cap / 2;  // complex_limit, Simulator.h:91
   }
   return sync_or<MODE>(c, 0);
 }
@@ -330,8 +357,30 @@ template <int MODE> JD uint32_t init_state(Ctx &c) {
 // ------------------------------------------------------------------------------------ circuit driver
 // Applies gates [E->next_gate, n_gates).  Collects when the arena passed gc_limit, or after every
 // gate when a level log was requested (parity tests: reference Active[v], QMDDpackage.h:199-201).
+template <int MODE> JD void cta_state_load(Ctx &c) {
+  if (MODE != MODE_CTA) return;
+  if (c.ltid == 0) {
+    CtaState *S = c.sh;
+    S->item_count = c.E->item_count; S->node_count = c.E->node_count;
+    S->pend_n[0] = S->pend_n[1] = 0;
+    S->nodes_created = 0; S->err = (uint32_t)c.E->status; S->want_grid = 0;
+  }
+  for (uint32_t i = c.ltid; i < JKQ_SNC_SLOTS; i += c.lnth) c.sh->ntag[i] = 0;
+  sync_or<MODE>(c, 0);
+}
+template <int MODE> JD void cta_state_store(Ctx &c) {
+  if (MODE != MODE_CTA) return;
+  if (c.ltid == 0) {
+    CtaState *S = c.sh;
+    c.E->item_count = S->item_count; c.E->node_count = S->node_count;
+    c.E->st_nodes_created += S->nodes_created;
+    S->nodes_created = 0;
+  }
+}
+
 template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
   JEng *E = c.E;
+  cta_state_load<MODE>(c);
   int g = ld_s<MODE>((const uint32_t *)&E->next_gate);
   for (; g < n_gates; g++) {
     uint32_t f = apply_gate<MODE>(c, gates[g]);
@@ -341,7 +390,7 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
       break;
     }
     bool log = E->lvl_log != 0;
-    if (log || ld_s<MODE>(&E->node_count) > ld_s<MODE>(&E->gc_limit)) {
+    if (log || rd_nodes<MODE>(c) > ld_s<MODE>(&E->gc_limit)) {
       if (gc_run<MODE>(c)) break;
       if (log && c.block0 && c.ltid == 0)
         for (uint32_t L = 0; L < E->n; L++) E->lvl_log[(size_t)g * E->n + L] = E->lvl_cnt[L];
@@ -349,6 +398,7 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
     if (c.block0 && c.ltid == 0) E->next_gate = g + 1;
   }
   sync_or<MODE>(c, 0);
+  cta_state_store<MODE>(c);
 }
 
 // ------------------------------------------------------------------------------------ sampling prep
@@ -358,7 +408,9 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
 // ids in a 16-byte sampling record.
 template <int MODE> JD uint32_t build_sampling(Ctx &c, JSNode *snodes, double *prob) {
   JEng *E = c.E;
+  cta_state_load<MODE>(c);
   if (gc_run<MODE>(c)) return JF_ERROR;
+  cta_state_store<MODE>(c);
   if (c.block0 && c.ltid == 0) prob[0] = 1.0;
   sync_or<MODE>(c, 0);
   for (uint32_t L = 0; L < E->n; L++) {

@@ -15,9 +15,14 @@
 #include "jkq_sample.cuh"
 
 // =============================================================================== kernels
+extern __shared__ __align__(16) unsigned char jkq_dyn_smem[];  // CtaState, MODE_CTA launches only
+
 template <int MODE> __device__ __forceinline__ Ctx make_ctx(JEng *E) {
   Ctx c;
   c.E = E;
+  c.sh = MODE == MODE_CTA ? reinterpret_cast<CtaState *>(jkq_dyn_smem) : nullptr;
+  c.items = MODE == MODE_CTA ? c.sh->items : E->items;
+  c.spare_node = 0;
   c.phase = 0;
   c.ltid = threadIdx.x;
   c.lnth = blockDim.x;
@@ -44,7 +49,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k_build_sampling(JEng
 
 __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *out) {
   Ctx c;
-  c.E = E; c.phase = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.E = E; c.sh = nullptr; c.items = E->items; c.spare_node = 0; c.phase = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
   c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
   for (uint64_t i = c.tid; i < count; i += c.nth) {
     double re, im;
@@ -257,7 +262,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   if (!cfg.cta_threads) cfg.cta_threads = 256;
   if (cfg.cta_threads > 256) cfg.cta_threads = 256;
   cfg.cta_threads = (cfg.cta_threads + 31) & ~31u;
-  if (!cfg.cta_item_limit) cfg.cta_item_limit = 4096;
+  if (!cfg.cta_item_limit || cfg.cta_item_limit > JKQ_SITEMS / 2) cfg.cta_item_limit = JKQ_SITEMS / 2;
   if (!cfg.gc_min) cfg.gc_min = 1u << 15;
   if (!cfg.grid_blocks_per_sm) cfg.grid_blocks_per_sm = 2;
   h->cfg = cfg;
@@ -300,6 +305,8 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaMalloc(&h->prob, (size_t)E.node_cap * 8));
   CU(cudaMalloc(&h->n_out, 8));
   CU(cudaMalloc(&h->overflow, 4));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaState)));
+  CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaState)));
   // cooperative grid size: every CTA must be resident
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID>, 256, 0));
@@ -313,7 +320,11 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!h || !name) return JKQ_E_ARGUMENT;
   if (!strcmp(name, "level_log")) { h->level_log = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "force_mode")) { h->cfg.force_mode = (int)value; return JKQ_E_OK; }
-  if (!strcmp(name, "cta_item_limit")) { h->cfg.cta_item_limit = (uint32_t)value; h->host.cta_item_limit = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_item_limit")) {
+    if (value < 1 || value > JKQ_SITEMS / 2) value = JKQ_SITEMS / 2;
+    h->cfg.cta_item_limit = (uint32_t)value; h->host.cta_item_limit = (uint32_t)value;
+    return JKQ_E_OK;
+  }
   return fail(h, JKQ_E_ARGUMENT, "unknown option %s", name);
 }
 
@@ -394,7 +405,7 @@ static int launch_gates(jkq_handle *h, bool grid, int upto) {
     CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
     h->stats.grid_launches++;
   } else {
-    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, 0, h->stream>>>(h->dev, h->gates_dev, upto);
+    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(h->dev, h->gates_dev, upto);
     CU(cudaGetLastError());
     h->stats.cta_launches++;
   }
@@ -409,6 +420,18 @@ static int run_segment(jkq_handle *h, int upto) {
     if (rc) return rc;
     rc = pull_state(h);
     if (rc) return rc;
+    if (h->host.status == JKQ_ERR_BARRIER_TIMEOUT) {
+      std::string s;
+      char tmp[64];
+      for (int b = 0; b < h->grid_blocks && b < 1024; b++) {
+        if (b == 0 || h->host.dbg_phase[b] != h->host.dbg_phase[b - 1]) {
+          snprintf(tmp, sizeof(tmp), " b%d:%u", b, h->host.dbg_phase[b]);
+          s += tmp;
+        }
+      }
+      return fail(h, h->host.status, "gate %d: grid barrier timeout (block %u gave up; bar_count=%u; last phase per block:%s)",
+                  h->host.next_gate, h->host.dbg_timeout_block, h->host.bar_count, s.c_str());
+    }
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
     if (h->host.next_gate >= upto) return JKQ_E_OK;
     if (h->host.want_grid && !grid) {
@@ -499,7 +522,7 @@ static int ensure_sampling(jkq_handle *h) {
     void *args[] = {&E, &sn, &pr};
     CU(cudaLaunchCooperativeKernel((void *)k_build_sampling<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
   } else {
-    k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, 0, h->stream>>>(E, sn, pr);
+    k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(E, sn, pr);
     CU(cudaGetLastError());
   }
   int rc = pull_state(h);

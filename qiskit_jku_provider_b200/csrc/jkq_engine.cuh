@@ -32,7 +32,7 @@
 template <class T> static inline T jatomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T jatomic_cas(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 template <class T> static inline T jatomic_max(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
-static inline void jfence() {}
+template <int MODE> static inline void jfence() {}
 #else
 #define JD __device__ __forceinline__
 #define JKQ_DMUL(a, b) __dmul_rn((a), (b))
@@ -42,16 +42,43 @@ static inline void jfence() {}
 template <class T> JD T jatomic_add(T *p, T v) { return atomicAdd(p, v); }
 template <class T> JD T jatomic_cas(T *p, T cmp, T v) { return atomicCAS(p, cmp, v); }
 template <class T> JD T jatomic_max(T *p, T v) { return atomicMax(p, v); }
-JD void jfence() { __threadfence(); }
+template <int MODE> JD void jfence() {
+  if (MODE == MODE_CTA) __threadfence_block();
+  else __threadfence();
+}
 #endif
+
+// MODE_CTA keeps the hot counters and the per-gate de-dup table in shared memory: a shared-memory
+// atomic costs tens of cycles, an HBM/L2 atomic several hundred, and on a 32-node DD the atomics are
+// the critical path.  The counters are written back to the JEng block at gate boundaries.
+#define JKQ_SITEMS 1536u     // work items of one gate that fit the shared pool; beyond: grid path
+#define JKQ_SDT_SLOTS 4096u  // shared de-dup slots (u32 item index + 1)
+#define JKQ_SNC_SLOTS 2048u  // shared node cache, direct-mapped by node id
+struct CtaState {
+  uint32_t item_count, node_count, pend_n[2];
+  uint32_t nodes_created, err, want_grid, pad;
+  uint32_t dtab[JKQ_SDT_SLOTS];
+  uint32_t ntag[JKQ_SNC_SLOTS];
+  JNode ncache[JKQ_SNC_SLOTS];
+  JItem items[JKQ_SITEMS];
+};
 
 struct Ctx {
   JEng *E;
+  CtaState *sh;       // MODE_CTA only
+  JItem *items;       // frontier pool: shared memory in MODE_CTA, HBM in MODE_GRID
+  uint32_t spare_node;  // node id allocated by this thread and not used yet (lost unique-table race)
   uint32_t tid, nth;  // index / count over all participating threads
   uint32_t phase;     // barrier counter, identical in every thread
   uint32_t block0;    // 1 if this thread belongs to the CTA that runs the serial sections
   uint32_t ltid, lnth;
 };
+
+template <int MODE> JD uint32_t *cnt_items(const Ctx &c) { return MODE == MODE_CTA ? &c.sh->item_count : &c.E->item_count; }
+template <int MODE> JD uint32_t *cnt_nodes(const Ctx &c) { return MODE == MODE_CTA ? &c.sh->node_count : &c.E->node_count; }
+template <int MODE> JD uint32_t *cnt_pend(const Ctx &c, uint32_t par) { return MODE == MODE_CTA ? &c.sh->pend_n[par] : &c.E->pend_n[par]; }
+template <int MODE> JD uint32_t rd_items(const Ctx &c);
+template <int MODE> JD uint32_t rd_nodes(const Ctx &c);
 
 // ------------------------------------------------------------------------------------ loads
 // ld_s: data not written since the last barrier.  ld_r: data that may be written concurrently.
@@ -92,12 +119,33 @@ JD JNode ld_r(const JNode *p) {
 }
 #endif
 
+// ld_p: probe of a slot / record that may be written concurrently.  One CTA = one SM = one coherent L1
+// for plain stores, and every claim goes through atomicCAS which returns the truth, so MODE_CTA can
+// probe through L1; MODE_GRID must read L2.
+#ifdef JKQ_EMU
+template <int MODE, class T> JD T ld_p(const T *p) { return *p; }
+template <int MODE> JD uint32_t rd_items(const Ctx &c) { return *cnt_items<MODE>(c); }
+template <int MODE> JD uint32_t rd_nodes(const Ctx &c) { return *cnt_nodes<MODE>(c); }
+template <int MODE> JD bool jhas_error(const Ctx &c) { return c.E->status != 0; }
+#else
+template <int MODE, class T> JD T ld_p(const T *p) { return MODE == MODE_CTA ? *p : ld_r(p); }
+template <int MODE> JD uint32_t rd_items(const Ctx &c) { return MODE == MODE_CTA ? c.sh->item_count : __ldcg(&c.E->item_count); }
+template <int MODE> JD uint32_t rd_nodes(const Ctx &c) { return MODE == MODE_CTA ? c.sh->node_count : __ldcg(&c.E->node_count); }
+template <int MODE> JD bool jhas_error(const Ctx &c) { return MODE == MODE_CTA ? c.sh->err != 0 : __ldcg(&c.E->status) != 0; }
+#endif
+
 JD uint64_t jmix(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
 }
 
 JD void jset_error(JEng *E, int code) { jatomic_cas(&E->status, 0, code); }
+// MODE_CTA polls a shared-memory copy of the error flag instead of an L2 round trip per phase
+template <int MODE> JD void jset_error_c(Ctx &c, int code) {
+  jatomic_cas(&c.E->status, 0, code);
+  if (MODE == MODE_CTA) c.sh->err = (uint32_t)code;
+}
+template <int MODE> JD bool jhas_error(const Ctx &c);
 
 // ------------------------------------------------------------------------------------ value table
 // Semantics of the reference's Clookup (QMDDcomplexD.cpp:372-466) with its tolerance comparator
@@ -159,11 +207,11 @@ template <int MODE> JD uint32_t real_insert_serial(JEng *E, double x) {
   return idx;
 }
 
-JD void pend_push(Ctx &c, double x) {
+template <int MODE> JD void pend_push(Ctx &c, double x) {
   JEng *E = c.E;
-  uint32_t i = jatomic_add(&E->pend_n[c.phase & 1], 1u);
+  uint32_t i = jatomic_add(cnt_pend<MODE>(c, c.phase & 1), 1u);
   if (i < E->pend_cap) E->pend[i] = x;
-  else jset_error(E, JKQ_ERR_PEND_FULL);
+  else jset_error_c<MODE>(c, JKQ_ERR_PEND_FULL);
 }
 
 // Clookup for one complex value.  false = at least one part is not in the table yet; the missing
@@ -173,8 +221,8 @@ template <int MODE> JD bool cx_find(Ctx &c, double re, double im, uint64_t *out)
   re = fabs(re); im = fabs(im);
   uint32_t r = 0, i = 0;
   bool okr = real_find<MODE>(c, re, &r), oki = real_find<MODE>(c, im, &i);
-  if (!okr) pend_push(c, re);
-  if (!oki) pend_push(c, im);
+  if (!okr) pend_push<MODE>(c, re);
+  if (!oki) pend_push<MODE>(c, im);
   if (!(okr && oki)) return false;
   if (sr && r) r |= 0x80000000u;
   if (si && i) i |= 0x80000000u;
@@ -245,26 +293,64 @@ JD uint64_t nd_w1(const JNode &n) { return nd_flag(n) ? JW_ONE : n.w; }
 // in a slot therefore always finds a complete record behind it (read with ld.cg).
 JD uint32_t ut_hash(const JNode &n) { return (uint32_t)jmix(((uint64_t)n.c0 << 32 | n.c1) ^ jmix(n.w)); }
 
+// MODE_CTA reads nodes through a direct-mapped shared-memory cache (a plain global store drops the
+// line from L1, so a node written by one gate would cost the next gate an L2 round trip).
+template <int MODE> JD JNode node_load(Ctx &c, uint32_t id) {
+  if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
+    uint32_t s = id & (JKQ_SNC_SLOTS - 1);
+    if (S->ntag[s] == id) {
+      JNode n = S->ncache[s];
+      if (S->ntag[s] == id) return n;  // (another thread may be replacing the slot: re-check)
+    }
+    JNode n = ld_s<MODE>(c.E->nodes + id);
+    return n;
+  }
+  return ld_s<MODE>(c.E->nodes + id);
+}
+template <int MODE> JD void node_cache_put(Ctx &c, uint32_t id, const JNode &n) {
+  if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
+    uint32_t s = id & (JKQ_SNC_SLOTS - 1);
+    S->ntag[s] = 0;  // invalidate, fill, publish: a reader that sees the new tag twice saw the new record
+    jfence<MODE>();
+    S->ncache[s] = n;
+    jfence<MODE>();
+    S->ntag[s] = id;
+  }
+}
+
 template <int MODE> JD uint32_t ut_find_or_insert(Ctx &c, const JNode &rec) {
   JEng *E = c.E;
   uint32_t h = ut_hash(rec) & E->utab_mask, mine = 0;
   for (uint32_t probes = 0; probes <= E->utab_mask; probes++) {
-    uint32_t s = ld_r(E->utab + h);
+    // MODE_CTA goes straight for the CAS (one L2 round trip when the slot is free, the common case on
+    // the latency path); MODE_GRID looks first so that a hit costs no node id
+    uint32_t s = MODE == MODE_CTA ? 0u : ld_r(E->utab + h);
     if (s == 0) {
       if (mine == 0) {
-        mine = jatomic_add(&E->node_count, 1u);
-        if (mine >= E->node_cap) { jset_error(E, JKQ_ERR_NODE_FULL); return 0; }
+        if (c.spare_node) { mine = c.spare_node; c.spare_node = 0; }
+        else mine = jatomic_add(cnt_nodes<MODE>(c), 1u);
+        if (mine >= E->node_cap) { jset_error_c<MODE>(c, JKQ_ERR_NODE_FULL); return 0; }
         E->nodes[mine] = rec;
-        jfence();
+        jfence<MODE>();
       }
       s = jatomic_cas(E->utab + h, 0u, mine);
-      if (s == 0) { jatomic_add(&E->st_nodes_created, 1ull); return mine; }
+      if (s == 0) {
+        if (MODE == MODE_CTA) jatomic_add(&c.sh->nodes_created, 1u);
+        else jatomic_add(&E->st_nodes_created, 1ull);
+        node_cache_put<MODE>(c, mine, rec);
+        return mine;
+      }
     }
-    JNode o = ld_r(E->nodes + s);
-    if (o.c0 == rec.c0 && o.c1 == rec.c1 && o.w == rec.w) return s;  // (a lost race burns `mine`; the collector reclaims it)
+    JNode o = MODE == MODE_CTA ? node_load<MODE>(c, s) : ld_r(E->nodes + s);
+    if (o.c0 == rec.c0 && o.c1 == rec.c1 && o.w == rec.w) {
+      c.spare_node = mine;  // keep the id for this thread's next insert
+      return s;
+    }
     h = (h + 1) & E->utab_mask;
   }
-  jset_error(E, JKQ_ERR_UTAB_FULL);
+  jset_error_c<MODE>(c, JKQ_ERR_UTAB_FULL);
   return 0;
 }
 
@@ -277,36 +363,71 @@ JD uint32_t dt_hash(uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t w
   return (uint32_t)jmix(((uint64_t)a << 32 | b) ^ jmix(wa + 0x9E3779B97F4A7C15ull * tag) ^ jmix(wb * 3 + 1) ^ jmix(wc * 5 + 2));
 }
 
+JD bool item_key_eq(const JItem *o, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+  return o->a == a && o->b == b && o->tag == tag && o->wa == wa && o->wb == wb && o->wc == wc;
+}
+
+// returns the item index; *ok = false: the table could not take the key (error flagged, or -- MODE_CTA --
+// the shared table is crowded and the gate has to be redone on the grid path: c.sh->want_grid)
 template <int MODE>
 JD uint32_t dt_find_or_insert(Ctx &c, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag, bool *ok) {
   JEng *E = c.E;
-  uint32_t h = dt_hash(a, b, wa, wb, wc, tag) & E->dtab_mask, mine = 0xFFFFFFFFu;
+  uint32_t mine = 0xFFFFFFFFu;
+  if (MODE == MODE_CTA) {
+    // shared-memory table of item indices, cleared at gate setup
+    CtaState *S = c.sh;
+    uint32_t h = dt_hash(a, b, wa, wb, wc, tag) & (JKQ_SDT_SLOTS - 1);
+    for (uint32_t probes = 0; probes < 64; probes++) {
+      uint32_t s = S->dtab[h];
+      if (s == 0) {
+        if (mine == 0xFFFFFFFFu) {
+          mine = jatomic_add(&S->item_count, 1u);
+          if (mine >= JKQ_SITEMS) { S->want_grid = 1; *ok = false; return 0; }
+          JItem *it = c.items + mine;
+          it->a = a; it->b = b; it->wa = wa; it->wb = wb; it->wc = wc; it->tag = tag;
+          it->state = JS_NEW;
+          jfence<MODE>();
+        }
+        s = jatomic_cas(&S->dtab[h], 0u, mine + 1);
+        if (s == 0) return mine;
+      }
+      if (item_key_eq(c.items + (s - 1), a, b, wa, wb, wc, tag)) {
+        if (mine != 0xFFFFFFFFu) c.items[mine].state = JS_DEAD;
+        return s - 1;
+      }
+      h = (h + 1) & (JKQ_SDT_SLOTS - 1);
+    }
+    S->want_grid = 1;
+    *ok = false;
+    return 0;
+  }
+  uint32_t h = dt_hash(a, b, wa, wb, wc, tag) & E->dtab_mask;
   unsigned long long gen = (unsigned long long)ld_s<MODE>(&E->gen) << 32;
   for (uint32_t probes = 0; probes <= E->dtab_mask; probes++) {
     unsigned long long s = ld_r(E->dtab + h);
     while ((s >> 32) != (gen >> 32)) {  // stale or empty: try to claim
       if (mine == 0xFFFFFFFFu) {
         mine = jatomic_add(&E->item_count, 1u);
-        if (mine >= E->item_cap) { jset_error(E, JKQ_ERR_ITEM_FULL); *ok = false; return 0; }
-        JItem *it = E->items + mine;
+        if (mine >= E->item_cap) { jset_error_c<MODE>(c, JKQ_ERR_ITEM_FULL); *ok = false; return 0; }
+        JItem *it = c.items + mine;
         it->a = a; it->b = b; it->wa = wa; it->wb = wb; it->wc = wc; it->tag = tag;
         it->state = JS_NEW;
-        jfence();
+        jfence<MODE>();
       }
       unsigned long long old = jatomic_cas(E->dtab + h, s, gen | (unsigned long long)(mine + 1));
       if (old == s) return mine;
       s = old;
     }
     uint32_t j = (uint32_t)s - 1;
-    const JItem *o = E->items + j;
+    const JItem *o = c.items + j;
     if (ld_r(&o->a) == a && ld_r(&o->b) == b && ld_r(&o->tag) == tag && ld_r(&o->wa) == wa && ld_r(&o->wb) == wb &&
         ld_r(&o->wc) == wc) {
-      if (mine != 0xFFFFFFFFu) E->items[mine].state = JS_DEAD;
+      if (mine != 0xFFFFFFFFu) c.items[mine].state = JS_DEAD;
       return j;
     }
     h = (h + 1) & E->dtab_mask;
   }
-  jset_error(E, JKQ_ERR_DTAB_FULL);
+  jset_error_c<MODE>(c, JKQ_ERR_DTAB_FULL);
   *ok = false;
   return 0;
 }
@@ -379,13 +500,13 @@ JD int role_satisfied(uint32_t role, int i) {
 // inserts) only after all arithmetic succeeded, so a retry simply runs the function again.
 template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
   JEng *E = c.E;
-  JItem *it = E->items + idx;
+  JItem *it = c.items + idx;
   const uint32_t tag = ld_s<MODE>(&it->tag), ia = ld_s<MODE>(&it->a), ib = ld_s<MODE>(&it->b);
   const uint32_t kind = tag & 15u, sel = (tag >> 4) & 1u;
   const uint32_t role = g.role[L];
   Slot s[2];
   if (kind == JK_M) {
-    JNode p = ld_s<MODE>(E->nodes + ia);
+    JNode p = node_load<MODE>(c, ia);
     uint32_t ch[2] = {nd_c0(p), p.c1};
     uint64_t w[2] = {nd_w0(p), nd_w1(p)};
     if (L > g.target) {
@@ -408,13 +529,30 @@ template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, in
     uint64_t aw[2] = {0, 0}, bw[2] = {0, 0};
     uint32_t ac[2] = {0, 0}, bc[2] = {0, 0};
     const uint64_t iwa = ld_s<MODE>(&it->wa), iwb = ld_s<MODE>(&it->wb), iwc = ld_s<MODE>(&it->wc);
-    if (ia) { na = ld_s<MODE>(E->nodes + ia); ac[0] = nd_c0(na); ac[1] = na.c1; aw[0] = nd_w0(na); aw[1] = nd_w1(na); }
-    if (ib) { nb = ld_s<MODE>(E->nodes + ib); bc[0] = nd_c0(nb); bc[1] = nb.c1; bw[0] = nd_w0(nb); bw[1] = nd_w1(nb); }
+    if (ia) { na = node_load<MODE>(c, ia); ac[0] = nd_c0(na); ac[1] = na.c1; aw[0] = nd_w0(na); aw[1] = nd_w1(na); }
+    if (ib) { nb = node_load<MODE>(c, ib); bc[0] = nd_c0(nb); bc[1] = nb.c1; bw[0] = nd_w0(nb); bw[1] = nd_w1(nb); }
     for (int i = 0; i < 2; i++) {
       if (kind == JK_S) {
         uint64_t be;
         if (!cmul<MODE>(c, iwb, bw[i], &be)) return false;
         if (!combine_sum<MODE>(c, L - 1, aw[i], ac[i], be, bc[i], s[i])) return false;
+      } else if (ia == ib) {
+        // Both operands are the SAME node: (alpha : beta : gamma) of the child is aw_i * (wa : wb : wc),
+        // i.e. the already normalised key, so the child item needs no arithmetic at all (the exact
+        // algebra the reference reaches through its Cmul/Cdiv memo tables, QMDDcomplex.h:93).
+        if (aw[i] == 0) { slot_zero(s[i]); continue; }
+        if (!role_satisfied(role, i)) {
+          uint64_t ga;
+          if (!cmul<MODE>(c, iwc, aw[i], &ga)) return false;
+          slot_pass(s[i], ac[i], ga);
+        } else if (L - 1 >= g.low) {
+          slot_ref(s[i], aw[i], ac[i], ac[i], iwa, iwb, iwc, tag);
+        } else {
+          uint64_t sum, w;
+          if (!cadd<MODE>(c, iwa, iwb, &sum)) return false;
+          if (!cmul<MODE>(c, aw[i], sum, &w)) return false;
+          slot_pass(s[i], ac[i], w);
+        }
       } else {
         uint64_t ga;
         if (!cmul<MODE>(c, iwc, sel ? bw[i] : aw[i], &ga)) return false;
@@ -430,7 +568,7 @@ template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, in
     if (s[i].kind == JC_REF) {
       bool ok = true;
       uint32_t j = dt_find_or_insert<MODE>(c, s[i].ia, s[i].ib, s[i].iwa, s[i].iwb, s[i].iwc, s[i].itag, &ok);
-      if (!ok) return true;  // error already flagged
+      if (!ok) return true;  // error / want_grid already flagged; the gate is abandoned
       s[i].target = j;
     }
     it->ch[i] = s[i].target; it->chw[i] = s[i].w; it->chk[i] = (uint8_t)s[i].kind;
@@ -442,38 +580,68 @@ template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, in
 // Bottom-up step: QMDDmakeNonterminal (QMDDpackage.cpp:1204-1233) = zero test, NormC normalisation
 // (QMDDnormalize :532-595: divide by the largest-magnitude child weight, first index wins ties),
 // hash-cons.  Result edge = (node, top weight), to be scaled by the parent's factor.
+// |a1| > |a0| beyond the snapping error of the canonical parts?  (index 0 wins ties, :565)
+template <int MODE> JD bool mag_greater(const Ctx &c, uint64_t a1, uint64_t a0) {
+  if (a1 == a0 || a1 == jneg(a0)) return false;
+  double m0 = jmag2<MODE>(c, a0), m1 = jmag2<MODE>(c, a1);
+#ifdef JKQ_EXACT_TIES
+  return m1 > m0;  // the reference's rule: exact compare, decided by rounding noise on true ties
+#else
+  // Index 0 also wins when the two magnitudes differ by less than the snapping error of their
+  // canonical parts (each real is only defined up to tol): H-type gates produce equal magnitudes all
+  // the time, and deciding such a tie by rounding noise gives two normal forms of one vector that
+  // never merge again (DESIGN.md "normalisation ties").
+  return m1 > JKQ_DADD(m0, JKQ_DMUL(JKQ_DMUL(4.0, c.E->tol), sqrt(m1 > m0 ? m1 : m0)));
+#endif
+}
+
 template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx) {
   JEng *E = c.E;
-  JItem *it = E->items + idx;
+  JItem *it = c.items + idx;
+  // each child edge is f_i * a_i: f_i = top weight of the child item's result (ONE for finished
+  // edges), a_i = the factor / edge weight recorded at expansion
   uint32_t rn[2];
-  uint64_t rw[2];
+  uint64_t f[2], a[2];
   for (int i = 0; i < 2; i++) {
     uint32_t k = ld_s<MODE>(&it->chk[i]);
     uint32_t cht = ld_s<MODE>(&it->ch[i]);
     uint64_t chw = ld_s<MODE>(&it->chw[i]);
-    if (k == JC_ZERO) { rn[i] = 0; rw[i] = 0; }
-    else if (k == JC_PASS) { rn[i] = cht; rw[i] = chw; }
+    if (k == JC_ZERO) { rn[i] = 0; f[i] = JW_ONE; a[i] = 0; }
+    else if (k == JC_PASS) { rn[i] = cht; f[i] = JW_ONE; a[i] = chw; }
     else {
-      const JItem *ci = E->items + cht;
-      uint64_t crw = ld_s<MODE>(&ci->rw);
-      if (!cmul<MODE>(c, crw, chw, &rw[i])) return false;
+      const JItem *ci = c.items + cht;
+      f[i] = ld_s<MODE>(&ci->rw);
       rn[i] = ld_s<MODE>(&ci->rnode);
+      a[i] = f[i] ? chw : 0;
     }
-    if (rw[i] == 0) rn[i] = 0;
+    if (a[i] == 0) rn[i] = 0;
   }
-  if (rw[0] == 0 && rw[1] == 0) { it->rnode = 0; it->rw = 0; return true; }
-  uint32_t mx = 0;
-  if (rw[0] == 0) mx = 1;
-  else if (rw[1] != 0 && rw[0] != rw[1]) {
-    if (jmag2<MODE>(c, rw[1]) > jmag2<MODE>(c, rw[0])) mx = 1;  // strict >: index 0 wins ties (:565)
+  if (a[0] == 0 && a[1] == 0) { it->rnode = 0; it->rw = 0; return true; }
+  uint32_t mx;
+  uint64_t other, top;
+  if (a[0] == 0 || a[1] == 0 || f[0] == f[1]) {
+    // Common factor: (F a0, F a1) normalises exactly like (a0, a1) and F moves to the top weight.
+    // For a product state or a basis-like state this removes ALL arithmetic from the levels above the
+    // gate (a_max is ONE there); the reference gets the same effect from its complex op caches.
+    mx = (a[0] == 0) ? 1u : (a[1] == 0 ? 0u : (mag_greater<MODE>(c, a[1], a[0]) ? 1u : 0u));
+    if (!cdiv<MODE>(c, a[1 - mx], a[mx], &other)) return false;
+    if (!cmul<MODE>(c, f[mx], a[mx], &top)) return false;
+  } else {
+    uint64_t rw[2];
+    if (!cmul<MODE>(c, f[0], a[0], &rw[0])) return false;
+    if (!cmul<MODE>(c, f[1], a[1], &rw[1])) return false;
+    if (rw[0] == 0 && rw[1] == 0) { it->rnode = 0; it->rw = 0; return true; }
+    mx = (rw[0] == 0) ? 1u : (rw[1] == 0 ? 0u : (mag_greater<MODE>(c, rw[1], rw[0]) ? 1u : 0u));
+    if (!cdiv<MODE>(c, rw[1 - mx], rw[mx], &other)) return false;
+    top = rw[mx];
+    if (rw[1 - mx] == 0) rn[1 - mx] = 0;
   }
-  uint64_t other;
-  if (!cdiv<MODE>(c, rw[1 - mx], rw[mx], &other)) return false;
+  if (top == 0) { it->rnode = 0; it->rw = 0; return true; }
   if (other == 0) rn[1 - mx] = 0;
   JNode rec;
   rec.c0 = rn[0] | (mx << 31); rec.c1 = rn[1]; rec.w = other;
   uint32_t id = ut_find_or_insert<MODE>(c, rec);
-  it->rnode = id; it->rw = rw[mx];
+  it->rnode = id; it->rw = top;
   return true;
 }
 

@@ -115,6 +115,8 @@ typedef struct {
   uint64_t cur_u[4];  // canonical ids of the current gate's matrix (device-written at gate setup)
   uint32_t gc_limit;
   uint32_t gc_count;   // collector cursor
+  uint32_t val_gc_limit;  // sweep the reals only above this many (reference complex_limit)
+  uint32_t pad_v;
   double norm;        // squared norm of the state at the last finalisation
   uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L+1], lvl_off[L]) ... see gc
   uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection
@@ -130,6 +132,8 @@ typedef struct {
   unsigned int bar_count;
   unsigned int bar_gen;
   unsigned int bar_flags[3];
+  unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was
+  unsigned int dbg_phase[1024];
 } JEng;
 
 // error codes (JEng.status, also returned by the C-ABI)

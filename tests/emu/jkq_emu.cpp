@@ -63,6 +63,7 @@ int main(int argc, char **argv) {
   int levels = 0, amps = 0;
   uint64_t seed = 1;
   uint32_t node_cap = 1u << 22, gc_min = 1u << 16;
+  int dump_level = -1;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--circuit") && i + 1 < argc) circuit = argv[++i];
     else if (!strcmp(argv[i], "--shots") && i + 1 < argc) shots = atol(argv[++i]);
@@ -72,6 +73,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--amp-limit") && i + 1 < argc) amp_limit = atol(argv[++i]);
     else if (!strcmp(argv[i], "--node-cap") && i + 1 < argc) node_cap = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--gc-min") && i + 1 < argc) gc_min = (uint32_t)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--dump-level") && i + 1 < argc) dump_level = atoi(argv[++i]);
   }
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
   if (!f) { fprintf(stderr, "usage: jkq_emu --circuit FILE ...\n"); return 2; }
@@ -113,7 +115,7 @@ int main(int argc, char **argv) {
   E->node_cap = node_cap; E->utab_mask = node_cap * 2 - 1;
   E->val_cap = 1u << 20; E->vtab_mask = (1u << 22) - 1;
   E->pend_cap = 1u << 20; E->item_cap = node_cap; E->dtab_mask = node_cap * 2 - 1;
-  E->cta_item_limit = 0xFFFFFFFFu; E->gc_min = gc_min;
+  E->cta_item_limit = JKQ_SITEMS / 2; E->gc_min = gc_min;
   E->nodes = (JNode *)calloc(E->node_cap, sizeof(JNode));
   E->nodes_alt = (JNode *)calloc(E->node_cap, sizeof(JNode));
   E->utab = (uint32_t *)calloc((size_t)E->utab_mask + 1, 4);
@@ -128,18 +130,40 @@ int main(int argc, char **argv) {
   if (levels) E->lvl_log = (uint32_t *)calloc(gates.size() * n + 1, 4);
 
   Ctx c;
+  static CtaState cta_state;
+  c.sh = &cta_state;
+  c.items = cta_state.items;
+  c.spare_node = 0;
   c.E = E; c.tid = 0; c.nth = 1; c.phase = 0; c.block0 = 1; c.ltid = 0; c.lnth = 1;
   init_state<MODE_CTA>(c);
   run_gates<MODE_CTA>(c, gates.data(), (int)gates.size());
+  int grid_switches = 0;
+  while (!E->status && E->want_grid && E->next_gate < (int)gates.size()) {
+    // same escalation as the host driver (run_segment in jkq_b200.cu): finish on the grid path
+    E->want_grid = 0;
+    grid_switches++;
+    Ctx g = c;
+    g.sh = nullptr; g.items = E->items; g.spare_node = 0;
+    run_gates<MODE_GRID>(g, gates.data(), (int)gates.size());
+  }
   if (E->status) { fprintf(stderr, "engine error %d at gate %d\n", E->status, E->next_gate); return 3; }
 
   std::vector<JSNode> sn(E->node_cap);
   std::vector<double> prob(E->node_cap);
   build_sampling<MODE_CTA>(c, sn.data(), prob.data());
 
+  if (dump_level >= 0) {
+    for (uint32_t i = 0; i < E->lvl_cnt[dump_level]; i++) {
+      uint32_t id = E->lvl_off[dump_level] + i;
+      JNode nd = E->nodes[id];
+      fprintf(stderr, "node %u: flag %u c0 %u c1 %u w=(%.17g, %.17g) ids %llx\n", id, nd_flag(nd), nd_c0(nd), nd.c1,
+              jre<MODE_CTA>(c, nd.w), jim<MODE_CTA>(c, nd.w), (unsigned long long)nd.w);
+    }
+  }
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n", n, gates.size());
   printf(" \"items\": %llu,\n \"nodes_created\": %llu,\n \"val_inserts\": %llu,\n \"gc_runs\": %llu,\n \"retry_rounds\": %llu,\n \"max_frontier\": %llu,\n",
          E->st_items, E->st_nodes_created, E->st_val_inserts, E->st_gc_runs, E->st_retry_rounds, E->st_max_frontier);
+  printf(" \"grid_switches\": %d,\n", grid_switches);
   printf(" \"ctable_size\": %u,\n \"norm\": %.17g,\n", E->val_count, E->norm);
   printf(" \"level_counts\": [");
   for (int v = 0; v < n; v++) printf("%s%u", v ? "," : "", E->lvl_cnt[v]);

@@ -1,0 +1,214 @@
+"""GPU: parity of the CUDA engine, called through the C ABI (ctypes -> libjkq_b200.so), with the oracle
+and with the golden outputs of the unmodified reference.  Run with `-m gpu` on the B200 box."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from test_oracle import level_parity
+from qiskit_jku_provider_b200 import circuits as C
+
+pytestmark = pytest.mark.gpu
+
+# amplitude tolerance: the reference's complex-table tolerance Ctol = 1e-10 per snapped weight
+# (QMDDcomplexD.cpp:336), an amplitude being a product of <= n+1 weights
+AMP_TOL = 1e-9
+TIE = ["--tie-tol"]  # the oracle restating the engine's tie rule (tests/test_emu_engine.py)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from qiskit_jku_provider_b200.engine import Engine
+    e = Engine(device=0, node_capacity=1 << 21)
+    yield e
+    e.close()
+
+
+def text_to_circuit(g):
+    import importlib.util
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return {c.name: c for c in mod.cases()}[g["name"]]
+
+
+def run(eng, circ, shots, seed, mode, levels=True):
+    eng.set_option("force_mode", mode)
+    eng.set_option("level_log", 1 if levels else 0)
+    eng.load(circ)
+    eng.run(shots, seed)
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["cta", "grid"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_reference_parity(eng, oracle_mod, name, mode):
+    g = load_golden(name)
+    circ = text_to_circuit(g)
+    run(eng, circ, 2048, 5, mode)
+    amps = eng.statevector()
+    ref = np.array([complex(*a) for a in g["amps"]])
+    assert np.abs(amps - ref).max() < AMP_TOL
+    lg = eng.level_log(len(circ))
+    level_parity(g["level_counts_per_gate"], lg, name)       # vs the unmodified reference
+    o = oracle_mod.run_oracle(circ, shots=2048, seed=5, levels=True, extra=TIE)
+    assert lg == o["level_counts_per_gate"]                    # vs the oracle, every gate, every level
+    assert eng.level_counts() == o["level_counts"]
+    assert eng.counts_bitstrings() == o["counts"]              # same Philox stream -> identical counts
+    assert abs(eng.stats()["norm"] - 1.0) < 1e-9
+
+
+CONFIGS = [C.ghz(24), C.ghz(24, star=True), C.qft(16), C.qft(24), C.grover(12, 20, marked=0x5A5),
+           C.random_circuit(18, 40, 1), C.random_circuit(18, 40, 2), C.random_circuit(18, 40, 3),
+           C.random_circuit(18, 80, 1), C.random_circuit(12, 80, 5)]
+
+
+@pytest.mark.parametrize("circ", CONFIGS, ids=lambda c: c.name)
+def test_oracle_parity_on_baseline_shapes(eng, oracle_mod, circ):
+    run(eng, circ, 4096, 3, 0)
+    k = min(1 << 12, 1 << circ.n)
+    o = oracle_mod.run_oracle(circ, shots=4096, seed=3, levels=True, amps=True, extra=["--amp-limit", str(k)] + TIE)
+    oa = np.array([complex(*a) for a in o["amps"]])
+    assert np.abs(eng.amplitudes(0, k) - oa).max() < AMP_TOL
+    assert eng.level_log(len(circ)) == o["level_counts_per_gate"]
+    assert eng.counts_bitstrings() == o["counts"]
+
+
+def test_qft32_full_size(eng, oracle_mod):
+    """BASELINE config 2 at full size: 2528 applies, DD stays 32 nodes, |amp|^2 uniform = 2^-32."""
+    circ = C.qft(32)
+    run(eng, circ, 100000, 11, 1)
+    o = oracle_mod.run_oracle(circ, shots=100000, seed=11, levels=True, amps=True, extra=["--amp-limit", "4096"] + TIE)
+    assert eng.level_log(len(circ)) == o["level_counts_per_gate"]
+    assert eng.level_counts() == [1] * 32
+    a = eng.amplitudes(0, 4096)
+    assert np.abs(a - np.array([complex(*x) for x in o["amps"]])).max() < AMP_TOL
+    assert np.allclose(np.abs(a) ** 2 * 2.0 ** 32, 1.0, atol=1e-4)
+    assert eng.counts_bitstrings() == o["counts"]
+    assert abs(eng.stats()["norm"] - 1.0) < 1e-4
+
+
+def test_grover20_full_size(eng, oracle_mod):
+    """BASELINE config 3: n = 20, native 19-control Z, 2 nodes per level; 60 iterations here (the
+    801-iteration run is bench.py's job), checked against the oracle and the analytic success
+    probability sin^2((2k+1) asin(2^-10))."""
+    k = 60
+    circ = C.grover(20, k)
+    run(eng, circ, 20000, 2, 1, levels=False)
+    o = oracle_mod.run_oracle(circ, shots=20000, seed=2, extra=TIE)
+    assert eng.level_counts() == o["level_counts"] == [2] * 19 + [1]
+    amp = eng.amplitudes(0x5A5A5, 1)[0]
+    p = np.sin((2 * k + 1) * np.arcsin(2.0 ** -10)) ** 2
+    assert abs(abs(amp) ** 2 - p) < 1e-6
+    assert eng.counts_bitstrings() == o["counts"]
+
+
+def test_random_blowup_uses_grid_path_and_collector(eng, oracle_mod):
+    """BASELINE config 4b: n = 18, 100 ops -> ~1.5k live nodes, 25k created; auto mode must escalate."""
+    circ = C.random_circuit(18, 100, 1)
+    eng.set_option("cta_item_limit", 256)
+    try:
+        run(eng, circ, 4096, 3, 0, levels=False)
+    finally:
+        eng.set_option("cta_item_limit", 4096)
+    st = eng.stats()
+    assert st["grid_launches"] >= 1
+    o = oracle_mod.run_oracle(circ, shots=4096, seed=3, amps=True, extra=["--amp-limit", "4096"] + TIE)
+    assert np.abs(eng.amplitudes(0, 4096) - np.array([complex(*x) for x in o["amps"]])).max() < AMP_TOL
+    assert abs(st["norm"] - 1.0) < 1e-9
+    # sum over levels within 1 % of the oracle (blown-up random DDs: equality only while no two
+    # distinct values fall within tol, SURVEY section 7 hard part 2)
+    assert abs(sum(eng.level_counts()) - sum(o["level_counts"])) <= 0.01 * sum(o["level_counts"])
+
+
+def test_collector_under_pressure():
+    """Arena of 4096 nodes: many collections, identical result."""
+    from qiskit_jku_provider_b200.engine import Engine
+    circ = C.qft(12)
+    with Engine(device=0, node_capacity=1 << 12, gc_min=64) as small, Engine(device=0, node_capacity=1 << 18) as big:
+        for e in (small, big):
+            e.load(circ)
+            e.run(1000, 4)
+        assert small.stats()["gc_runs"] > 5
+        assert np.abs(small.statevector() - big.statevector()).max() < AMP_TOL
+        assert small.counts() == big.counts()
+
+
+def test_arena_exhaustion_is_an_error_not_a_crash():
+    from qiskit_jku_provider_b200 import JKUSimulatorError
+    from qiskit_jku_provider_b200.engine import Engine
+    with Engine(device=0, node_capacity=1 << 10, item_capacity=1 << 10) as e:
+        e.load(C.random_circuit(14, 80, 2))
+        with pytest.raises(JKUSimulatorError):
+            e.run(10, 1)
+        e.load(C.ghz(5))   # the handle stays usable
+        e.run(100, 1)
+        assert set(e.counts_bitstrings()) <= {"00000", "11111"}
+
+
+def test_edge_cases(eng):
+    # empty circuit on one qubit, zero shots, measured subset, snapshots mid-circuit
+    from qiskit_jku_provider_b200.engine import OP_MEASURE, OP_SNAPSHOT, gate_op, simple_op
+    eng.set_option("force_mode", 0)
+    eng.set_option("level_log", 0)
+    eng.load(C.Circuit(1))
+    eng.run(10, 1)
+    assert eng.counts() == {0: 10}
+    assert eng.statevector().tolist() == [1 + 0j, 0j]
+    eng.load(C.ghz(3))
+    eng.run(0, 1)
+    assert eng.counts() == {}
+    h = C.expand("h", [0])[0]
+    x = C.expand("cx", [0, 1])[0]
+    ops = [gate_op(0, h.matrix()), simple_op(OP_SNAPSHOT, 0, 7), gate_op(1, x.matrix(), x.controls),
+           simple_op(OP_MEASURE, 1, 0)]
+    eng.load_ops(3, ops)
+    eng.run(1000, 9)
+    snap = eng.statevector(7)
+    assert abs(abs(snap[0]) ** 2 - 0.5) < 1e-12 and abs(abs(snap[1]) ** 2 - 0.5) < 1e-12 and snap[3] == 0
+    c = eng.counts()
+    assert set(c) == {0, 1} and sum(c.values()) == 1000 and abs(c[0] - 500) < 80
+    final = eng.statevector()
+    assert final[1] == 0 and final[2] == 0 and abs(abs(final[3]) ** 2 - 0.5) < 1e-12
+
+
+def test_shot_split_is_exact(eng):
+    """Counts of [0,N) == counts of [0,a) + [a,N): the multi-GPU invariant, on one GPU."""
+    circ = C.random_circuit(10, 50, 8)
+    eng.set_option("level_log", 0)
+    eng.load(circ)
+    eng.apply()
+    eng.sample(50000, seed=21)
+    whole = eng.counts()
+    eng.sample(12345, seed=21, shot_offset=0)
+    eng.sample(50000 - 12345, seed=21, shot_offset=12345, accumulate=True)
+    assert eng.counts() == whole
+
+
+def test_dd_export_import_roundtrip(eng):
+    from qiskit_jku_provider_b200.engine import Engine
+    circ = C.qft(10)
+    eng.set_option("level_log", 0)
+    eng.load(circ, measure={q: q for q in range(10)})
+    eng.apply()
+    eng.sample(20000, seed=5)
+    ref = eng.counts()
+    nodes, root = eng.dd_export()
+    assert len(nodes) == 11 and root == 1
+    with Engine(device=0, node_capacity=1 << 12) as other:
+        other.dd_import(10, nodes, root, eng.measure_map())
+        other.sample(20000, seed=5)
+        assert other.counts() == ref
+
+
+def test_sampling_statistics_large(eng):
+    """1e7 shots on GHZ-24: two outcomes, chi-squared p > 0.01 against 1/2, 1/2."""
+    from scipy.stats import chisquare
+    eng.set_option("level_log", 0)
+    eng.load(C.ghz(24))
+    eng.run(10 ** 7, 1234)
+    c = eng.counts()
+    assert set(c) == {0, (1 << 24) - 1} and sum(c.values()) == 10 ** 7
+    assert chisquare(list(c.values())).pvalue > 0.01
+    # total-variation distance to the exact distribution
+    assert abs(c[0] / 1e7 - 0.5) < 1e-3
