@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -37,7 +38,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k_init(JEng *E) {
 }
 
 // Persistent circuit kernel: all gates of a segment in one launch, no host round trip per gate.
-template <int MODE> __global__ void __launch_bounds__(256) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
+template <int MODE> __global__ void __launch_bounds__(256, 1) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
   Ctx c = make_ctx<MODE>(E);
   run_gates<MODE>(c, gates, n_gates);
 }
@@ -170,6 +171,9 @@ struct jkq_handle {
   double *prob = nullptr;
   uint32_t *lvl_log = nullptr;
   JGate *gates_dev = nullptr;
+  uint64_t *mat_u = nullptr;
+  uint32_t *mat_epoch = nullptr;
+  uint32_t n_mats = 0;
   std::vector<jkq_op> ops;
   std::vector<JGate> gates;         // GATE ops only
   std::vector<int> gate_of_op;      // ops index -> number of gates before it
@@ -240,6 +244,7 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
   cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.fwd); cudaFree(E.vfwd);
   cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
+  cudaFree(h->mat_u); cudaFree(h->mat_epoch);
   cudaFree(h->n_out); cudaFree(h->overflow);
   free_hist(h);
   free_snapshots(h);
@@ -284,6 +289,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
   JEng &E = h->host;
   E.tol = cfg.tolerance;
+  E.inv_tol = 1.0 / cfg.tolerance;
   E.node_cap = cfg.node_capacity; E.utab_mask = cfg.node_capacity * 2 - 1;
   E.val_cap = cfg.value_capacity; E.vtab_mask = cfg.value_capacity * 4 - 1;
   E.pend_cap = cfg.value_capacity;
@@ -338,6 +344,7 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
   h->gates.clear();
   h->gate_of_op.clear();
   bool any_measure = false;
+  std::vector<std::array<double, 8>> mats;
   for (int L = 0; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
   const uint64_t qmask = n_qubits == 64 ? ~0ull : ((1ull << n_qubits) - 1);
   for (size_t i = 0; i < n_ops; i++) {
@@ -361,6 +368,12 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
         if (L < g.low) g.low = L;
         if (L > g.top) g.top = L;
       }
+      // index among the distinct matrices of this circuit (bit-exact compare of the 8 doubles)
+      uint32_t mid = 0;
+      for (; mid < mats.size(); mid++)
+        if (!memcmp(mats[mid].data(), o.m, sizeof(o.m))) break;
+      if (mid == mats.size()) { std::array<double, 8> a; memcpy(a.data(), o.m, sizeof(o.m)); mats.push_back(a); }
+      g.pad = (int32_t)mid;
       h->gates.push_back(g);
     } else if (o.kind == JKQ_OP_MEASURE) {
       if (o.target >= n_qubits || o.arg >= 64) return fail(h, JKQ_E_ARGUMENT, "op %zu: bad measure", i);
@@ -372,8 +385,13 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
   }
   if (!any_measure)  // engine-level default: every qubit, key bit q = qubit q
     for (uint32_t q = 0; q < n_qubits && q < 64; q++) h->sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
-  cudaFree(h->gates_dev);
-  h->gates_dev = nullptr;
+  cudaFree(h->gates_dev); cudaFree(h->mat_u); cudaFree(h->mat_epoch);
+  h->gates_dev = nullptr; h->mat_u = nullptr; h->mat_epoch = nullptr;
+  h->n_mats = (uint32_t)mats.size();
+  if (h->n_mats) {
+    CU(cudaMalloc(&h->mat_u, (size_t)h->n_mats * 4 * 8));
+    CU(cudaMalloc(&h->mat_epoch, (size_t)h->n_mats * 4));
+  }
   if (!h->gates.empty()) {
     CU(cudaMalloc(&h->gates_dev, h->gates.size() * sizeof(JGate)));
     CU(cudaMemcpyAsync(h->gates_dev, h->gates.data(), h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
@@ -435,7 +453,7 @@ static int run_segment(jkq_handle *h, int upto) {
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
     if (h->host.next_gate >= upto) return JKQ_E_OK;
     if (h->host.want_grid && !grid) {
-      if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: frontier exceeds cta_item_limit and force_mode=1", h->host.next_gate);
+      if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: state or frontier exceeds the single-CTA path and force_mode=1", h->host.next_gate);
       grid = true;
       h->host.want_grid = 0;
       CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -460,6 +478,8 @@ extern "C" int jkq_apply(jkq_handle *h) {
     CU(cudaMemsetAsync(h->lvl_log, 0, h->gates.size() * h->n * 4, h->stream));
   }
   E.lvl_log = h->lvl_log;
+  E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
+  if (h->n_mats) CU(cudaMemsetAsync(h->mat_epoch, 0, (size_t)h->n_mats * 4, h->stream));
   E.status = 0; E.next_gate = 0; E.want_grid = 0;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));
@@ -511,22 +531,33 @@ extern "C" int jkq_apply(jkq_handle *h) {
 static int ensure_sampling(jkq_handle *h) {
   if (h->sampling_ready) return JKQ_E_OK;
   if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply or jkq_dd_import first");
-  // level-ordered compaction + bottom-up probabilities; grid path only for big DDs
-  bool grid = h->cfg.force_mode == 2 || (h->cfg.force_mode != 1 && h->host.node_count > 65536);
+  // level-ordered compaction + bottom-up probabilities; the CTA path first unless the DD is clearly too big for it
+  bool grid = h->cfg.force_mode == 2 || (h->cfg.force_mode != 1 && h->host.node_count > 8 * JKQ_SNODES);
   JEng *E = h->dev;
   JSNode *sn = h->snodes;
   double *pr = h->prob;
-  if (grid) {
-    int rb = reset_barrier(h);
-    if (rb) return rb;
-    void *args[] = {&E, &sn, &pr};
-    CU(cudaLaunchCooperativeKernel((void *)k_build_sampling<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
-  } else {
-    k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(E, sn, pr);
-    CU(cudaGetLastError());
+  int rc = JKQ_E_OK;
+  for (;;) {
+    if (grid) {
+      int rb = reset_barrier(h);
+      if (rb) return rb;
+      void *args[] = {&E, &sn, &pr};
+      CU(cudaLaunchCooperativeKernel((void *)k_build_sampling<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
+    } else {
+      k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(E, sn, pr);
+      CU(cudaGetLastError());
+    }
+    rc = pull_state(h);
+    if (rc) return rc;
+    if (!grid && !h->host.status && h->host.want_grid) {
+      if (h->cfg.force_mode == 1) return fail(h, JKQ_E_NODE_FULL, "state does not fit the single-CTA path and force_mode=1");
+      grid = true;
+      h->host.want_grid = 0;
+      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      continue;
+    }
+    break;
   }
-  int rc = pull_state(h);
-  if (rc) return rc;
   if (h->host.status) return fail(h, h->host.status, "build_sampling: %s", status_text(h->host.status));
   h->dd_root = h->host.root;
   h->dd_nodes = h->host.node_count;
@@ -681,6 +712,18 @@ extern "C" int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_
 extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   if (!h || !out) return JKQ_E_ARGUMENT;
   const JEng &E = h->host;
+#ifdef JKQ_PROFILE
+  fprintf(stderr, "JKQ_PROFILE cycles: expand %llu reduce %llu barrier %llu phases %llu setup %llu finalize %llu gate_total %llu\n",
+          E.prof[0], E.prof[1], E.prof[2], E.prof[3], E.prof[4], E.prof[5], E.prof[6]);
+  {
+    const char *nm[4] = {"M>t", "M@t", "F", "S"};
+    for (int e = 0; e < 2; e++)
+      for (int cls = 0; cls < 4; cls++)
+        if (E.prof2[8 + e * 4 + cls])
+          fprintf(stderr, "  %s %-3s: %llu phases, %llu cycles each\n", e ? "reduce" : "expand", nm[cls], E.prof2[8 + e * 4 + cls],
+                  E.prof2[e * 4 + cls] / E.prof2[8 + e * 4 + cls]);
+  }
+#endif
   h->stats.gates = E.st_gates; h->stats.items = E.st_items; h->stats.nodes_created = E.st_nodes_created;
   h->stats.value_inserts = E.st_val_inserts; h->stats.gc_runs = E.st_gc_runs; h->stats.gc_nodes_copied = E.st_gc_nodes_copied;
   h->stats.retry_rounds = E.st_retry_rounds; h->stats.max_frontier = E.st_max_frontier;

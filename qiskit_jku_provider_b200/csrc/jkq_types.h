@@ -76,7 +76,7 @@ typedef struct {
   int32_t target;  // level
   int32_t low;     // lowest level carrying a control or the target
   int32_t top;     // highest such level
-  int32_t pad;
+  int32_t pad;     // index of this gate's matrix among the distinct matrices of the circuit
   uint8_t role[JKQ_MAXQ];
 } JGate;
 
@@ -93,6 +93,7 @@ typedef struct {
   uint32_t cta_item_limit;  // CTA mode bails out to grid mode above this frontier size
   uint32_t gc_min;          // never collect below this many allocated nodes
   double tol;
+  double inv_tol;
   // ---- arrays ----
   JNode *nodes, *nodes_alt;
   uint32_t *utab;
@@ -104,6 +105,8 @@ typedef struct {
   uint32_t *fwd;      // node_cap entries: forwarding ids for the collector
   uint32_t *vfwd;     // val_cap entries: value id remap for the collector
   uint32_t *lvl_log;  // optional [gate][level] live-node counts
+  uint64_t *mat_u;      // [n distinct matrices][4] cached canonical ids of gate-matrix entries
+  uint32_t *mat_epoch;  // [n distinct matrices] val_epoch at which mat_u was filled (0 = never)
   // ---- mutable state ----
   uint32_t node_count;  // next free node id (id 0 = terminal)
   uint32_t val_count;
@@ -116,7 +119,7 @@ typedef struct {
   uint32_t gc_limit;
   uint32_t gc_count;   // collector cursor
   uint32_t val_gc_limit;  // sweep the reals only above this many (reference complex_limit)
-  uint32_t pad_v;
+  uint32_t val_epoch;     // bumped whenever a sweep renumbers the reals
   double norm;        // squared norm of the state at the last finalisation
   uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L+1], lvl_off[L]) ... see gc
   uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection
@@ -124,7 +127,7 @@ typedef struct {
   int32_t status;       // 0 ok, >0 error code
   int32_t next_gate;    // first gate not yet applied
   int32_t want_grid;    // CTA mode asked for the grid path
-  int32_t pad_s;
+  uint32_t tables_valid;  // HBM unique / value hash tables match the arena (MODE_CTA lets them go stale)
   // ---- counters ----
   unsigned long long st_items, st_nodes_created, st_val_inserts, st_gc_runs, st_retry_rounds,
       st_ut_probes, st_dt_probes, st_vt_probes, st_max_frontier, st_gates, st_gc_nodes_copied;
@@ -132,6 +135,8 @@ typedef struct {
   unsigned int bar_count;
   unsigned int bar_gen;
   unsigned int bar_flags[3];
+  unsigned long long prof2[16];
+  unsigned long long prof[8];  // JKQ_PROFILE builds: cycles in expand work / reduce work / barriers / phases / setup / finalize / gate
   unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was
   unsigned int dbg_phase[1024];
 } JEng;

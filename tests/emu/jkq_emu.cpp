@@ -64,6 +64,7 @@ int main(int argc, char **argv) {
   uint64_t seed = 1;
   uint32_t node_cap = 1u << 22, gc_min = 1u << 16;
   int dump_level = -1;
+  bool force_grid = false;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--circuit") && i + 1 < argc) circuit = argv[++i];
     else if (!strcmp(argv[i], "--shots") && i + 1 < argc) shots = atol(argv[++i]);
@@ -74,6 +75,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--node-cap") && i + 1 < argc) node_cap = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--gc-min") && i + 1 < argc) gc_min = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--dump-level") && i + 1 < argc) dump_level = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--grid")) force_grid = true;
   }
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
   if (!f) { fprintf(stderr, "usage: jkq_emu --circuit FILE ...\n"); return 2; }
@@ -111,7 +113,7 @@ int main(int argc, char **argv) {
   fclose(f);
 
   JEng *E = (JEng *)calloc(1, sizeof(JEng));
-  E->n = n; E->tol = 1e-10;
+  E->n = n; E->tol = 1e-10; E->inv_tol = 1.0 / E->tol;
   E->node_cap = node_cap; E->utab_mask = node_cap * 2 - 1;
   E->val_cap = 1u << 20; E->vtab_mask = (1u << 22) - 1;
   E->pend_cap = 1u << 20; E->item_cap = node_cap; E->dtab_mask = node_cap * 2 - 1;
@@ -135,29 +137,37 @@ int main(int argc, char **argv) {
   c.items = cta_state.items;
   c.spare_node = 0;
   c.E = E; c.tid = 0; c.nth = 1; c.phase = 0; c.block0 = 1; c.ltid = 0; c.lnth = 1;
-  init_state<MODE_CTA>(c);
-  run_gates<MODE_CTA>(c, gates.data(), (int)gates.size());
+  Ctx gctx = c;
+  gctx.sh = nullptr; gctx.items = E->items; gctx.spare_node = 0;
+  init_state<MODE_GRID>(gctx);
   int grid_switches = 0;
-  while (!E->status && E->want_grid && E->next_gate < (int)gates.size()) {
-    // same escalation as the host driver (run_segment in jkq_b200.cu): finish on the grid path
+  bool grid = force_grid;
+  // same escalation as the host driver (run_segment in jkq_b200.cu): CTA path until it does not fit
+  while (!E->status && E->next_gate < (int)gates.size()) {
     E->want_grid = 0;
-    grid_switches++;
-    Ctx g = c;
-    g.sh = nullptr; g.items = E->items; g.spare_node = 0;
-    run_gates<MODE_GRID>(g, gates.data(), (int)gates.size());
+    if (grid) run_gates<MODE_GRID>(gctx, gates.data(), (int)gates.size());
+    else run_gates<MODE_CTA>(c, gates.data(), (int)gates.size());
+    if (E->want_grid && !grid) { grid = true; grid_switches++; }
+    else if (E->next_gate < (int)gates.size() && !E->status) { fprintf(stderr, "stopped without reason\n"); return 3; }
   }
   if (E->status) { fprintf(stderr, "engine error %d at gate %d\n", E->status, E->next_gate); return 3; }
 
   std::vector<JSNode> sn(E->node_cap);
   std::vector<double> prob(E->node_cap);
-  build_sampling<MODE_CTA>(c, sn.data(), prob.data());
-
+  E->want_grid = 0;
+  bool sampling_cta = !force_grid;
+  if (sampling_cta) {
+    build_sampling<MODE_CTA>(c, sn.data(), prob.data());
+    if (E->want_grid) { sampling_cta = false; E->want_grid = 0; }
+  }
+  if (!sampling_cta) build_sampling<MODE_GRID>(gctx, sn.data(), prob.data());
+  if (E->status) { fprintf(stderr, "engine error %d in build_sampling\n", E->status); return 3; }
   if (dump_level >= 0) {
     for (uint32_t i = 0; i < E->lvl_cnt[dump_level]; i++) {
       uint32_t id = E->lvl_off[dump_level] + i;
       JNode nd = E->nodes[id];
       fprintf(stderr, "node %u: flag %u c0 %u c1 %u w=(%.17g, %.17g) ids %llx\n", id, nd_flag(nd), nd_c0(nd), nd.c1,
-              jre<MODE_CTA>(c, nd.w), jim<MODE_CTA>(c, nd.w), (unsigned long long)nd.w);
+              jre<MODE_GRID>(gctx, nd.w), jim<MODE_GRID>(gctx, nd.w), (unsigned long long)nd.w);
     }
   }
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n", n, gates.size());
@@ -183,7 +193,7 @@ int main(int argc, char **argv) {
     printf(",\n \"amps\": [");
     for (uint64_t i = 0; i < len; i++) {
       double re, im;
-      amp_walk<MODE_CTA>(c, i, &re, &im);
+      amp_walk<MODE_GRID>(gctx, i, &re, &im);
       printf("%s[%.17g,%.17g]", i ? "," : "", re, im);
     }
     printf("]");
