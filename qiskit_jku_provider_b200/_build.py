@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjkq_b200.so")
 SOURCES = ["jkq_b200.cu"]
-HEADERS = ["jkq_types.h", "jkq_engine.cuh", "jkq_apply.cuh", "jkq_sample.cuh", os.path.join("..", "..", "include", "jkq.h")]
+HEADERS = ["jkq_types.h", "jkq_engine.cuh", "jkq_thin.cuh", "jkq_apply.cuh", "jkq_sample.cuh", os.path.join("..", "..", "include", "jkq.h")]
 
 
 def nvcc_path():
@@ -33,5 +33,7 @@ def build_native(force=False, verbose=False):
            "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for d in os.environ.get("JKQ_DEFINES", "").split():  # e.g. JKQ_DEFINES="JKQ_PROFILE" for the cycle counters
+        cmd.insert(1, "-D" + d)
     subprocess.check_call(cmd)
     return LIB

@@ -1,37 +1,65 @@
-// Phase drivers of the B200 QMDD engine: barriers, serial value-insert section, level-synchronous
-// gate application (top-down expand, bottom-up reduce), copying collector, state initialisation and
-// the bottom-up probability pass that prepares shot sampling.  See jkq_engine.cuh for the MODE /
-// JKQ_EMU conventions.
+// Phase drivers of the B200 QMDD engine: barriers, level-synchronous gate application (thin warp
+// walk above the gate, top-down expand / bottom-up reduce of work items below), copying collector,
+// state initialisation and the bottom-up probability pass that prepares shot sampling.
+// See jkq_engine.cuh for the MODE / JKQ_EMU conventions.
 #ifndef JKQ_APPLY_CUH
 #define JKQ_APPLY_CUH
 
 #include "jkq_engine.cuh"
+#include "jkq_thin.cuh"
+
+#if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
+#define JPROF_T(var) long long var = clock64()
+#define JPROF_ADD(c, slot, t0, t1) do { if ((c).tid == 0) prof_add<MODE>((c).E, (c).sh, slot, (unsigned long long)((t1) - (t0))); } while (0)
+#define JPROF_INC(c, slot) do { if ((c).tid == 0) prof_add<MODE>((c).E, (c).sh, slot, 1); } while (0)
+#else
+#define JPROF_T(var) do {} while (0)
+#define JPROF_ADD(c, slot, t0, t1) do {} while (0)
+#define JPROF_INC(c, slot) do {} while (0)
+#endif
+// prof slots: 0 thin descent (+ gate set-up)  1 thin ascent (+ root update)  2 expand work  3 reduce work
+//             4 barrier wait  5 value commit  6 gates  7 generic phases  8 gate total  9 collector
 
 // ------------------------------------------------------------------------------------ barriers
+// Barrier that also OR-reduces a small flag word, so every thread takes the same branch afterwards.
+// One flag word per phase in a ring of three: word r is written during phase p (p % 3 == r), read
+// right after the barrier, and cleared -- together with the pending-value counter of the same ring
+// slot -- by thread 0 during phase p+2, when nobody can be looking at it any more.
 #ifdef JKQ_EMU
-template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) { c.phase++; return flags; }
+template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
+  const uint32_t nxt = c.ring == 2 ? 0 : c.ring + 1;
+  *cnt_pend<MODE>(c, nxt) = 0;
+  c.phase++; c.ring = nxt;
+  if (c.E->status) flags |= JF_ERROR;
+  if (MODE == MODE_CTA && c.sh->want_grid) flags |= JF_GRID;
+  return flags;
+}
 JD void block_sync() {}
 #else
 JD void block_sync() { __syncthreads(); }
 
-JD uint32_t block_or_bits(uint32_t flags) {
-  if (!__syncthreads_or(flags != 0)) return 0;
-  uint32_t r = 0;
-  if (__syncthreads_or(flags & JF_RETRY)) r |= JF_RETRY;
-  if (__syncthreads_or(flags & JF_ERROR)) r |= JF_ERROR;
-  if (__syncthreads_or(flags & JF_GRID)) r |= JF_GRID;
-  return r;
-}
-
-// Barrier that also OR-reduces a small flag word, so every thread takes the same branch afterwards.
-// MODE_CTA: __syncthreads_or.  MODE_GRID: sense-reversing counter barrier in HBM; the kernel is
-// launched cooperatively (all CTAs co-resident), one flag word per barrier phase in a ring of three.
+// MODE_CTA: one __syncthreads.  MODE_GRID: sense-reversing counter barrier in HBM; the kernel is
+// launched cooperatively (all CTAs co-resident).
 template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
-  uint32_t r = block_or_bits(flags);
-  if (MODE == MODE_GRID) {
+  const uint32_t slot = c.ring, nxt = slot == 2 ? 0 : slot + 1;
+  uint32_t r;
+  if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
+    if (flags) atomicOr(&S->bflags[slot], flags);
+    if (c.ltid == 0) { S->bflags[nxt] = 0; S->pend_n[nxt] = 0; }
+    __syncthreads();
+    r = *(volatile uint32_t *)&S->bflags[slot];
+    if (*(volatile uint32_t *)&S->err) r |= JF_ERROR;          // sticky words raised by the table functions
+    if (*(volatile uint32_t *)&S->want_grid) r |= JF_GRID;
+  } else {
     __shared__ uint32_t s_flags;
     JEng *E = c.E;
-    const uint32_t slot = c.phase % 3u;
+    r = 0;
+    if (__syncthreads_or(flags != 0)) {
+      if (__syncthreads_or(flags & JF_RETRY)) r |= JF_RETRY;
+      if (__syncthreads_or(flags & JF_ERROR)) r |= JF_ERROR;
+      if (__syncthreads_or(flags & JF_GRID)) r |= JF_GRID;
+    }
     if (threadIdx.x == 0) {
       if (blockIdx.x < 1024) E->dbg_phase[blockIdx.x] = c.phase;
       if (r) atomicOr(&E->bar_flags[slot], r);
@@ -39,13 +67,14 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
       __threadfence();
       if (atomicAdd(&E->bar_count, 1u) == gridDim.x - 1) {
         E->bar_count = 0;
-        E->bar_flags[(slot + 1) % 3u] = 0;  // next phase's word: nobody reads or writes it now
+        E->bar_flags[nxt] = 0;  // next phase's word and counter: nobody reads or writes them now
+        E->pend_n[nxt] = 0;
         __threadfence();
         atomicAdd(&E->bar_gen, 1u);
       } else {
         long long t0 = clock64();
         while (*(volatile unsigned int *)&E->bar_gen == gen) {
-          __nanosleep(64);
+          __nanosleep(32);
           if (clock64() - t0 > 8000000000ll) {
             if (atomicCAS(&E->status, 0, JKQ_ERR_BARRIER_TIMEOUT) == 0) E->dbg_timeout_block = blockIdx.x;
             break;
@@ -54,108 +83,52 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
       }
       __threadfence();
       s_flags = *(volatile unsigned int *)&E->bar_flags[slot];
-      if (*(volatile int *)&E->status == JKQ_ERR_BARRIER_TIMEOUT) s_flags |= JF_ERROR;
+      if (*(volatile int *)&E->status != 0) s_flags |= JF_ERROR;  // sticky: raised by the table functions or a timeout
     }
     __syncthreads();
     r = s_flags;
     __syncthreads();
   }
-  c.phase++;
+  c.phase++; c.ring = nxt;
   return r;
 }
 #endif
 
-// ------------------------------------------------------------------------------------ serial insert
-// All values that missed the table in the phase just finished are inserted by ONE thread, in
-// ascending order, re-checking each against the table first.  This reproduces the reference's
-// "first inserted wins / pairwise more than tol apart" invariant (QMDDcomplexD.cpp:402-437)
-// independently of how the GPU scheduled the threads that produced the values.
-template <int MODE> JD void serial_insert(Ctx &c) {
-  JEng *E = c.E;
-  const uint32_t par = (c.phase - 1) & 1u;  // the phase that produced the values ended at the last barrier
-  if (c.block0) {
-    uint32_t n = ld_s<MODE>(cnt_pend<MODE>(c, par));
-    if (n > E->pend_cap) n = E->pend_cap;
-    double *p = E->pend;
-    if (n > 32) {  // bitonic sort by the whole CTA, padded with +inf
-      uint32_t P = 1;
-      while (P < n) P <<= 1;
-      for (uint32_t i = n + c.ltid; i < P; i += c.lnth) p[i] = 1.0e300;
-      block_sync();
-      for (uint32_t k = 2; k <= P; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-          for (uint32_t i = c.ltid; i < P; i += c.lnth) {
-            uint32_t ixj = i ^ j;
-            if (ixj > i) {
-              double a = ld_r(p + i), b = ld_r(p + ixj);
-              if ((a > b) == ((i & k) == 0)) { p[i] = b; p[ixj] = a; }
-            }
-          }
-          block_sync();
-        }
-    }
-    if (c.ltid == 0) {
-      if (n <= 32)
-        for (uint32_t i = 1; i < n; i++) {  // insertion sort
-          double x = ld_r(p + i);
-          uint32_t j = i;
-          for (; j > 0 && ld_r(p + j - 1) > x; j--) p[j] = ld_r(p + j - 1);
-          p[j] = x;
-        }
-      for (uint32_t i = 0; i < n; i++) {
-        double x = ld_r(p + i);
-        uint32_t idx;
-        if (!real_find<MODE>(c, x, &idx)) real_insert_serial<MODE>(c, x);
-      }
-      *cnt_pend<MODE>(c, par) = 0;
-      E->st_retry_rounds++;
-    }
-  }
-  sync_or<MODE>(c, 0);
-}
-
 // ------------------------------------------------------------------------------------ level phases
-template <int MODE>
-JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L, bool expand) {
+// One level of the generic path: run every item of [b, e), and while some item met a value that is
+// not in the table yet, commit the proposed values (vals_commit) and run those items again.
+template <int MODE, bool expand>
+JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   for (uint32_t round = 0;; round++) {
     uint32_t my = 0;
-#ifdef JKQ_PROFILE
-    long long pt0 = clock64();
-#endif
+    JPROF_T(pt0);
     for (uint32_t i = b + c.tid; i < e; i += c.nth) {
       JItem *it = c.items + i;
-      uint32_t st = ld_i<MODE>(&it->state);
+      uint32_t fl = ld_i<MODE>(&it->flags);
+      const uint32_t st = fl & 3u;
       if (st == JS_DEAD) continue;
       if (round > 0 && st != JS_RETRY) continue;
-      bool ok = expand ? expand_item<MODE>(c, g, i, L) : reduce_item<MODE>(c, i);
-      it->state = ok ? JS_DONE : JS_RETRY;
-      if (!ok) my |= JF_RETRY;
+      if (expand) fl = expand_item<MODE>(c, g, i, L);
+      else fl = (fl & ~3u) | (reduce_item<MODE>(c, i, fl) ? JS_DONE : JS_RETRY);
+      it->flags = fl;
+      if ((fl & 3u) == JS_RETRY) my |= JF_RETRY;
     }
-    if (jhas_error<MODE>(c)) my |= JF_ERROR;
-    if (MODE == MODE_CTA && c.sh->want_grid) my |= JF_GRID;
-#ifdef JKQ_PROFILE
-    long long pt1 = clock64();
-#endif
+    JPROF_T(pt1);
     uint32_t flags = sync_or<MODE>(c, my);
-#ifdef JKQ_PROFILE
-    if (c.tid == 0) {
-      long long pt2 = clock64();
-      c.E->prof[expand ? 0 : 1] += (unsigned long long)(pt1 - pt0);
-      c.E->prof[2] += (unsigned long long)(pt2 - pt1);
-      c.E->prof[3] += 1;
-      {  // classify the phase by its first item: 0 = M above target, 1 = M at target, 2 = F, 3 = S
-        uint32_t tg = c.items[b].tag & 15u;
-        int cls = tg == JK_M ? (L > g.target ? 0 : 1) : (tg == JK_F ? 2 : 3);
-        c.E->prof2[(expand ? 0 : 4) + cls] += (unsigned long long)(pt1 - pt0);
-        c.E->prof2[8 + (expand ? 0 : 4) + cls] += 1;
-      }
-    }
-#endif
+    JPROF_T(pt2);
+    JPROF_ADD(c, expand ? 2 : 3, pt0, pt1);
+    JPROF_ADD(c, 4, pt1, pt2);
+    JPROF_INC(c, 7);
     if (flags & JF_ERROR) return JF_ERROR;
     if (flags & JF_GRID) return JF_GRID;
     if (!(flags & JF_RETRY)) return 0;
-    serial_insert<MODE>(c);
-    if (MODE == MODE_CTA && c.sh->want_grid) return JF_GRID;  // shared value table full (uniform: read after the barrier)
+    vals_commit<MODE>(c.E, c.sh, c.ring == 0 ? 2u : c.ring - 1u, c.tid, c.nth);  // the candidates of the phase just ended
+    if (c.tid == 0) jstat<MODE>(c.E, c.sh, JST_RETRY, 1u);
+    flags = sync_or<MODE>(c, 0);
+    JPROF_T(pt3);
+    JPROF_ADD(c, 5, pt2, pt3);
+    if (flags & JF_ERROR) return JF_ERROR;
+    if (flags & JF_GRID) return JF_GRID;
   }
 }
 
@@ -171,99 +144,147 @@ template <int MODE> struct LevelRanges {
   JDM uint32_t end(const Ctx &c, int L) const { return MODE == MODE_CTA ? c.sh->le[L] : le[L]; }
 };
 
+// ------------------------------------------------------------------------------------ gate set-up
+// canonical ids of the four matrix entries, cached per distinct matrix of the circuit until the next
+// sweep of the reals renumbers them (the reference re-runs Cmake per gate, QASMsimulator.cpp:295-298).
+// One thread, nobody else touches the value table.
+template <int MODE> JD void gate_setup(Ctx &c, const JGate &g) {
+  JEng *E = c.E;
+  const uint32_t mid = (uint32_t)g.pad;
+  if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
+    const uint32_t slot = mid & (JKQ_SMATS - 1);
+    if (S->mtag[slot] == mid + 1) {
+      for (int k = 0; k < 4; k++) S->cur_u[k] = S->mu[slot][k];
+    } else {
+      for (int k = 0; k < 4; k++) {
+        uint64_t u = cx_make_serial<MODE>(c.E, c.sh, g.m[2 * k], g.m[2 * k + 1]);
+        S->cur_u[k] = u; S->mu[slot][k] = u;
+      }
+      S->mtag[slot] = mid + 1;
+    }
+    return;  // (the generation was bumped at the end of the previous gate)
+  }
+  const uint32_t epoch = E->val_epoch;
+  const bool cached = E->mat_epoch && ld_s<MODE>(E->mat_epoch + mid) == epoch;
+  for (int k = 0; k < 4; k++) {
+    uint64_t u = cached ? ld_s<MODE>(E->mat_u + 4 * mid + k) : cx_make_serial<MODE>(c.E, c.sh, g.m[2 * k], g.m[2 * k + 1]);
+    if (!cached && E->mat_epoch) E->mat_u[4 * mid + k] = u;
+    E->cur_u[k] = u;
+  }
+  if (!cached && E->mat_epoch) E->mat_epoch[mid] = epoch;
+  E->gen++;
+}
+
 // ------------------------------------------------------------------------------------ one gate
 // Simulator::ApplyGate (Simulator.cpp:466-503) = QMDDmultiply(gate, state) as one top-down and one
 // bottom-up sweep over the levels.  Returns 0, JF_ERROR, or JF_GRID (CTA mode only: the gate does not
 // fit the shared-memory pools and is left unapplied).
-template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g_hbm) {
+template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n) {
   JEng *E = c.E;
-  const int n = (int)E->n;
-#ifdef JKQ_PROFILE
-  long long gt0 = clock64();
-#endif
-  if (MODE == MODE_CTA) {  // stage the gate descriptor and clear the de-dup table while thread 0 does the setup
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&c.sh->gate);
-    const uint32_t *srcw = reinterpret_cast<const uint32_t *>(&g_hbm);
-    for (uint32_t i = c.ltid; i < sizeof(JGate) / 4; i += c.lnth) dst[i] = srcw[i];
-    for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) c.sh->dtab[i] = 0;
-  }
-  if (c.block0 && c.ltid == 0) {
-    // canonical ids of the four matrix entries, cached per distinct matrix of the circuit until the
-    // next sweep of the reals renumbers them (the reference re-runs Cmake per gate, QASMsimulator.cpp:295-298)
-    const uint32_t mid = (uint32_t)g_hbm.pad;
-    const uint32_t epoch = E->val_epoch;
-    const bool cached = E->mat_epoch && ld_s<MODE>(E->mat_epoch + mid) == epoch;
-    for (int k = 0; k < 4; k++) {
-      uint64_t u = cached ? ld_s<MODE>(E->mat_u + 4 * mid + k) : cx_make_serial<MODE>(c, g_hbm.m[2 * k], g_hbm.m[2 * k + 1]);
-      if (!cached && E->mat_epoch) E->mat_u[4 * mid + k] = u;
-      if (MODE == MODE_CTA) c.sh->cur_u[k] = u;
-      else E->cur_u[k] = u;
+  const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
+  JPROF_T(gt0);
+  if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
+    if (S->gen >= 0xFFF0u) {  // generation tags about to wrap: clear the de-dup tables (uniform branch)
+      for (uint32_t i = c.ltid; i < JKQ_SNODES; i += c.lnth) S->mdir[i] = 0;
+      for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) S->dtab[i] = 0;
+      block_sync();
+      if (c.ltid == 0) S->gen = 1;
+      block_sync();
     }
-    if (!cached && E->mat_epoch) E->mat_epoch[mid] = epoch;
-    if (MODE == MODE_GRID) E->gen++;
-    JItem *it = c.items;
-    it->a = E->root; it->b = 0; it->wa = 0; it->wb = 0; it->wc = 0; it->tag = JK_M; it->state = JS_NEW;
-    *cnt_items<MODE>(c) = 1;
+    // stage the NEXT gate's descriptor while this one runs (warps other than the thin one when there are any)
+    if (gi + 1 < n_gates && (c.lnth <= JKQ_WARP || c.ltid >= JKQ_WARP)) {
+      const uint32_t first = c.lnth <= JKQ_WARP ? c.ltid : c.ltid - JKQ_WARP, step = c.lnth <= JKQ_WARP ? c.lnth : c.lnth - JKQ_WARP;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(&S->gate[(gi + 1) & 1]);
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(gates + gi + 1);
+      for (uint32_t i = first; i < sizeof(JGate) / 4; i += step) dst[i] = src[i];
+    }
+  }
+  const JGate &g = MODE == MODE_CTA ? c.sh->gate[gi & 1] : gates[gi];
+  if (thin_warp) {
+    if (c.ltid == 0) gate_setup<MODE>(c, g);
+    jsyncwarp();
+    int lsw = 0;
+    uint32_t icount = 0, blocked = 0;
+    cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);  // (a failure is in the sticky words: the barrier sees it)
+    if (c.ltid == 0) {
+      *cnt_items<MODE>(c) = icount;
+      if (MODE == MODE_CTA) { c.sh->lsw = (uint32_t)lsw; c.sh->thin_blocked = blocked; }
+      else { E->thin_lsw = (uint32_t)lsw; E->thin_blocked = blocked; }
+    }
   }
   {
-    uint32_t f0 = jhas_error<MODE>(c) ? JF_ERROR : 0;
-    uint32_t fl = sync_or<MODE>(c, f0);
+    uint32_t fl = sync_or<MODE>(c, 0);
     if (fl & JF_ERROR) return JF_ERROR;
-    if (MODE == MODE_CTA && c.sh->want_grid) return JF_GRID;
+    if (fl & JF_GRID) return JF_GRID;
   }
-  const JGate &g = MODE == MODE_CTA ? c.sh->gate : g_hbm;
-#ifdef JKQ_PROFILE
-  long long gt1 = clock64();
-  if (c.tid == 0) E->prof[4] += (unsigned long long)(gt1 - gt0);
-#endif
+  JPROF_T(gt1);
+  JPROF_ADD(c, 0, gt0, gt1);
+  const int lsw = (int)(MODE == MODE_CTA ? c.sh->lsw : ld_s<MODE>(&E->thin_lsw));
+  const uint32_t blocked = MODE == MODE_CTA ? c.sh->thin_blocked : ld_s<MODE>(&E->thin_blocked);
+  const uint32_t item_limit = MODE == MODE_CTA ? c.sh->item_limit : 0xFFFFFFFFu;
   LevelRanges<MODE> lr;
-  uint32_t b = 0, e = 1;
-  int lowest = n;
-  for (int L = n - 1; L >= 0 && e > b; L--) {
+  uint32_t b = 0, e = rd_items<MODE>(c);
+  int lowest = lsw + 1;
+  for (int L = lsw; L >= 0 && e > b; L--) {
     lr.set(c, L, b, e);
     lowest = L;
-    uint32_t f = run_level<MODE>(c, g, b, e, L, true);
+    uint32_t f = run_level<MODE, true>(c, g, b, e, L);
     if (f) return f;
     b = e; e = rd_items<MODE>(c);  // children of level 0 are terminals, never items
-    if (MODE == MODE_CTA && e - b > E->cta_item_limit) return JF_GRID;
+    if (MODE == MODE_CTA && e - b > item_limit) return JF_GRID;
   }
-  for (int L = lowest; L < n; L++) {
-    uint32_t f = run_level<MODE>(c, g, lr.begin(c, L), lr.end(c, L), L, false);
+  for (int L = lowest; L <= lsw; L++) {
+    uint32_t f = run_level<MODE, false>(c, g, lr.begin(c, L), lr.end(c, L), L);
     if (f) return f;
   }
-#ifdef JKQ_PROFILE
-  long long gt2 = clock64();
-#endif
-  if (c.block0 && c.ltid == 0) {
-    const JItem *it = c.items;
-    uint64_t rw = ld_i<MODE>(&it->rw), w = 0;
-    uint32_t rn = ld_i<MODE>(&it->rnode);
-    if (rw == JW_ONE) w = E->rootw;
-    else if (E->rootw == JW_ONE) w = rw;
-    else if (rw != 0) {
-      double ar = jre<MODE>(c, rw), ai = jim<MODE>(c, rw), br = jre<MODE>(c, E->rootw), bi = jim<MODE>(c, E->rootw);
-      w = cx_make_serial<MODE>(c, JKQ_DSUB(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi)), JKQ_DADD(JKQ_DMUL(ar, bi), JKQ_DMUL(ai, br)));
-    }
-    if (MODE == MODE_CTA && c.sh->want_grid) {
-      // the shared value table filled up while the root weight was made: keep the old root, redo on the grid
-    } else {
-      if (w == 0 || rn == 0) jset_error_c<MODE>(c, JKQ_ERR_ZERO_STATE);
-      E->root = rn; E->rootw = w;
-      unsigned long long cnt = rd_items<MODE>(c);
-      E->st_items += cnt;
-      if (cnt > E->st_max_frontier) E->st_max_frontier = cnt;
-      E->st_gates++;
+  JPROF_T(gt2);
+  if (thin_warp) {
+    const uint32_t f = cursor_finish<MODE>(c, lsw, blocked);
+    if (!f && c.ltid == 0) {
+      const uint32_t cnt = rd_items<MODE>(c);
+      jstat<MODE>(E, c.sh, JST_ITEMS, cnt);
+      jstat_max<MODE>(E, c.sh, cnt);
+      jstat<MODE>(E, c.sh, JST_GATES, 1u);
+      if (MODE == MODE_CTA) c.sh->gen++;  // read by everybody only after the barrier below
     }
   }
   {
-    uint32_t fl = sync_or<MODE>(c, jhas_error<MODE>(c) ? JF_ERROR : 0);
+    uint32_t fl = sync_or<MODE>(c, 0);
+    JPROF_T(gt3);
+    JPROF_ADD(c, 1, gt2, gt3);
+    JPROF_ADD(c, 8, gt0, gt3);
+    JPROF_INC(c, 6);
     if (fl & JF_ERROR) return JF_ERROR;
-    if (MODE == MODE_CTA && c.sh->want_grid) return JF_GRID;
+    if (fl & JF_GRID) return JF_GRID;
   }
-#ifdef JKQ_PROFILE
-  if (c.tid == 0) { E->prof[5] += (unsigned long long)(clock64() - gt2); E->prof[6] += (unsigned long long)(clock64() - gt0); }
-#endif
   return 0;
+}
+
+// ------------------------------------------------------------------------------------ MODE_CTA write-back
+// The single-CTA path works on shared memory only; nodes and reals created since the last write-back,
+// the root edge and the counters go to the HBM arena in bulk: before a collection (which works on the
+// arena) and when the kernel ends.  All threads; ends with a barrier.
+template <int MODE> JD void cta_flush(Ctx &c) {
+  if (MODE != MODE_CTA) return;
+  CtaState *S = c.sh;
+  JEng *E = c.E;
+  const uint32_t nn = S->node_count < S->node_hard ? S->node_count : S->node_hard, nv = S->val_count < S->val_hard ? S->val_count : S->val_hard;
+  for (uint32_t i = S->flushed_nodes + c.ltid; i < nn; i += c.lnth) E->nodes[i] = S->nodes[i];
+  for (uint32_t i = S->flushed_vals + c.ltid; i < nv; i += c.lnth) E->vals[i] = S->vals[i];
+  block_sync();
+  if (c.ltid == 0) {
+    S->flushed_nodes = nn; S->flushed_vals = nv;
+    E->root = S->root; E->rootw = S->rootw; E->next_gate = S->next_gate;
+    for (int k = 0; k < JST_N; k++) {
+      if (k == JST_MAXF) { if (S->st[k] > E->st[k]) E->st[k] = S->st[k]; }
+      else E->st[k] += S->st[k];
+      S->st[k] = 0;
+    }
+    for (int k = 0; k < 16; k++) { E->prof[k] += S->prof[k]; S->prof[k] = 0; }
+  }
+  block_sync();
 }
 
 // ------------------------------------------------------------------------------------ collector
@@ -276,17 +297,21 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate &g_hbm) {
 // The HBM frontier pool is idle between gates and serves as scratch.
 //   reload      MODE_CTA at kernel start: shared memory is empty, (re)load reals and tables
 //   force_vals  sweep / rebuild the value table regardless of the limit
-template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
+JD void vt_clear_slot(JVSlot *s) { s->vbits = JV_INF; s->keylo = 0; s->id1 = 0; }
+
+// Out of line, context by value (the caller's stays in registers): gc_call() below takes over the ring index.
+template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   JEng *E = c.E;
   const int n = (int)E->n;
+  JPROF_T(ct0);
+  cta_flush<MODE>(c);  // MODE_CTA: the HBM arena is complete from here on
   uint32_t *list = (uint32_t *)E->items;  // list[new_id - 1] = old id
-  c.spare_node = 0;  // ids are renumbered: a spare id from before the collection is meaningless
   const uint32_t old_count = rd_nodes<MODE>(c), old_vals = rd_vals<MODE>(c);
   // the reals are only swept when the table outgrew its limit, like the reference's
   // `Ctable.size() > complex_limit` (Simulator.cpp:488-498): dropping an unreferenced value changes
   // which representative later values snap to
   uint32_t vlimit = ld_s<MODE>(&E->val_gc_limit);
-  if (MODE == MODE_CTA && vlimit > (JKQ_SVALS / 4) * 3) vlimit = (JKQ_SVALS / 4) * 3;
+  if (MODE == MODE_CTA && vlimit > (c.sh->val_hard / 4) * 3) vlimit = (c.sh->val_hard / 4) * 3;
   const bool clean_vals = force_vals || old_vals > vlimit;
   for (uint32_t i = c.tid; i < old_count; i += c.nth) E->fwd[i] = 0;
   if (MODE == MODE_GRID)
@@ -296,10 +321,12 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
   if (clean_vals) {
     for (uint32_t i = c.tid; i < old_vals; i += c.nth) E->vfwd[i] = 0;
     if (MODE == MODE_GRID)
-      for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) E->vtab[i].id1 = 0;
+      for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
   }
-  if (MODE == MODE_CTA && (clean_vals || reload))
-    for (uint32_t i = c.ltid; i < JKQ_SVT_SLOTS; i += c.lnth) c.sh->vtab[i].id1 = 0;
+  if (MODE == MODE_CTA && (clean_vals || reload)) {
+    for (uint32_t i = c.ltid; i < JKQ_SVT_SLOTS; i += c.lnth) vt_clear_slot(c.sh->vtab + i);
+    for (uint32_t i = c.ltid; i < JKQ_SMATS; i += c.lnth) c.sh->mtag[i] = 0;  // cached matrix ids are void
+  }
   if (c.block0 && c.ltid == 0) {
     list[0] = E->root;
     E->gc_count = 1;
@@ -311,7 +338,7 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
     if (c.block0 && c.ltid == 0) { E->lvl_off[L] = b + 1; E->lvl_cnt[L] = e - b; }
     if (L > 0)
       for (uint32_t i = b + c.tid; i < e; i += c.nth) {
-        JNode nd = ld_s<MODE>(E->nodes + ld_s<MODE>(list + i));
+        JNode nd = ld_s<MODE_GRID>(E->nodes + ld_s<MODE_GRID>(list + i));
         uint32_t ch[2] = {nd_c0(nd), nd.c1};
         for (int k = 0; k < 2; k++)
           if (ch[k] != 0 && jatomic_cas(E->fwd + ch[k], 0u, 0xFFFFFFFFu) == 0) {
@@ -321,16 +348,16 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
           }
       }
     sync_or<MODE>(c, 0);
-    b = e; e = ld_s<MODE>(&E->gc_count);
+    b = e; e = ld_s<MODE_GRID>(&E->gc_count);
   }
   const uint32_t live = b;  // == gc_count
   // copy nodes with forwarded children; mark the reals they use
   for (uint32_t i = c.tid; i < live; i += c.nth) {
-    JNode nd = ld_s<MODE>(E->nodes + ld_s<MODE>(list + i));
+    JNode nd = ld_s<MODE_GRID>(E->nodes + ld_s<MODE_GRID>(list + i));
     uint32_t c0 = nd_c0(nd), c1 = nd.c1;
     JNode nn;
-    nn.c0 = (c0 ? ld_s<MODE>(E->fwd + c0) : 0) | (nd.c0 & 0x80000000u);
-    nn.c1 = c1 ? ld_s<MODE>(E->fwd + c1) : 0;
+    nn.c0 = (c0 ? ld_s<MODE_GRID>(E->fwd + c0) : 0) | (nd.c0 & 0x80000000u);
+    nn.c1 = c1 ? ld_s<MODE_GRID>(E->fwd + c1) : 0;
     nn.w = nd.w;
     E->nodes_alt[i + 1] = nn;
     if (clean_vals) {
@@ -346,8 +373,8 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
       E->vfwd[(uint32_t)rw & 0x7FFFFFFFu] = 1;
       uint32_t nv = 0;
       for (uint32_t i = 0; i < old_vals; i++) {
-        if (i < 4 || ld_s<MODE>(E->vfwd + i)) {
-          E->vals_alt[nv] = ld_s<MODE>(E->vals + i);
+        if (i < 4 || ld_s<MODE_GRID>(E->vfwd + i)) {
+          E->vals_alt[nv] = ld_s<MODE_GRID>(E->vals + i);
           E->vfwd[i] = nv++;
         }
       }
@@ -360,30 +387,31 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
       if (E->val_gc_limit > E->val_cap / 2) E->val_gc_limit = E->val_cap / 2;
     }
     E->root = 1;
+    if (MODE == MODE_CTA) { c.sh->root = 1; c.sh->rootw = E->rootw; c.sh->flushed_nodes = live + 1; c.sh->flushed_vals = *cnt_vals<MODE>(c); }
     *cnt_nodes<MODE>(c) = live + 1;
     E->node_count = live + 1;
     uint32_t lim = 4 * (live + 1);
     if (lim < E->gc_min) lim = E->gc_min;
     if (lim > E->node_cap / 2) lim = E->node_cap / 2;
     E->gc_limit = lim;
-    E->st_gc_runs++;
-    E->st_gc_nodes_copied += live;
+    E->st[JST_GC_RUNS]++;
+    E->st[JST_GC_COPIED] += live;
     if (live + 1 >= E->node_cap / 2) jset_error_c<MODE>(c, JKQ_ERR_NODE_FULL);
     if (MODE == MODE_CTA) {
       // too big for the shared-memory pools: hand over to the grid path
-      if (live + 1 > JKQ_SNODES / 4 || *cnt_vals<MODE>(c) > (JKQ_SVALS / 8) * 7) c.sh->want_grid = 1;
+      if (live + 1 > c.sh->node_hard / 4 || *cnt_vals<MODE>(c) > (c.sh->val_hard / 8) * 7) jwant_grid(c.sh);
     }
   }
-  sync_or<MODE>(c, 0);
+  sync_or<MODE>(c, 0);  // (a JF_GRID raised here is picked up below through sh->want_grid)
   const uint32_t nv = rd_vals<MODE>(c);
   const bool fits = MODE != MODE_CTA || !c.sh->want_grid;
   // copy back with remapped weights, rebuild the unique table
   for (uint32_t i = c.tid; i < live; i += c.nth) {
-    JNode nn = ld_s<MODE>(E->nodes_alt + i + 1);
+    JNode nn = ld_s<MODE_GRID>(E->nodes_alt + i + 1);
     if (clean_vals) {
       uint32_t hr = (uint32_t)(nn.w >> 32), hi = (uint32_t)nn.w;
-      hr = (hr & 0x80000000u) | ld_s<MODE>(E->vfwd + (hr & 0x7FFFFFFFu));
-      hi = (hi & 0x80000000u) | ld_s<MODE>(E->vfwd + (hi & 0x7FFFFFFFu));
+      hr = (hr & 0x80000000u) | ld_s<MODE_GRID>(E->vfwd + (hr & 0x7FFFFFFFu));
+      hi = (hi & 0x80000000u) | ld_s<MODE_GRID>(E->vfwd + (hi & 0x7FFFFFFFu));
       nn.w = ((uint64_t)hr << 32) | hi;
     }
     E->nodes[i + 1] = nn;
@@ -398,19 +426,27 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
   }
   // the reals: copy the compacted array back; rebuild the value table
   if (clean_vals)
-    for (uint32_t i = c.tid; i < nv; i += c.nth) E->vals[i] = ld_s<MODE>(E->vals_alt + i);
+    for (uint32_t i = c.tid; i < nv; i += c.nth) E->vals[i] = ld_s<MODE_GRID>(E->vals_alt + i);
   if (MODE == MODE_GRID) {
     if (clean_vals)
-      for (uint32_t i = c.tid + 1; i < nv; i += c.nth) vt_put<MODE>(c, i, ld_s<MODE>(E->vals_alt + i));  // 0.0 is never hashed
+      for (uint32_t i = c.tid + 1; i < nv; i += c.nth) vt_put<MODE>(c.E, c.sh, i, ld_s<MODE_GRID>(E->vals_alt + i));  // 0.0 is never hashed
   } else if (fits && (clean_vals || reload)) {
     const double *srcv = clean_vals ? E->vals_alt : E->vals;
     for (uint32_t i = c.ltid; i < nv; i += c.lnth) {
-      double x = srcv[i];
+      double x = ld_s<MODE_GRID>(srcv + i);
       c.sh->vals[i] = x;
-      if (i > 0) vt_put<MODE>(c, i, x);
+      if (i > 0) vt_put<MODE>(c.E, c.sh, i, x);
     }
   }
-  return sync_or<MODE>(c, jhas_error<MODE>(c) ? JF_ERROR : 0) & JF_ERROR;
+  uint32_t r = sync_or<MODE>(c, 0) & JF_ERROR;
+  JPROF_T(ct1);
+  JPROF_ADD(c, 9, ct0, ct1);
+  return r | (c.ring << 8) | (c.phase << 10);
+}
+template <int MODE> JD uint32_t gc_call(Ctx &c, bool reload, bool force_vals) {
+  const uint32_t r = gc_run<MODE>(c, reload, force_vals);
+  c.ring = (r >> 8) & 3u; c.phase = r >> 10;
+  return r & JF_ERROR;
 }
 
 // ------------------------------------------------------------------------------------ init
@@ -420,25 +456,24 @@ template <int MODE> JD uint32_t gc_run(Ctx &c, bool reload, bool force_vals) {
 template <int MODE> JD uint32_t init_state(Ctx &c) {
   JEng *E = c.E;
   for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
-  for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) { JVSlot z; z.value = 0; z.id1 = 0; z.keylo = 0; E->vtab[i] = z; }
+  for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
   for (uint32_t i = c.tid; i <= E->dtab_mask; i += c.nth) E->dtab[i] = 0;
+  for (uint32_t i = c.tid; i < E->node_cap; i += c.nth) E->mdir[i] = 0;
   if (c.block0 && c.ltid == 0) {
     E->status = 0; E->want_grid = 0; E->next_gate = 0;
-    E->val_count = 0; E->node_count = 1; E->item_count = 0; E->pend_n[0] = E->pend_n[1] = 0;
+    E->val_count = 0; E->node_count = 1; E->item_count = 0; E->pend_n[0] = E->pend_n[1] = E->pend_n[2] = 0;
     E->gen = 1;
-    E->st_items = E->st_nodes_created = E->st_val_inserts = E->st_gc_runs = E->st_retry_rounds = 0;
-    for (int k = 0; k < 8; k++) E->prof[k] = 0;
-    for (int k = 0; k < 16; k++) E->prof2[k] = 0;
-    E->st_ut_probes = E->st_dt_probes = E->st_vt_probes = E->st_max_frontier = E->st_gates = E->st_gc_nodes_copied = 0;
+    for (int k = 0; k < 12; k++) E->st[k] = 0;
+    for (int k = 0; k < 16; k++) E->prof[k] = 0;
     JNode t; t.c0 = 0; t.c1 = 0; t.w = 0;
     E->nodes[0] = t;
   }
   sync_or<MODE>(c, 0);
   if (c.block0 && c.ltid == 0) {
     E->vals[0] = 0.0; E->val_count = 1;  // index 0 never sits in the hash: real_find short-cuts x <= tol
-    real_insert_serial<MODE>(c, 1.0);
-    real_insert_serial<MODE>(c, 0.5);
-    real_insert_serial<MODE>(c, 0.70710678118654757);
+    real_insert_direct<MODE>(c.E, c.sh, 1.0);
+    real_insert_direct<MODE>(c.E, c.sh, 0.5);
+    real_insert_direct<MODE>(c.E, c.sh, 0.70710678118654757);
     uint32_t prev = 0;
     for (uint32_t L = 0; L < E->n; L++) {
       JNode nd; nd.c0 = prev; nd.c1 = 0; nd.w = 0;  // child 0 carries ONE, child 1 is the zero edge
@@ -466,21 +501,35 @@ template <int MODE> JD uint32_t init_state(Ctx &c) {
 template <int MODE> JD uint32_t mode_enter(Ctx &c) {
   JEng *E = c.E;
   if (MODE == MODE_CTA) {
+    CtaState *S = c.sh;
     if (c.ltid == 0) {
-      CtaState *S = c.sh;
       S->item_count = E->item_count; S->node_count = E->node_count; S->val_count = E->val_count;
-      S->pend_n[0] = S->pend_n[1] = 0;
-      S->nodes_created = 0; S->val_inserts = 0; S->err = (uint32_t)E->status; S->want_grid = 0;
+      S->item_limit = E->cta_item_limit;
+      S->node_hard = E->node_cap < JKQ_SNODES ? E->node_cap : JKQ_SNODES;
+      S->val_hard = E->val_cap < JKQ_SVALS ? E->val_cap : JKQ_SVALS;
+      S->node_soft = S->node_hard - S->node_hard / 8;  // the rest is the reserve of cursor_to_root
+      S->val_soft = S->val_hard - S->val_hard / 16;
+      S->node_limit = S->node_soft; S->val_limit = S->val_soft; S->thin_blocked = 0;
+      S->pend_n[0] = S->pend_n[1] = S->pend_n[2] = 0;
+      S->bflags[0] = S->bflags[1] = S->bflags[2] = S->bflags[3] = 0;
+      S->err = (uint32_t)E->status; S->want_grid = 0;
+      S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw;
+      S->flushed_nodes = S->node_count; S->flushed_vals = S->val_count;  // shared memory holds nothing yet
+      S->next_gate = E->next_gate;
+      for (int k = 0; k <= JST_N; k++) S->st[k] = 0;
+      for (int k = 0; k < 16; k++) S->prof[k] = 0;
       S->tol = E->tol; S->inv_tol = E->inv_tol;
       E->tables_valid = 0;
     }
-    sync_or<MODE>(c, 0);
+    for (uint32_t i = c.ltid; i < JKQ_SNODES; i += c.lnth) S->mdir[i] = 0;
+    for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) S->dtab[i] = 0;
+    block_sync();
     // reals beyond the shared table: sweep them first; still too many -> grid path
-    if (gc_run<MODE>(c, true, c.sh->val_count > (JKQ_SVALS / 4) * 3)) return JF_ERROR;
+    if (gc_call<MODE>(c, true, c.sh->val_count > (c.sh->val_hard / 4) * 3)) return JF_ERROR;
     return c.sh->want_grid ? JF_GRID : 0;
   }
   if (!ld_s<MODE>(&E->tables_valid)) {
-    if (gc_run<MODE>(c, false, true)) return JF_ERROR;
+    if (gc_call<MODE>(c, false, true)) return JF_ERROR;
     if (c.block0 && c.ltid == 0) E->tables_valid = 1;
     sync_or<MODE>(c, 0);
   }
@@ -488,12 +537,12 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
 }
 template <int MODE> JD void mode_leave(Ctx &c) {
   if (MODE != MODE_CTA) return;
+  cta_flush<MODE>(c);
   if (c.ltid == 0) {
     CtaState *S = c.sh;
-    c.E->item_count = S->item_count; c.E->node_count = S->node_count; c.E->val_count = S->val_count;
-    c.E->st_nodes_created += S->nodes_created;
-    c.E->st_val_inserts += S->val_inserts;
-    S->nodes_created = 0; S->val_inserts = 0;
+    c.E->item_count = S->item_count;
+    c.E->node_count = S->node_count < S->node_hard ? S->node_count : S->node_hard;
+    c.E->val_count = S->val_count < S->val_hard ? S->val_count : S->val_hard;
   }
 }
 
@@ -502,22 +551,41 @@ template <int MODE> JD void mode_leave(Ctx &c) {
 // gate when a level log was requested (parity tests: reference Active[v], QMDDpackage.h:199-201).
 template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
   JEng *E = c.E;
+  const int n = (int)E->n;
+  const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
   uint32_t f = mode_enter<MODE>(c);
-  int g = ld_s<MODE>((const uint32_t *)&E->next_gate);
+  int g = MODE == MODE_CTA ? c.sh->next_gate : ld_s<MODE>(&E->next_gate);
+  if (MODE == MODE_CTA && !f && g < n_gates) {  // stage the first gate descriptor
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&c.sh->gate[g & 1]);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(gates + g);
+    for (uint32_t i = c.ltid; i < sizeof(JGate) / 4; i += c.lnth) dst[i] = src[i];
+  }
+  if (thin_warp) cursor_reset<MODE>(c, n);
+  sync_or<MODE>(c, 0);
+  const bool log = E->lvl_log != 0;
   for (; !f && g < n_gates; g++) {
-    f = apply_gate<MODE>(c, gates[g]);
+    f = apply_gate<MODE>(c, gates, g, n_gates, n);
     if (f) break;
-    const bool log = E->lvl_log != 0;
     const uint32_t nodes_now = rd_nodes<MODE>(c), vals_now = rd_vals<MODE>(c);
-    bool collect = log || nodes_now > ld_s<MODE>(&E->gc_limit);
-    if (MODE == MODE_CTA) collect = collect || nodes_now > JKQ_SNODES / 2 || vals_now > (JKQ_SVALS / 4) * 3;
+    bool collect = log;
+    if (MODE == MODE_CTA) collect = collect || nodes_now > c.sh->node_hard / 2 || vals_now > (c.sh->val_hard / 4) * 3;
+    else collect = collect || nodes_now > ld_s<MODE>(&E->gc_limit);
     if (collect) {
-      if (gc_run<MODE>(c, false, false)) { f = JF_ERROR; break; }
+      if (thin_warp) cursor_to_root<MODE>(c, n);
+      f = sync_or<MODE>(c, 0) & (JF_ERROR | JF_GRID);
+      if (f) break;
+      if (gc_call<MODE>(c, false, false)) { f = JF_ERROR; break; }
+      if (thin_warp) cursor_reset<MODE>(c, n);
       if (log && c.block0 && c.ltid == 0)
         for (uint32_t L = 0; L < E->n; L++) E->lvl_log[(size_t)g * E->n + L] = E->lvl_cnt[L];
     }
-    if (c.block0 && c.ltid == 0) E->next_gate = g + 1;
+    if (c.block0 && c.ltid == 0) { if (MODE == MODE_CTA) c.sh->next_gate = g + 1; else E->next_gate = g + 1; }
     if (MODE == MODE_CTA && c.sh->want_grid) { f = JF_GRID; g++; break; }  // (uniform: set before gc_run's last barrier)
+  }
+  // the state goes back to the arena as a DD with a root: rebuild the levels above the cursor
+  if (!(f & JF_ERROR)) {
+    if (thin_warp) cursor_to_root<MODE>(c, n);
+    f |= sync_or<MODE>(c, 0) & JF_ERROR;
   }
   if ((f & JF_GRID) && c.block0 && c.ltid == 0) { E->want_grid = 1; if (MODE == MODE_GRID) E->gen++; }
   sync_or<MODE>(c, 0);
@@ -538,18 +606,18 @@ template <int MODE> JD uint32_t build_sampling(Ctx &c, JSNode *snodes, double *p
     mode_leave<MODE>(c);
     return f;
   }
-  if (MODE == MODE_GRID && gc_run<MODE>(c, false, false)) return JF_ERROR;
+  if (MODE == MODE_GRID && gc_call<MODE>(c, false, false)) return JF_ERROR;
   if (c.block0 && c.ltid == 0) prob[0] = 1.0;
   sync_or<MODE>(c, 0);
   for (uint32_t L = 0; L < E->n; L++) {
-    uint32_t off = ld_s<MODE>(&E->lvl_off[L]), cnt = ld_s<MODE>(&E->lvl_cnt[L]);
+    uint32_t off = ld_s<MODE_GRID>(&E->lvl_off[L]), cnt = ld_s<MODE_GRID>(&E->lvl_cnt[L]);
     for (uint32_t i = c.tid; i < cnt; i += c.nth) {
       uint32_t id = off + i;
-      JNode nd = ld_s<MODE>(E->nodes + id);
+      JNode nd = ld_s<MODE_GRID>(E->nodes + id);
       uint64_t w0 = nd_w0(nd), w1 = nd_w1(nd);
       uint32_t c0 = nd_c0(nd), c1 = nd.c1;
-      double p0 = w0 ? JKQ_DMUL(ld_s<MODE>(prob + c0), jmag2<MODE>(c, w0)) : 0.0;
-      double p1 = w1 ? JKQ_DMUL(ld_s<MODE>(prob + c1), jmag2<MODE>(c, w1)) : 0.0;
+      double p0 = w0 ? JKQ_DMUL(ld_s<MODE_GRID>(prob + c0), jmag2<MODE>(c, w0)) : 0.0;
+      double p1 = w1 ? JKQ_DMUL(ld_s<MODE_GRID>(prob + c1), jmag2<MODE>(c, w1)) : 0.0;
       double tot = JKQ_DADD(p0, p1);
       prob[id] = tot;
       JSNode s;
@@ -558,7 +626,7 @@ template <int MODE> JD uint32_t build_sampling(Ctx &c, JSNode *snodes, double *p
     }
     sync_or<MODE>(c, 0);
   }
-  if (c.block0 && c.ltid == 0) E->norm = JKQ_DMUL(ld_s<MODE>(prob + ld_s<MODE>(&E->root)), jmag2<MODE>(c, E->rootw));
+  if (c.block0 && c.ltid == 0) E->norm = JKQ_DMUL(ld_s<MODE_GRID>(prob + ld_s<MODE_GRID>(&E->root)), jmag2<MODE>(c, E->rootw));
   uint32_t r = sync_or<MODE>(c, 0);
   mode_leave<MODE>(c);
   return r;

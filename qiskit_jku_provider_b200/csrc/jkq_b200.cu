@@ -16,15 +16,24 @@
 #include "jkq_sample.cuh"
 
 // =============================================================================== kernels
-extern __shared__ __align__(16) unsigned char jkq_dyn_smem[];  // CtaState, MODE_CTA launches only
+extern __shared__ __align__(16) unsigned char jkq_dyn_smem[];  // MODE_CTA: CtaState + ThinState; MODE_GRID k_run_gates: ThinState
+struct CtaSmem {
+  CtaState s;
+  ThinState t;
+};
 
 template <int MODE> __device__ __forceinline__ Ctx make_ctx(JEng *E) {
   Ctx c;
   c.E = E;
-  c.sh = MODE == MODE_CTA ? reinterpret_cast<CtaState *>(jkq_dyn_smem) : nullptr;
+  if constexpr (MODE == MODE_CTA) {
+    c.sh = &reinterpret_cast<CtaSmem *>(jkq_dyn_smem)->s;
+    c.T = &reinterpret_cast<CtaSmem *>(jkq_dyn_smem)->t;
+  } else {
+    c.sh = nullptr;
+    c.T = reinterpret_cast<ThinState *>(jkq_dyn_smem);  // the cursor runs in warp 0 of block 0 (k_run_gates only)
+  }
   c.items = MODE == MODE_CTA ? c.sh->items : E->items;
-  c.spare_node = 0;
-  c.phase = 0;
+  c.phase = 0; c.ring = 0;
   c.ltid = threadIdx.x;
   c.lnth = blockDim.x;
   if (MODE == MODE_CTA) { c.tid = threadIdx.x; c.nth = blockDim.x; c.block0 = 1; }
@@ -50,7 +59,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k_build_sampling(JEng
 
 __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *out) {
   Ctx c;
-  c.E = E; c.sh = nullptr; c.items = E->items; c.spare_node = 0; c.phase = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = E->items; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
   c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
   for (uint64_t i = c.tid; i < count; i += c.nth) {
     double re, im;
@@ -242,7 +251,7 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   cudaSetDevice(h->device);
   JEng &E = h->host;
   cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
-  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.fwd); cudaFree(E.vfwd);
+  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.mdir); cudaFree(E.fwd); cudaFree(E.vfwd);
   cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
   cudaFree(h->mat_u); cudaFree(h->mat_epoch);
   cudaFree(h->n_out); cudaFree(h->overflow);
@@ -301,9 +310,10 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaMalloc(&E.vals, (size_t)E.val_cap * 8));
   CU(cudaMalloc(&E.vals_alt, (size_t)E.val_cap * 8));
   CU(cudaMalloc(&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)));
-  CU(cudaMalloc(&E.pend, (size_t)E.pend_cap * 8));
+  CU(cudaMalloc(&E.pend, (size_t)E.pend_cap * 4));
   CU(cudaMalloc(&E.items, (size_t)E.item_cap * sizeof(JItem)));
   CU(cudaMalloc(&E.dtab, ((size_t)E.dtab_mask + 1) * 8));
+  CU(cudaMalloc(&E.mdir, (size_t)E.node_cap * 8));
   CU(cudaMalloc(&E.fwd, (size_t)E.node_cap * 4));
   CU(cudaMalloc(&E.vfwd, (size_t)E.val_cap * 4));
   CU(cudaMalloc(&h->dev, sizeof(JEng)));
@@ -311,11 +321,12 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaMalloc(&h->prob, (size_t)E.node_cap * 8));
   CU(cudaMalloc(&h->n_out, 8));
   CU(cudaMalloc(&h->overflow, 4));
-  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaState)));
-  CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaState)));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   // cooperative grid size: every CTA must be resident
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID>, 256, 0));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThinState)));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID>, 256, sizeof(ThinState)));
   if (per_sm < 1) return fail(h, JKQ_E_CUDA, "grid kernel does not fit on an SM");
   if ((uint32_t)per_sm > cfg.grid_blocks_per_sm) per_sm = (int)cfg.grid_blocks_per_sm;
   h->grid_blocks = per_sm * h->sm_count;
@@ -410,6 +421,7 @@ static int pull_state(jkq_handle *h) {
 static int reset_barrier(jkq_handle *h) {
   CU(cudaMemsetAsync(&h->dev->bar_count, 0, sizeof(unsigned int), h->stream));
   CU(cudaMemsetAsync(&h->dev->bar_flags[0], 0, 3 * sizeof(unsigned int), h->stream));
+  CU(cudaMemsetAsync(&h->dev->pend_n[0], 0, 3 * sizeof(uint32_t), h->stream));
   return JKQ_E_OK;
 }
 
@@ -420,10 +432,10 @@ static int launch_gates(jkq_handle *h, bool grid, int upto) {
     JEng *E = h->dev;
     const JGate *g = h->gates_dev;
     void *args[] = {&E, &g, &upto};
-    CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
+    CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, sizeof(ThinState), h->stream));
     h->stats.grid_launches++;
   } else {
-    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(h->dev, h->gates_dev, upto);
+    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
     CU(cudaGetLastError());
     h->stats.cta_launches++;
   }
@@ -482,6 +494,7 @@ extern "C" int jkq_apply(jkq_handle *h) {
   if (h->n_mats) CU(cudaMemsetAsync(h->mat_epoch, 0, (size_t)h->n_mats * 4, h->stream));
   E.status = 0; E.next_gate = 0; E.want_grid = 0;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
+  E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));
   CU(cudaMemcpyAsync(h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice, h->stream));
   {
@@ -544,7 +557,7 @@ static int ensure_sampling(jkq_handle *h) {
       void *args[] = {&E, &sn, &pr};
       CU(cudaLaunchCooperativeKernel((void *)k_build_sampling<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
     } else {
-      k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaState), h->stream>>>(E, sn, pr);
+      k_build_sampling<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaSmem), h->stream>>>(E, sn, pr);
       CU(cudaGetLastError());
     }
     rc = pull_state(h);
@@ -713,20 +726,18 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   if (!h || !out) return JKQ_E_ARGUMENT;
   const JEng &E = h->host;
 #ifdef JKQ_PROFILE
-  fprintf(stderr, "JKQ_PROFILE cycles: expand %llu reduce %llu barrier %llu phases %llu setup %llu finalize %llu gate_total %llu\n",
-          E.prof[0], E.prof[1], E.prof[2], E.prof[3], E.prof[4], E.prof[5], E.prof[6]);
-  {
-    const char *nm[4] = {"M>t", "M@t", "F", "S"};
-    for (int e = 0; e < 2; e++)
-      for (int cls = 0; cls < 4; cls++)
-        if (E.prof2[8 + e * 4 + cls])
-          fprintf(stderr, "  %s %-3s: %llu phases, %llu cycles each\n", e ? "reduce" : "expand", nm[cls], E.prof2[8 + e * 4 + cls],
-                  E.prof2[e * 4 + cls] / E.prof2[8 + e * 4 + cls]);
-  }
+  fprintf(stderr, "JKQ_PROFILE cycles/gate over %llu gates: total %llu | thin-descent+setup %llu  expand %llu  reduce %llu  barrier %llu  commit %llu  "
+          "thin-ascent+root %llu | generic phases/gate %.2f  collector total %llu\n",
+          E.prof[6], E.prof[6] ? E.prof[8] / E.prof[6] : 0, E.prof[6] ? E.prof[0] / E.prof[6] : 0, E.prof[6] ? E.prof[2] / E.prof[6] : 0,
+          E.prof[6] ? E.prof[3] / E.prof[6] : 0, E.prof[6] ? E.prof[4] / E.prof[6] : 0, E.prof[6] ? E.prof[5] / E.prof[6] : 0,
+          E.prof[6] ? E.prof[1] / E.prof[6] : 0, E.prof[6] ? (double)E.prof[7] / E.prof[6] : 0.0, E.prof[9]);
+  if (E.prof[13])
+    fprintf(stderr, "  thin ascent per level (%llu levels): loads %llu  reduce_core %llu  whole-after-loads %llu\n", E.prof[13], E.prof[10] / E.prof[13],
+            E.prof[11] / E.prof[13], E.prof[12] / E.prof[13]);
 #endif
-  h->stats.gates = E.st_gates; h->stats.items = E.st_items; h->stats.nodes_created = E.st_nodes_created;
-  h->stats.value_inserts = E.st_val_inserts; h->stats.gc_runs = E.st_gc_runs; h->stats.gc_nodes_copied = E.st_gc_nodes_copied;
-  h->stats.retry_rounds = E.st_retry_rounds; h->stats.max_frontier = E.st_max_frontier;
+  h->stats.gates = E.st[JST_GATES]; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
+  h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];
+  h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF];
   h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;
   *out = h->stats;
   return JKQ_E_OK;

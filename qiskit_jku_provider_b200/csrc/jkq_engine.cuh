@@ -1,18 +1,19 @@
-// Device side of the B200 QMDD engine: value table, unique table, frontier de-dup, level-synchronous
-// gate application.  Hand-written CUDA for sm_100a.
+// Device side of the B200 QMDD engine: value table, unique table, frontier de-dup, the per-item
+// expand / reduce steps of the level-synchronous gate application.  Hand-written CUDA for sm_100a.
 //
 // The same code runs in two launch shapes (template parameter MODE):
 //   MODE_CTA   one CTA, __syncthreads between phases.  The whole working set of a SMALL decision
-//              diagram lives in that SM's shared memory (160 KB): node records, unique table, value
-//              table, frontier pool, de-dup table, the current gate.  A gate on a 32-node DD is a
-//              dependent chain of ~2n level phases, so its cost is latency: an L2 round trip is ~0.23 us
+//              diagram lives in that SM's shared memory (~210 KB): node records, unique table, value
+//              table, frontier pool, de-dup tables, the current gate.  A gate on a 32-node DD is a
+//              dependent chain of ~2n level steps, so its cost is latency: an L2 round trip is ~0.3 us
 //              on B200, a shared-memory access ~15 ns.  The HBM arena is written through (nodes, reals)
 //              so the state is always complete in HBM; the HBM hash tables go stale and are rebuilt by
 //              the collector when the grid path takes over.
 //   MODE_GRID  cooperative grid, software grid barrier, every table in HBM, ld.global.cg everywhere --
 //              the throughput path for blown-up DDs.
-// With JKQ_EMU defined the header compiles as plain C++ and runs as ONE emulated thread.  That build
-// exists only under tests/emu (logic debugging in a GPU-less container); the product never loads it.
+// With JKQ_EMU defined the header compiles as plain C++ and runs as ONE emulated thread (warp width 1).
+// That build exists only under tests/emu (logic debugging in a GPU-less container); the product never
+// loads it.
 #ifndef JKQ_ENGINE_CUH
 #define JKQ_ENGINE_CUH
 
@@ -31,45 +32,81 @@
 #include <string.h>
 #define JD static inline
 #define JDM inline
+#define JNI static
 #define JKQ_UNROLL
+#define JKQ_WARP 1u
 #define JKQ_DMUL(a, b) ((a) * (b))
 #define JKQ_DADD(a, b) ((a) + (b))
 #define JKQ_DSUB(a, b) ((a) - (b))
 #define JKQ_DDIV(a, b) ((a) / (b))
 template <class T> static inline T jatomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T jatomic_cas(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+static inline void jatomic_min(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
 template <int MODE> static inline void jfence() {}
+static inline unsigned long long jd2u(double x) { unsigned long long u; memcpy(&u, &x, 8); return u; }
+static inline double ju2d(unsigned long long u) { double x; memcpy(&x, &u, 8); return x; }
+static inline uint32_t jballot(bool p) { return p ? 1u : 0u; }
+static inline uint32_t jshfl(uint32_t v, uint32_t) { return v; }
+static inline uint32_t jmatch(uint32_t) { return 1u; }
+static inline void jsyncwarp() {}
+static inline uint32_t jpopc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+static inline uint32_t jffs(uint32_t x) { return (uint32_t)__builtin_ffs((int)x); }
 #else
 #define JD __device__ __forceinline__
 #define JDM __device__ __forceinline__
+#define JNI __device__ __noinline__
 #define JKQ_UNROLL _Pragma("unroll")
+#define JKQ_WARP 32u
 #define JKQ_DMUL(a, b) __dmul_rn((a), (b))
 #define JKQ_DADD(a, b) __dadd_rn((a), (b))
 #define JKQ_DSUB(a, b) __dsub_rn((a), (b))
 #define JKQ_DDIV(a, b) __ddiv_rn((a), (b))
 template <class T> JD T jatomic_add(T *p, T v) { return atomicAdd(p, v); }
 template <class T> JD T jatomic_cas(T *p, T cmp, T v) { return atomicCAS(p, cmp, v); }
+JD void jatomic_min(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
 template <int MODE> JD void jfence() {
   if (MODE == MODE_CTA) __threadfence_block();
   else __threadfence();
 }
+JD unsigned long long jd2u(double x) { return (unsigned long long)__double_as_longlong(x); }
+JD double ju2d(unsigned long long u) { return __longlong_as_double((long long)u); }
+JD uint32_t jballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+JD uint32_t jshfl(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
+JD uint32_t jmatch(uint32_t v) { return __match_any_sync(0xFFFFFFFFu, v); }
+JD void jsyncwarp() { __syncwarp(); }
+JD uint32_t jpopc(uint32_t x) { return (uint32_t)__popc(x); }
+JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #endif
 
 // ------------------------------------------------------------------------------------ MODE_CTA state
-#define JKQ_SITEMS 768u      // work items of one gate
-#define JKQ_SDT_SLOTS 2048u  // de-dup slots (u32 item index + 1)
+#define JKQ_SITEMS 640u      // work items of one gate
+#define JKQ_SDT_SLOTS 2048u  // F/S de-dup slots (generation << 16 | item index + 1)
 #define JKQ_SNODES 2048u     // node ids held in shared memory; the collector keeps ids below this
 #define JKQ_SUT_SLOTS 4096u  // unique-table slots (u32 node id)
 #define JKQ_SVALS 1024u      // reals
 #define JKQ_SVT_SLOTS 2048u  // value-table slots
+#define JKQ_SPEND 512u       // value-table slots claimed in one phase
+#define JKQ_SMATS 128u       // cached canonical ids of gate matrices
 struct CtaState {
-  uint32_t item_count, node_count, pend_n[2];
-  uint32_t nodes_created, err, want_grid, val_count;
-  uint32_t val_inserts, pad0, pad1, pad2;
+  uint32_t item_count, node_count, val_count, item_limit;
+  uint32_t node_limit, val_limit, thin_blocked, pad4;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
+  uint32_t node_hard, val_hard, node_soft, val_soft;
+  uint32_t pend_n[3], err;
+  uint32_t want_grid, gen, pad2, pad3;
+  uint32_t lsw, root, flushed_nodes, flushed_vals;  // [flushed, count): not yet copied to the HBM arena
+  uint64_t rootw;
+  uint32_t st[JST_N + 1];
+  int32_t next_gate, pad0;
+  unsigned long long prof[16];
+  uint32_t bflags[4];
   double tol, inv_tol;
   uint64_t cur_u[4];
   uint32_t lb[JKQ_MAXQ + 1], le[JKQ_MAXQ + 1];
-  JGate gate;
+  JGate gate[2];
+  uint32_t mtag[JKQ_SMATS];
+  uint64_t mu[JKQ_SMATS][4];
+  uint32_t pend[JKQ_SPEND];
+  uint32_t mdir[JKQ_SNODES];
   uint32_t dtab[JKQ_SDT_SLOTS];
   uint32_t utab[JKQ_SUT_SLOTS];
   double vals[JKQ_SVALS];
@@ -78,32 +115,86 @@ struct CtaState {
   JItem items[JKQ_SITEMS];
 };
 
+// ------------------------------------------------------------------------------------ thin path state
+// Levels above the gate's highest control/target only forward a node's two edges.  While such a level
+// holds at most one warp's worth of nodes, ONE warp walks it with the frontier in registers and these
+// per-level records in shared memory (jkq_thin.cuh) instead of the generic item phases.
+struct __attribute__((aligned(8))) ThinEnt {
+  uint32_t pk;   // s0 | s1 << 8 | nz0 << 16 | nz1 << 17 | norm flag << 18
+  uint32_t pad;
+  uint64_t w;    // weight of the child that does not carry ONE
+  uint64_t f;    // weight the cursor edge carried when the cursor moved below it: re-applied on the way up
+};
+struct __attribute__((aligned(16))) ThinRes {
+  uint64_t rw;
+  uint32_t rnode, pad;
+};
+struct ThinState {
+  ThinRes res[2][JKQ_WARP];          // the cursor edges (level parity)
+  ThinEnt ent[JKQ_MAXQ][JKQ_WARP];   // levels above the cursor
+  uint32_t cnt[JKQ_MAXQ + 1];
+  int32_t M;                         // cursor level
+  uint32_t walked;                   // nodes passed on the way down since the last cursor_to_root (statistics)
+};
+
 struct Ctx {
   JEng *E;
   CtaState *sh;         // MODE_CTA only
+  ThinState *T;
   JItem *items;         // frontier pool: shared memory in MODE_CTA, HBM in MODE_GRID
-  uint32_t spare_node;  // node id allocated by this thread and not used yet (the node already existed)
   uint32_t tid, nth;    // index / count over all participating threads
   uint32_t phase;       // barrier counter, identical in every thread
+  uint32_t ring;        // phase % 3
   uint32_t block0;      // 1 if this thread belongs to the CTA that runs the serial sections
   uint32_t ltid, lnth;
 };
 
+// counters nobody waits for: atomics whose result is unused compile to fire-and-forget RED instructions,
+// where a load-add-store would stall the (in-order) thread for an L2 round trip
+// (MODE_CTA counts in shared memory: a global memory operation in flight makes the next
+// __threadfence_block of the same thread wait for an L2 round trip)
+#ifdef JKQ_EMU
+template <int MODE> JD void jstat(JEng *E, CtaState *S, int which, uint32_t v) {
+  if (MODE == MODE_CTA) S->st[which] += v;
+  else E->st[which] += v;
+}
+template <int MODE> JD void jstat_max(JEng *E, CtaState *S, uint32_t v) {
+  if (MODE == MODE_CTA) { if (v > S->st[JST_MAXF]) S->st[JST_MAXF] = v; }
+  else if (v > E->st[JST_MAXF]) E->st[JST_MAXF] = v;
+}
+#else
+template <int MODE> JD void jstat(JEng *E, CtaState *S, int which, uint32_t v) {
+  if (MODE == MODE_CTA) atomicAdd(&S->st[which], v);
+  else atomicAdd(&E->st[which], (unsigned long long)v);
+}
+template <int MODE> JD void jstat_max(JEng *E, CtaState *S, uint32_t v) {
+  if (MODE == MODE_CTA) atomicMax(&S->st[JST_MAXF], v);
+  else atomicMax(&E->st[JST_MAXF], (unsigned long long)v);
+}
+#endif
+
 template <int MODE> JD uint32_t *cnt_items(const Ctx &c) { return MODE == MODE_CTA ? &c.sh->item_count : &c.E->item_count; }
 template <int MODE> JD uint32_t *cnt_nodes(const Ctx &c) { return MODE == MODE_CTA ? &c.sh->node_count : &c.E->node_count; }
 template <int MODE> JD uint32_t *cnt_vals(const Ctx &c) { return MODE == MODE_CTA ? &c.sh->val_count : &c.E->val_count; }
-template <int MODE> JD uint32_t *cnt_pend(const Ctx &c, uint32_t par) { return MODE == MODE_CTA ? &c.sh->pend_n[par] : &c.E->pend_n[par]; }
+template <int MODE> JD uint32_t *cnt_pend(const Ctx &c, uint32_t r) { return MODE == MODE_CTA ? &c.sh->pend_n[r] : &c.E->pend_n[r]; }
 template <int MODE> JD double jtol(const Ctx &c) { return MODE == MODE_CTA ? c.sh->tol : c.E->tol; }
 template <int MODE> JD double jinv_tol(const Ctx &c) { return MODE == MODE_CTA ? c.sh->inv_tol : c.E->inv_tol; }
 
 // ------------------------------------------------------------------------------------ loads
-// ld_s: HBM data not written since the last barrier (MODE_GRID: ld.global.cg, L1 may be stale).
-// ld_r: HBM data that may be written concurrently.
+// ld_s: data not written since the last barrier (MODE_GRID: ld.global.cg, L1 may be stale).
+// ld_r: data that may be written concurrently (HBM: ld.global.cg; shared memory: volatile).
 #ifdef JKQ_EMU
 template <int MODE, class T> JD T ld_s(const T *p) { return *p; }
-template <class T> JD T ld_r(const T *p) { return *p; }
+template <int MODE, class T> JD T ld_r(const T *p) { return *p; }
 #else
+// 16-byte volatile load from shared memory (MODE_CTA tables that other threads write concurrently)
+JD uint4 ld_vol16_shared(const void *p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
 template <int MODE> JD uint32_t ld_s(const uint32_t *p) { return MODE == MODE_GRID ? __ldcg(p) : *p; }
+template <int MODE> JD int32_t ld_s(const int32_t *p) { return MODE == MODE_GRID ? __ldcg(p) : *p; }
 template <int MODE> JD unsigned long long ld_s(const unsigned long long *p) { return MODE == MODE_GRID ? __ldcg(p) : *p; }
 template <int MODE> JD uint64_t ld_s(const uint64_t *p) {
   return MODE == MODE_GRID ? (uint64_t)__ldcg((const unsigned long long *)p) : *p;
@@ -117,64 +208,84 @@ template <int MODE> JD JNode ld_s(const JNode *p) {
   return n;
 }
 template <int MODE> JD JVSlot ld_s(const JVSlot *p) {
-  uint4 v = MODE == MODE_GRID ? __ldcg((const uint4 *)p) : *(const uint4 *)p;
+  uint4 v = MODE == MODE_GRID ? __ldcg((const uint4 *)p) : ld_vol16_shared(p);
   JVSlot s;
-  s.value = __hiloint2double((int)v.y, (int)v.x); s.id1 = v.z; s.keylo = v.w;
+  s.vbits = ((unsigned long long)v.y << 32) | v.x; s.keylo = v.z; s.id1 = v.w;
   return s;
 }
-JD uint32_t ld_r(const uint32_t *p) { return __ldcg(p); }
-JD unsigned long long ld_r(const unsigned long long *p) { return __ldcg(p); }
-JD uint64_t ld_r(const uint64_t *p) { return (uint64_t)__ldcg((const unsigned long long *)p); }
-JD uint8_t ld_r(const uint8_t *p) { return __ldcg(p); }
-JD int32_t ld_r(const int32_t *p) { return __ldcg(p); }
-JD double ld_r(const double *p) { return __ldcg(p); }
-JD JNode ld_r(const JNode *p) {
-  uint4 v = __ldcg((const uint4 *)p);
+template <int MODE> JD uint32_t ld_r(const uint32_t *p) { return MODE == MODE_GRID ? __ldcg(p) : *(const volatile uint32_t *)p; }
+template <int MODE> JD int32_t ld_r(const int32_t *p) { return MODE == MODE_GRID ? __ldcg(p) : *(const volatile int32_t *)p; }
+template <int MODE> JD unsigned long long ld_r(const unsigned long long *p) {
+  return MODE == MODE_GRID ? __ldcg(p) : *(const volatile unsigned long long *)p;
+}
+template <int MODE> JD uint64_t ld_r(const uint64_t *p) {
+  return MODE == MODE_GRID ? (uint64_t)__ldcg((const unsigned long long *)p) : (uint64_t)*(const volatile unsigned long long *)p;
+}
+template <int MODE> JD double ld_r(const double *p) { return MODE == MODE_GRID ? __ldcg(p) : *(const volatile double *)p; }
+template <int MODE> JD JNode ld_r(const JNode *p) {
+  uint4 v = MODE == MODE_GRID ? __ldcg((const uint4 *)p) : ld_vol16_shared(p);
   JNode n;
   n.c0 = v.x; n.c1 = v.y; n.w = ((uint64_t)v.w << 32) | v.z;
   return n;
 }
 #endif
 
-#ifdef JKQ_EMU
-template <int MODE> JD uint32_t rd_items(const Ctx &c) { return *cnt_items<MODE>(c); }
-template <int MODE> JD uint32_t rd_nodes(const Ctx &c) { return *cnt_nodes<MODE>(c); }
-template <int MODE> JD uint32_t rd_vals(const Ctx &c) { return *cnt_vals<MODE>(c); }
-template <int MODE> JD bool jhas_error(const Ctx &c) { return c.E->status != 0; }
-#else
-template <int MODE> JD uint32_t rd_items(const Ctx &c) { return MODE == MODE_CTA ? c.sh->item_count : __ldcg(&c.E->item_count); }
-template <int MODE> JD uint32_t rd_nodes(const Ctx &c) { return MODE == MODE_CTA ? c.sh->node_count : __ldcg(&c.E->node_count); }
-template <int MODE> JD uint32_t rd_vals(const Ctx &c) { return MODE == MODE_CTA ? c.sh->val_count : __ldcg(&c.E->val_count); }
-template <int MODE> JD bool jhas_error(const Ctx &c) { return MODE == MODE_CTA ? c.sh->err != 0 : __ldcg(&c.E->status) != 0; }
-#endif
+template <int MODE> JD uint32_t rd_items(const Ctx &c) { return ld_r<MODE>(cnt_items<MODE>(c)); }
+template <int MODE> JD uint32_t rd_nodes(const Ctx &c) { return ld_r<MODE>(cnt_nodes<MODE>(c)); }
+template <int MODE> JD uint32_t rd_vals(const Ctx &c) { return ld_r<MODE>(cnt_vals<MODE>(c)); }
+template <int MODE> JD bool jhas_error(const Ctx &c) { return MODE == MODE_CTA ? ld_r<MODE>(&c.sh->err) != 0 : ld_r<MODE>(&c.E->status) != 0; }
 
 JD uint64_t jmix(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
 }
-// 32-bit finaliser (Wellons' lowbias32): the table hashes sit on the latency path of every item, and a
-// 64-bit multiply is four 32-bit IMADs on the GPU
-JD uint32_t h32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+// The table hashes sit on the latency path of every item: 32-bit multiplies side by side, one
+// xor-shift-multiply round to finish.
+JD uint32_t hfin(uint32_t x) {
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 13;
   return x;
 }
-JD uint32_t h64(uint64_t x) { return h32((uint32_t)x ^ h32((uint32_t)(x >> 32) + 0x9E3779B9u)); }
+JD uint32_t h32(uint32_t x) { return hfin(x * 0x9E3779B1u); }
+JD uint32_t hw64(uint64_t w) { return (uint32_t)w * 0xC2B2AE3Du + (uint32_t)(w >> 32) * 0x27D4EB2Fu; }
 
-// MODE_CTA polls a shared-memory copy of the error flag instead of an L2 round trip per phase
-template <int MODE> JD void jset_error_c(Ctx &c, int code) {
-  jatomic_cas(&c.E->status, 0, code);
-  if (MODE == MODE_CTA) c.sh->err = (uint32_t)code;
+// Errors and the "does not fit the single-CTA pools" condition are sticky words (JEng.status,
+// CtaState.err / want_grid) that every barrier folds into its flag word, so the out-of-line table
+// functions below need no per-thread state.
+template <int MODE> JD void jset_error(JEng *E, CtaState *S, int code) {
+  jatomic_cas(&E->status, 0, code);
+  if (MODE == MODE_CTA) S->err = (uint32_t)code;
 }
+// MODE_CTA: the gate does not fit the shared-memory pools; it is abandoned and redone on the grid path
+JD void jwant_grid(CtaState *S) { S->want_grid = 1; }
+template <int MODE> JD void jset_error_c(Ctx &c, int code) { jset_error<MODE>(c.E, c.sh, code); }
 
 // ------------------------------------------------------------------------------------ value table
 // Semantics of the reference's Clookup (QMDDcomplexD.cpp:372-466) with its tolerance comparator
-// (:85-98): table entries are pairwise more than tol apart, a lookup returns the SMALLEST entry in
-// [x-tol, x+tol], a miss appends x.  One bucket of width tol holds at most one entry, so a lookup
-// probes the buckets k-1, k, k+1 in that order.  Anything within tol of 0 is index 0.
-template <int MODE> JD double jval(const Ctx &c, uint32_t half) {
+// (:85-98): table entries are pairwise more than tol apart, a lookup returns the entry within tol of
+// x, a miss appends x.  One bucket of width tol holds at most one entry, so a lookup probes the
+// buckets k-1, k, k+1.  Anything within tol of 0 is index 0.
+//
+// Misses of a phase are inserted in parallel AND schedule-independently:
+//   propose  the thread claims the slot of bucket k (64-bit CAS on (keylo, id1)) and atomicMin's its value
+//            into it: after the phase every bucket holds the smallest value proposed for it;
+//   commit   (next phase) a candidate becomes an entry unless the bucket below holds a candidate within
+//            tol of it -- then it is dropped, and its proposers find the lower one on retry.
+// Which values enter the table therefore depends only on the SET of values proposed in the phase.
+//
+// The arithmetic and table functions are deliberately NOT inlined (JNI): a gate on a small DD is one
+// warp running a long dependent chain, and with everything inlined the kernel grew to 0.7 MB of SASS --
+// instruction-cache misses, not data latency, then set the pace.  They take (E, S, ring) by value so
+// that the caller's context stays in registers.
+#define JKQ_VAL_MAX 1.0e8
+#define JV_MISS 0xFFFFFFFFu
+#define JW_MISS 0xFFFFFFFFFFFFFFFFull
+template <int MODE> JD double jtol2(const JEng *E, const CtaState *S) { return MODE == MODE_CTA ? S->tol : E->tol; }
+template <int MODE> JD double jinv_tol2(const JEng *E, const CtaState *S) { return MODE == MODE_CTA ? S->inv_tol : E->inv_tol; }
+template <int MODE> JD double jval2(const JEng *E, const CtaState *S, uint32_t half) {
   uint32_t idx = half & 0x7FFFFFFFu;
-  return MODE == MODE_CTA ? c.sh->vals[idx] : ld_s<MODE>(c.E->vals + idx);
+  return MODE == MODE_CTA ? S->vals[idx] : ld_s<MODE>(E->vals + idx);
 }
+template <int MODE> JD double jval(const Ctx &c, uint32_t half) { return jval2<MODE>(c.E, c.sh, half); }
 template <int MODE> JD double jre(const Ctx &c, uint64_t w) {
   double v = jval<MODE>(c, (uint32_t)(w >> 32));
   return (w >> 63) ? -v : v;
@@ -195,119 +306,201 @@ JD uint64_t jneg(uint64_t a) {  // Cnegative, QMDDcomplexD.cpp:483-496
   return (r << 32) | i;
 }
 
-template <int MODE> JD uint32_t vt_mask(const Ctx &c) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : c.E->vtab_mask; }
-template <int MODE> JD JVSlot vt_load(const Ctx &c, uint32_t h) { return MODE == MODE_CTA ? c.sh->vtab[h] : ld_s<MODE>(c.E->vtab + h); }
+template <int MODE> JD uint32_t vt_mask2(const JEng *E) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : E->vtab_mask; }
+template <int MODE> JD JVSlot *vt_tab2(JEng *E, CtaState *S) { return MODE == MODE_CTA ? S->vtab : E->vtab; }
 JD long long vt_bucket(double x, double inv_tol) { return (long long)floor(JKQ_DMUL(x, inv_tol)); }
+// eight consecutive buckets share one 128-byte line (8 x 16-byte slots): the three probes of a lookup
+// mostly touch one line; collisions step by whole lines
+JD uint32_t vt_slot0(long long k, uint32_t mask) {
+  uint64_t g = (uint64_t)k >> 3;
+  uint32_t m = hfin((uint32_t)g * 0x9E3779B1u + (uint32_t)(g >> 32) * 0x85EBCA6Bu);
+  return ((m << 3) | ((uint32_t)k & 7u)) & mask;
+}
+JD uint32_t vt_next(uint32_t h, uint32_t mask) { return (h + 8u) & mask; }
+JD unsigned long long *vt_meta(JVSlot *s) { return reinterpret_cast<unsigned long long *>(&s->keylo); }
+JD unsigned long long vt_meta_of(uint32_t keylo, uint32_t id1) { return (unsigned long long)keylo | ((unsigned long long)id1 << 32); }
 
-template <int MODE> JD bool real_find(const Ctx &c, double x, uint32_t *idx) {
-  const double tol = jtol<MODE>(c);
-  if (x <= tol) { *idx = 0; return true; }
-  if (!(x < 1.0e8)) return false;  // absurd magnitude: treated as a miss, caught as VAL_FULL later
-  const long long k = vt_bucket(x, jinv_tol<MODE>(c));
-  const uint32_t mask = vt_mask<MODE>(c);
-  for (int d = -1; d <= 1; d++) {
-    long long kk = k + d;
-    uint32_t h = h64((uint64_t)kk) & mask;
-    for (uint32_t probes = 0; probes <= mask; probes++) {
-      JVSlot s = vt_load<MODE>(c, h);
-      if (s.id1 == 0) break;
-      if (s.keylo == (uint32_t)kk && fabs(JKQ_DSUB(s.value, x)) <= tol) { *idx = s.id1 - 1; return true; }
-      h = (h + 1) & mask;
-    }
+template <int MODE> JD void pend_push(JEng *E, CtaState *S, uint32_t ring, uint32_t slot) {
+  uint32_t i = jatomic_add(MODE == MODE_CTA ? &S->pend_n[ring] : &E->pend_n[ring], 1u);
+  if (MODE == MODE_CTA) {
+    if (i < JKQ_SPEND) S->pend[i] = slot;
+    else jwant_grid(S);
+  } else {
+    if (i < E->pend_cap) E->pend[i] = slot;
+    else jset_error<MODE>(E, S, JKQ_ERR_PEND_FULL);
   }
-  return false;
 }
 
-// hash-only insert of an existing real (collector / table reload): slot claimed by CAS on id1
-template <int MODE> JD void vt_put(Ctx &c, uint32_t idx, double x) {
-  const long long k = vt_bucket(x, jinv_tol<MODE>(c));
-  const uint32_t mask = vt_mask<MODE>(c);
-  JVSlot *tab = MODE == MODE_CTA ? c.sh->vtab : c.E->vtab;
-  uint32_t h = h64((uint64_t)k) & mask;
-  while (jatomic_cas(&tab[h].id1, 0u, idx + 1) != 0) h = (h + 1) & mask;
-  tab[h].value = x;
+// a value that missed the table: leave it as a candidate of its bucket
+template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, double x, long long k) {
+  const uint32_t klo = (uint32_t)k, mask = vt_mask2<MODE>(E);
+  const unsigned long long xb = jd2u(x), claim = vt_meta_of(klo, JV_PENDING);
+  JVSlot *tab = vt_tab2<MODE>(E, S);
+  uint32_t h = vt_slot0(k, mask);
+  for (uint32_t probes = 0; probes <= (mask >> 3);) {
+    unsigned long long *mp = vt_meta(tab + h);
+    unsigned long long meta = ld_r<MODE>(mp);
+    if (meta == 0) {
+      meta = jatomic_cas(mp, 0ull, claim);
+      if (meta == 0) { jatomic_min(&tab[h].vbits, xb); pend_push<MODE>(E, S, ring, h); return; }
+    }
+    if ((uint32_t)meta == klo) {
+      const uint32_t id1 = (uint32_t)(meta >> 32);
+      if (id1 == JV_PENDING) { jatomic_min(&tab[h].vbits, xb); return; }
+      if (id1 == JV_DROPPED) {
+        if (jatomic_cas(mp, meta, claim) == meta) { jatomic_min(&tab[h].vbits, xb); pend_push<MODE>(E, S, ring, h); return; }
+        continue;  // somebody else re-claimed it: look at the slot again
+      }
+    }
+    h = vt_next(h, mask);
+    probes++;
+  }
+  if (MODE == MODE_CTA) jwant_grid(S);
+  else jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+}
+
+// index of the entry within tol of x (x >= 0), or JV_MISS; with `propose` a miss leaves x as a candidate
+template <int MODE> JNI uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
+  const double tol = jtol2<MODE>(E, S);
+  if (x <= tol) return 0;
+  if (!(x < JKQ_VAL_MAX)) {  // absurd magnitude
+    if (propose) jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+    return JV_MISS;
+  }
+  const long long k = vt_bucket(x, jinv_tol2<MODE>(E, S));
+  const uint32_t mask = vt_mask2<MODE>(E);
+  const JVSlot *tab = vt_tab2<MODE>(E, S);
+  uint32_t h[3];
+  JVSlot s[3];
+  JKQ_UNROLL
+  for (int d = 0; d < 3; d++) { h[d] = vt_slot0(k - 1 + d, mask); s[d] = ld_s<MODE>(tab + h[d]); }  // three loads in flight
+  JKQ_UNROLL
+  for (int d = 0; d < 3; d++) {
+    const uint32_t klo = (uint32_t)(k - 1 + d);
+    uint32_t hh = h[d];
+    JVSlot sl = s[d];
+    for (uint32_t probes = 0; sl.id1 != 0 && probes <= (mask >> 3); probes++) {
+      if (sl.keylo == klo && sl.id1 < JV_DROPPED && fabs(JKQ_DSUB(ju2d(sl.vbits), x)) <= tol) return sl.id1 - 1;
+      hh = vt_next(hh, mask);
+      sl = ld_s<MODE>(tab + hh);
+    }
+  }
+  if (propose) real_propose<MODE>(E, S, ring, x, k);
+  return JV_MISS;
+}
+
+// commit the candidates collected under pend counter `par` (the ring index of the phase that proposed
+// them); threads tid, tid+nth, ...
+template <int MODE> JNI void vals_commit(JEng *E, CtaState *S, uint32_t par, uint32_t tid, uint32_t nth) {
+  uint32_t n = ld_s<MODE>(MODE == MODE_CTA ? &S->pend_n[par] : &E->pend_n[par]);
+  const uint32_t cap = MODE == MODE_CTA ? JKQ_SPEND : E->pend_cap;
+  if (n > cap) n = cap;
+  const uint32_t *pend = MODE == MODE_CTA ? S->pend : E->pend;
+  JVSlot *tab = vt_tab2<MODE>(E, S);
+  const uint32_t mask = vt_mask2<MODE>(E);
+  const double tol = jtol2<MODE>(E, S), inv_tol = jinv_tol2<MODE>(E, S);
+  for (uint32_t i = tid; i < n; i += nth) {
+    const uint32_t h = ld_s<MODE>(pend + i);
+    const unsigned long long vb = ld_r<MODE>(&tab[h].vbits);
+    const double v = ju2d(vb);
+    const long long kk = vt_bucket(v, inv_tol) - 1;
+    bool drop = false;
+    uint32_t hh = vt_slot0(kk, mask);
+    for (uint32_t probes = 0; probes <= (mask >> 3); probes++) {
+      JVSlot sl = ld_s<MODE>(tab + hh);  // (a neighbour being committed right now reads as present or as gone: same final table)
+      if (sl.id1 == 0) break;
+      if (sl.keylo == (uint32_t)kk && sl.id1 != JV_DROPPED) {
+        double d = JKQ_DSUB(v, ju2d(sl.vbits));
+        if (d > 0.0 && d <= tol) { drop = true; break; }
+      }
+      hh = vt_next(hh, mask);
+    }
+    uint32_t id1 = JV_DROPPED;
+    if (!drop) {
+      uint32_t idx = jatomic_add(MODE == MODE_CTA ? &S->val_count : &E->val_count, 1u);
+      if (MODE == MODE_CTA) {
+        if (idx >= S->val_limit) jwant_grid(S);  // the shared table is full: grid path
+        else { S->vals[idx] = v; id1 = idx + 1; jstat<MODE>(E, S, JST_VALS, 1u); }  // (copied to HBM by cta_flush)
+      } else {
+        if (idx >= E->val_cap || (uint64_t)idx * 2 >= E->vtab_mask) jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+        else { E->vals[idx] = v; id1 = idx + 1; jstat<MODE>(E, S, JST_VALS, 1u); }
+      }
+    }
+    if (id1 == JV_DROPPED) tab[h].vbits = JV_INF;
+    tab[h].id1 = id1;
+  }
+}
+
+// single-thread insert while nobody else touches the table (init, gate set-up, root update, collector)
+template <int MODE> JNI uint32_t real_insert_direct(JEng *E, CtaState *S, double x) {
+  uint32_t idx;
+  if (MODE == MODE_CTA) {
+    if (S->val_count >= S->val_limit) { jwant_grid(S); return 0; }
+    idx = S->val_count++;
+    S->vals[idx] = x;  // (copied to HBM by cta_flush)
+    jstat<MODE>(E, S, JST_VALS, 1u);
+  } else {
+    if (E->val_count >= E->val_cap || (uint64_t)E->val_count * 2 >= E->vtab_mask) { jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL); return 0; }
+    idx = E->val_count++;
+    E->vals[idx] = x;
+    jstat<MODE>(E, S, JST_VALS, 1u);
+  }
+  const long long k = vt_bucket(x, jinv_tol2<MODE>(E, S));
+  const uint32_t mask = vt_mask2<MODE>(E);
+  JVSlot *tab = vt_tab2<MODE>(E, S);
+  uint32_t h = vt_slot0(k, mask);
+  for (;;) {
+    JVSlot sl = ld_s<MODE>(tab + h);
+    if (sl.id1 == 0 || (sl.id1 == JV_DROPPED && sl.keylo == (uint32_t)k)) break;
+    h = vt_next(h, mask);
+  }
+  JVSlot sl;
+  sl.vbits = jd2u(x); sl.keylo = (uint32_t)k; sl.id1 = idx + 1;
+  tab[h] = sl;
+  return idx;
+}
+// parallel hash-only insert of an existing real (collector / table reload): slot claimed by CAS on id1
+template <int MODE> JD void vt_put(JEng *E, CtaState *S, uint32_t idx, double x) {
+  const long long k = vt_bucket(x, jinv_tol2<MODE>(E, S));
+  const uint32_t mask = vt_mask2<MODE>(E);
+  JVSlot *tab = vt_tab2<MODE>(E, S);
+  uint32_t h = vt_slot0(k, mask);
+  while (jatomic_cas(&tab[h].id1, 0u, idx + 1) != 0) h = vt_next(h, mask);
+  tab[h].vbits = jd2u(x);
   tab[h].keylo = (uint32_t)k;
 }
 
-// serial section only (one thread): append x, QMDDcomplexD.cpp:409-418
-template <int MODE> JD uint32_t real_insert_serial(Ctx &c, double x) {
-  JEng *E = c.E;
-  if (MODE == MODE_CTA) {
-    CtaState *S = c.sh;
-    if (S->val_count >= JKQ_SVALS) { S->want_grid = 1; return 0; }  // the shared table is full: grid path
-    uint32_t idx = S->val_count++;
-    S->vals[idx] = x;
-    E->vals[idx] = x;  // write-through: the HBM array is always complete
-    vt_put<MODE>(c, idx, x);
-    S->val_inserts++;
-    return idx;
-  }
-  if (E->val_count >= E->val_cap || (uint64_t)E->val_count * 2 >= E->vtab_mask) { jset_error_c<MODE>(c, JKQ_ERR_VAL_FULL); return 0; }
-  uint32_t idx = E->val_count++;
-  E->vals[idx] = x;
-  const long long k = vt_bucket(x, E->inv_tol);
-  uint32_t h = h64((uint64_t)k) & E->vtab_mask;
-  while (ld_s<MODE>(E->vtab + h).id1 != 0) h = (h + 1) & E->vtab_mask;
-  JVSlot s;
-  s.value = x; s.id1 = idx + 1; s.keylo = (uint32_t)k;
-  E->vtab[h] = s;
-  E->st_val_inserts++;
-  return idx;
-}
-
-template <int MODE> JD void pend_push(Ctx &c, double x) {
-  JEng *E = c.E;
-  uint32_t i = jatomic_add(cnt_pend<MODE>(c, c.phase & 1), 1u);
-  if (i < E->pend_cap) E->pend[i] = x;
-  else jset_error_c<MODE>(c, JKQ_ERR_PEND_FULL);
-}
-
-// Clookup for one complex value.  false = at least one part is not in the table yet; the missing
-// parts have been queued for the next serial insert section.
-template <int MODE> JD bool cx_find(Ctx &c, double re, double im, uint64_t *out) {
-  uint32_t sr = re < 0.0, si = im < 0.0;
-  re = fabs(re); im = fabs(im);
-  uint32_t r = 0, i = 0;
-  bool okr = real_find<MODE>(c, re, &r), oki = real_find<MODE>(c, im, &i);
-  if (!okr) pend_push<MODE>(c, re);
-  if (!oki) pend_push<MODE>(c, im);
-  if (!(okr && oki)) return false;
+// Clookup for one complex value.  JW_MISS = at least one part is not in the table yet; the missing
+// parts have been proposed for the next commit.
+template <int MODE> JD uint64_t cx_lookup(JEng *E, CtaState *S, uint32_t ring, double re, double im) {
+  const uint32_t sr = re < 0.0, si = im < 0.0;
+  uint32_t r = real_lookup<MODE>(E, S, ring, fabs(re), true), i = real_lookup<MODE>(E, S, ring, fabs(im), true);
+  if (r == JV_MISS || i == JV_MISS) return JW_MISS;
   if (sr && r) r |= 0x80000000u;
   if (si && i) i |= 0x80000000u;
-  *out = ((uint64_t)r << 32) | (uint64_t)i;
-  return true;
+  return ((uint64_t)r << 32) | (uint64_t)i;
 }
 
-// Cmul / Cadd / Cdiv: the id short-cuts of QMDDcomplexD.cpp:498-777, arithmetic on the canonical
-// values in FP64 (no op caches: recomputing is cheaper than a memo probe on a GPU).
-template <int MODE> JD bool cmul(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
-  if (a == JW_ONE) { *out = b; return true; }
-  if (b == JW_ONE) { *out = a; return true; }
-  if (a == 0 || b == 0) { *out = 0; return true; }
-  if (a == JW_MONE) { *out = jneg(b); return true; }
-  if (b == JW_MONE) { *out = jneg(a); return true; }
-  double ar = jre<MODE>(c, a), ai = jim<MODE>(c, a), br = jre<MODE>(c, b), bi = jim<MODE>(c, b);
-  double re = JKQ_DSUB(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi));
-  double im = JKQ_DADD(JKQ_DMUL(ar, bi), JKQ_DMUL(ai, br));
-  return cx_find<MODE>(c, re, im, out);
-}
-template <int MODE> JD bool cadd(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
-  if (a == 0) { *out = b; return true; }
-  if (b == 0) { *out = a; return true; }
-  if (a == jneg(b)) { *out = 0; return true; }
-  double re = JKQ_DADD(jre<MODE>(c, a), jre<MODE>(c, b));
-  double im = JKQ_DADD(jim<MODE>(c, a), jim<MODE>(c, b));
-  return cx_find<MODE>(c, re, im, out);
-}
-template <int MODE> JD bool cdiv(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
-  if (a == b) { *out = JW_ONE; return true; }
-  if (a == 0) { *out = 0; return true; }
-  if (b == JW_ONE) { *out = a; return true; }
-  if (b == JW_MONE) { *out = jneg(a); return true; }
-  if (a == jneg(b)) { *out = JW_MONE; return true; }
-  double ar = jre<MODE>(c, a), ai = jim<MODE>(c, a), br = jre<MODE>(c, b), bi = jim<MODE>(c, b);
+// Cmul / Cadd / Cdiv on operands that passed the id short-cuts of QMDDcomplexD.cpp:498-777: arithmetic
+// on the canonical values in FP64 (no op caches: recomputing is cheaper than a memo probe on a GPU).
+#define JOP_MUL 0u
+#define JOP_ADD 1u
+#define JOP_DIV 2u
+template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, uint32_t op, uint64_t a, uint64_t b) {
+  double ar = jval2<MODE>(E, S, (uint32_t)(a >> 32)), ai = jval2<MODE>(E, S, (uint32_t)a);
+  double br = jval2<MODE>(E, S, (uint32_t)(b >> 32)), bi = jval2<MODE>(E, S, (uint32_t)b);
+  if (a >> 63) ar = -ar;
+  if ((a >> 31) & 1) ai = -ai;
+  if (b >> 63) br = -br;
+  if ((b >> 31) & 1) bi = -bi;
   double re, im;
-  if ((b & 0x7FFFFFFFull) == 0) {  // purely real divisor, :727-736
+  if (op == JOP_MUL) {
+    re = JKQ_DSUB(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi));
+    im = JKQ_DADD(JKQ_DMUL(ar, bi), JKQ_DMUL(ai, br));
+  } else if (op == JOP_ADD) {
+    re = JKQ_DADD(ar, br);
+    im = JKQ_DADD(ai, bi);
+  } else if ((b & 0x7FFFFFFFull) == 0) {  // purely real divisor, :727-736
     re = JKQ_DDIV(ar, br);
     im = JKQ_DDIV(ai, br);
   } else {
@@ -315,15 +508,45 @@ template <int MODE> JD bool cdiv(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) 
     re = JKQ_DDIV(JKQ_DADD(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi)), d);
     im = JKQ_DDIV(JKQ_DSUB(JKQ_DMUL(ai, br), JKQ_DMUL(ar, bi)), d);
   }
-  return cx_find<MODE>(c, re, im, out);
+  return cx_lookup<MODE>(E, S, ring, re, im);
+}
+template <int MODE> JD bool cmul(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
+  if (a == JW_ONE) { *out = b; return true; }
+  if (b == JW_ONE) { *out = a; return true; }
+  if (a == 0 || b == 0) { *out = 0; return true; }
+  if (a == JW_MONE) { *out = jneg(b); return true; }
+  if (b == JW_MONE) { *out = jneg(a); return true; }
+  const uint64_t r = cx_arith<MODE>(c.E, c.sh, c.ring, JOP_MUL, a, b);
+  *out = r;
+  return r != JW_MISS;
+}
+template <int MODE> JD bool cadd(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
+  if (a == 0) { *out = b; return true; }
+  if (b == 0) { *out = a; return true; }
+  if (a == jneg(b)) { *out = 0; return true; }
+  const uint64_t r = cx_arith<MODE>(c.E, c.sh, c.ring, JOP_ADD, a, b);
+  *out = r;
+  return r != JW_MISS;
+}
+template <int MODE> JD bool cdiv(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
+  if (a == b) { *out = JW_ONE; return true; }
+  if (a == 0) { *out = 0; return true; }
+  if (b == JW_ONE) { *out = a; return true; }
+  if (b == JW_MONE) { *out = jneg(a); return true; }
+  if (a == jneg(b)) { *out = JW_MONE; return true; }
+  const uint64_t r = cx_arith<MODE>(c.E, c.sh, c.ring, JOP_DIV, a, b);
+  *out = r;
+  return r != JW_MISS;
 }
 
-// serial canonicalisation (one thread, may insert): gate setup and root update
-template <int MODE> JD uint64_t cx_make_serial(Ctx &c, double re, double im) {
-  uint32_t sr = re < 0.0, si = im < 0.0, r, i;
+// serial canonicalisation (one thread, may insert): gate set-up and root update
+template <int MODE> JNI uint64_t cx_make_serial(JEng *E, CtaState *S, double re, double im) {
+  const uint32_t sr = re < 0.0, si = im < 0.0;
   re = fabs(re); im = fabs(im);
-  if (!real_find<MODE>(c, re, &r)) r = real_insert_serial<MODE>(c, re);
-  if (!real_find<MODE>(c, im, &i)) i = real_insert_serial<MODE>(c, im);
+  uint32_t r = real_lookup<MODE>(E, S, 0, re, false), i;
+  if (r == JV_MISS) r = real_insert_direct<MODE>(E, S, re);
+  i = real_lookup<MODE>(E, S, 0, im, false);
+  if (i == JV_MISS) i = real_insert_direct<MODE>(E, S, im);
   if (sr && r) r |= 0x80000000u;
   if (si && i) i |= 0x80000000u;
   return ((uint64_t)r << 32) | (uint64_t)i;
@@ -342,140 +565,184 @@ template <int MODE> JD JNode node_load(const Ctx &c, uint32_t id) {
 // ------------------------------------------------------------------------------------ unique table
 // QMDDutLookup (QMDDpackage.cpp:693-763) as a lock-free open-addressing table of node ids.
 // Protocol: write the record, fence, publish the id with atomicCAS.  A reader that observes an id
-// in a slot therefore always finds a complete record behind it.
-JD uint32_t ut_hash(const JNode &n) { return h32(n.c0 ^ h32(n.c1 + 0x9E3779B9u) ^ h64(n.w)); }
+// in a slot therefore always finds a complete record behind it.  Returns 0 when a pool is exhausted
+// (sticky error / want_grid raised).
+JD uint32_t ut_hash3(uint32_t c0, uint32_t c1, uint64_t w) { return hfin(c0 * 0x9E3779B1u + c1 * 0x85EBCA77u + hw64(w)); }
+JD uint32_t ut_hash(const JNode &n) { return ut_hash3(n.c0, n.c1, n.w); }
 
-template <int MODE> JD uint32_t ut_find_or_insert(Ctx &c, const JNode &rec) {
-  JEng *E = c.E;
+template <int MODE> JNI uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_t c0, uint32_t c1, uint64_t w) {
+  JNode rec;
+  rec.c0 = c0; rec.c1 = c1; rec.w = w;
   if (MODE == MODE_CTA) {
-    CtaState *S = c.sh;
-    uint32_t h = ut_hash(rec) & (JKQ_SUT_SLOTS - 1), mine = 0;
+    uint32_t h = ut_hash3(c0, c1, w) & (JKQ_SUT_SLOTS - 1), mine = 0;
     for (uint32_t probes = 0; probes < JKQ_SUT_SLOTS; probes++) {
-      uint32_t s = S->utab[h];
+      uint32_t s = ld_r<MODE>(&S->utab[h]);
       if (s == 0) {
         if (mine == 0) {
-          if (c.spare_node) { mine = c.spare_node; c.spare_node = 0; }
-          else mine = jatomic_add(&S->node_count, 1u);
-          if (mine >= JKQ_SNODES) { S->want_grid = 1; return 0; }  // gate abandoned, redone on the grid path
-          S->nodes[mine] = rec;
-          E->nodes[mine] = rec;  // write-through
+          mine = jatomic_add(&S->node_count, 1u);
+          if (mine >= S->node_limit) { jwant_grid(S); return 0; }  // gate abandoned, redone on the grid path
+          S->nodes[mine] = rec;  // (copied to HBM by cta_flush)
           jfence<MODE>();
         }
         s = jatomic_cas(&S->utab[h], 0u, mine);
-        if (s == 0) { jatomic_add(&S->nodes_created, 1u); return mine; }
+        if (s == 0) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
       }
-      JNode o = S->nodes[s];
-      if (o.c0 == rec.c0 && o.c1 == rec.c1 && o.w == rec.w) { c.spare_node = mine; return s; }
+      JNode o = ld_r<MODE>(&S->nodes[s]);
+      if (o.c0 == c0 && o.c1 == c1 && o.w == w) return s;  // (an id allocated above and not published stays unused: garbage)
       h = (h + 1) & (JKQ_SUT_SLOTS - 1);
     }
-    S->want_grid = 1;
+    jwant_grid(S);
     return 0;
   }
-  uint32_t h = ut_hash(rec) & E->utab_mask, mine = 0;
+  uint32_t h = ut_hash3(c0, c1, w) & E->utab_mask, mine = 0;
   for (uint32_t probes = 0; probes <= E->utab_mask; probes++) {
-    uint32_t s = ld_r(E->utab + h);
+    uint32_t s = ld_r<MODE>(E->utab + h);
     if (s == 0) {
       if (mine == 0) {
-        if (c.spare_node) { mine = c.spare_node; c.spare_node = 0; }
-        else mine = jatomic_add(&E->node_count, 1u);
-        if (mine >= E->node_cap) { jset_error_c<MODE>(c, JKQ_ERR_NODE_FULL); return 0; }
+        mine = jatomic_add(&E->node_count, 1u);
+        if (mine >= E->node_cap) { jset_error<MODE>(E, S, JKQ_ERR_NODE_FULL); return 0; }
         E->nodes[mine] = rec;
         jfence<MODE>();
       }
       s = jatomic_cas(E->utab + h, 0u, mine);
-      if (s == 0) { jatomic_add(&E->st_nodes_created, 1ull); return mine; }
+      if (s == 0) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
     }
-    JNode o = ld_r(E->nodes + s);
-    if (o.c0 == rec.c0 && o.c1 == rec.c1 && o.w == rec.w) { c.spare_node = mine; return s; }
+    JNode o = ld_r<MODE>(E->nodes + s);
+    if (o.c0 == c0 && o.c1 == c1 && o.w == w) return s;
     h = (h + 1) & E->utab_mask;
   }
-  jset_error_c<MODE>(c, JKQ_ERR_UTAB_FULL);
+  jset_error<MODE>(E, S, JKQ_ERR_UTAB_FULL);
   return 0;
 }
 
 // ------------------------------------------------------------------------------------ frontier de-dup
 // The compute tables of the reference (CTlookup/CTinsert, QMDDpackage.cpp:986-1072) exist so that a
 // (gate,node) or (a,b,ratio) pair is expanded once.  Here the pairs of one gate are the work items of
-// the frontier; this table maps an item key to its index.  MODE_GRID: HBM slots carry the gate
-// generation in the high word, so nothing is ever cleared.  MODE_CTA: shared slots, cleared per gate.
-JD uint32_t dt_hash(uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
-  if ((tag & 15u) == JK_M) return h32(a);
-  return h32(a ^ h32(b + tag * 0x9E3779B9u) ^ h64(wa) * 3u ^ h64(wb) * 5u ^ h64(wc) * 7u);
+// the frontier.  M items (gate x node) are keyed by the node alone: a direct-indexed array, no hashing.
+// F/S items go through a hash table.  Every slot carries the gate's generation, so nothing is ever
+// cleared between gates.  Both return JI_FAIL when a pool is exhausted (sticky error / want_grid).
+#define JI_FAIL 0xFFFFFFFFu
+JD void item_init(JItem *it, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+  it->a = a; it->b = b; it->tag = tag; it->flags = JS_NEW;
+  it->wa = wa; it->wb = wb; it->wc = wc;
 }
-JD bool item_key_eq(const JItem *o, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
-  return o->a == a && o->b == b && o->tag == tag && o->wa == wa && o->wb == wb && o->wc == wc;
+JD void item_init_m(JItem *it, uint32_t node) { it->a = node; it->b = 0; it->tag = JK_M; it->flags = JS_NEW; }
+
+template <int MODE> JD uint32_t item_alloc(JEng *E, CtaState *S) {
+  if (MODE == MODE_CTA) {
+    uint32_t mine = jatomic_add(&S->item_count, 1u);
+    if (mine >= JKQ_SITEMS) { jwant_grid(S); return JI_FAIL; }
+    return mine;
+  }
+  uint32_t mine = jatomic_add(&E->item_count, 1u);
+  if (mine >= E->item_cap) { jset_error<MODE>(E, S, JKQ_ERR_ITEM_FULL); return JI_FAIL; }
+  return mine;
 }
 
-// returns the item index; *ok = false: the table could not take the key (error flagged, or -- MODE_CTA --
-// the shared pool is full and the gate has to be redone on the grid path: c.sh->want_grid)
-template <int MODE>
-JD uint32_t dt_find_or_insert(Ctx &c, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag, bool *ok) {
-  JEng *E = c.E;
-  uint32_t mine = 0xFFFFFFFFu;
+template <int MODE> JD uint32_t dt_find_or_insert_m(JEng *E, CtaState *S, JItem *items, uint32_t node) {
+  uint32_t mine = JI_FAIL;
   if (MODE == MODE_CTA) {
-    CtaState *S = c.sh;
+    const uint32_t gen = S->gen << 16;
+    uint32_t s = ld_r<MODE>(&S->mdir[node]);
+    for (;;) {
+      if ((s & 0xFFFF0000u) == gen) {
+        if (mine != JI_FAIL) items[mine].flags = JS_DEAD;
+        return (s & 0xFFFFu) - 1;
+      }
+      if (mine == JI_FAIL) {
+        mine = item_alloc<MODE>(E, S);
+        if (mine == JI_FAIL) return JI_FAIL;
+        item_init_m(items + mine, node);
+      }
+      uint32_t old = jatomic_cas(&S->mdir[node], s, gen | (mine + 1));
+      if (old == s) return mine;
+      s = old;
+    }
+  }
+  const unsigned long long gen = (unsigned long long)ld_s<MODE>(&E->gen) << 32;
+  unsigned long long s = ld_r<MODE>(E->mdir + node);
+  for (;;) {
+    if ((s >> 32) == (gen >> 32)) {
+      if (mine != JI_FAIL) items[mine].flags = JS_DEAD;
+      return (uint32_t)s - 1;
+    }
+    if (mine == JI_FAIL) {
+      mine = item_alloc<MODE>(E, S);
+      if (mine == JI_FAIL) return JI_FAIL;
+      item_init_m(items + mine, node);
+    }
+    unsigned long long old = jatomic_cas(E->mdir + node, s, gen | (unsigned long long)(mine + 1));
+    if (old == s) return mine;
+    s = old;
+  }
+}
+
+JD uint32_t dt_hash(uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+  return hfin(a * 0x9E3779B1u + b * 0x85EBCA77u + tag * 0x165667B1u + hw64(wa) * 3u + hw64(wb) * 5u + hw64(wc) * 7u);
+}
+template <int MODE> JD bool item_key_eq(const JItem *o, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+  return ld_r<MODE>(&o->a) == a && ld_r<MODE>(&o->b) == b && ld_r<MODE>(&o->tag) == tag && ld_r<MODE>(&o->wa) == wa &&
+         ld_r<MODE>(&o->wb) == wb && ld_r<MODE>(&o->wc) == wc;
+}
+
+template <int MODE>
+JNI uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+  if ((tag & 15u) == JK_M) return dt_find_or_insert_m<MODE>(E, S, items, a);
+  uint32_t mine = JI_FAIL;
+  if (MODE == MODE_CTA) {
+    const uint32_t gen = S->gen << 16;
     uint32_t h = dt_hash(a, b, wa, wb, wc, tag) & (JKQ_SDT_SLOTS - 1);
     for (uint32_t probes = 0; probes < JKQ_SDT_SLOTS; probes++) {
-      uint32_t s = S->dtab[h];
-      if (s == 0) {
-        if (mine == 0xFFFFFFFFu) {
-          mine = jatomic_add(&S->item_count, 1u);
-          if (mine >= JKQ_SITEMS) { S->want_grid = 1; *ok = false; return 0; }
-          JItem *it = c.items + mine;
-          it->a = a; it->b = b; it->wa = wa; it->wb = wb; it->wc = wc; it->tag = tag;
-          it->state = JS_NEW;
+      uint32_t s = ld_r<MODE>(&S->dtab[h]);
+      while ((s & 0xFFFF0000u) != gen) {  // stale or empty: try to claim
+        if (mine == JI_FAIL) {
+          mine = item_alloc<MODE>(E, S);
+          if (mine == JI_FAIL) return JI_FAIL;
+          item_init(items + mine, a, b, wa, wb, wc, tag);
           jfence<MODE>();
         }
-        s = jatomic_cas(&S->dtab[h], 0u, mine + 1);
-        if (s == 0) return mine;
+        uint32_t old = jatomic_cas(&S->dtab[h], s, gen | (mine + 1));
+        if (old == s) return mine;
+        s = old;
       }
-      if (item_key_eq(c.items + (s - 1), a, b, wa, wb, wc, tag)) {
-        if (mine != 0xFFFFFFFFu) c.items[mine].state = JS_DEAD;
-        return s - 1;
+      const uint32_t j = (s & 0xFFFFu) - 1;
+      if (item_key_eq<MODE>(items + j, a, b, wa, wb, wc, tag)) {
+        if (mine != JI_FAIL) items[mine].flags = JS_DEAD;
+        return j;
       }
       h = (h + 1) & (JKQ_SDT_SLOTS - 1);
     }
-    S->want_grid = 1;
-    *ok = false;
-    return 0;
+    jwant_grid(S);
+    return JI_FAIL;
   }
   uint32_t h = dt_hash(a, b, wa, wb, wc, tag) & E->dtab_mask;
-  unsigned long long gen = (unsigned long long)ld_s<MODE>(&E->gen) << 32;
+  const unsigned long long gen = (unsigned long long)ld_s<MODE>(&E->gen) << 32;
   for (uint32_t probes = 0; probes <= E->dtab_mask; probes++) {
-    unsigned long long s = ld_r(E->dtab + h);
+    unsigned long long s = ld_r<MODE>(E->dtab + h);
     while ((s >> 32) != (gen >> 32)) {  // stale or empty: try to claim
-      if (mine == 0xFFFFFFFFu) {
-        mine = jatomic_add(&E->item_count, 1u);
-        if (mine >= E->item_cap) { jset_error_c<MODE>(c, JKQ_ERR_ITEM_FULL); *ok = false; return 0; }
-        JItem *it = c.items + mine;
-        it->a = a; it->b = b; it->wa = wa; it->wb = wb; it->wc = wc; it->tag = tag;
-        it->state = JS_NEW;
+      if (mine == JI_FAIL) {
+        mine = item_alloc<MODE>(E, S);
+        if (mine == JI_FAIL) return JI_FAIL;
+        item_init(items + mine, a, b, wa, wb, wc, tag);
         jfence<MODE>();
       }
       unsigned long long old = jatomic_cas(E->dtab + h, s, gen | (unsigned long long)(mine + 1));
       if (old == s) return mine;
       s = old;
     }
-    uint32_t j = (uint32_t)s - 1;
-    const JItem *o = c.items + j;
-    if (ld_r(&o->a) == a && ld_r(&o->b) == b && ld_r(&o->tag) == tag && ld_r(&o->wa) == wa && ld_r(&o->wb) == wb &&
-        ld_r(&o->wc) == wc) {
-      if (mine != 0xFFFFFFFFu) c.items[mine].state = JS_DEAD;
+    const uint32_t j = (uint32_t)s - 1;
+    if (item_key_eq<MODE>(items + j, a, b, wa, wb, wc, tag)) {
+      if (mine != JI_FAIL) items[mine].flags = JS_DEAD;
       return j;
     }
     h = (h + 1) & E->dtab_mask;
   }
-  jset_error_c<MODE>(c, JKQ_ERR_DTAB_FULL);
-  *ok = false;
-  return 0;
+  jset_error<MODE>(E, S, JKQ_ERR_DTAB_FULL);
+  return JI_FAIL;
 }
 
-// item field access: shared memory (plain) in MODE_CTA, ld.global.cg in MODE_GRID
-#ifdef JKQ_EMU
-template <int MODE, class T> JD T ld_i(const T *p) { return *p; }
-#else
-template <int MODE, class T> JD T ld_i(const T *p) { return MODE == MODE_CTA ? *p : ld_r(p); }
-#endif
+// item field access: shared memory in MODE_CTA, ld.global.cg in MODE_GRID
+template <int MODE, class T> JD T ld_i(const T *p) { return ld_r<MODE>(p); }
 
 // ------------------------------------------------------------------------------------ child slots
 struct Slot {
@@ -527,9 +794,8 @@ JD bool combine(Ctx &c, int low, int m, uint64_t al, uint32_t A, uint64_t be, ui
   if (sel == 0 && be == 0 && al == ga) { slot_pass(s, A, ga); return true; }  // gate row acts as identity
   if (sel == 1 && al == 0 && be == ga) { slot_pass(s, B, ga); return true; }
   uint64_t f = al ? al : (be ? be : ga), wa, wb, wc;
-  if (!cdiv<MODE>(c, al, f, &wa)) return false;
-  if (!cdiv<MODE>(c, be, f, &wb)) return false;
-  if (!cdiv<MODE>(c, ga, f, &wc)) return false;
+  bool o1 = cdiv<MODE>(c, al, f, &wa), o2 = cdiv<MODE>(c, be, f, &wb), o3 = cdiv<MODE>(c, ga, f, &wc);
+  if (!(o1 && o2 && o3)) return false;
   uint32_t An = (wa != 0 || (sel == 0 && wc != 0)) ? A : 0;
   uint32_t Bn = (wb != 0 || (sel == 1 && wc != 0)) ? B : 0;
   slot_ref(s, f, An, Bn, wa, wb, wc, JK_F | (sel << 4));
@@ -542,7 +808,7 @@ JD int role_satisfied(uint32_t role, int i) {
 
 template <int MODE> JD uint64_t gate_u(const Ctx &c, int k) { return MODE == MODE_CTA ? c.sh->cur_u[k] : ld_s<MODE>(&c.E->cur_u[k]); }
 
-// one child slot of an item of level L.  kind M: p = the state node.  kind F/S: na/nb = operand nodes.
+// one child slot of an item of level L.  kind M: na = the state node.  kind F/S: na/nb = operand nodes.
 template <int MODE>
 JD bool expand_child(Ctx &c, const JGate &g, int L, int i, uint32_t kind, uint32_t sel, uint32_t tag, uint32_t role,
                      uint32_t ia, uint32_t ib, uint64_t iwa, uint64_t iwb, uint64_t iwc, const JNode &na, const JNode &nb, Slot &s) {
@@ -557,8 +823,8 @@ JD bool expand_child(Ctx &c, const JGate &g, int L, int i, uint32_t kind, uint32
     }
     // target level: row i of the 2x2 matrix, QMDDpackage.cpp:1488-1509
     uint64_t al, be;
-    if (!cmul<MODE>(c, gate_u<MODE>(c, 2 * i), nd_w0(na), &al)) return false;
-    if (!cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), nd_w1(na), &be)) return false;
+    bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), nd_w0(na), &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), nd_w1(na), &be);
+    if (!(o1 && o2)) return false;
     return combine<MODE>(c, g.low, L - 1, al, nd_c0(na), be, na.c1, w, (uint32_t)i, s);
   }
   const uint32_t ac = ia ? (i ? na.c1 : nd_c0(na)) : 0, bc = ib ? (i ? nb.c1 : nd_c0(nb)) : 0;
@@ -588,79 +854,52 @@ JD bool expand_child(Ctx &c, const JGate &g, int L, int i, uint32_t kind, uint32
     return true;
   }
   uint64_t ga;
-  if (!cmul<MODE>(c, iwc, sel ? bw : aw, &ga)) return false;
-  if (!role_satisfied(role, i)) { slot_pass(s, sel ? bc : ac, ga); return true; }
+  bool o0 = cmul<MODE>(c, iwc, sel ? bw : aw, &ga);
+  if (!role_satisfied(role, i)) {
+    if (!o0) return false;
+    slot_pass(s, sel ? bc : ac, ga);
+    return true;
+  }
   uint64_t al, be;
-  if (!cmul<MODE>(c, iwa, aw, &al)) return false;
-  if (!cmul<MODE>(c, iwb, bw, &be)) return false;
+  bool o1 = cmul<MODE>(c, iwa, aw, &al), o2 = cmul<MODE>(c, iwb, bw, &be);
+  if (!(o0 && o1 && o2)) return false;
   return combine<MODE>(c, g.low, L - 1, al, ac, be, bc, ga, sel, s);
 }
 
 // ------------------------------------------------------------------------------------ expand
 // Top-down step for one work item of level L: compute its two child slots.  Side effects (de-dup
 // inserts) only after all arithmetic succeeded, so a retry simply runs the function again.
-// M item key = the state node alone: a leaner probe than the generic 6-field key
-template <int MODE> JD uint32_t dt_find_or_insert_m(Ctx &c, uint32_t node, bool *ok) {
-  if (MODE == MODE_CTA) {
-    CtaState *S = c.sh;
-    uint32_t h = h32(node) & (JKQ_SDT_SLOTS - 1), mine = 0xFFFFFFFFu;
-    for (uint32_t probes = 0; probes < JKQ_SDT_SLOTS; probes++) {
-      uint32_t s = S->dtab[h];
-      if (s == 0) {
-        if (mine == 0xFFFFFFFFu) {
-          mine = jatomic_add(&S->item_count, 1u);
-          if (mine >= JKQ_SITEMS) { S->want_grid = 1; *ok = false; return 0; }
-          JItem *it = c.items + mine;
-          it->a = node; it->b = 0; it->wa = 0; it->wb = 0; it->wc = 0; it->tag = JK_M;
-          it->state = JS_NEW;
-          jfence<MODE>();
-        }
-        s = jatomic_cas(&S->dtab[h], 0u, mine + 1);
-        if (s == 0) return mine;
-      }
-      const JItem *o = c.items + (s - 1);
-      if (o->a == node && o->tag == JK_M) {
-        if (mine != 0xFFFFFFFFu) c.items[mine].state = JS_DEAD;
-        return s - 1;
-      }
-      h = (h + 1) & (JKQ_SDT_SLOTS - 1);
-    }
-    S->want_grid = 1;
-    *ok = false;
-    return 0;
-  }
-  return dt_find_or_insert<MODE>(c, node, 0, 0, 0, 0, JK_M, ok);
-}
+JD uint32_t item_flags(uint32_t state, uint32_t k0, uint32_t k1, uint32_t hint) { return state | (k0 << 2) | (k1 << 4) | (hint << 6); }
 
-template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
+// returns the new flags word of the item (state JS_DONE or JS_RETRY)
+template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
   JItem *it = c.items + idx;
-  const uint32_t tag = ld_i<MODE>(&it->tag), ia = ld_i<MODE>(&it->a), ib = ld_i<MODE>(&it->b);
+  const uint32_t tag = ld_i<MODE>(&it->tag), ia = ld_i<MODE>(&it->a);
   const uint32_t kind = tag & 15u, sel = (tag >> 4) & 1u;
   const uint32_t role = g.role[L];
   if (kind == JK_M && L > g.target) {
-    // Fast path, the bulk of every gate on a thin DD: a level above the target only forwards the node's
-    // two edges (QMDDmultiply2 with a block-diagonal gate node, QMDDpackage.cpp:1488-1509) -- no arithmetic.
+    // Fast path: a level above the target only forwards the node's two edges (QMDDmultiply2 with a
+    // block-diagonal gate node, QMDDpackage.cpp:1488-1509) -- no arithmetic.
     const JNode p = node_load<MODE>(c, ia);
     const uint32_t ch0 = nd_c0(p), ch1 = p.c1;
     const uint64_t w0 = nd_w0(p), w1 = nd_w1(p);
     uint32_t t0 = ch0, t1 = ch1, k0, k1;
     bool ok = true;
     if (w0 == 0) { k0 = JC_ZERO; t0 = 0; }
-    else if (role_satisfied(role, 0)) { k0 = JC_REF; t0 = dt_find_or_insert_m<MODE>(c, ch0, &ok); }
+    else if (role_satisfied(role, 0)) { k0 = JC_REF; t0 = dt_find_or_insert_m<MODE>(c.E, c.sh, c.items, ch0); ok = t0 != JI_FAIL; }
     else k0 = JC_PASS;
     if (w1 == 0) { k1 = JC_ZERO; t1 = 0; }
     else if (role_satisfied(role, 1)) {
       k1 = JC_REF;
       if (k0 == JC_REF && ch1 == ch0) t1 = t0;
-      else if (ok) t1 = dt_find_or_insert_m<MODE>(c, ch1, &ok);
+      else if (ok) { t1 = dt_find_or_insert_m<MODE>(c.E, c.sh, c.items, ch1); ok = t1 != JI_FAIL; }
     } else k1 = JC_PASS;
-    if (!ok) return true;  // error / want_grid flagged; the gate is abandoned
-    it->ch[0] = t0; it->chw[0] = w0; it->chk[0] = (uint8_t)k0;
-    it->ch[1] = t1; it->chw[1] = w1; it->chk[1] = (uint8_t)k1;
-    it->pad0 = (uint8_t)(1u + nd_flag(p));  // (chw0, chw1) are the weights of a normalised node: max = this index
-    return true;
+    if (!ok) return JS_DONE;  // error / want_grid flagged; the gate is abandoned
+    it->ch[0] = t0; it->ch[1] = t1; it->chw[0] = w0; it->chw[1] = w1;
+    // (chw0, chw1) are the weights of a normalised node: hint = 1 + index of the ONE
+    return item_flags(JS_DONE, k0, k1, 1u + nd_flag(p));
   }
-  it->pad0 = 0;
+  const uint32_t ib = ld_i<MODE>(&it->b);
   uint64_t iwa = 0, iwb = 0, iwc = 0;
   JNode na, nb;
   na.c0 = na.c1 = 0; na.w = 0; nb = na;
@@ -670,18 +909,18 @@ template <int MODE> JD bool expand_item(Ctx &c, const JGate &g, uint32_t idx, in
     if (ib) nb = (ib == ia) ? na : node_load<MODE>(c, ib);
   }
   Slot s0, s1;
-  if (!expand_child<MODE>(c, g, L, 0, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s0)) return false;
-  if (!expand_child<MODE>(c, g, L, 1, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s1)) return false;
+  bool e0 = expand_child<MODE>(c, g, L, 0, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s0);
+  bool e1 = expand_child<MODE>(c, g, L, 1, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s1);
+  if (!(e0 && e1)) return JS_RETRY;  // both children were tried: all their missing values are proposed
   bool ok = true;
-  if (s0.kind == JC_REF) s0.target = dt_find_or_insert<MODE>(c, s0.ia, s0.ib, s0.iwa, s0.iwb, s0.iwc, s0.itag, &ok);
-  if (ok && s1.kind == JC_REF) s1.target = dt_find_or_insert<MODE>(c, s1.ia, s1.ib, s1.iwa, s1.iwb, s1.iwc, s1.itag, &ok);
-  if (!ok) return true;  // error / want_grid already flagged; the gate is abandoned
-  it->ch[0] = s0.target; it->chw[0] = s0.w; it->chk[0] = (uint8_t)s0.kind;
-  it->ch[1] = s1.target; it->chw[1] = s1.w; it->chk[1] = (uint8_t)s1.kind;
+  if (s0.kind == JC_REF) { s0.target = dt_find_or_insert<MODE>(c.E, c.sh, c.items, s0.ia, s0.ib, s0.iwa, s0.iwb, s0.iwc, s0.itag); ok = s0.target != JI_FAIL; }
+  if (ok && s1.kind == JC_REF) { s1.target = dt_find_or_insert<MODE>(c.E, c.sh, c.items, s1.ia, s1.ib, s1.iwa, s1.iwb, s1.iwc, s1.itag); ok = s1.target != JI_FAIL; }
+  if (!ok) return JS_DONE;  // error / want_grid already flagged; the gate is abandoned
+  it->ch[0] = s0.target; it->ch[1] = s1.target; it->chw[0] = s0.w; it->chw[1] = s1.w;
   // same-node fused item whose two children carry the node's own weights: normalised pair again
-  if (kind == JK_F && ia == ib && s0.w == nd_w0(na) && s1.w == nd_w1(na) && s0.kind != JC_ZERO && s1.kind != JC_ZERO)
-    it->pad0 = (uint8_t)(1u + nd_flag(na));
-  return true;
+  uint32_t hint = 0;
+  if (kind == JK_F && ia == ib && s0.w == nd_w0(na) && s1.w == nd_w1(na) && s0.kind != JC_ZERO && s1.kind != JC_ZERO) hint = 1u + nd_flag(na);
+  return item_flags(JS_DONE, s0.kind, s1.kind, hint);
 }
 
 // ------------------------------------------------------------------------------------ reduce
@@ -704,31 +943,12 @@ template <int MODE> JD bool mag_greater(const Ctx &c, uint64_t a1, uint64_t a0) 
 #endif
 }
 
-template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx) {
-  JItem *it = c.items + idx;
-  // each child edge is f_i * a_i: f_i = top weight of the child item's result (ONE for finished
-  // edges), a_i = the factor / edge weight recorded at expansion
-  uint32_t rn[2];
-  uint64_t f[2], a[2];
-  JKQ_UNROLL
-  for (int i = 0; i < 2; i++) {
-    uint32_t k = ld_i<MODE>(&it->chk[i]);
-    uint32_t cht = ld_i<MODE>(&it->ch[i]);
-    uint64_t chw = ld_i<MODE>(&it->chw[i]);
-    if (k == JC_ZERO) { rn[i] = 0; f[i] = JW_ONE; a[i] = 0; }
-    else if (k == JC_PASS) { rn[i] = cht; f[i] = JW_ONE; a[i] = chw; }
-    else {
-      const JItem *ci = c.items + cht;
-      f[i] = ld_i<MODE>(&ci->rw);
-      rn[i] = ld_i<MODE>(&ci->rnode);
-      a[i] = f[i] ? chw : 0;
-    }
-    if (a[i] == 0) rn[i] = 0;
-  }
-  if (a[0] == 0 && a[1] == 0) { it->rnode = 0; it->rw = 0; return true; }
+// child edge i = f[i] * a[i] -> rn[i]; hint = 1 + index of a ONE among (a0, a1) known to be a normalised pair
+template <int MODE>
+JD bool reduce_core(Ctx &c, uint32_t rn[2], const uint64_t f[2], const uint64_t a[2], uint32_t hint, uint32_t *out_node, uint64_t *out_w) {
+  if (a[0] == 0 && a[1] == 0) { *out_node = 0; *out_w = 0; return true; }
   uint32_t mx;
   uint64_t other, top;
-  const uint32_t hint = ld_i<MODE>(&it->pad0);
   if (hint && a[hint - 1] == JW_ONE && (f[0] == f[1] || a[2 - hint] == 0)) {
     // (a0, a1) are the weights of an already normalised node and both children scale by the same factor:
     // same normal form, the factor is the new top weight -- no arithmetic, no value-table access
@@ -740,24 +960,49 @@ template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx) {
     // For a product state or a basis-like state this removes ALL arithmetic from the levels above the
     // gate (a_max is ONE there); the reference gets the same effect from its complex op caches.
     mx = (a[0] == 0) ? 1u : (a[1] == 0 ? 0u : (mag_greater<MODE>(c, a[1], a[0]) ? 1u : 0u));
-    if (!cdiv<MODE>(c, mx ? a[0] : a[1], mx ? a[1] : a[0], &other)) return false;
-    if (!cmul<MODE>(c, mx ? f[1] : f[0], mx ? a[1] : a[0], &top)) return false;
+    bool o1 = cdiv<MODE>(c, mx ? a[0] : a[1], mx ? a[1] : a[0], &other);
+    bool o2 = cmul<MODE>(c, mx ? f[1] : f[0], mx ? a[1] : a[0], &top);
+    if (!(o1 && o2)) return false;
   } else {
     uint64_t rw0, rw1;
-    if (!cmul<MODE>(c, f[0], a[0], &rw0)) return false;
-    if (!cmul<MODE>(c, f[1], a[1], &rw1)) return false;
-    if (rw0 == 0 && rw1 == 0) { it->rnode = 0; it->rw = 0; return true; }
+    bool o1 = cmul<MODE>(c, f[0], a[0], &rw0), o2 = cmul<MODE>(c, f[1], a[1], &rw1);
+    if (!(o1 && o2)) return false;
+    if (rw0 == 0 && rw1 == 0) { *out_node = 0; *out_w = 0; return true; }
     mx = (rw0 == 0) ? 1u : (rw1 == 0 ? 0u : (mag_greater<MODE>(c, rw1, rw0) ? 1u : 0u));
     if (!cdiv<MODE>(c, mx ? rw0 : rw1, mx ? rw1 : rw0, &other)) return false;
     top = mx ? rw1 : rw0;
   }
-  if (top == 0) { it->rnode = 0; it->rw = 0; return true; }
-  JNode rec;
-  rec.c0 = ((mx == 1 && other == 0) ? 0u : rn[0]) | (mx << 31);
-  rec.c1 = (mx == 0 && other == 0) ? 0u : rn[1];
-  rec.w = other;
-  uint32_t id = ut_find_or_insert<MODE>(c, rec);
-  it->rnode = id; it->rw = top;
+  if (top == 0) { *out_node = 0; *out_w = 0; return true; }
+  *out_node = ut_find_or_insert<MODE>(c.E, c.sh, ((mx == 1 && other == 0) ? 0u : rn[0]) | (mx << 31), (mx == 0 && other == 0) ? 0u : rn[1], other);
+  *out_w = top;
+  return true;
+}
+
+template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx, uint32_t flags) {
+  JItem *it = c.items + idx;
+  // each child edge is f_i * a_i: f_i = top weight of the child item's result (ONE for finished
+  // edges), a_i = the factor / edge weight recorded at expansion
+  uint32_t rn[2];
+  uint64_t f[2], a[2];
+  JKQ_UNROLL
+  for (int i = 0; i < 2; i++) {
+    const uint32_t k = (flags >> (2 + 2 * i)) & 3u;
+    const uint32_t cht = ld_i<MODE>(&it->ch[i]);
+    const uint64_t chw = ld_i<MODE>(&it->chw[i]);
+    if (k == JC_ZERO) { rn[i] = 0; f[i] = JW_ONE; a[i] = 0; }
+    else if (k == JC_PASS) { rn[i] = cht; f[i] = JW_ONE; a[i] = chw; }
+    else {
+      const JItem *ci = c.items + cht;
+      f[i] = ld_i<MODE>(&ci->rw);
+      rn[i] = ld_i<MODE>(&ci->rnode);
+      a[i] = f[i] ? chw : 0;
+    }
+    if (a[i] == 0) rn[i] = 0;
+  }
+  uint32_t rnode;
+  uint64_t rw;
+  if (!reduce_core<MODE>(c, rn, f, a, (flags >> 6) & 3u, &rnode, &rw)) return false;
+  it->rw = rw; it->rnode = rnode;
   return true;
 }
 

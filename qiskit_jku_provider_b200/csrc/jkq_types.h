@@ -9,7 +9,7 @@
 //                     QMDDpackage.h:235, QMDDutLookup QMDDpackage.cpp:693-763);
 //   * value table     tolerance-bucketed reals, 16-byte slots (replaces Ctable/Ctable2/Cmag,
 //                     QMDDcomplexD.cpp:45,372-466);
-//   * frontier pool   80-byte work items + generation-tagged de-dup table (replaces the recursion
+//   * frontier pool   80-byte work items + generation-tagged de-dup tables (replace the recursion
 //                     of QMDDmultiply2/QMDDadd and their compute tables, QMDDpackage.cpp:986-1072,
 //                     1319-1517).
 #ifndef JKQ_TYPES_H
@@ -30,10 +30,15 @@ typedef struct __attribute__((aligned(16))) {
   uint64_t w;   // weight id of the OTHER child (may be JW_ZERO -> that child is the terminal 0)
 } JNode;
 
+// value-table slot.  (keylo, id1) form one 64-bit word that is claimed by atomicCAS; vbits takes
+// atomicMin proposals while the slot is pending.
+#define JV_PENDING 0xFFFFFFFFu  // claimed in the current phase, value = min of the proposals so far
+#define JV_DROPPED 0xFFFFFFFEu  // claimed once, no entry (the candidate joined a lower neighbour)
+#define JV_INF 0x7FF0000000000000ull
 typedef struct __attribute__((aligned(16))) {
-  double value;    // non-negative real
-  uint32_t id1;    // value index + 1 (0 = empty slot)
-  uint32_t keylo;  // low 32 bits of the bucket number floor(value / tol)
+  unsigned long long vbits;  // non-negative real as raw bits; JV_INF = none
+  uint32_t keylo;            // low 32 bits of the bucket number floor(value / tol)
+  uint32_t id1;              // 0 = empty, JV_PENDING, JV_DROPPED, else value index + 1
 } JVSlot;
 
 // work-item kinds
@@ -50,19 +55,19 @@ typedef struct __attribute__((aligned(16))) {
 #define JS_DONE 2u
 #define JS_DEAD 3u
 
+// flags word of an item: state | chk0 << 2 | chk1 << 4 | hint << 6
 typedef struct __attribute__((aligned(16))) {
-  uint32_t a, b;        // operand node ids (0 = absent)
-  uint64_t wa, wb, wc;  // normalised operand weights (kind dependent)
-  uint64_t chw[2];      // child-slot weight: factor (REF) or edge weight (PASS)
-  uint64_t rw;          // result edge weight
-  uint32_t ch[2];       // child-slot target: item index (REF) or node id (PASS)
-  uint32_t rnode;       // result edge node
-  uint32_t tag;         // kind | sel << 4
-  uint8_t chk[2];       // child-slot kinds
-  uint8_t state;
-  uint8_t pad0;
-  uint32_t pad1;
-} JItem;  // 80 bytes
+  uint32_t a, b;     // operand node ids (0 = absent)            -- key, written before publication
+  uint32_t tag;      // kind | sel << 4                           -- key
+  uint32_t flags;    // owner-written
+  uint64_t wa, wb;   // normalised operand weights (kind dependent) -- key
+  uint64_t wc;       //                                            -- key
+  uint32_t ch[2];    // child-slot target: item index (REF) or node id (PASS)
+  uint64_t chw[2];   // child-slot weight: factor (REF) or edge weight (PASS)
+  uint64_t rw;       // result edge weight
+  uint32_t rnode;    // result edge node
+  uint32_t pad;
+} JItem;  // 80 bytes = five 16-byte quads
 
 // level roles of a gate (bottom variable = level 0; qubit q lives on level n-1-q,
 // reference QASMsimulator.cpp:300)
@@ -71,14 +76,14 @@ typedef struct __attribute__((aligned(16))) {
 #define JR_CNEG 2
 #define JR_TARGET 3
 
-typedef struct {
+typedef struct __attribute__((aligned(16))) {
   double m[8];  // 2x2 matrix, row major, (re, im) pairs -- FP64 entries from the host
   int32_t target;  // level
   int32_t low;     // lowest level carrying a control or the target
   int32_t top;     // highest such level
   int32_t pad;     // index of this gate's matrix among the distinct matrices of the circuit
   uint8_t role[JKQ_MAXQ];
-} JGate;
+} JGate;  // 144 bytes
 
 // sampling record: one per node, level-ordered arena
 typedef struct __attribute__((aligned(16))) {
@@ -99,9 +104,10 @@ typedef struct {
   uint32_t *utab;
   double *vals, *vals_alt;
   JVSlot *vtab;
-  double *pend;
+  uint32_t *pend;     // value-table slots claimed in the current phase
   JItem *items;
-  unsigned long long *dtab;
+  unsigned long long *dtab;  // F/S item de-dup: generation << 32 | item index + 1
+  unsigned long long *mdir;  // M item de-dup, indexed by node id: generation << 32 | item index + 1
   uint32_t *fwd;      // node_cap entries: forwarding ids for the collector
   uint32_t *vfwd;     // val_cap entries: value id remap for the collector
   uint32_t *lvl_log;  // optional [gate][level] live-node counts
@@ -111,17 +117,19 @@ typedef struct {
   uint32_t node_count;  // next free node id (id 0 = terminal)
   uint32_t val_count;
   uint32_t item_count;
-  uint32_t pend_n[2];
-  uint32_t gen;  // de-dup table generation (one per gate attempt)
+  uint32_t pend_n[3];  // one per barrier-ring slot
+  uint32_t gen;  // de-dup generation (one per gate attempt)
   uint32_t root;
   uint64_t rootw;
   uint64_t cur_u[4];  // canonical ids of the current gate's matrix (device-written at gate setup)
+  uint32_t thin_lsw;  // first level handled by the generic phases of the current gate
+  uint32_t thin_blocked;  // 1: the cursor sits one level above thin_lsw (jkq_thin.cuh)
   uint32_t gc_limit;
   uint32_t gc_count;   // collector cursor
   uint32_t val_gc_limit;  // sweep the reals only above this many (reference complex_limit)
   uint32_t val_epoch;     // bumped whenever a sweep renumbers the reals
   double norm;        // squared norm of the state at the last finalisation
-  uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L+1], lvl_off[L]) ... see gc
+  uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L], lvl_off[L] + lvl_cnt[L])
   uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection
   // ---- status ----
   int32_t status;       // 0 ok, >0 error code
@@ -129,17 +137,27 @@ typedef struct {
   int32_t want_grid;    // CTA mode asked for the grid path
   uint32_t tables_valid;  // HBM unique / value hash tables match the arena (MODE_CTA lets them go stale)
   // ---- counters ----
-  unsigned long long st_items, st_nodes_created, st_val_inserts, st_gc_runs, st_retry_rounds,
-      st_ut_probes, st_dt_probes, st_vt_probes, st_max_frontier, st_gates, st_gc_nodes_copied;
+  unsigned long long st[12];  // JST_* below
   // ---- grid barrier ----
   unsigned int bar_count;
   unsigned int bar_gen;
   unsigned int bar_flags[3];
-  unsigned long long prof2[16];
-  unsigned long long prof[8];  // JKQ_PROFILE builds: cycles in expand work / reduce work / barriers / phases / setup / finalize / gate
+  unsigned long long prof[16];  // JKQ_PROFILE builds: cycle counters, see jkq_b200.cu jkq_get_stats
   unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was
   unsigned int dbg_phase[1024];
 } JEng;
+
+// counters (JEng.st; MODE_CTA keeps 32-bit copies in shared memory and adds them in when it leaves)
+#define JST_ITEMS 0      // frontier pairs processed (the reference's CTlook, QMDDpackage.cpp:993)
+#define JST_NODES 1      // unique-table inserts
+#define JST_VALS 2       // reals appended to the value table
+#define JST_RETRY 3      // value-commit rounds
+#define JST_THIN 4       // levels walked by the thin path
+#define JST_GATES 5
+#define JST_MAXF 6       // largest per-gate item count (max, not sum)
+#define JST_GC_RUNS 7
+#define JST_GC_COPIED 8
+#define JST_N 9
 
 // error codes (JEng.status, also returned by the C-ABI)
 #define JKQ_OK 0

@@ -1,15 +1,18 @@
-"""One QFT apply (for ncu): python scripts/one_apply.py [n_qubits] [reps]"""
+"""One jkq_apply of a named circuit (for ncu).  usage: one_apply.py [qft32|ghz24|grover|r100|r120] [cta_threads] [repeat]"""
 import sys
 
 sys.path.insert(0, ".")
 from qiskit_jku_provider_b200 import circuits as C
 from qiskit_jku_provider_b200.engine import Engine
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-eng = Engine(device=0, node_capacity=1 << 20)
-eng.load(C.qft(n))
-for _ in range(reps):
+name = sys.argv[1] if len(sys.argv) > 1 else "qft32"
+threads = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+repeat = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+circ = {"qft32": lambda: C.qft(32), "ghz24": lambda: C.ghz(24), "grover": lambda: C.grover(20, 20),
+        "r100": lambda: C.random_circuit(18, 100, 1), "r120": lambda: C.random_circuit(18, 120, 1)}[name]()
+eng = Engine(device=0, node_capacity=1 << 20, cta_threads=threads)
+eng.load(circ)
+for _ in range(repeat):
     eng.apply()
-print("apply_ms", eng.stats()["apply_ms"])
-eng.close()
+st = eng.stats()
+print("apply_ms", st["apply_ms"], "us_per_gate", 1e3 * st["apply_ms"] / len(circ), "items", st["items"], "nodes", st["nodes_created"])

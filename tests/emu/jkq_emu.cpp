@@ -80,7 +80,7 @@ int main(int argc, char **argv) {
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
   if (!f) { fprintf(stderr, "usage: jkq_emu --circuit FILE ...\n"); return 2; }
   int n = 0;
-  std::vector<JGate> gates;
+  std::vector<JGate> gates, mats;
   char w[64], a1[64], a2[64], a3[64];
   while (fscanf(f, "%63s", w) == 1) {
     if (w[0] == '#') { int ch; while ((ch = fgetc(f)) != EOF && ch != '\n') {} continue; }
@@ -108,6 +108,13 @@ int main(int argc, char **argv) {
       }
     }
     finish_gate(g, n, target, nctl, ctl, cv);
+    {  // index among the distinct matrices of the circuit, as jkq_load_circuit assigns it
+      size_t mid = 0;
+      for (; mid < mats.size(); mid++)
+        if (!memcmp(mats[mid].m, g.m, sizeof(g.m))) break;
+      if (mid == mats.size()) mats.push_back(g);
+      g.pad = (int32_t)mid;
+    }
     gates.push_back(g);
   }
   fclose(f);
@@ -124,21 +131,23 @@ int main(int argc, char **argv) {
   E->vals = (double *)calloc(E->val_cap, 8);
   E->vals_alt = (double *)calloc(E->val_cap, 8);
   E->vtab = (JVSlot *)calloc((size_t)E->vtab_mask + 1, sizeof(JVSlot));
-  E->pend = (double *)calloc(E->pend_cap, 8);
+  E->pend = (uint32_t *)calloc(E->pend_cap, 4);
   E->items = (JItem *)calloc(E->item_cap, sizeof(JItem));
   E->dtab = (unsigned long long *)calloc((size_t)E->dtab_mask + 1, 8);
+  E->mdir = (unsigned long long *)calloc(E->node_cap, 8);
   E->fwd = (uint32_t *)calloc(E->node_cap, 4);
   E->vfwd = (uint32_t *)calloc(E->val_cap, 4);
   if (levels) E->lvl_log = (uint32_t *)calloc(gates.size() * n + 1, 4);
 
   Ctx c;
   static CtaState cta_state;
+  static ThinState thin_state;
   c.sh = &cta_state;
+  c.T = &thin_state;
   c.items = cta_state.items;
-  c.spare_node = 0;
-  c.E = E; c.tid = 0; c.nth = 1; c.phase = 0; c.block0 = 1; c.ltid = 0; c.lnth = 1;
+  c.E = E; c.tid = 0; c.nth = 1; c.phase = 0; c.ring = 0; c.block0 = 1; c.ltid = 0; c.lnth = 1;
   Ctx gctx = c;
-  gctx.sh = nullptr; gctx.items = E->items; gctx.spare_node = 0;
+  gctx.sh = nullptr; gctx.items = E->items;
   init_state<MODE_GRID>(gctx);
   int grid_switches = 0;
   bool grid = force_grid;
@@ -172,7 +181,7 @@ int main(int argc, char **argv) {
   }
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n", n, gates.size());
   printf(" \"items\": %llu,\n \"nodes_created\": %llu,\n \"val_inserts\": %llu,\n \"gc_runs\": %llu,\n \"retry_rounds\": %llu,\n \"max_frontier\": %llu,\n",
-         E->st_items, E->st_nodes_created, E->st_val_inserts, E->st_gc_runs, E->st_retry_rounds, E->st_max_frontier);
+         E->st[JST_ITEMS], E->st[JST_NODES], E->st[JST_VALS], E->st[JST_GC_RUNS], E->st[JST_RETRY], E->st[JST_MAXF]);
   printf(" \"grid_switches\": %d,\n", grid_switches);
   printf(" \"ctable_size\": %u,\n \"norm\": %.17g,\n", E->val_count, E->norm);
   printf(" \"level_counts\": [");

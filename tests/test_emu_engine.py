@@ -52,7 +52,7 @@ def test_emu_matches_oracle(emu_bin, oracle_mod, circ):
 def test_emu_collector_keeps_state(emu_bin, oracle_mod):
     """Tiny arena: the collector must run many times without changing the result."""
     circ = C.qft(10)
-    e = run_emu(emu_bin, circ.text(), amps=True, extra=["--node-cap", "4096", "--gc-min", "64"])
+    e = run_emu(emu_bin, circ.text(), amps=True, extra=["--node-cap", "4096", "--gc-min", "64", "--grid"])
     o = oracle_mod.run_oracle(circ, amps=True)
-    assert e["gc_runs"] > 5
+    assert e["gc_runs"] >= 3
     assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL
