@@ -45,12 +45,14 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
   uint32_t r;
   if (MODE == MODE_CTA) {
     CtaState *S = c.sh;
+    // sticky words raised by the table functions: folded in BEFORE the barrier (a thread sees its own
+    // failure), never read after it -- the cursor warp may already be raising them for the next gate
+    if (*(volatile uint32_t *)&S->err) flags |= JF_ERROR;
+    if (*(volatile uint32_t *)&S->want_grid) flags |= JF_GRID;
     if (flags) atomicOr(&S->bflags[slot], flags);
     if (c.ltid == 0) { S->bflags[nxt] = 0; S->pend_n[nxt] = 0; }
     __syncthreads();
     r = *(volatile uint32_t *)&S->bflags[slot];
-    if (*(volatile uint32_t *)&S->err) r |= JF_ERROR;          // sticky words raised by the table functions
-    if (*(volatile uint32_t *)&S->want_grid) r |= JF_GRID;
   } else {
     __shared__ uint32_t s_flags;
     JEng *E = c.E;
@@ -132,17 +134,39 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   }
 }
 
-// item ranges of the levels of one gate: registers / local memory on the grid path, shared memory on
-// the CTA path (a local array would live in L1, which the CTA path gives up for shared memory)
-template <int MODE> struct LevelRanges {
-  uint32_t lb[MODE == MODE_CTA ? 1 : JKQ_MAXQ + 1], le[MODE == MODE_CTA ? 1 : JKQ_MAXQ + 1];
-  JDM void set(Ctx &c, int L, uint32_t b, uint32_t e) {
-    if (MODE == MODE_CTA) { if (c.ltid == 0) { c.sh->lb[L] = b; c.sh->le[L] = e; } }
-    else { lb[L] = b; le[L] = e; }
+// item ranges of the levels of one gate: shared memory on the CTA path, the control block on the grid
+// path (written by the warp that ran the level, read by everybody after a barrier)
+template <int MODE> JD void lr_set(Ctx &c, int L, uint32_t b, uint32_t e) {
+  if (MODE == MODE_CTA) { c.sh->lb[L] = b; c.sh->le[L] = e; }
+  else { c.E->lb[L] = b; c.E->le[L] = e; }
+}
+template <int MODE> JD uint32_t lr_begin(const Ctx &c, int L) { return MODE == MODE_CTA ? c.sh->lb[L] : ld_s<MODE>(&c.E->lb[L]); }
+template <int MODE> JD uint32_t lr_end(const Ctx &c, int L) { return MODE == MODE_CTA ? c.sh->le[L] : ld_s<MODE>(&c.E->le[L]); }
+
+// One level run by the cursor warp alone (at most one item per lane): no CTA / grid barrier, values are
+// committed warp-locally.  Returns 0 or barrier flags.
+template <int MODE, bool expand>
+JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
+  const uint32_t i = b + c.ltid;
+  JItem *it = c.items + i;
+  bool need = i < e;
+  uint32_t fl = 0;
+  if (need) { fl = ld_i<MODE>(&it->flags); need = (fl & 3u) != JS_DEAD; }
+  for (;;) {
+    if (need) {
+      if (expand) fl = expand_item<MODE>(c, g, i, L);
+      else fl = (fl & ~3u) | (reduce_item<MODE>(c, i, fl) ? JS_DONE : JS_RETRY);
+      it->flags = fl;
+      need = (fl & 3u) == JS_RETRY;
+    }
+    const uint32_t bad = jballot(need);
+    jsyncwarp();
+    const uint32_t tr = thin_trouble<MODE>(c);  // pools exhausted / errors are sticky words
+    if (tr) return tr;
+    if (!bad) return 0;
+    thin_commit<MODE>(c);
   }
-  JDM uint32_t begin(const Ctx &c, int L) const { return MODE == MODE_CTA ? c.sh->lb[L] : lb[L]; }
-  JDM uint32_t end(const Ctx &c, int L) const { return MODE == MODE_CTA ? c.sh->le[L] : le[L]; }
-};
+}
 
 // ------------------------------------------------------------------------------------ gate set-up
 // canonical ids of the four matrix entries, cached per distinct matrix of the circuit until the next
@@ -180,19 +204,20 @@ template <int MODE> JD void gate_setup(Ctx &c, const JGate &g) {
 // Simulator::ApplyGate (Simulator.cpp:466-503) = QMDDmultiply(gate, state) as one top-down and one
 // bottom-up sweep over the levels.  Returns 0, JF_ERROR, or JF_GRID (CTA mode only: the gate does not
 // fit the shared-memory pools and is left unapplied).
-template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n) {
+// should the collector run after this gate?  (one thread decides, everybody reads the hand-over word)
+template <int MODE> JD uint32_t want_collect(const Ctx &c, bool log) {
+  const uint32_t nodes_now = rd_nodes<MODE>(c), vals_now = rd_vals<MODE>(c);
+  if (log) return 1;
+  if (MODE == MODE_CTA) return nodes_now > c.sh->node_hard / 2 || vals_now > (c.sh->val_hard / 4) * 3;
+  return nodes_now > ld_s<MODE>(&c.E->gc_limit);
+}
+
+template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n, bool log) {
   JEng *E = c.E;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
   JPROF_T(gt0);
   if (MODE == MODE_CTA) {
     CtaState *S = c.sh;
-    if (S->gen >= 0xFFF0u) {  // generation tags about to wrap: clear the de-dup tables (uniform branch)
-      for (uint32_t i = c.ltid; i < JKQ_SNODES; i += c.lnth) S->mdir[i] = 0;
-      for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) S->dtab[i] = 0;
-      block_sync();
-      if (c.ltid == 0) S->gen = 1;
-      block_sync();
-    }
     // stage the NEXT gate's descriptor while this one runs (warps other than the thin one when there are any)
     if (gi + 1 < n_gates && (c.lnth <= JKQ_WARP || c.ltid >= JKQ_WARP)) {
       const uint32_t first = c.lnth <= JKQ_WARP ? c.ltid : c.ltid - JKQ_WARP, step = c.lnth <= JKQ_WARP ? c.lnth : c.lnth - JKQ_WARP;
@@ -202,33 +227,74 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     }
   }
   const JGate &g = MODE == MODE_CTA ? c.sh->gate[gi & 1] : gates[gi];
+  // ---- the cursor warp: set-up, cursor move, and -- while no level holds more than one warp of items --
+  // the whole gate by itself (solo), without a barrier
+  JHand *hand = MODE == MODE_CTA ? &c.sh->hand[gi & 1] : &E->hand[gi & 1];
   if (thin_warp) {
+    if (MODE == MODE_CTA && c.sh->gen >= 0xFFF0u) {  // generation tags about to wrap: clear the de-dup tables (nobody else is using them)
+      for (uint32_t i = c.ltid; i < JKQ_SNODES; i += JKQ_WARP) c.sh->mdir[i] = 0;
+      for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += JKQ_WARP) c.sh->dtab[i] = 0;
+      jsyncwarp();
+      if (c.ltid == 0) c.sh->gen = 1;
+      jsyncwarp();
+    }
     if (c.ltid == 0) gate_setup<MODE>(c, g);
     jsyncwarp();
-    int lsw = 0;
+    int lsw = 0, wide_L = -1;
     uint32_t icount = 0, blocked = 0;
-    cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);  // (a failure is in the sticky words: the barrier sees it)
+    uint32_t f = cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);
+    uint32_t b = 0, e = icount;
+    int lowest = lsw + 1;
+    if (!f) {
+      if (c.ltid == 0) *cnt_items<MODE>(c) = icount;
+      jsyncwarp();
+      for (int L = lsw; L >= 0 && e > b; L--) {
+        if (e - b > JKQ_WARP) { wide_L = L; break; }
+        if (c.ltid == 0) lr_set<MODE>(c, L, b, e);
+        lowest = L;
+        f = solo_level<MODE, true>(c, g, b, e, L);
+        if (f) break;
+        b = e; e = rd_items<MODE>(c);
+      }
+    }
+    if (!f && wide_L < 0) {
+      for (int L = lowest; L <= lsw && !f; L++) f = solo_level<MODE, false>(c, g, lr_begin<MODE>(c, L), lr_end<MODE>(c, L), L);
+      if (!f) f = cursor_finish<MODE>(c, lsw, blocked);
+    }
     if (c.ltid == 0) {
-      *cnt_items<MODE>(c) = icount;
-      if (MODE == MODE_CTA) { c.sh->lsw = (uint32_t)lsw; c.sh->thin_blocked = blocked; }
-      else { E->thin_lsw = (uint32_t)lsw; E->thin_blocked = blocked; }
+      hand->lsw = (uint32_t)lsw; hand->blocked = blocked; hand->wide_L = wide_L; hand->wide_b = b; hand->wide_low = lowest;
+      hand->collect = want_collect<MODE>(c, log);
+      if (!f && wide_L < 0) {
+        const uint32_t cnt = rd_items<MODE>(c);
+        jstat<MODE>(E, c.sh, JST_ITEMS, cnt);
+        jstat_max<MODE>(E, c.sh, cnt);
+        jstat<MODE>(E, c.sh, JST_GATES, 1u);
+        if (MODE == MODE_CTA) c.sh->gen++;  // read by everybody only after the barrier below
+      }
     }
   }
   {
     uint32_t fl = sync_or<MODE>(c, 0);
+    JPROF_T(gt1);
+    JPROF_ADD(c, 0, gt0, gt1);
     if (fl & JF_ERROR) return JF_ERROR;
     if (fl & JF_GRID) return JF_GRID;
   }
-  JPROF_T(gt1);
-  JPROF_ADD(c, 0, gt0, gt1);
-  const int lsw = (int)(MODE == MODE_CTA ? c.sh->lsw : ld_s<MODE>(&E->thin_lsw));
-  const uint32_t blocked = MODE == MODE_CTA ? c.sh->thin_blocked : ld_s<MODE>(&E->thin_blocked);
+  const int wide_L = ld_s<MODE>(&hand->wide_L);
+  if (wide_L < 0) {  // the gate is done
+    JPROF_INC(c, 6);
+    return 0;
+  }
+  // ---- a level outgrew the warp: everybody continues from there
+  JPROF_T(gt1b);
+  const int lsw = (int)ld_s<MODE>(&hand->lsw);
+  const uint32_t blocked = ld_s<MODE>(&hand->blocked);
   const uint32_t item_limit = MODE == MODE_CTA ? c.sh->item_limit : 0xFFFFFFFFu;
-  LevelRanges<MODE> lr;
-  uint32_t b = 0, e = rd_items<MODE>(c);
-  int lowest = lsw + 1;
-  for (int L = lsw; L >= 0 && e > b; L--) {
-    lr.set(c, L, b, e);
+  uint32_t b = ld_s<MODE>(&hand->wide_b), e = rd_items<MODE>(c);
+  int lowest = ld_s<MODE>(&hand->wide_low);
+  if (MODE == MODE_CTA && e - b > item_limit) return JF_GRID;
+  for (int L = wide_L; L >= 0 && e > b; L--) {
+    if (c.block0 && c.ltid == 0) lr_set<MODE>(c, L, b, e);
     lowest = L;
     uint32_t f = run_level<MODE, true>(c, g, b, e, L);
     if (f) return f;
@@ -236,7 +302,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     if (MODE == MODE_CTA && e - b > item_limit) return JF_GRID;
   }
   for (int L = lowest; L <= lsw; L++) {
-    uint32_t f = run_level<MODE, false>(c, g, lr.begin(c, L), lr.end(c, L), L);
+    uint32_t f = run_level<MODE, false>(c, g, lr_begin<MODE>(c, L), lr_end<MODE>(c, L), L);
     if (f) return f;
   }
   JPROF_T(gt2);
@@ -249,13 +315,15 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       jstat<MODE>(E, c.sh, JST_GATES, 1u);
       if (MODE == MODE_CTA) c.sh->gen++;  // read by everybody only after the barrier below
     }
+    if (c.ltid == 0) hand->collect = want_collect<MODE>(c, log);
   }
   {
     uint32_t fl = sync_or<MODE>(c, 0);
     JPROF_T(gt3);
     JPROF_ADD(c, 1, gt2, gt3);
-    JPROF_ADD(c, 8, gt0, gt3);
+    JPROF_ADD(c, 8, gt1b, gt3);
     JPROF_INC(c, 6);
+    JPROF_INC(c, 10);
     if (fl & JF_ERROR) return JF_ERROR;
     if (fl & JF_GRID) return JF_GRID;
   }
@@ -438,7 +506,7 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
       if (i > 0) vt_put<MODE>(c.E, c.sh, i, x);
     }
   }
-  uint32_t r = sync_or<MODE>(c, 0) & JF_ERROR;
+  uint32_t r = sync_or<MODE>(c, 0) & (JF_ERROR | JF_GRID);
   JPROF_T(ct1);
   JPROF_ADD(c, 9, ct0, ct1);
   return r | (c.ring << 8) | (c.phase << 10);
@@ -446,7 +514,7 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
 template <int MODE> JD uint32_t gc_call(Ctx &c, bool reload, bool force_vals) {
   const uint32_t r = gc_run<MODE>(c, reload, force_vals);
   c.ring = (r >> 8) & 3u; c.phase = r >> 10;
-  return r & JF_ERROR;
+  return r & (JF_ERROR | JF_GRID);  // JF_GRID (MODE_CTA): the live DD no longer fits the shared-memory pools
 }
 
 // ------------------------------------------------------------------------------------ init
@@ -509,7 +577,7 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       S->val_hard = E->val_cap < JKQ_SVALS ? E->val_cap : JKQ_SVALS;
       S->node_soft = S->node_hard - S->node_hard / 8;  // the rest is the reserve of cursor_to_root
       S->val_soft = S->val_hard - S->val_hard / 16;
-      S->node_limit = S->node_soft; S->val_limit = S->val_soft; S->thin_blocked = 0;
+      S->node_limit = S->node_soft; S->val_limit = S->val_soft;
       S->pend_n[0] = S->pend_n[1] = S->pend_n[2] = 0;
       S->bflags[0] = S->bflags[1] = S->bflags[2] = S->bflags[3] = 0;
       S->err = (uint32_t)E->status; S->want_grid = 0;
@@ -525,11 +593,11 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
     for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += c.lnth) S->dtab[i] = 0;
     block_sync();
     // reals beyond the shared table: sweep them first; still too many -> grid path
-    if (gc_call<MODE>(c, true, c.sh->val_count > (c.sh->val_hard / 4) * 3)) return JF_ERROR;
-    return c.sh->want_grid ? JF_GRID : 0;
+    const uint32_t r = gc_call<MODE>(c, true, c.sh->val_count > (c.sh->val_hard / 4) * 3);
+    return (r & JF_ERROR) ? JF_ERROR : (r & JF_GRID);
   }
   if (!ld_s<MODE>(&E->tables_valid)) {
-    if (gc_call<MODE>(c, false, true)) return JF_ERROR;
+    if (gc_call<MODE>(c, false, true) & JF_ERROR) return JF_ERROR;
     if (c.block0 && c.ltid == 0) E->tables_valid = 1;
     sync_or<MODE>(c, 0);
   }
@@ -564,27 +632,35 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
   sync_or<MODE>(c, 0);
   const bool log = E->lvl_log != 0;
   for (; !f && g < n_gates; g++) {
-    f = apply_gate<MODE>(c, gates, g, n_gates, n);
+    f = apply_gate<MODE>(c, gates, g, n_gates, n, log);
     if (f) break;
-    const uint32_t nodes_now = rd_nodes<MODE>(c), vals_now = rd_vals<MODE>(c);
-    bool collect = log;
-    if (MODE == MODE_CTA) collect = collect || nodes_now > c.sh->node_hard / 2 || vals_now > (c.sh->val_hard / 4) * 3;
-    else collect = collect || nodes_now > ld_s<MODE>(&E->gc_limit);
+    const bool collect = ld_s<MODE>(MODE == MODE_CTA ? &c.sh->hand[g & 1].collect : &E->hand[g & 1].collect) != 0;
+    uint32_t gcf = 0;
     if (collect) {
       if (thin_warp) cursor_to_root<MODE>(c, n);
       f = sync_or<MODE>(c, 0) & (JF_ERROR | JF_GRID);
       if (f) break;
-      if (gc_call<MODE>(c, false, false)) { f = JF_ERROR; break; }
+      gcf = gc_call<MODE>(c, false, false);
+      if (gcf & JF_ERROR) { f = JF_ERROR; break; }
       if (thin_warp) cursor_reset<MODE>(c, n);
       if (log && c.block0 && c.ltid == 0)
         for (uint32_t L = 0; L < E->n; L++) E->lvl_log[(size_t)g * E->n + L] = E->lvl_cnt[L];
     }
     if (c.block0 && c.ltid == 0) { if (MODE == MODE_CTA) c.sh->next_gate = g + 1; else E->next_gate = g + 1; }
-    if (MODE == MODE_CTA && c.sh->want_grid) { f = JF_GRID; g++; break; }  // (uniform: set before gc_run's last barrier)
+    if (gcf & JF_GRID) { f = JF_GRID; g++; break; }  // MODE_CTA: the live DD outgrew the shared-memory pools
   }
-  // the state goes back to the arena as a DD with a root: rebuild the levels above the cursor
+  // The state goes back to the arena as a DD with a root: rebuild the levels above the cursor.  An
+  // abandoned gate (JF_GRID) left the cursor describing the state BEFORE that gate; the sticky want_grid
+  // word is cleared first, or the first value miss of the rebuild would give up.
   if (!(f & JF_ERROR)) {
-    if (thin_warp) cursor_to_root<MODE>(c, n);
+    if (MODE == MODE_CTA && (f & JF_GRID)) {
+      if (c.ltid == 0) c.sh->want_grid = 0;
+      block_sync();
+    }
+    if (thin_warp) {
+      const uint32_t r = cursor_to_root<MODE>(c, n);
+      if (r && !(r & JF_ERROR) && c.ltid == 0) jset_error<MODE>(E, c.sh, JKQ_ERR_NODE_FULL);  // not even the reserve was enough
+    }
     f |= sync_or<MODE>(c, 0) & JF_ERROR;
   }
   if ((f & JF_GRID) && c.block0 && c.ltid == 0) { E->want_grid = 1; if (MODE == MODE_GRID) E->gen++; }
@@ -606,7 +682,7 @@ template <int MODE> JD uint32_t build_sampling(Ctx &c, JSNode *snodes, double *p
     mode_leave<MODE>(c);
     return f;
   }
-  if (MODE == MODE_GRID && gc_call<MODE>(c, false, false)) return JF_ERROR;
+  if (MODE == MODE_GRID && (gc_call<MODE>(c, false, false) & JF_ERROR)) return JF_ERROR;
   if (c.block0 && c.ltid == 0) prob[0] = 1.0;
   sync_or<MODE>(c, 0);
   for (uint32_t L = 0; L < E->n; L++) {

@@ -89,8 +89,9 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
-  uint32_t node_limit, val_limit, thin_blocked, pad4;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
+  uint32_t node_limit, val_limit, pad4, pad5;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
   uint32_t node_hard, val_hard, node_soft, val_soft;
+  JHand hand[2];
   uint32_t pend_n[3], err;
   uint32_t want_grid, gen, pad2, pad3;
   uint32_t lsw, root, flushed_nodes, flushed_vals;  // [flushed, count): not yet copied to the HBM arena

@@ -85,6 +85,18 @@ typedef struct __attribute__((aligned(16))) {
   uint8_t role[JKQ_MAXQ];
 } JGate;  // 144 bytes
 
+// What the cursor warp tells everybody else about the gate it just prepared (or finished).  Two copies,
+// indexed by gate parity: the warp may already be writing the next gate's while the others read this one's.
+typedef struct {
+  int32_t wide_L;    // first level left to everybody (-1: the cursor warp ran the whole gate)
+  int32_t wide_low;  // lowest level expanded so far
+  uint32_t wide_b;   // first item of level wide_L
+  uint32_t lsw;      // first level handled by work items
+  uint32_t blocked;  // 1: the cursor sits one level above lsw (jkq_thin.cuh)
+  uint32_t collect;  // run the collector after this gate (decided by ONE thread: the pools keep changing)
+  uint32_t pad[2];
+} JHand;
+
 // sampling record: one per node, level-ordered arena
 typedef struct __attribute__((aligned(16))) {
   uint32_t c0, c1;
@@ -122,8 +134,8 @@ typedef struct {
   uint32_t root;
   uint64_t rootw;
   uint64_t cur_u[4];  // canonical ids of the current gate's matrix (device-written at gate setup)
-  uint32_t thin_lsw;  // first level handled by the generic phases of the current gate
-  uint32_t thin_blocked;  // 1: the cursor sits one level above thin_lsw (jkq_thin.cuh)
+  JHand hand[2];  // per-gate hand-over from the cursor warp to everybody else, by gate parity
+  uint32_t lb[JKQ_MAXQ + 1], le[JKQ_MAXQ + 1];  // item ranges of the levels of the current gate (grid path)
   uint32_t gc_limit;
   uint32_t gc_count;   // collector cursor
   uint32_t val_gc_limit;  // sweep the reals only above this many (reference complex_limit)

@@ -11,6 +11,10 @@ OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER = 0, 1, 2, 3
 FINAL_SLOT = 0xFFFFFFFF
 
 SNODE_DTYPE = np.dtype([("c0", "<u4"), ("c1", "<u4"), ("q0", "<f8")])
+# memory layout of jkq_op (include/jkq.h)
+OP_DTYPE = np.dtype([("kind", "<u4"), ("target", "<u4"), ("ctrl_pos", "<u8"), ("ctrl_neg", "<u8"), ("m", "<f8", (8,)),
+                     ("arg", "<u4"), ("reserved", "<u4")])
+assert OP_DTYPE.itemsize == C.sizeof(_native.JkqOp)
 
 
 def gate_op(target, matrix, controls=()):
@@ -85,8 +89,14 @@ class Engine:
 
     # -- circuit ----------------------------------------------------------------------------
     def load_ops(self, n_qubits, ops):
-        arr = (_native.JkqOp * max(1, len(ops)))(*ops)
-        self._check(self._lib.jkq_load_circuit(self._h, int(n_qubits), arr, len(ops)))
+        """``ops``: sequence of _native.JkqOp, or a numpy array of OP_DTYPE (passed without a copy)."""
+        if isinstance(ops, np.ndarray):
+            ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+            ptr = ops.ctypes.data_as(C.POINTER(_native.JkqOp)) if len(ops) else None
+            self._check(self._lib.jkq_load_circuit(self._h, int(n_qubits), ptr, len(ops)))
+        else:
+            arr = (_native.JkqOp * max(1, len(ops)))(*ops)
+            self._check(self._lib.jkq_load_circuit(self._h, int(n_qubits), arr, len(ops)))
         self.n = int(n_qubits)
 
     def load(self, circuit, measure=None, final_snapshot=False):

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import circuits
 from .compat import BackendConfiguration, BackendStatus, BaseBackend, Result
-from .engine import OP_BARRIER, OP_MEASURE, OP_SNAPSHOT, Engine, gate_op, simple_op
+from .engine import OP_BARRIER, OP_DTYPE, OP_GATE, OP_MEASURE, OP_SNAPSHOT, Engine
 from .jkujob import JKUJob
 from .jkusimulatorerror import JKUSimulatorError
 
@@ -34,6 +34,30 @@ logger = logging.getLogger(__name__)
 # (``:116-120,138``).  Above this many qubits the final state vector is only produced on request
 # (experiment.config.data contains 'statevector').
 STATEVECTOR_AUTO_MAX_QUBITS = 20
+
+
+_TEMPLATES = {}
+
+
+def _gate_template(name, n_qubits, params):
+    """(name, params) -> ((target position, ((control position, value), ...), 8 floats), ...), positions into the
+    instruction's qubit list.  Raises JKUSimulatorError for a gate qelib1 does not define."""
+    key = (name, n_qubits, params)
+    tpl = _TEMPLATES.get(key)
+    if tpl is None:
+        try:
+            prims = circuits.expand(name, list(range(n_qubits)), params)
+        except (KeyError, IndexError, ValueError):
+            raise JKUSimulatorError("Undefined gate: {}".format(name))
+        out = []
+        for p in prims:
+            m = p.matrix()
+            flat = tuple(x for row in m for z in row for x in (complex(z).real, complex(z).imag))
+            out.append((p.target, tuple(p.controls), flat))
+        tpl = tuple(out)
+        if len(_TEMPLATES) < 65536:
+            _TEMPLATES[key] = tpl
+    return tpl
 
 
 class JKUSimulatorWrapper:
@@ -76,33 +100,53 @@ class JKUSimulatorWrapper:
         return measurement_data
 
     def convert_qobj_circuit_to_ops(self, experiment, want_final_statevector):
-        """Qobj instructions -> list of jkq_op (replaces convert_qobj_circuit_to_jku_qasm, :123-140)."""
-        ops = []
+        """Qobj instructions -> packed array of jkq_op (replaces convert_qobj_circuit_to_jku_qasm, :123-140).
+
+        Each named gate is macro-expanded once per (name, params) into a template of primitives
+        (``circuits.expand`` restates qelib1) and stamped onto the instruction's qubits; the result is one
+        numpy structured array with the memory layout of ``jkq_op`` (include/jkq.h)."""
+        kinds, targets, cpos, cneg, mats, args = [], [], [], [], [], []
         self.max_snapshot_index = 0
         snapshot_slots = []
+        zero_m = (0.0,) * 8
         for op in experiment.instructions:
             name = op.name
-            params = list(getattr(op, 'params', []) or [])
             if name == 'measure':
-                ops.append(simple_op(OP_MEASURE, op.qubits[0], op.memory[0]))
+                kinds.append(OP_MEASURE); targets.append(op.qubits[0]); cpos.append(0); cneg.append(0)
+                mats.append(zero_m); args.append(op.memory[0])
             elif name == 'snapshot':
+                params = list(getattr(op, 'params', []) or [])
                 slot = int(params[0]) if params else int(getattr(op, 'label', 0))
                 self.max_snapshot_index = max(self.max_snapshot_index, slot)
                 snapshot_slots.append(slot)
-                ops.append(simple_op(OP_SNAPSHOT, 0, slot))
+                kinds.append(OP_SNAPSHOT); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(slot)
             elif name == 'barrier':
-                ops.append(simple_op(OP_BARRIER))
+                kinds.append(OP_BARRIER); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
             else:
-                try:
-                    prims = circuits.expand(name, op.qubits, params)
-                except KeyError:
-                    raise JKUSimulatorError("Undefined gate: {}".format(name))
-                for p in prims:
-                    ops.append(gate_op(p.target, p.matrix(), p.controls))
+                params = tuple(getattr(op, 'params', None) or ())
+                qubits = op.qubits
+                for t_pos, ctl, m in _gate_template(name, len(qubits), params):
+                    pos = neg = 0
+                    for c_pos, val in ctl:
+                        if val:
+                            pos |= 1 << qubits[c_pos]
+                        else:
+                            neg |= 1 << qubits[c_pos]
+                    kinds.append(OP_GATE); targets.append(qubits[t_pos]); cpos.append(pos); cneg.append(neg)
+                    mats.append(m); args.append(0)
         self.max_snapshot_index += 1  # add_final_snapshot, :116-120
         if want_final_statevector:
-            ops.append(simple_op(OP_SNAPSHOT, 0, self.max_snapshot_index))
+            kinds.append(OP_SNAPSHOT); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m)
+            args.append(self.max_snapshot_index)
             snapshot_slots.append(self.max_snapshot_index)
+        ops = np.zeros(len(kinds), dtype=OP_DTYPE)
+        if len(kinds):
+            ops['kind'] = kinds
+            ops['target'] = targets
+            ops['ctrl_pos'] = np.array(cpos, dtype=np.uint64)
+            ops['ctrl_neg'] = np.array(cneg, dtype=np.uint64)
+            ops['m'] = np.array(mats, dtype=np.float64)
+            ops['arg'] = args
         return ops, snapshot_slots
 
     def run_experiment(self, config, experiment):

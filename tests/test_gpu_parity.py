@@ -113,8 +113,8 @@ def test_random_blowup_uses_grid_path_and_collector(eng, oracle_mod):
         eng.set_option("cta_item_limit", 4096)
     st = eng.stats()
     assert st["grid_launches"] >= 1
-    o = oracle_mod.run_oracle(circ, shots=4096, seed=3, amps=True, extra=["--amp-limit", "4096"] + TIE)
-    assert np.abs(eng.amplitudes(0, 4096) - np.array([complex(*x) for x in o["amps"]])).max() < AMP_TOL
+    o = oracle_mod.run_oracle(circ, shots=4096, seed=3, amps=True, extra=["--amp-limit", "65536"] + TIE)
+    assert np.abs(eng.amplitudes(0, 65536) - np.array([complex(*x) for x in o["amps"]])).max() < AMP_TOL
     assert abs(st["norm"] - 1.0) < 1e-9
     # sum over levels within 1 % of the oracle (blown-up random DDs: equality only while no two
     # distinct values fall within tol, SURVEY section 7 hard part 2)

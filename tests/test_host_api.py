@@ -1,5 +1,6 @@
 """CPU: host-side logic -- the C ABI library loads and exports every symbol include/jkq.h declares
 (no compute without a GPU), the provider/backend/job mirror, Qobj conversion, count formatting."""
+import numpy as np
 import ctypes
 import os
 import re
@@ -71,10 +72,12 @@ def test_qobj_conversion_without_gpu():
     md = w.compute_measurement_data(exp)
     assert md["mapping"] == {0: 0, 1: 1} and md["clbits_num"] == 2 and md["qubits_num"] == 2
     ops, slots = w.convert_qobj_circuit_to_ops(exp, True)
-    kinds = [o.kind for o in ops]
-    assert kinds == [0, 0, 2, 2, 1]  # h, cx, measure x2, final snapshot
+    assert ops["kind"].tolist() == [0, 0, 2, 2, 1]  # h, cx, measure x2, final snapshot
     assert slots == [1] and w.max_snapshot_index == 1
-    assert ops[1].ctrl_pos == 1 and ops[1].target == 1
+    assert ops[1]["ctrl_pos"] == 1 and ops[1]["target"] == 1
+    assert ops.dtype.itemsize == 96  # sizeof(jkq_op), include/jkq.h
+    h = 2 ** -0.5
+    assert np.allclose(ops[0]["m"], [h, 0, h, 0, h, 0, -h, 0]) or np.allclose(np.abs(ops[0]["m"][::2] + 1j * ops[0]["m"][1::2]), [h] * 4)
 
 
 def test_qubit_reuse_after_measure_raises():
