@@ -367,6 +367,35 @@ template <int MODE> JD void cta_flush(Ctx &c) {
 //   force_vals  sweep / rebuild the value table regardless of the limit
 JD void vt_clear_slot(JVSlot *s) { s->vbits = JV_INF; s->keylo = 0; s->id1 = 0; }
 
+// CTA-wide sum, and exclusive rank of a flag among the threads of the CTA (+ the CTA's count); all threads call
+#ifdef JKQ_EMU
+JD uint32_t block_sum(Ctx &, uint32_t v) { return v; }
+JD uint32_t block_scan_flag(Ctx &, bool flag, uint32_t *total) { *total = flag ? 1u : 0u; return 0; }
+#else
+JD uint32_t block_sum(Ctx &c, uint32_t v) {
+  __shared__ uint32_t s_sum;
+  if (c.ltid == 0) s_sum = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+  if ((c.ltid & 31u) == 0 && v) atomicAdd(&s_sum, v);
+  __syncthreads();
+  const uint32_t r = s_sum;
+  __syncthreads();
+  return r;
+}
+JD uint32_t block_scan_flag(Ctx &c, bool flag, uint32_t *total) {
+  __shared__ uint32_t s_w[32];
+  const uint32_t b = __ballot_sync(0xFFFFFFFFu, flag), lane = c.ltid & 31u, w = c.ltid >> 5, nw = (c.lnth + 31u) >> 5;
+  if (lane == 0) s_w[w] = __popc(b);
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+  for (uint32_t k = 0; k < nw; k++) { const uint32_t x = s_w[k]; if (k < w) off += x; tot += x; }
+  __syncthreads();
+  *total = tot;
+  return off + __popc(b & ((1u << lane) - 1u));
+}
+#endif
+
 // Out of line, context by value (the caller's stays in registers): gc_call() below takes over the ring index.
 template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   JEng *E = c.E;
@@ -433,23 +462,46 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
       E->vfwd[(uint32_t)nd.w & 0x7FFFFFFFu] = 1;
     }
   }
+  if (clean_vals && c.block0 && c.ltid == 0) {  // the root weight is referenced too
+    const uint64_t rw = E->rootw;
+    E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu] = 1;
+    E->vfwd[(uint32_t)rw & 0x7FFFFFFFu] = 1;
+  }
   sync_or<MODE>(c, 0);
+  if (clean_vals) {
+    // Compact the reals, keeping insertion order (constants 0..3 stay): a two-pass prefix sum, one
+    // contiguous chunk per CTA -- count, barrier, then every CTA adds up the counts of the chunks before
+    // its own and scatters.
+    const uint32_t nblk = MODE == MODE_CTA ? 1u : c.nth / c.lnth, blk = MODE == MODE_CTA ? 0u : c.tid / c.lnth;
+    const uint32_t chunk = (old_vals + nblk - 1) / nblk, lo = blk * chunk, hi = lo + chunk < old_vals ? lo + chunk : old_vals;
+    uint32_t mine = 0;
+    for (uint32_t i = lo + c.ltid; i < hi; i += c.lnth) mine += (i < 4 || ld_s<MODE_GRID>(E->vfwd + i)) ? 1u : 0u;
+    const uint32_t total = block_sum(c, mine);
+    if (c.ltid == 0) E->gc_bsum[blk] = total;
+    sync_or<MODE>(c, 0);
+    uint32_t base = 0;
+    if (MODE != MODE_CTA)
+      for (uint32_t k = 0; k < blk; k++) base += ld_s<MODE_GRID>(E->gc_bsum + k);
+    for (uint32_t t = lo; t < hi; t += c.lnth) {
+      const uint32_t i = t + c.ltid;
+      const bool keep = i < hi && (i < 4 || ld_s<MODE_GRID>(E->vfwd + i));
+      uint32_t tile_total;
+      const uint32_t pos = base + block_scan_flag(c, keep, &tile_total);
+      if (keep) { E->vals_alt[pos] = ld_s<MODE_GRID>(E->vals + i); E->vfwd[i] = pos; }
+      base += tile_total;
+    }
+    sync_or<MODE>(c, 0);
+  }
   if (c.block0 && c.ltid == 0) {
-    if (clean_vals) {  // compact the reals, keeping insertion order; constants stay
-      uint64_t rw = E->rootw;
-      E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu] = 1;
-      E->vfwd[(uint32_t)rw & 0x7FFFFFFFu] = 1;
+    if (clean_vals) {
+      const uint32_t nblk = MODE == MODE_CTA ? 1u : c.nth / c.lnth;
       uint32_t nv = 0;
-      for (uint32_t i = 0; i < old_vals; i++) {
-        if (i < 4 || ld_s<MODE_GRID>(E->vfwd + i)) {
-          E->vals_alt[nv] = ld_s<MODE_GRID>(E->vals + i);
-          E->vfwd[i] = nv++;
-        }
-      }
+      for (uint32_t k = 0; k < nblk; k++) nv += ld_s<MODE_GRID>(E->gc_bsum + k);
+      const uint64_t rw = E->rootw;
       *cnt_vals<MODE>(c) = nv;
       E->val_count = nv;
-      E->rootw = ((uint64_t)(((uint32_t)(rw >> 32) & 0x80000000u) | E->vfwd[(uint32_t)(rw >> 32) & 0x7FFFFFFFu]) << 32) |
-                 (((uint32_t)rw & 0x80000000u) | E->vfwd[(uint32_t)rw & 0x7FFFFFFFu]);
+      E->rootw = ((uint64_t)(((uint32_t)(rw >> 32) & 0x80000000u) | ld_s<MODE_GRID>(E->vfwd + ((uint32_t)(rw >> 32) & 0x7FFFFFFFu))) << 32) |
+                 (((uint32_t)rw & 0x80000000u) | ld_s<MODE_GRID>(E->vfwd + ((uint32_t)rw & 0x7FFFFFFFu)));
       E->val_epoch++;  // ids renumbered: cached gate-matrix ids are void
       if (E->val_gc_limit < 2 * nv) E->val_gc_limit *= 2;  // Simulator.cpp:495-497
       if (E->val_gc_limit > E->val_cap / 2) E->val_gc_limit = E->val_cap / 2;

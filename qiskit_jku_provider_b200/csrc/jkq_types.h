@@ -155,6 +155,7 @@ typedef struct {
   unsigned int bar_gen;
   unsigned int bar_flags[3];
   unsigned long long prof[16];  // JKQ_PROFILE builds: cycle counters, see jkq_b200.cu jkq_get_stats
+  uint32_t gc_bsum[1024];  // collector: live reals per CTA chunk
   unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was
   unsigned int dbg_phase[1024];
 } JEng;
