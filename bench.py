@@ -283,12 +283,21 @@ def main():
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         achieved = items * ALGO_BYTES_PER_ITEM / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                t = json.load(f)["k_run_gates<MODE_CTA>"]
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_src,
-                "kernel": "k_run_gates<MODE_CTA> (persistent single-CTA circuit kernel: 1 launch per step)",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
+                "kernel": "k_run_gates<MODE_CTA> (persistent single-CTA circuit kernel: 1 launch per step, 99.7 % of the step's "
+                          "GPU time in profiles/r1_bench_launches.csv)",
                 "algorithmic_bytes": "%d frontier items/step x %d B" % (items, ALGO_BYTES_PER_ITEM),
-                "note": "latency-bound by design on this config (DD of 32 nodes, a dependent chain of ~64 level phases per "
-                        "gate); figure of merit = us per gate vs the reference's 40-130 us"}
+                "note": "latency-bound by design on this config: the DD (32 nodes) and every table live in one SM's shared "
+                        "memory, HBM sees %s bytes per circuit; one warp runs a dependent chain of ~11 level phases per gate. "
+                        "Figure of merit = us per gate against the reference's 27 us" % (traffic if traffic is not None else "~0.5 M")}
         if "random_sector" in extra:
             roof["random_sector_gbs_measured"] = extra["random_sector"]["random_sector_gbs"]
             roof["frac_of_random_sector"] = achieved / extra["random_sector"]["random_sector_gbs"]
