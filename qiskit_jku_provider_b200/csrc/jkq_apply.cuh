@@ -574,43 +574,35 @@ template <int MODE> JD uint32_t gc_call(Ctx &c, bool reload, bool force_vals) {
 // the reals 0, 1 and the reference's gate constants 1/2 and FP64 sqrt(2)/2 in its insertion order
 // (QMDDpackage.cpp:44-53), then the |0...0> chain.  Runs on the grid path (HBM tables).
 template <int MODE> JD uint32_t init_state(Ctx &c) {
+  // One thread.  The HBM hash tables are NOT touched: they are marked stale (tables_valid = 0) and get
+  // rebuilt by the collector if the grid path ever needs them; the de-dup tables are generation-tagged and
+  // the generation keeps counting across circuits, so they are never cleared either.
   JEng *E = c.E;
-  for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
-  for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
-  for (uint32_t i = c.tid; i <= E->dtab_mask; i += c.nth) E->dtab[i] = 0;
-  for (uint32_t i = c.tid; i < E->node_cap; i += c.nth) E->mdir[i] = 0;
   if (c.block0 && c.ltid == 0) {
     E->status = 0; E->want_grid = 0; E->next_gate = 0;
-    E->val_count = 0; E->node_count = 1; E->item_count = 0; E->pend_n[0] = E->pend_n[1] = E->pend_n[2] = 0;
-    E->gen = 1;
+    E->item_count = 0; E->pend_n[0] = E->pend_n[1] = E->pend_n[2] = 0;
+    E->gen += 2;
     for (int k = 0; k < 12; k++) E->st[k] = 0;
     for (int k = 0; k < 16; k++) E->prof[k] = 0;
     JNode t; t.c0 = 0; t.c1 = 0; t.w = 0;
     E->nodes[0] = t;
-  }
-  sync_or<MODE>(c, 0);
-  if (c.block0 && c.ltid == 0) {
-    E->vals[0] = 0.0; E->val_count = 1;  // index 0 never sits in the hash: real_find short-cuts x <= tol
-    real_insert_direct<MODE>(c.E, c.sh, 1.0);
-    real_insert_direct<MODE>(c.E, c.sh, 0.5);
-    real_insert_direct<MODE>(c.E, c.sh, 0.70710678118654757);
+    // the reals 0, 1 and the reference's gate constants 1/2, FP64 sqrt(2)/2 in its insertion order
+    E->vals[0] = 0.0; E->vals[1] = 1.0; E->vals[2] = 0.5; E->vals[3] = 0.70710678118654757;
+    E->val_count = 4;
     uint32_t prev = 0;
     for (uint32_t L = 0; L < E->n; L++) {
       JNode nd; nd.c0 = prev; nd.c1 = 0; nd.w = 0;  // child 0 carries ONE, child 1 is the zero edge
-      uint32_t id = E->node_count++;
-      E->nodes[id] = nd;
-      uint32_t h = ut_hash(nd) & E->utab_mask;
-      while (ld_s<MODE>(E->utab + h) != 0) h = (h + 1) & E->utab_mask;
-      E->utab[h] = id;
-      prev = id;
+      E->nodes[L + 1] = nd;
+      prev = L + 1;
     }
+    E->node_count = E->n + 1;
     E->root = prev; E->rootw = JW_ONE;
     E->gc_limit = E->gc_min > E->node_cap / 2 ? E->node_cap / 2 : E->gc_min;
     E->val_gc_limit = 10000 < E->val_cap / 2 ? 10000 : E->val_cap / 2;  // complex_limit, Simulator.h:91
-    E->tables_valid = 1;
-    E->val_epoch = 1;
+    E->tables_valid = 0;
+    E->val_epoch += 1;
   }
-  return sync_or<MODE>(c, 0);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------ mode hand-over
@@ -626,6 +618,7 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       S->item_count = E->item_count; S->node_count = E->node_count; S->val_count = E->val_count;
       S->item_limit = E->cta_item_limit;
       S->node_hard = E->node_cap < JKQ_SNODES ? E->node_cap : JKQ_SNODES;
+      if (E->cta_node_limit && E->cta_node_limit < S->node_hard) S->node_hard = E->cta_node_limit;
       S->val_hard = E->val_cap < JKQ_SVALS ? E->val_cap : JKQ_SVALS;
       S->node_soft = S->node_hard - S->node_hard / 8;  // the rest is the reserve of cursor_to_root
       S->val_soft = S->val_hard - S->val_hard / 16;
@@ -649,7 +642,21 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
     return (r & JF_ERROR) ? JF_ERROR : (r & JF_GRID);
   }
   if (!ld_s<MODE>(&E->tables_valid)) {
-    if (gc_call<MODE>(c, false, true) & JF_ERROR) return JF_ERROR;
+    if (ld_s<MODE>(&E->cursor_saved)) {
+      // No root to collect from (the state is a saved cursor): hash every arena node and every real as
+      // they are.  Ids stay what they are; slots that lost an insertion race carry a tombstone.
+      const uint32_t nn = ld_s<MODE>(&E->node_count), nv = ld_s<MODE>(&E->val_count);
+      for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
+      for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
+      sync_or<MODE>(c, 0);
+      for (uint32_t i = 1 + c.tid; i < nn; i += c.nth) {
+        const JNode nd = ld_s<MODE>(E->nodes + i);
+        if (nd.c1 == JN_TOMB) continue;
+        uint32_t h = ut_hash(nd) & E->utab_mask;
+        while (jatomic_cas(E->utab + h, 0u, i) != 0) h = (h + 1) & E->utab_mask;
+      }
+      for (uint32_t i = 1 + c.tid; i < nv; i += c.nth) vt_put<MODE>(c.E, c.sh, i, ld_s<MODE>(E->vals + i));
+    } else if (gc_call<MODE>(c, false, true) & JF_ERROR) return JF_ERROR;
     if (c.block0 && c.ltid == 0) E->tables_valid = 1;
     sync_or<MODE>(c, 0);
   }
@@ -680,8 +687,15 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(gates + g);
     for (uint32_t i = c.ltid; i < sizeof(JGate) / 4; i += c.lnth) dst[i] = src[i];
   }
-  if (thin_warp) cursor_reset<MODE>(c, n);
+  if (MODE == MODE_GRID && ld_s<MODE>(&E->cursor_saved)) {  // continue from the cursor a single-CTA kernel left behind
+    if (c.block0) {
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(E->thin_spill);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(c.T);
+      for (uint32_t i = c.ltid; i < sizeof(ThinState) / 4; i += c.lnth) dst[i] = ld_s<MODE>(src + i);
+    }
+  } else if (thin_warp) cursor_reset<MODE>(c, n);
   sync_or<MODE>(c, 0);
+  if (MODE == MODE_GRID && c.block0 && c.ltid == 0) E->cursor_saved = 0;
   const bool log = E->lvl_log != 0;
   for (; !f && g < n_gates; g++) {
     f = apply_gate<MODE>(c, gates, g, n_gates, n, log);
@@ -709,11 +723,19 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
       if (c.ltid == 0) c.sh->want_grid = 0;
       block_sync();
     }
-    if (thin_warp) {
-      const uint32_t r = cursor_to_root<MODE>(c, n);
-      if (r && !(r & JF_ERROR) && c.ltid == 0) jset_error<MODE>(E, c.sh, JKQ_ERR_NODE_FULL);  // not even the reserve was enough
+    if (thin_warp) cursor_to_root<MODE>(c, n);
+    const uint32_t r = sync_or<MODE>(c, 0);
+    f |= r & JF_ERROR;
+    if (MODE == MODE_CTA && !(r & JF_ERROR) && (r & JF_GRID)) {
+      // Not even the reserve of the shared pools was enough to rebuild up to the root: hand the cursor
+      // itself to the grid path (which has the room).  The arena goes out as it is.
+      uint32_t *dst = reinterpret_cast<uint32_t *>(E->thin_spill);
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(c.T);
+      for (uint32_t i = c.ltid; i < sizeof(ThinState) / 4; i += c.lnth) dst[i] = src[i];
+      if (c.ltid == 0) { E->cursor_saved = 1; c.sh->want_grid = 0; }
+      block_sync();
+      f |= JF_GRID;
     }
-    f |= sync_or<MODE>(c, 0) & JF_ERROR;
   }
   if ((f & JF_GRID) && c.block0 && c.ltid == 0) { E->want_grid = 1; if (MODE == MODE_GRID) E->gen++; }
   sync_or<MODE>(c, 0);

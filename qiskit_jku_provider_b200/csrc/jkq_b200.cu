@@ -182,7 +182,8 @@ struct jkq_handle {
   JGate *gates_dev = nullptr;
   uint64_t *mat_u = nullptr;
   uint32_t *mat_epoch = nullptr;
-  uint32_t n_mats = 0;
+  uint32_t n_mats = 0, mats_cap = 0;
+  size_t gates_cap = 0;
   std::vector<jkq_op> ops;
   std::vector<JGate> gates;         // GATE ops only
   std::vector<int> gate_of_op;      // ops index -> number of gates before it
@@ -251,7 +252,7 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   cudaSetDevice(h->device);
   JEng &E = h->host;
   cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
-  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.mdir); cudaFree(E.fwd); cudaFree(E.vfwd);
+  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.mdir); cudaFree(E.thin_spill); cudaFree(E.fwd); cudaFree(E.vfwd);
   cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
   cudaFree(h->mat_u); cudaFree(h->mat_epoch);
   cudaFree(h->n_out); cudaFree(h->overflow);
@@ -314,6 +315,10 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaMalloc(&E.items, (size_t)E.item_cap * sizeof(JItem)));
   CU(cudaMalloc(&E.dtab, ((size_t)E.dtab_mask + 1) * 8));
   CU(cudaMalloc(&E.mdir, (size_t)E.node_cap * 8));
+  CU(cudaMalloc(&E.thin_spill, sizeof(ThinState)));
+  // generation-tagged de-dup tables: zeroed once, never cleared again (the generation counts across circuits)
+  CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
+  CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
   CU(cudaMalloc(&E.fwd, (size_t)E.node_cap * 4));
   CU(cudaMalloc(&E.vfwd, (size_t)E.val_cap * 4));
   CU(cudaMalloc(&h->dev, sizeof(JEng)));
@@ -337,6 +342,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!h || !name) return JKQ_E_ARGUMENT;
   if (!strcmp(name, "level_log")) { h->level_log = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "force_mode")) { h->cfg.force_mode = (int)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
     if (value < 1 || value > JKQ_SITEMS / 2) value = JKQ_SITEMS / 2;
     h->cfg.cta_item_limit = (uint32_t)value; h->host.cta_item_limit = (uint32_t)value;
@@ -396,17 +402,24 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
   }
   if (!any_measure)  // engine-level default: every qubit, key bit q = qubit q
     for (uint32_t q = 0; q < n_qubits && q < 64; q++) h->sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
-  cudaFree(h->gates_dev); cudaFree(h->mat_u); cudaFree(h->mat_epoch);
-  h->gates_dev = nullptr; h->mat_u = nullptr; h->mat_epoch = nullptr;
+  // device copies of the gate list: buffers are kept and only grow (cudaFree synchronises the whole device,
+  // which would serialise the engines of a batch)
   h->n_mats = (uint32_t)mats.size();
-  if (h->n_mats) {
-    CU(cudaMalloc(&h->mat_u, (size_t)h->n_mats * 4 * 8));
-    CU(cudaMalloc(&h->mat_epoch, (size_t)h->n_mats * 4));
+  if (h->n_mats > h->mats_cap) {
+    cudaFree(h->mat_u); cudaFree(h->mat_epoch);
+    h->mat_u = nullptr; h->mat_epoch = nullptr;
+    h->mats_cap = pow2_at_least(h->n_mats, 64);
+    CU(cudaMalloc(&h->mat_u, (size_t)h->mats_cap * 4 * 8));
+    CU(cudaMalloc(&h->mat_epoch, (size_t)h->mats_cap * 4));
   }
-  if (!h->gates.empty()) {
-    CU(cudaMalloc(&h->gates_dev, h->gates.size() * sizeof(JGate)));
+  if (h->gates.size() > h->gates_cap) {
+    cudaFree(h->gates_dev);
+    h->gates_dev = nullptr;
+    h->gates_cap = pow2_at_least(h->gates.size(), 256);
+    CU(cudaMalloc(&h->gates_dev, h->gates_cap * sizeof(JGate)));
+  }
+  if (!h->gates.empty())
     CU(cudaMemcpyAsync(h->gates_dev, h->gates.data(), h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
-  }
   h->loaded = true; h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
   return JKQ_E_OK;
 }
@@ -463,8 +476,8 @@ static int run_segment(jkq_handle *h, int upto) {
                   h->host.next_gate, h->host.dbg_timeout_block, h->host.bar_count, s.c_str());
     }
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
-    if (h->host.next_gate >= upto) return JKQ_E_OK;
-    if (h->host.want_grid && !grid) {
+    if (h->host.next_gate >= upto && !h->host.cursor_saved) return JKQ_E_OK;
+    if ((h->host.want_grid || h->host.cursor_saved) && !grid) {
       if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: state or frontier exceeds the single-CTA path and force_mode=1", h->host.next_gate);
       grid = true;
       h->host.want_grid = 0;
@@ -483,8 +496,7 @@ extern "C" int jkq_apply(jkq_handle *h) {
   h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
   JEng &E = h->host;
   E.n = h->n;
-  cudaFree(h->lvl_log);
-  h->lvl_log = nullptr;
+  if (h->lvl_log) { cudaFree(h->lvl_log); h->lvl_log = nullptr; }
   if (h->level_log && !h->gates.empty()) {
     CU(cudaMalloc(&h->lvl_log, h->gates.size() * h->n * 4));
     CU(cudaMemsetAsync(h->lvl_log, 0, h->gates.size() * h->n * 4, h->stream));
@@ -492,16 +504,13 @@ extern "C" int jkq_apply(jkq_handle *h) {
   E.lvl_log = h->lvl_log;
   E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
   if (h->n_mats) CU(cudaMemsetAsync(h->mat_epoch, 0, (size_t)h->n_mats * 4, h->stream));
-  E.status = 0; E.next_gate = 0; E.want_grid = 0;
+  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));
   CU(cudaMemcpyAsync(h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice, h->stream));
-  {
-    JEng *Ed = h->dev;
-    void *args[] = {&Ed};
-    CU(cudaLaunchCooperativeKernel((void *)k_init<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, 0, h->stream));
-  }
+  k_init<MODE_GRID><<<1, 32, 0, h->stream>>>(h->dev);
+  CU(cudaGetLastError());
   const uint64_t cta0 = h->stats.cta_launches, grid0 = h->stats.grid_launches;
   size_t i = 0;
   while (i < h->ops.size()) {

@@ -554,6 +554,7 @@ template <int MODE> JNI uint64_t cx_make_serial(JEng *E, CtaState *S, double re,
 }
 
 // ------------------------------------------------------------------------------------ node access
+#define JN_TOMB 0xFFFFFFFFu  // c1 of an arena slot that was allocated but never published
 JD uint32_t nd_flag(const JNode &n) { return n.c0 >> 31; }
 JD uint32_t nd_c0(const JNode &n) { return n.c0 & 0x7FFFFFFFu; }
 JD uint64_t nd_w0(const JNode &n) { return nd_flag(n) ? n.w : JW_ONE; }
@@ -589,7 +590,10 @@ template <int MODE> JNI uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_
         if (s == 0) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
       }
       JNode o = ld_r<MODE>(&S->nodes[s]);
-      if (o.c0 == c0 && o.c1 == c1 && o.w == w) return s;  // (an id allocated above and not published stays unused: garbage)
+      if (o.c0 == c0 && o.c1 == c1 && o.w == w) {
+        if (mine) S->nodes[mine].c1 = JN_TOMB;  // allocated above, lost the race: never referenced, must never be hashed
+        return s;
+      }
       h = (h + 1) & (JKQ_SUT_SLOTS - 1);
     }
     jwant_grid(S);
@@ -609,7 +613,10 @@ template <int MODE> JNI uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_
       if (s == 0) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
     }
     JNode o = ld_r<MODE>(E->nodes + s);
-    if (o.c0 == c0 && o.c1 == c1 && o.w == w) return s;
+    if (o.c0 == c0 && o.c1 == c1 && o.w == w) {
+      if (mine) E->nodes[mine].c1 = JN_TOMB;
+      return s;
+    }
     h = (h + 1) & E->utab_mask;
   }
   jset_error<MODE>(E, S, JKQ_ERR_UTAB_FULL);

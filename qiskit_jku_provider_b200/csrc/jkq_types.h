@@ -109,6 +109,8 @@ typedef struct {
   uint32_t node_cap, utab_mask, val_cap, vtab_mask, pend_cap, item_cap, dtab_mask;
   uint32_t cta_item_limit;  // CTA mode bails out to grid mode above this frontier size
   uint32_t gc_min;          // never collect below this many allocated nodes
+  uint32_t cta_node_limit;  // testing aid: cap on the shared-memory node pool of the CTA path (0 = its real size)
+  uint32_t pad_c;
   double tol;
   double inv_tol;
   // ---- arrays ----
@@ -123,6 +125,7 @@ typedef struct {
   uint32_t *fwd;      // node_cap entries: forwarding ids for the collector
   uint32_t *vfwd;     // val_cap entries: value id remap for the collector
   uint32_t *lvl_log;  // optional [gate][level] live-node counts
+  void *thin_spill;   // the cursor (ThinState) of a single-CTA kernel that could not rebuild up to the root
   uint64_t *mat_u;      // [n distinct matrices][4] cached canonical ids of gate-matrix entries
   uint32_t *mat_epoch;  // [n distinct matrices] val_epoch at which mat_u was filled (0 = never)
   // ---- mutable state ----
@@ -148,6 +151,8 @@ typedef struct {
   int32_t next_gate;    // first gate not yet applied
   int32_t want_grid;    // CTA mode asked for the grid path
   uint32_t tables_valid;  // HBM unique / value hash tables match the arena (MODE_CTA lets them go stale)
+  uint32_t cursor_saved;  // thin_spill holds the state; root / rootw are stale; only the grid path may continue
+  uint32_t pad_s;
   // ---- counters ----
   unsigned long long st[12];  // JST_* below
   // ---- grid barrier ----

@@ -38,6 +38,43 @@ def gate_op(target, matrix, controls=()):
     return op
 
 
+def circuit_ops(circuit, measure=None, final_snapshot=False):
+    """circuits.Circuit -> numpy array of OP_DTYPE (one GATE per primitive, then the optional final snapshot and
+    the measure map).  Cached on the circuit object for the plain case."""
+    plain = not measure and not final_snapshot
+    if plain and getattr(circuit, "_jkq_ops", None) is not None and len(circuit._jkq_ops) == len(circuit.ops):
+        return circuit._jkq_ops
+    n_extra = (1 if final_snapshot else 0) + len(measure or {})
+    arr = np.zeros(len(circuit.ops) + n_extra, dtype=OP_DTYPE)
+    mcache = {}
+    for i, op in enumerate(circuit.ops):
+        key = (op.kind, op.name, op.theta.const, op.theta.frac, op.phi.const, op.phi.frac, op.lam.const, op.lam.frac)
+        m = mcache.get(key)
+        if m is None:
+            mm = op.matrix()
+            m = mcache[key] = [x for row in mm for z in row for x in (complex(z).real, complex(z).imag)]
+        pos = neg = 0
+        for q, v in op.controls:
+            if v:
+                pos |= 1 << q
+            else:
+                neg |= 1 << q
+        arr[i] = (OP_GATE, op.target, pos, neg, m, 0, 0)
+    k = len(circuit.ops)
+    if final_snapshot:
+        arr[k] = (OP_SNAPSHOT, 0, 0, 0, [0.0] * 8, 0, 0)
+        k += 1
+    for q, cbit in (measure or {}).items():
+        arr[k] = (OP_MEASURE, int(q), 0, 0, [0.0] * 8, int(cbit), 0)
+        k += 1
+    if plain:
+        try:
+            circuit._jkq_ops = arr
+        except AttributeError:
+            pass
+    return arr
+
+
 def simple_op(kind, target=0, arg=0):
     op = _native.JkqOp()
     op.kind, op.target, op.arg = kind, int(target), int(arg)
@@ -101,12 +138,7 @@ class Engine:
 
     def load(self, circuit, measure=None, final_snapshot=False):
         """``circuit``: circuits.Circuit; ``measure``: {qubit: clbit} (None = all qubits, bit q = qubit q)."""
-        ops = [gate_op(op.target, op.matrix(), op.controls) for op in circuit.ops]
-        if final_snapshot:
-            ops.append(simple_op(OP_SNAPSHOT, 0, 0))
-        for q, cbit in (measure or {}).items():
-            ops.append(simple_op(OP_MEASURE, q, cbit))
-        self.load_ops(circuit.n, ops)
+        self.load_ops(circuit.n, circuit_ops(circuit, measure, final_snapshot))
 
     def set_option(self, name, value):
         self._check(self._lib.jkq_set_option(self._h, name.encode(), int(value)))

@@ -135,6 +135,7 @@ int main(int argc, char **argv) {
   E->items = (JItem *)calloc(E->item_cap, sizeof(JItem));
   E->dtab = (unsigned long long *)calloc((size_t)E->dtab_mask + 1, 8);
   E->mdir = (unsigned long long *)calloc(E->node_cap, 8);
+  E->thin_spill = calloc(1, sizeof(ThinState));
   E->fwd = (uint32_t *)calloc(E->node_cap, 4);
   E->vfwd = (uint32_t *)calloc(E->val_cap, 4);
   if (levels) E->lvl_log = (uint32_t *)calloc(gates.size() * n + 1, 4);
@@ -152,11 +153,11 @@ int main(int argc, char **argv) {
   int grid_switches = 0;
   bool grid = force_grid;
   // same escalation as the host driver (run_segment in jkq_b200.cu): CTA path until it does not fit
-  while (!E->status && E->next_gate < (int)gates.size()) {
+  while (!E->status && (E->next_gate < (int)gates.size() || E->cursor_saved)) {
     E->want_grid = 0;
     if (grid) run_gates<MODE_GRID>(gctx, gates.data(), (int)gates.size());
     else run_gates<MODE_CTA>(c, gates.data(), (int)gates.size());
-    if (E->want_grid && !grid) { grid = true; grid_switches++; }
+    if ((E->want_grid || E->cursor_saved) && !grid) { grid = true; grid_switches++; }
     else if (E->next_gate < (int)gates.size() && !E->status) { fprintf(stderr, "stopped without reason\n"); return 3; }
   }
   if (E->status) { fprintf(stderr, "engine error %d at gate %d\n", E->status, E->next_gate); return 3; }

@@ -213,3 +213,26 @@ def test_sampling_statistics_large(eng):
     assert chisquare(list(c.values())).pvalue > 0.01
     # total-variation distance to the exact distribution
     assert abs(c[0] / 1e7 - 0.5) < 1e-3
+
+
+def test_cursor_handed_to_the_grid_path_when_the_cta_pools_run_out(oracle_mod):
+    """A tiny shared-memory node pool: the single-CTA kernel cannot even rebuild the levels above its cursor,
+    saves the cursor, and the grid path continues from it (jkq_apply.cuh run_gates / mode_enter)."""
+    from qiskit_jku_provider_b200.engine import Engine
+    for circ in (C.random_circuit(14, 80, 2), C.qft(12), C.grover(10, 4, marked=0x155)):
+        o = oracle_mod.run_oracle(circ, amps=True, extra=["--amp-limit", "16384"] + TIE)
+        oa = np.array([complex(*x) for x in o["amps"]])
+        for limit in (96, 160):
+            with Engine(device=0, node_capacity=1 << 18) as e:
+                e.set_option("cta_node_limit", limit)
+                e.load(circ)
+                e.apply()
+                if circ.name.startswith("random"):
+                    assert e.stats()["grid_launches"] >= 1
+                k = min(16384, 1 << circ.n)
+                assert np.abs(e.amplitudes(0, k) - oa[:k]).max() < AMP_TOL, (circ.name, limit)
+                lc = e.level_counts()
+                if circ.name.startswith("random"):  # blown-up DD: equal up to values that straddle the tolerance
+                    assert abs(sum(lc) - sum(o["level_counts"])) <= 0.01 * sum(o["level_counts"]), (circ.name, limit)
+                else:
+                    assert lc == o["level_counts"], (circ.name, limit)
