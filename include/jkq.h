@@ -130,6 +130,21 @@ int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *host_nodes,
                   const uint8_t *clbit_of_level);
 int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n);
 
+/* Batches of independent circuits (the reference runs one `jku_simulator` process per experiment,
+ * sequentially: qasm_simulator_jku.py:340-359).  A pool of `n_engines` small engines; each circuit runs as one
+ * persistent single-CTA kernel chain on its own stream, so circuits of the batch occupy different SMs.
+ * Circuit i = ops[op_offsets[i] .. op_offsets[i+1]) on n_qubits[i] qubits (GATE / MEASURE / BARRIER ops),
+ * `shots` shots of the Philox stream seeds[i]; its outcomes land in keys/counts[i*cap .. i*cap + n_distinct[i]).
+ * status[i] != 0: the circuit was not finished on this path (too large for one SM's shared memory, more than
+ * `cap` distinct outcomes, ...) and is left to a full jkq_handle.  cfg may be NULL (small pools). */
+typedef struct jkq_batch jkq_batch;
+int jkq_batch_create(jkq_batch **out, int device, int n_engines, const jkq_config *cfg);
+void jkq_batch_destroy(jkq_batch *b);
+const char *jkq_batch_last_error(const jkq_batch *b);
+int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_qubits, const jkq_op *ops, const uint64_t *op_offsets,
+                  uint64_t shots, const uint64_t *seeds, size_t cap, uint64_t *keys, uint64_t *counts, uint32_t *n_distinct,
+                  int32_t *status, uint64_t *gates_applied, double *apply_ms_sum);
+
 /* GPU-measured roofline denominators: uniform random 32-byte sector reads and 64-bit atomicCAS over
  * a `bytes`-sized buffer; returns giga-operations per second */
 int jkq_random_sector_bench(jkq_handle *h, uint64_t bytes, int iters, double *gsectors_per_s, double *gcas_per_s);

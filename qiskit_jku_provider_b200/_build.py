@@ -30,7 +30,7 @@ def build_native(force=False, verbose=False):
     if not force and not stale():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     for d in os.environ.get("JKQ_DEFINES", "").split():  # e.g. JKQ_DEFINES="JKQ_PROFILE" for the cycle counters

@@ -53,6 +53,12 @@ SYMBOLS = [
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("jkq_dd_import", C.c_int, [_H, C.c_uint32, C.POINTER(JkqSNode), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     ("jkq_get_measure_map", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_size_t]),
+    ("jkq_batch_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.POINTER(JkqConfig)]),
+    ("jkq_batch_destroy", None, [_H]),
+    ("jkq_batch_last_error", C.c_char_p, [_H]),
+    ("jkq_batch_run", C.c_int, [_H, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(JkqOp), C.POINTER(C.c_uint64), C.c_uint64,
+                                C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     ("jkq_random_sector_bench", C.c_int, [_H, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 

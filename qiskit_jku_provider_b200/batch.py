@@ -2,87 +2,114 @@
 
 A canonical DD does not shard, but independent circuits do: the single-CTA path of the engine keeps one
 circuit's whole working set in ONE SM's shared memory, so a B200 runs up to 148 circuits side by side.
-``BatchRunner`` owns a pool of small engines (one ``jkq_handle`` = one CUDA stream each) and a thread per
-engine; the ctypes calls release the GIL, so the persistent circuit kernels of different engines overlap on
-different SMs.  Across GPUs the batch is split by circuit index (``i % world == rank``), one process per
-GPU, no data-path collective; per-circuit counts are gathered on the host.
+``BatchRunner`` wraps ``jkq_batch_*`` (include/jkq.h): a pool of small engines, one CUDA stream each; every
+circuit is one asynchronous kernel chain (init, gates, sampling records, shots, histogram compaction, results
+into pinned memory) and the host only synchronises with an engine when it needs it for the next circuit.
+A circuit that outgrows one SM's shared memory is redone on a full engine (grid path).
+Across GPUs the batch is split by circuit index (``i % world == rank``), one process per GPU, no data-path
+collective; per-circuit counts are gathered on the host.
 
 The reference runs one circuit per ``jku_simulator`` process, sequentially
 (``qiskit_jku_provider/qasm_simulator_jku.py:340-359``).
 """
 
-import threading
-from concurrent.futures import ThreadPoolExecutor
+import ctypes as C
 
-from .engine import Engine, circuit_ops
+import numpy as np
+
+from . import _native
+from .engine import OP_DTYPE, Engine, circuit_ops
 from .jkusimulatorerror import JKUSimulatorError
-
-# small pools: a circuit that outgrows them is redone on the shared big engine
-SMALL = dict(node_capacity=1 << 15, value_capacity=1 << 13, item_capacity=1 << 15, gc_min=1 << 12)
 
 
 class BatchRunner:
     def __init__(self, workers=64, device=0, small=None, big=None):
+        """``workers``: engines in the pool (circuits in flight); ``small``: jkq_config fields of the pool engines;
+        ``big``: options of the fall-back Engine."""
+        self._lib = _native.load()
         self.device = int(device)
         self.workers = int(workers)
-        self.small = dict(SMALL, **(small or {}))
+        cfg = _native.JkqConfig()
+        cfg.device = self.device
+        for k, v in (small or {}).items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown engine option %r" % k)
+            setattr(cfg, k, v)
+        self._b = C.c_void_p()
+        rc = self._lib.jkq_batch_create(C.byref(self._b), self.device, self.workers, C.byref(cfg))
+        if rc != 0:
+            msg = self._lib.jkq_batch_last_error(self._b).decode() if self._b else "no usable CUDA device"
+            if self._b:
+                self._lib.jkq_batch_destroy(self._b)
+                self._b = None
+            raise JKUSimulatorError("jkq_batch_create failed (%d): %s" % (rc, msg))
         self.big_opts = dict(big or {})
-        self._local = threading.local()
-        self._engines = []
-        self._lock = threading.Lock()
         self._big = None
-        self._big_lock = threading.Lock()
-        self._pool = ThreadPoolExecutor(max_workers=self.workers)
         self.fallbacks = 0
-
-    def _engine(self):
-        e = getattr(self._local, "engine", None)
-        if e is None:
-            e = Engine(device=self.device, **self.small)
-            self._local.engine = e
-            with self._lock:
-                self._engines.append(e)
-        return e
-
-    def _run_one(self, job):
-        idx, circ, shots, seed = job
-        ops = circuit_ops(circ)
-        eng = self._engine()
-        try:
-            eng.load_ops(circ.n, ops)
-            eng.run(shots, seed)
-            keys, vals = eng.counts_arrays()
-            st = eng.stats()
-        except JKUSimulatorError:
-            with self._big_lock:  # the DD outgrew the small pools: one big engine, serialised
-                if self._big is None:
-                    self._big = Engine(device=self.device, **self.big_opts)
-                self.fallbacks += 1
-                self._big.load_ops(circ.n, ops)
-                self._big.run(shots, seed)
-                keys, vals = self._big.counts_arrays()
-                st = self._big.stats()
-        return idx, dict(zip(keys.tolist(), vals.tolist())), st["gates"], st["apply_ms"]
 
     def run(self, circuits, shots=1024, seed=1, rank=0, world=1):
         """Runs ``circuits[i]`` for ``i % world == rank``; returns {i: {outcome: count}}, total gate applies,
         sum of the per-circuit device times in ms.  Circuit i samples with seed ``seed + i``."""
-        jobs = [(i, c, shots, seed + i) for i, c in enumerate(circuits) if i % world == rank]
-        out, gates, dev_ms = {}, 0, 0.0
-        for idx, counts, g, ms in self._pool.map(self._run_one, jobs):
-            out[idx] = counts
-            gates += g
-            dev_ms += ms
-        return out, gates, dev_ms
+        mine = [i for i in range(len(circuits)) if i % world == rank]
+        if not mine:
+            return {}, 0, 0.0
+        arrs = [circuit_ops(circuits[i]) for i in mine]
+        offs = np.zeros(len(mine) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(a) for a in arrs])
+        ops = np.ascontiguousarray(np.concatenate(arrs) if len(arrs) > 1 else arrs[0], dtype=OP_DTYPE)
+        nq = np.array([circuits[i].n for i in mine], dtype=np.uint32)
+        seeds = np.array([seed + i for i in mine], dtype=np.uint64)
+        cap = int(max(1, min(shots, 1 << 16)))
+        keys = np.zeros((len(mine), cap), dtype=np.uint64)
+        cnts = np.zeros((len(mine), cap), dtype=np.uint64)
+        nd = np.zeros(len(mine), dtype=np.uint32)
+        status = np.zeros(len(mine), dtype=np.int32)
+        gates, ms = C.c_uint64(0), C.c_double(0)
+        u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+        import time
+        t0 = time.perf_counter()
+        rc = self._lib.jkq_batch_run(self._b, len(mine), nq.ctypes.data_as(u32p), ops.ctypes.data_as(C.POINTER(_native.JkqOp)),
+                                     offs.ctypes.data_as(u64p), int(shots), seeds.ctypes.data_as(u64p), cap,
+                                     keys.ctypes.data_as(u64p), cnts.ctypes.data_as(u64p), nd.ctypes.data_as(u32p),
+                                     status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(gates), C.byref(ms))
+        self.native_s = time.perf_counter() - t0  # time inside the C call (launches + waits), without the dict building
+        if rc != 0:
+            raise JKUSimulatorError("jkq_batch_run failed (%d): %s" % (rc, self._lib.jkq_batch_last_error(self._b).decode()))
+        self.last_fast_path_error = self._lib.jkq_batch_last_error(self._b).decode() if status.any() else ""
+        out, total_gates, dev_ms = {}, int(gates.value), float(ms.value)
+        for j, i in enumerate(mine):
+            if status[j] == 0:
+                k = int(nd[j])
+                out[i] = dict(zip(keys[j, :k].tolist(), cnts[j, :k].tolist()))
+                continue
+            # outgrew one SM's shared memory (or the small pools): the full engine, grid path included
+            if self._big is None:
+                try:
+                    self._big = Engine(device=self.device, **self.big_opts)
+                except JKUSimulatorError as e:
+                    raise JKUSimulatorError("%s (batch fast path said: %s)" % (e, self.last_fast_path_error))
+            self.fallbacks += 1
+            self._big.load_ops(circuits[i].n, arrs[j])
+            self._big.run(shots, seed + i)
+            out[i] = self._big.counts()
+            st = self._big.stats()
+            total_gates += st["gates"]
+            dev_ms += st["apply_ms"]
+        return out, total_gates, dev_ms
 
     def close(self):
-        self._pool.shutdown(wait=True)
-        for e in self._engines:
-            e.close()
-        self._engines = []
+        if getattr(self, "_b", None):
+            self._lib.jkq_batch_destroy(self._b)
+            self._b = None
         if self._big is not None:
             self._big.close()
             self._big = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -184,6 +185,7 @@ struct jkq_handle {
   uint32_t *mat_epoch = nullptr;
   uint32_t n_mats = 0, mats_cap = 0;
   size_t gates_cap = 0;
+  JGate *gates_pin = nullptr;       // pinned staging copy of `gates` (truly asynchronous H2D)
   std::vector<jkq_op> ops;
   std::vector<JGate> gates;         // GATE ops only
   std::vector<int> gate_of_op;      // ops index -> number of gates before it
@@ -256,6 +258,7 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
   cudaFree(h->mat_u); cudaFree(h->mat_epoch);
   cudaFree(h->n_out); cudaFree(h->overflow);
+  if (h->gates_pin) cudaFreeHost(h->gates_pin);
   free_hist(h);
   free_snapshots(h);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
@@ -351,26 +354,26 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   return fail(h, JKQ_E_ARGUMENT, "unknown option %s", name);
 }
 
-extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *ops, size_t n_ops) {
-  if (!h) return JKQ_E_ARGUMENT;
-  if (n_qubits < 1 || n_qubits > JKQ_MAXQ) return fail(h, JKQ_E_ARGUMENT, "n_qubits must be 1..%d", JKQ_MAXQ);
-  if (n_ops && !ops) return JKQ_E_ARGUMENT;
-  CU(cudaSetDevice(h->device));
-  h->n = n_qubits;
-  h->ops.assign(ops, ops + n_ops);
-  h->gates.clear();
-  h->gate_of_op.clear();
+// ops -> gate descriptors (level roles, index of the matrix among the distinct matrices of the circuit) and the
+// measurement map.  Returns 0 or JKQ_E_ARGUMENT with a message in *err.
+static int parse_ops(std::string *err, uint32_t n_qubits, const jkq_op *ops, size_t n_ops, std::vector<JGate> &gates, std::vector<int> *gate_of_op,
+                     SampleParams &sp, uint32_t *n_mats, bool *has_snapshot) {
+  char buf[128];
+  if (n_qubits < 1 || n_qubits > JKQ_MAXQ) { snprintf(buf, sizeof(buf), "n_qubits must be 1..%d", JKQ_MAXQ); *err = buf; return JKQ_E_ARGUMENT; }
   bool any_measure = false;
+  if (has_snapshot) *has_snapshot = false;
   std::vector<std::array<double, 8>> mats;
-  for (int L = 0; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
+  for (int L = 0; L < JKQ_MAXQ; L++) sp.bitpos[L] = 255;
   const uint64_t qmask = n_qubits == 64 ? ~0ull : ((1ull << n_qubits) - 1);
   for (size_t i = 0; i < n_ops; i++) {
     const jkq_op &o = ops[i];
-    h->gate_of_op.push_back((int)h->gates.size());
+    if (gate_of_op) gate_of_op->push_back((int)gates.size());
     if (o.kind == JKQ_OP_GATE) {
       if (o.target >= n_qubits || ((o.ctrl_pos | o.ctrl_neg) & ~qmask) || ((o.ctrl_pos | o.ctrl_neg) >> o.target & 1) ||
-          (o.ctrl_pos & o.ctrl_neg))
-        return fail(h, JKQ_E_ARGUMENT, "op %zu: bad target/control qubits", i);
+          (o.ctrl_pos & o.ctrl_neg)) {
+        snprintf(buf, sizeof(buf), "op %zu: bad target/control qubits", i); *err = buf;
+        return JKQ_E_ARGUMENT;
+      }
       JGate g;
       memset(&g, 0, sizeof(g));
       memcpy(g.m, o.m, sizeof(g.m));
@@ -391,35 +394,63 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
         if (!memcmp(mats[mid].data(), o.m, sizeof(o.m))) break;
       if (mid == mats.size()) { std::array<double, 8> a; memcpy(a.data(), o.m, sizeof(o.m)); mats.push_back(a); }
       g.pad = (int32_t)mid;
-      h->gates.push_back(g);
+      gates.push_back(g);
     } else if (o.kind == JKQ_OP_MEASURE) {
-      if (o.target >= n_qubits || o.arg >= 64) return fail(h, JKQ_E_ARGUMENT, "op %zu: bad measure", i);
-      h->sp.bitpos[n_qubits - 1 - o.target] = (uint8_t)o.arg;
+      if (o.target >= n_qubits || o.arg >= 64) { snprintf(buf, sizeof(buf), "op %zu: bad measure", i); *err = buf; return JKQ_E_ARGUMENT; }
+      sp.bitpos[n_qubits - 1 - o.target] = (uint8_t)o.arg;
       any_measure = true;
-    } else if (o.kind != JKQ_OP_SNAPSHOT && o.kind != JKQ_OP_BARRIER) {
-      return fail(h, JKQ_E_ARGUMENT, "op %zu: unknown kind %u", i, o.kind);
+    } else if (o.kind == JKQ_OP_SNAPSHOT) {
+      if (has_snapshot) *has_snapshot = true;
+    } else if (o.kind != JKQ_OP_BARRIER) {
+      snprintf(buf, sizeof(buf), "op %zu: unknown kind %u", i, o.kind); *err = buf;
+      return JKQ_E_ARGUMENT;
     }
   }
   if (!any_measure)  // engine-level default: every qubit, key bit q = qubit q
-    for (uint32_t q = 0; q < n_qubits && q < 64; q++) h->sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
+    for (uint32_t q = 0; q < n_qubits && q < 64; q++) sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
+  if (n_mats) *n_mats = (uint32_t)mats.size();
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *ops, size_t n_ops) {
+  if (!h) return JKQ_E_ARGUMENT;
+  if (n_ops && !ops) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  h->gates.clear();
+  h->gate_of_op.clear();
+  uint32_t n_mats = 0;
+  {
+    std::string err;
+    int rc = parse_ops(&err, n_qubits, ops, n_ops, h->gates, &h->gate_of_op, h->sp, &n_mats, nullptr);
+    if (rc) return fail(h, rc, "%s", err.c_str());
+  }
+  h->n = n_qubits;
+  h->ops.assign(ops, ops + n_ops);
   // device copies of the gate list: buffers are kept and only grow (cudaFree synchronises the whole device,
   // which would serialise the engines of a batch)
-  h->n_mats = (uint32_t)mats.size();
+  h->n_mats = n_mats;
   if (h->n_mats > h->mats_cap) {
     cudaFree(h->mat_u); cudaFree(h->mat_epoch);
     h->mat_u = nullptr; h->mat_epoch = nullptr;
     h->mats_cap = pow2_at_least(h->n_mats, 64);
     CU(cudaMalloc(&h->mat_u, (size_t)h->mats_cap * 4 * 8));
     CU(cudaMalloc(&h->mat_epoch, (size_t)h->mats_cap * 4));
+    // never cleared again: an entry is valid only if it carries the CURRENT value epoch, which init bumps per circuit
+    CU(cudaMemsetAsync(h->mat_epoch, 0, (size_t)h->mats_cap * 4, h->stream));
   }
   if (h->gates.size() > h->gates_cap) {
     cudaFree(h->gates_dev);
-    h->gates_dev = nullptr;
+    if (h->gates_pin) cudaFreeHost(h->gates_pin);
+    h->gates_dev = nullptr; h->gates_pin = nullptr;
     h->gates_cap = pow2_at_least(h->gates.size(), 256);
     CU(cudaMalloc(&h->gates_dev, h->gates_cap * sizeof(JGate)));
+    CU(cudaMallocHost(&h->gates_pin, h->gates_cap * sizeof(JGate)));
   }
-  if (!h->gates.empty())
-    CU(cudaMemcpyAsync(h->gates_dev, h->gates.data(), h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  if (!h->gates.empty()) {
+    // (the previous circuit's copy has completed: every path synchronises the stream before a new load)
+    memcpy(h->gates_pin, h->gates.data(), h->gates.size() * sizeof(JGate));
+    CU(cudaMemcpyAsync(h->gates_dev, h->gates_pin, h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  }
   h->loaded = true; h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
   return JKQ_E_OK;
 }
@@ -503,7 +534,6 @@ extern "C" int jkq_apply(jkq_handle *h) {
   }
   E.lvl_log = h->lvl_log;
   E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
-  if (h->n_mats) CU(cudaMemsetAsync(h->mat_epoch, 0, (size_t)h->n_mats * 4, h->stream));
   E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
@@ -786,6 +816,303 @@ extern "C" int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *
 extern "C" int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n) {
   if (!h || !clbit_of_level || n < h->n) return JKQ_E_ARGUMENT;
   memcpy(clbit_of_level, h->sp.bitpos, h->n);
+  return JKQ_E_OK;
+}
+
+// =============================================================================== batches of circuits
+// Independent circuits shard over SMs.  ONE persistent kernel, one CTA per engine of the pool
+// (at most one per SM: a CTA owns ~216 KB of shared memory); every CTA pulls circuits from a queue and runs
+// the whole path for each -- init, gates (single-CTA path), sampling records, shots, histogram compaction
+// into the result block -- without any host involvement in between.  A circuit the single-CTA path cannot
+// finish (frontier or DD too large) is reported in status[] and left to the caller's full engine.
+struct JBatchEng {   // device-side view of one engine of the pool
+  JEng *E;
+  JSNode *sn;
+  double *prob;
+  unsigned long long *hk, *hc;
+};
+struct JBatchCirc {
+  uint32_t n, n_gates;
+  uint64_t gate_off, seed;
+  SampleParams sp;
+};
+struct JBatchOut {
+  int32_t status;
+  uint32_t n_distinct;
+  uint64_t gates;
+};
+
+__global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const JBatchCirc *circ, const JGate *gates, unsigned int n_circ,
+                                                 unsigned int *next, uint64_t shots, uint32_t hslots, uint32_t cap, JBatchOut *out,
+                                                 unsigned long long *keys, unsigned long long *counts) {
+  __shared__ unsigned int s_i, s_cnt;
+  __shared__ int s_ovf;
+  const JBatchEng be = engs[blockIdx.x];
+  JEng *E = be.E;
+  for (;;) {
+    if (threadIdx.x == 0) s_i = atomicAdd(next, 1u);
+    __syncthreads();
+    const unsigned int i = s_i;
+    __syncthreads();
+    if (i >= n_circ) break;
+    const JBatchCirc cd = circ[i];
+    if (threadIdx.x == 0) { E->n = cd.n; E->lvl_log = nullptr; E->mat_u = nullptr; E->mat_epoch = nullptr; E->cursor_saved = 0; }
+    {
+      Ctx c = make_ctx<MODE_CTA>(E);
+      init_state<MODE_CTA>(c);
+      __threadfence();
+      __syncthreads();
+      if (cd.n_gates) run_gates<MODE_CTA>(c, gates + cd.gate_off, (int)cd.n_gates);
+    }
+    __threadfence();
+    __syncthreads();
+    int st = *(volatile int *)&E->status;
+    if (!st && (*(volatile int *)&E->next_gate < (int)cd.n_gates || *(volatile int *)&E->want_grid || *(volatile unsigned int *)&E->cursor_saved))
+      st = JKQ_ERR_ITEM_FULL;  // outgrew the single-CTA path
+    if (!st) {
+      Ctx c = make_ctx<MODE_CTA>(E);
+      build_sampling<MODE_CTA>(c, be.sn, be.prob);
+      __threadfence();
+      __syncthreads();
+      st = *(volatile int *)&E->status;
+      if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
+    }
+    unsigned int nd = 0;
+    if (!st) {
+      // MeasureAll x shots (Simulator.cpp:148-224): this CTA's threads walk the shots of the circuit
+      for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x) { be.hk[k] = JH_EMPTY; be.hc[k] = 0; }
+      if (threadIdx.x == 0) { s_cnt = 0; s_ovf = 0; }
+      __syncthreads();
+      const uint64_t rounded = (shots + 31) & ~31ull;
+      const uint32_t lane = threadIdx.x & 31;
+      for (uint64_t s = threadIdx.x; s < rounded; s += blockDim.x) {
+        const bool active = s < shots;
+        const uint64_t key = active ? sample_walk(be.sn, 1u, (int)cd.n, cd.sp.bitpos, cd.seed, s) : JH_EMPTY;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hk, be.hc, hslots - 1, key, __popc(peers), &s_ovf);
+      }
+      __syncthreads();
+      for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x)
+        if (be.hk[k] != JH_EMPTY) {
+          const unsigned int p = atomicAdd(&s_cnt, 1u);
+          if (p < cap) { keys[(size_t)i * cap + p] = be.hk[k]; counts[(size_t)i * cap + p] = be.hc[k]; }
+        }
+      __syncthreads();
+      nd = s_cnt;
+      if (s_ovf || nd > cap) st = 103;  // JKQ_E_CAPACITY
+    }
+    if (threadIdx.x == 0) {
+      JBatchOut o;
+      o.status = st; o.n_distinct = nd; o.gates = (uint64_t)E->st[JST_GATES];
+      out[i] = o;
+      E->status = 0; E->want_grid = 0; E->cursor_saved = 0;
+    }
+    __syncthreads();
+  }
+}
+
+struct jkq_batch {
+  int device = 0, sm_count = 0;
+  jkq_config cfg;
+  std::vector<jkq_handle *> eng;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  JBatchEng *engs_dev = nullptr;
+  unsigned int *next_dev = nullptr;
+  // grow-only device / pinned buffers of a run
+  JGate *gates_dev = nullptr, *gates_pin = nullptr;
+  size_t gates_cap = 0;
+  JBatchCirc *circ_dev = nullptr, *circ_pin = nullptr;
+  JBatchOut *out_dev = nullptr, *out_pin = nullptr;
+  size_t circ_cap = 0;
+  unsigned long long *res_dev = nullptr, *res_pin = nullptr;  // keys then counts
+  size_t res_cap = 0;
+  uint64_t hslots = 0;
+};
+
+extern "C" const char *jkq_batch_last_error(const jkq_batch *b) { return b ? b->err.c_str() : "null batch"; }
+
+extern "C" void jkq_batch_destroy(jkq_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  for (jkq_handle *h : b->eng) jkq_destroy(h);
+  cudaFree(b->engs_dev); cudaFree(b->next_dev); cudaFree(b->gates_dev); cudaFree(b->circ_dev); cudaFree(b->out_dev); cudaFree(b->res_dev);
+  if (b->gates_pin) cudaFreeHost(b->gates_pin);
+  if (b->circ_pin) cudaFreeHost(b->circ_pin);
+  if (b->out_pin) cudaFreeHost(b->out_pin);
+  if (b->res_pin) cudaFreeHost(b->res_pin);
+  if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+static int bfail(jkq_batch *b, int code, const char *what, cudaError_t e) {
+  b->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return code;
+}
+#define BCU(call)                                                       \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) return bfail(b, JKQ_E_CUDA, #call, e_);      \
+  } while (0)
+
+extern "C" int jkq_batch_create(jkq_batch **out, int device, int n_engines, const jkq_config *cfg_in) {
+  if (!out || n_engines < 1) return JKQ_E_ARGUMENT;
+  *out = nullptr;
+  jkq_batch *b = new jkq_batch();
+  *out = b;
+  b->device = device;
+  jkq_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  if (cfg_in) cfg = *cfg_in;
+  cfg.device = device;
+  if (!cfg.node_capacity) cfg.node_capacity = 1u << 15;
+  if (!cfg.value_capacity) cfg.value_capacity = 1u << 13;
+  if (!cfg.item_capacity) cfg.item_capacity = 1u << 12;  // (the HBM frontier pool only serves the collector's scratch list here)
+  if (!cfg.gc_min) cfg.gc_min = 1u << 12;
+  if (!cfg.cta_threads) cfg.cta_threads = 128;
+  b->cfg = cfg;
+  BCU(cudaSetDevice(device));
+  BCU(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (n_engines > b->sm_count) n_engines = b->sm_count;  // one CTA per SM: more engines would only queue
+  for (int i = 0; i < n_engines; i++) {
+    jkq_handle *h = nullptr;
+    int rc = jkq_create(&h, &cfg);
+    if (rc) {
+      b->err = h ? h->err : "jkq_create failed";
+      if (h) jkq_destroy(h);
+      return rc;
+    }
+    b->eng.push_back(h);
+  }
+  BCU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  BCU(cudaEventCreate(&b->ev0));
+  BCU(cudaEventCreate(&b->ev1));
+  BCU(cudaMalloc(&b->engs_dev, b->eng.size() * sizeof(JBatchEng)));
+  BCU(cudaMalloc(&b->next_dev, 4));
+  BCU(cudaFuncSetAttribute(k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  // the control blocks of the engines: written once (the kernel initialises the per-circuit part itself)
+  for (jkq_handle *h : b->eng) {
+    JEng &E = h->host;
+    E.lvl_log = nullptr; E.mat_u = nullptr; E.mat_epoch = nullptr;
+    BCU(cudaMemcpy(h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice));
+  }
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_qubits, const jkq_op *ops, const uint64_t *op_offsets,
+                             uint64_t shots, const uint64_t *seeds, size_t cap, uint64_t *keys, uint64_t *counts, uint32_t *n_distinct,
+                             int32_t *status, uint64_t *gates_applied, double *apply_ms_sum) {
+  if (!b || !n_qubits || !ops || !op_offsets || !seeds || !keys || !counts || !n_distinct || !status || cap == 0) return JKQ_E_ARGUMENT;
+  BCU(cudaSetDevice(b->device));
+  b->err.clear();
+  if (gates_applied) *gates_applied = 0;
+  if (apply_ms_sum) *apply_ms_sum = 0;
+  if (n_circuits == 0) return JKQ_E_OK;
+  // ---- host: parse every circuit into gate descriptors (concatenated) + a descriptor per circuit
+  std::vector<JGate> gates;
+  std::vector<JBatchCirc> cd(n_circuits);
+  std::vector<int32_t> pre(n_circuits, 0);
+  int max_measured = 0;
+  for (size_t i = 0; i < n_circuits; i++) {
+    JBatchCirc &c = cd[i];
+    memset(&c, 0, sizeof(c));
+    c.n = n_qubits[i]; c.gate_off = gates.size(); c.seed = seeds[i];
+    std::string err;
+    bool snap = false;
+    const size_t before = gates.size();
+    int rc = parse_ops(&err, n_qubits[i], ops + op_offsets[i], (size_t)(op_offsets[i + 1] - op_offsets[i]), gates, nullptr, c.sp, nullptr, &snap);
+    if (!rc && snap) { rc = JKQ_E_ARGUMENT; err = "snapshots are not served by the batch path"; }
+    if (rc) {  // left out of the launch
+      gates.resize(before);
+      c.n = 1; c.n_gates = 0;
+      pre[i] = rc;
+      if (b->err.empty()) b->err = err;
+      continue;
+    }
+    c.n_gates = (uint32_t)(gates.size() - before);
+    int measured = 0;
+    for (uint32_t L = 0; L < c.n; L++) measured += c.sp.bitpos[L] < 64;
+    if (measured > max_measured) max_measured = measured;
+  }
+  // ---- buffers (grow-only)
+  uint64_t distinct = shots < (1ull << 30) ? shots : (1ull << 30);
+  if (max_measured < 30 && (1ull << max_measured) < distinct) distinct = 1ull << max_measured;
+  const uint64_t hslots = pow2_at_least(distinct * 2, 1u << 10);
+  if (hslots > b->hslots) {
+    for (jkq_handle *h : b->eng) {
+      free_hist(h);
+      CU(cudaMalloc(&h->hk, hslots * 8));
+      CU(cudaMalloc(&h->hc, hslots * 8));
+      h->hslots = hslots;
+    }
+    b->hslots = hslots;
+    std::vector<JBatchEng> be(b->eng.size());
+    for (size_t e = 0; e < b->eng.size(); e++) {
+      jkq_handle *h = b->eng[e];
+      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hk = h->hk; be[e].hc = h->hc;
+    }
+    BCU(cudaMemcpy(b->engs_dev, be.data(), be.size() * sizeof(JBatchEng), cudaMemcpyHostToDevice));
+  }
+  if (gates.size() > b->gates_cap) {
+    cudaFree(b->gates_dev);
+    if (b->gates_pin) cudaFreeHost(b->gates_pin);
+    b->gates_cap = pow2_at_least(gates.size(), 1024);
+    BCU(cudaMalloc(&b->gates_dev, b->gates_cap * sizeof(JGate)));
+    BCU(cudaMallocHost(&b->gates_pin, b->gates_cap * sizeof(JGate)));
+  }
+  if (n_circuits > b->circ_cap) {
+    cudaFree(b->circ_dev); cudaFree(b->out_dev);
+    if (b->circ_pin) cudaFreeHost(b->circ_pin);
+    if (b->out_pin) cudaFreeHost(b->out_pin);
+    b->circ_cap = pow2_at_least(n_circuits, 64);
+    BCU(cudaMalloc(&b->circ_dev, b->circ_cap * sizeof(JBatchCirc)));
+    BCU(cudaMalloc(&b->out_dev, b->circ_cap * sizeof(JBatchOut)));
+    BCU(cudaMallocHost(&b->circ_pin, b->circ_cap * sizeof(JBatchCirc)));
+    BCU(cudaMallocHost(&b->out_pin, b->circ_cap * sizeof(JBatchOut)));
+  }
+  const size_t res_words = 2 * n_circuits * cap;
+  if (res_words > b->res_cap) {
+    cudaFree(b->res_dev);
+    if (b->res_pin) cudaFreeHost(b->res_pin);
+    b->res_cap = res_words;
+    BCU(cudaMalloc(&b->res_dev, res_words * 8));
+    BCU(cudaMallocHost(&b->res_pin, res_words * 8));
+  }
+  // ---- one launch
+  memcpy(b->gates_pin, gates.data(), gates.size() * sizeof(JGate));
+  memcpy(b->circ_pin, cd.data(), n_circuits * sizeof(JBatchCirc));
+  BCU(cudaMemcpyAsync(b->gates_dev, b->gates_pin, gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, b->stream));
+  BCU(cudaMemcpyAsync(b->circ_dev, b->circ_pin, n_circuits * sizeof(JBatchCirc), cudaMemcpyHostToDevice, b->stream));
+  BCU(cudaMemsetAsync(b->next_dev, 0, 4, b->stream));
+  const unsigned int blocks = (unsigned int)(n_circuits < b->eng.size() ? n_circuits : b->eng.size());
+  BCU(cudaEventRecord(b->ev0, b->stream));
+  k_batch<<<blocks, b->cfg.cta_threads, sizeof(CtaSmem), b->stream>>>(b->engs_dev, b->circ_dev, b->gates_dev, (unsigned int)n_circuits, b->next_dev,
+                                                                     shots, (uint32_t)hslots, (uint32_t)cap, b->out_dev, b->res_dev,
+                                                                     b->res_dev + n_circuits * cap);
+  BCU(cudaGetLastError());
+  BCU(cudaEventRecord(b->ev1, b->stream));
+  BCU(cudaMemcpyAsync(b->out_pin, b->out_dev, n_circuits * sizeof(JBatchOut), cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaMemcpyAsync(b->res_pin, b->res_dev, res_words * 8, cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaStreamSynchronize(b->stream));
+  uint64_t total = 0;
+  for (size_t i = 0; i < n_circuits; i++) {
+    const JBatchOut &o = b->out_pin[i];
+    status[i] = pre[i] ? pre[i] : o.status;
+    n_distinct[i] = 0;
+    if (status[i]) {
+      if (b->err.empty()) b->err = "circuit " + std::to_string(i) + ": " + (o.status == 103 ? "more distinct outcomes than `cap`" : status_text(o.status));
+      continue;
+    }
+    n_distinct[i] = o.n_distinct;
+    memcpy(keys + i * cap, b->res_pin + i * cap, (size_t)o.n_distinct * 8);
+    memcpy(counts + i * cap, b->res_pin + (n_circuits + i) * cap, (size_t)o.n_distinct * 8);
+    total += o.gates;
+  }
+  if (gates_applied) *gates_applied = total;
+  float ms = 0;
+  if (apply_ms_sum && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *apply_ms_sum = ms;
   return JKQ_E_OK;
 }
 
