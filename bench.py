@@ -102,24 +102,40 @@ def cpu_reference_run(circ, runs):
 
 
 def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU engine on the host cores, same metric and config.
+    The reference is single-threaded and gate application does not shard, so N GPUs are mirrored the way our
+    own arm is: N independent replicas of the circuit, here N concurrent processes on N host cores (weak
+    scaling), value = N x applies / slowest replica."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    oracle.build()
     circ = workload()
-    kind, _ = cpu_reference_run(circ, max(0, args.warmup))
+    kind = "reference" if oracle.have_reference() else "port"
+    fn = oracle.run_reference if kind == "reference" else oracle.run_oracle
+    replicas = max(1, args.gpus)
+
+    def one_step():
+        with ThreadPoolExecutor(replicas) as ex:
+            return max(r["t_apply_s"] for r in ex.map(lambda _: fn(circ), range(replicas)))
+
+    for _ in range(max(0, args.warmup)):
+        one_step()
     t0 = time.perf_counter()
-    kind, times = cpu_reference_run(circ, args.steps)
+    times = [one_step() for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     t = sum(times) / len(times)
-    value = len(circ) / t
-    sample = "%s: full QFT-32 circuit (2528 applies) x %d runs, apply loop timed inside the engine (std::chrono), 1 thread" % (
-        "oracle/_ref/jku_ref = unmodified reference engine, MPFR 200-bit" if kind == "reference" else "oracle/qmdd_oracle.c FP64 port", args.steps)
+    value = replicas * len(circ) / t
+    sample = "%s: full QFT-32 circuit (2528 applies) x %d steps x %d concurrent replica process(es), apply loop timed inside the engine (std::chrono), 1 thread each" % (
+        "oracle/_ref/jku_ref = unmodified reference engine, MPFR 200-bit" if kind == "reference" else "oracle/qmdd_oracle.c FP64 port", args.steps, replicas)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "mpfr200" if kind == "reference" else "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "host_threads": 1, "note": "the reference engine is single-threaded"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD, "host_threads": replicas, "note": "the reference engine is single-threaded; one replica process per GPU of our arm"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall}))
 
@@ -268,6 +284,34 @@ def main():
                     best = cur
             best["algorithmic_bytes_per_shot"] = (c2.n + 1) * 32
             extra["sampling_" + name] = best
+        # batch of independent circuits (BASELINE configs[4]): sharded over the SMs of each GPU and over the GPUs
+        from qiskit_jku_provider_b200.batch import BatchRunner
+        from qiskit_jku_provider_b200.engine import circuit_ops
+        n_batch = 1024
+        batch = [C.random_circuit(18, 40, s) for s in range(n_batch)]
+        for c2 in batch:
+            circuit_ops(c2)
+        with BatchRunner(workers=148, device=local) as br:
+            br.run(batch, shots=1024, seed=1, rank=rank, world=world)  # warm-up: sizes every buffer
+            barrier()
+            t2 = time.perf_counter()
+            _, b_gates, b_ms = br.run(batch, shots=1024, seed=1, rank=rank, world=world)
+            barrier()
+            b_wall = time.perf_counter() - t2
+            fb = br.fallbacks
+        tt = torch.tensor([float(b_gates), b_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            g_all = tt.clone()
+            dist.all_reduce(g_all, op=dist.ReduceOp.SUM)
+            m_all = tt.clone()
+            dist.all_reduce(m_all, op=dist.ReduceOp.MAX)
+            b_gates, b_ms = float(g_all[0]), float(m_all[1])
+        extra["batch_1024_random18_40"] = {
+            "circuits": n_batch, "shots_each": 1024, "gate_applies": int(b_gates), "kernel_ms_max_over_ranks": b_ms,
+            "gate_applies_per_s_kernel": b_gates / (b_ms * 1e-3), "wall_s_host_ops_in_counts_out": b_wall,
+            "gate_applies_per_s_wall": b_gates / b_wall, "circuits_per_s_wall": n_batch / b_wall, "engines_per_gpu": 148,
+            "full_engine_fallbacks_rank0": fb,
+            "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue; circuits split i % world == rank"}
         if rank == 0:
             for c3 in (C.ghz(24), C.grover(20, 20), C.random_circuit(18, 100, 1), C.random_circuit(18, 120, 1)):
                 eng.load(c3)
