@@ -260,6 +260,21 @@ def main():
         bw = eng.random_sector_bench(1 << 32, 3) if rank == 0 else None
         if rank == 0:
             extra["random_sector"] = bw
+        # shot-sampling sweep (BASELINE configs[4]): kernel time only, shots sharded over the ranks
+        sweep = {}
+        for name, c2, counts_list in (("ghz24", C.ghz(24), (10 ** 6, 10 ** 7, 10 ** 8, 10 ** 9)), ("qft32", circ, (10 ** 6, 10 ** 7, 10 ** 8))):
+            eng.load(c2)
+            eng.apply()
+            for shots in counts_list:
+                lo, hi = multi_gpu.shard(shots, rank, world)
+                eng.sample(hi - lo, seed=7, shot_offset=lo)
+                k_ms = eng.stats()["sample_kernel_ms"]
+                if dist is not None:
+                    t = torch.tensor([k_ms], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    k_ms = float(t[0])
+                sweep["%s_%.0e" % (name, shots)] = {"shots": shots, "kernel_ms_max_over_ranks": k_ms, "shots_per_s_kernel": shots / (k_ms * 1e-3)}
+        extra["sampling_sweep"] = sweep
         for name, c2, shots in (("ghz24", C.ghz(24), 10 ** 8), ("qft32", circ, 10 ** 7)):
             best = None
             for _ in range(3):

@@ -88,6 +88,21 @@ def test_qft32_full_size(eng, oracle_mod):
     assert abs(eng.stats()["norm"] - 1.0) < 1e-4
 
 
+def test_grover20_801_iterations(eng):
+    """BASELINE config 3 at full length: 801 iterations = 81 722 applies (the last count at which the reference
+    itself stays at 39 nodes).  2 nodes per level throughout, success probability
+    sin^2((2k+1) asin(2^-10)) = 0.99997."""
+    k = 801
+    circ = C.grover(20, k)
+    run(eng, circ, 4096, 2, 1, levels=False)
+    assert eng.level_counts() == [2] * 19 + [1]
+    p = np.sin((2 * k + 1) * np.arcsin(2.0 ** -10)) ** 2
+    assert abs(abs(eng.amplitudes(0x5A5A5, 1)[0]) ** 2 - p) < 1e-6 and p > 0.9999
+    counts = eng.counts()
+    assert counts.get(0x5A5A5, 0) >= 4090
+    assert abs(eng.stats()["norm"] - 1.0) < 1e-6
+
+
 def test_grover20_full_size(eng, oracle_mod):
     """BASELINE config 3: n = 20, native 19-control Z, 2 nodes per level; 60 iterations here (the
     801-iteration run is bench.py's job), checked against the oracle and the analytic success
