@@ -242,7 +242,10 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     jsyncwarp();
     int lsw = 0, wide_L = -1;
     uint32_t icount = 0, blocked = 0;
+    JPROF_T(sp0);
     uint32_t f = cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);
+    JPROF_T(sp1);
+    JPROF_ADD(c, 11, sp0, sp1);
     uint32_t b = 0, e = icount;
     int lowest = lsw + 1;
     if (!f) {
@@ -253,13 +256,20 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
         if (c.ltid == 0) lr_set<MODE>(c, L, b, e);
         lowest = L;
         f = solo_level<MODE, true>(c, g, b, e, L);
+        JPROF_INC(c, 15);
         if (f) break;
         b = e; e = rd_items<MODE>(c);
       }
     }
+    JPROF_T(sp2);
+    JPROF_ADD(c, 12, sp1, sp2);
     if (!f && wide_L < 0) {
       for (int L = lowest; L <= lsw && !f; L++) f = solo_level<MODE, false>(c, g, lr_begin<MODE>(c, L), lr_end<MODE>(c, L), L);
+      JPROF_T(sp3);
+      JPROF_ADD(c, 13, sp2, sp3);
       if (!f) f = cursor_finish<MODE>(c, lsw, blocked);
+      JPROF_T(sp4);
+      JPROF_ADD(c, 14, sp3, sp4);
     }
     if (c.ltid == 0) {
       hand->lsw = (uint32_t)lsw; hand->blocked = blocked; hand->wide_L = wide_L; hand->wide_b = b; hand->wide_low = lowest;

@@ -770,9 +770,9 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
           E.prof[6], E.prof[6] ? E.prof[8] / E.prof[6] : 0, E.prof[6] ? E.prof[0] / E.prof[6] : 0, E.prof[6] ? E.prof[2] / E.prof[6] : 0,
           E.prof[6] ? E.prof[3] / E.prof[6] : 0, E.prof[6] ? E.prof[4] / E.prof[6] : 0, E.prof[6] ? E.prof[5] / E.prof[6] : 0,
           E.prof[6] ? E.prof[1] / E.prof[6] : 0, E.prof[6] ? (double)E.prof[7] / E.prof[6] : 0.0, E.prof[9]);
-  if (E.prof[13])
-    fprintf(stderr, "  thin ascent per level (%llu levels): loads %llu  reduce_core %llu  whole-after-loads %llu\n", E.prof[13], E.prof[10] / E.prof[13],
-            E.prof[11] / E.prof[13], E.prof[12] / E.prof[13]);
+  if (E.prof[6])
+    fprintf(stderr, "  per gate: cursor_prepare %llu  solo expand %llu  solo reduce %llu  cursor_finish %llu | solo levels/gate %.2f  wide gates %llu\n",
+            E.prof[11] / E.prof[6], E.prof[12] / E.prof[6], E.prof[13] / E.prof[6], E.prof[14] / E.prof[6], (double)E.prof[15] / E.prof[6], E.prof[10]);
 #endif
   h->stats.gates = E.st[JST_GATES]; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
   h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];

@@ -273,10 +273,11 @@ template <int MODE> JD void jset_error_c(Ctx &c, int code) { jset_error<MODE>(c.
 //            tol of it -- then it is dropped, and its proposers find the lower one on retry.
 // Which values enter the table therefore depends only on the SET of values proposed in the phase.
 //
-// The arithmetic and table functions are deliberately NOT inlined (JNI): a gate on a small DD is one
-// warp running a long dependent chain, and with everything inlined the kernel grew to 0.7 MB of SASS --
-// instruction-cache misses, not data latency, then set the pace.  They take (E, S, ring) by value so
-// that the caller's context stays in registers.
+// Inlining policy (measured on B200, QFT-32): a call costs the single warp ~100 cycles, so the table
+// functions that run once or twice per item (unique table, item de-dup, the real lookups inside cx_arith)
+// are inlined; the complex arithmetic itself (cx_arith, ~55 call sites) is not: inlining it as well buys
+// 1 % and takes the kernels from 25 k to 90 k instructions and the build from 1 to 5 minutes.  Out-of-line
+// functions take (E, S, ring) by value so that the caller's context stays in registers.
 #define JKQ_VAL_MAX 1.0e8
 #define JV_MISS 0xFFFFFFFFu
 #define JW_MISS 0xFFFFFFFFFFFFFFFFull
@@ -361,7 +362,7 @@ template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, do
 }
 
 // index of the entry within tol of x (x >= 0), or JV_MISS; with `propose` a miss leaves x as a candidate
-template <int MODE> JNI uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
+template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
   const double tol = jtol2<MODE>(E, S);
   if (x <= tol) return 0;
   if (!(x < JKQ_VAL_MAX)) {  // absurd magnitude
@@ -572,7 +573,7 @@ template <int MODE> JD JNode node_load(const Ctx &c, uint32_t id) {
 JD uint32_t ut_hash3(uint32_t c0, uint32_t c1, uint64_t w) { return hfin(c0 * 0x9E3779B1u + c1 * 0x85EBCA77u + hw64(w)); }
 JD uint32_t ut_hash(const JNode &n) { return ut_hash3(n.c0, n.c1, n.w); }
 
-template <int MODE> JNI uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_t c0, uint32_t c1, uint64_t w) {
+template <int MODE> JD uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_t c0, uint32_t c1, uint64_t w) {
   JNode rec;
   rec.c0 = c0; rec.c1 = c1; rec.w = w;
   if (MODE == MODE_CTA) {
@@ -694,7 +695,7 @@ template <int MODE> JD bool item_key_eq(const JItem *o, uint32_t a, uint32_t b, 
 }
 
 template <int MODE>
-JNI uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
   if ((tag & 15u) == JK_M) return dt_find_or_insert_m<MODE>(E, S, items, a);
   uint32_t mine = JI_FAIL;
   if (MODE == MODE_CTA) {
