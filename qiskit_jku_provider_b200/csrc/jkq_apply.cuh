@@ -97,6 +97,26 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
 #endif
 
 // ------------------------------------------------------------------------------------ level phases
+// Work of level L = the items created for it by the level above ([b, e), minus those that belong further
+// down) plus the items that chain compression (expand_item) parked for it.
+template <int MODE> JD uint32_t defer_count(const Ctx &c, int L) {
+  if (MODE != MODE_CTA) return 0;
+  const uint32_t n = ld_r<MODE>(&c.sh->defer_n[L]);
+  return n < JKQ_SDEFER ? n : JKQ_SDEFER;
+}
+// item index of work slot j of level L (JI_FAIL: nothing to do in this slot)
+template <int MODE> JD uint32_t level_item(const Ctx &c, int L, uint32_t b, uint32_t e, uint32_t j) {
+  uint32_t i;
+  if (j < e - b) i = b + j;
+  else {
+    if (MODE != MODE_CTA) return JI_FAIL;
+    i = c.sh->defer[L][j - (e - b)];
+    if (i == 0xFFFFu) return JI_FAIL;
+  }
+  const uint32_t lvl = (ld_i<MODE>(&c.items[i].tag) >> 8) & 0xFFu;
+  return (lvl == 0 || lvl == (uint32_t)L + 1u) ? i : JI_FAIL;  // (an item of [b, e) parked for a lower level)
+}
+
 // One level of the generic path: run every item of [b, e), and while some item met a value that is
 // not in the table yet, commit the proposed values (vals_commit) and run those items again.
 template <int MODE, bool expand>
@@ -104,7 +124,10 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   for (uint32_t round = 0;; round++) {
     uint32_t my = 0;
     JPROF_T(pt0);
-    for (uint32_t i = b + c.tid; i < e; i += c.nth) {
+    const uint32_t nwork = e - b + defer_count<MODE>(c, L);
+    for (uint32_t j = c.tid; j < nwork; j += c.nth) {
+      const uint32_t i = level_item<MODE>(c, L, b, e, j);
+      if (i == JI_FAIL) continue;
       JItem *it = c.items + i;
       uint32_t fl = ld_i<MODE>(&it->flags);
       const uint32_t st = fl & 3u;
@@ -147,9 +170,10 @@ template <int MODE> JD uint32_t lr_end(const Ctx &c, int L) { return MODE == MOD
 // committed warp-locally.  Returns 0 or barrier flags.
 template <int MODE, bool expand>
 JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
-  const uint32_t i = b + c.ltid;
-  JItem *it = c.items + i;
-  bool need = i < e;
+  const uint32_t nwork = e - b + defer_count<MODE>(c, L);
+  const uint32_t i = c.ltid < nwork ? level_item<MODE>(c, L, b, e, c.ltid) : JI_FAIL;
+  JItem *it = c.items + (i == JI_FAIL ? 0 : i);
+  bool need = i != JI_FAIL;
   uint32_t fl = 0;
   if (need) { fl = ld_i<MODE>(&it->flags); need = (fl & 3u) != JS_DEAD; }
   for (;;) {
@@ -238,6 +262,10 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       if (c.ltid == 0) c.sh->gen = 1;
       jsyncwarp();
     }
+    if (MODE == MODE_CTA) {  // chain-compression scratch of the previous gate
+      for (uint32_t L = c.ltid; L < (uint32_t)n; L += JKQ_WARP) c.sh->defer_n[L] = 0;
+      if (c.ltid == 0) { c.sh->chain_n = 0; c.sh->min_def = 0x7FFFFFFF; }
+    }
     if (c.ltid == 0) gate_setup<MODE>(c, g);
     jsyncwarp();
     int lsw = 0, wide_L = -1;
@@ -251,10 +279,12 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     if (!f) {
       if (c.ltid == 0) *cnt_items<MODE>(c) = icount;
       jsyncwarp();
-      for (int L = lsw; L >= 0 && e > b; L--) {
-        if (e - b > JKQ_WARP) { wide_L = L; break; }
+      for (int L = lsw; L >= 0 && (e > b || (MODE == MODE_CTA && ld_r<MODE>(&c.sh->min_def) <= L)); L--) {
+        const uint32_t nwork = e - b + defer_count<MODE>(c, L);
+        if (nwork > JKQ_WARP) { wide_L = L; break; }
         if (c.ltid == 0) lr_set<MODE>(c, L, b, e);
         lowest = L;
+        if (nwork == 0) continue;  // a level skipped by chain compression
         f = solo_level<MODE, true>(c, g, b, e, L);
         JPROF_INC(c, 15);
         if (f) break;
@@ -264,7 +294,11 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     JPROF_T(sp2);
     JPROF_ADD(c, 12, sp1, sp2);
     if (!f && wide_L < 0) {
-      for (int L = lowest; L <= lsw && !f; L++) f = solo_level<MODE, false>(c, g, lr_begin<MODE>(c, L), lr_end<MODE>(c, L), L);
+      for (int L = lowest; L <= lsw && !f; L++) {
+        const uint32_t lb = lr_begin<MODE>(c, L), le = lr_end<MODE>(c, L);
+        if (le - lb + defer_count<MODE>(c, L) == 0) continue;
+        f = solo_level<MODE, false>(c, g, lb, le, L);
+      }
       JPROF_T(sp3);
       JPROF_ADD(c, 13, sp2, sp3);
       if (!f) f = cursor_finish<MODE>(c, lsw, blocked);
@@ -303,7 +337,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
   uint32_t b = ld_s<MODE>(&hand->wide_b), e = rd_items<MODE>(c);
   int lowest = ld_s<MODE>(&hand->wide_low);
   if (MODE == MODE_CTA && e - b > item_limit) return JF_GRID;
-  for (int L = wide_L; L >= 0 && e > b; L--) {
+  for (int L = wide_L; L >= 0 && (e > b || (MODE == MODE_CTA && c.sh->min_def <= L)); L--) {
     if (c.block0 && c.ltid == 0) lr_set<MODE>(c, L, b, e);
     lowest = L;
     uint32_t f = run_level<MODE, true>(c, g, b, e, L);

@@ -79,7 +79,7 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #endif
 
 // ------------------------------------------------------------------------------------ MODE_CTA state
-#define JKQ_SITEMS 640u      // work items of one gate
+#define JKQ_SITEMS 512u      // work items of one gate
 #define JKQ_SDT_SLOTS 2048u  // F/S de-dup slots (generation << 16 | item index + 1)
 #define JKQ_SNODES 2048u     // node ids held in shared memory; the collector keeps ids below this
 #define JKQ_SUT_SLOTS 4096u  // unique-table slots (u32 node id)
@@ -87,6 +87,8 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SVT_SLOTS 2048u  // value-table slots
 #define JKQ_SPEND 512u       // value-table slots claimed in one phase
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
+#define JKQ_SCHAIN 1024u     // scratch words of compressed chains (per gate)
+#define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
   uint32_t node_limit, val_limit, pad4, pad5;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
@@ -103,6 +105,11 @@ struct CtaState {
   double tol, inv_tol;
   uint64_t cur_u[4];
   uint32_t lb[JKQ_MAXQ + 1], le[JKQ_MAXQ + 1];
+  uint32_t defer_n[JKQ_MAXQ];               // chain compression: items waiting for level L ...
+  uint16_t defer[JKQ_MAXQ][JKQ_SDEFER];     // ... their indices (0xFFFF: slot reserved but not needed)
+  uint32_t chain_n;
+  int32_t min_def;                          // lowest level with a waiting item
+  unsigned long long chain[JKQ_SCHAIN];     // per chain: bit mask of norm flags, then the k weights
   JGate gate[2];
   uint32_t mtag[JKQ_SMATS];
   uint64_t mu[JKQ_SMATS][4];
@@ -695,7 +702,9 @@ template <int MODE> JD bool item_key_eq(const JItem *o, uint32_t a, uint32_t b, 
 }
 
 template <int MODE>
-JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag) {
+JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, uint32_t b, uint64_t wa, uint64_t wb, uint64_t wc, uint32_t tag,
+                              bool *created = nullptr) {
+  if (created) *created = false;
   if ((tag & 15u) == JK_M) return dt_find_or_insert_m<MODE>(E, S, items, a);
   uint32_t mine = JI_FAIL;
   if (MODE == MODE_CTA) {
@@ -711,7 +720,7 @@ JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, ui
           jfence<MODE>();
         }
         uint32_t old = jatomic_cas(&S->dtab[h], s, gen | (mine + 1));
-        if (old == s) return mine;
+        if (old == s) { if (created) *created = true; return mine; }
         s = old;
       }
       const uint32_t j = (s & 0xFFFFu) - 1;
@@ -736,7 +745,7 @@ JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, ui
         jfence<MODE>();
       }
       unsigned long long old = jatomic_cas(E->dtab + h, s, gen | (unsigned long long)(mine + 1));
-      if (old == s) return mine;
+      if (old == s) { if (created) *created = true; return mine; }
       s = old;
     }
     const uint32_t j = (uint32_t)s - 1;
@@ -754,6 +763,9 @@ JD uint32_t dt_find_or_insert(JEng *E, CtaState *S, JItem *items, uint32_t a, ui
 template <int MODE, class T> JD T ld_i(const T *p) { return ld_r<MODE>(p); }
 
 // ------------------------------------------------------------------------------------ child slots
+#define JFLAG_CHAIN 0x100u  // ch[0] = the one child item several levels down, ch[1] = skipped levels | scratch offset << 8
+// level of an F / S item: bits 8..15 of its tag hold level + 1 (0: not recorded -- M items)
+JD uint32_t tag_level(uint32_t tag, int level) { return (tag & 0xFFu) | ((uint32_t)(level + 1) << 8); }
 struct Slot {
   uint32_t kind, target;
   uint64_t w;
@@ -788,7 +800,7 @@ JD bool combine_sum(Ctx &c, int m, uint64_t al, uint32_t A, uint64_t be, uint32_
   if (A > B) { uint32_t t = A; A = B; B = t; uint64_t tw = al; al = be; be = tw; }
   uint64_t r;
   if (!cdiv<MODE>(c, be, al, &r)) return false;
-  slot_ref(s, al, A, B, JW_ONE, r, 0, JK_S);
+  slot_ref(s, al, A, B, JW_ONE, r, 0, tag_level(JK_S, m));
   return true;
 }
 
@@ -807,7 +819,7 @@ JD bool combine(Ctx &c, int low, int m, uint64_t al, uint32_t A, uint64_t be, ui
   if (!(o1 && o2 && o3)) return false;
   uint32_t An = (wa != 0 || (sel == 0 && wc != 0)) ? A : 0;
   uint32_t Bn = (wb != 0 || (sel == 1 && wc != 0)) ? B : 0;
-  slot_ref(s, f, An, Bn, wa, wb, wc, JK_F | (sel << 4));
+  slot_ref(s, f, An, Bn, wa, wb, wc, tag_level(JK_F | (sel << 4), m));
   return true;
 }
 
@@ -853,7 +865,7 @@ JD bool expand_child(Ctx &c, const JGate &g, int L, int i, uint32_t kind, uint32
       if (!cmul<MODE>(c, iwc, aw, &ga)) return false;
       slot_pass(s, ac, ga);
     } else if (L - 1 >= g.low) {
-      slot_ref(s, aw, ac, ac, iwa, iwb, iwc, tag);
+      slot_ref(s, aw, ac, ac, iwa, iwb, iwc, tag_level(tag, L - 1));
     } else {
       uint64_t sum, w;
       if (!cadd<MODE>(c, iwa, iwb, &sum)) return false;
@@ -879,6 +891,13 @@ JD bool expand_child(Ctx &c, const JGate &g, int L, int i, uint32_t kind, uint32
 // Top-down step for one work item of level L: compute its two child slots.  Side effects (de-dup
 // inserts) only after all arithmetic succeeded, so a retry simply runs the function again.
 JD uint32_t item_flags(uint32_t state, uint32_t k0, uint32_t k1, uint32_t hint) { return state | (k0 << 2) | (k1 << 4) | (hint << 6); }
+
+// all non-zero edges of the node lead to ONE child?  (two edges to the same node, or one edge and the zero edge)
+JD bool chain_node(const JNode &n, uint32_t *child) {
+  if (n.w != 0) { *child = n.c1; return nd_c0(n) == n.c1; }
+  *child = nd_flag(n) ? n.c1 : nd_c0(n);
+  return true;
+}
 
 // returns the new flags word of the item (state JS_DONE or JS_RETRY)
 template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
@@ -916,6 +935,53 @@ template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx
   if (kind != JK_M) {
     iwa = ld_i<MODE>(&it->wa); iwb = ld_i<MODE>(&it->wb); iwc = ld_i<MODE>(&it->wc);
     if (ib) nb = (ib == ia) ? na : node_load<MODE>(c, ib);
+  }
+  uint32_t chain_c = 0;
+  if (MODE == MODE_CTA && kind == JK_F && ia == ib && ia != 0 && role == JR_IDLE && L - 1 >= g.low && chain_node(na, &chain_c)) {
+    // Chain compression.  Both operands are the same node, all its non-zero edges go to the same child c
+    // (a basis-state node with one zero edge, or a product-state node with two edges to one child), and the
+    // level carries no control: the item's only child is the same key on c, and the result is the old node
+    // over that child's result with the top weight passed through.  For the states of QFT / GHZ-like
+    // circuits that repeats level after level down to the next control: walk the chain of such
+    // nodes once, keep their (norm flag, weight) in scratch, and refer directly to the item at its end --
+    // reduce_item rebuilds the chain in one go.  The skipped levels cost a node load and a unique-table
+    // insert each instead of two phases.
+    CtaState *S = c.sh;
+    uint32_t cur = chain_c, k = 0;
+    int Lc = L - 1;
+    while (Lc > g.low && g.role[Lc] == JR_IDLE && k < 60) {
+      const JNode nd = node_load<MODE>(c, cur);
+      uint32_t nxt;
+      if (!chain_node(nd, &nxt)) break;
+      cur = nxt; k++; Lc--;
+    }
+    if (k >= 1) {
+      const uint32_t off = jatomic_add(&S->chain_n, k + 1u);
+      const uint32_t dn = off + k + 1u <= JKQ_SCHAIN ? jatomic_add(&S->defer_n[Lc], 1u) : JKQ_SDEFER;
+      if (dn < JKQ_SDEFER) {
+        unsigned long long mask = 0;
+        uint32_t cur2 = chain_c;
+        for (uint32_t j = 0; j < k; j++) {
+          const JNode nd = node_load<MODE>(c, cur2);
+          S->chain[off + 1 + j] = nd.w;
+          mask |= (unsigned long long)nd_flag(nd) << j;
+          chain_node(nd, &cur2);
+        }
+        S->chain[off] = mask;
+        bool created = false;
+        const uint32_t child = dt_find_or_insert<MODE>(c.E, S, c.items, cur, cur, iwa, iwb, iwc, tag_level(tag, Lc), &created);
+        S->defer[Lc][dn] = (child != JI_FAIL && created) ? (uint16_t)child : (uint16_t)0xFFFFu;
+        if (child == JI_FAIL) return JS_DONE;  // want_grid flagged; the gate is abandoned
+#ifndef JKQ_EMU
+        atomicMin(&S->min_def, Lc);
+#else
+        if (Lc < S->min_def) S->min_def = Lc;
+#endif
+        it->ch[0] = child; it->ch[1] = k | (off << 8); it->chw[0] = nd_w0(na); it->chw[1] = nd_w1(na);
+        return item_flags(JS_DONE, JC_REF, JC_REF, 1u + nd_flag(na)) | JFLAG_CHAIN;
+      }
+      // (scratch or waiting list full: the plain path below; readers clamp defer_n to JKQ_SDEFER)
+    }
   }
   Slot s0, s1;
   bool e0 = expand_child<MODE>(c, g, L, 0, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s0);
@@ -989,6 +1055,28 @@ JD bool reduce_core(Ctx &c, uint32_t rn[2], const uint64_t f[2], const uint64_t 
 
 template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx, uint32_t flags) {
   JItem *it = c.items + idx;
+  if (MODE == MODE_CTA && (flags & JFLAG_CHAIN)) {
+    // compressed chain (expand_item): rebuild the skipped nodes over the child's result, bottom-up
+    const JItem *ci = c.items + ld_i<MODE>(&it->ch[0]);
+    const uint64_t f0 = ld_i<MODE>(&ci->rw);
+    uint32_t r = ld_i<MODE>(&ci->rnode);
+    if (f0 == 0) { it->rw = 0; it->rnode = 0; return true; }
+    const uint32_t info = ld_i<MODE>(&it->ch[1]), k = info & 0xFFu, off = info >> 8;
+    const unsigned long long mask = c.sh->chain[off];
+    for (uint32_t j = k; j-- > 0 && r != 0;) {
+      const uint32_t fl = (uint32_t)((mask >> j) & 1ull);
+      const uint64_t w = c.sh->chain[off + 1 + j];  // 0: the node's other edge is the zero edge
+      r = ut_find_or_insert<MODE>(c.E, c.sh, ((fl == 1 && w == 0) ? 0u : r) | (fl << 31), (fl == 0 && w == 0) ? 0u : r, w);
+    }
+    uint32_t rn[2] = {r, r};
+    const uint64_t f[2] = {f0, f0}, a[2] = {ld_i<MODE>(&it->chw[0]), ld_i<MODE>(&it->chw[1])};
+    uint32_t rnode;
+    uint64_t rw;
+    if (r == 0) { it->rw = f0; it->rnode = 0; return true; }  // a pool ran out: the sticky word is set
+    if (!reduce_core<MODE>(c, rn, f, a, (flags >> 6) & 3u, &rnode, &rw)) return false;
+    it->rw = rw; it->rnode = rnode;
+    return true;
+  }
   // each child edge is f_i * a_i: f_i = top weight of the child item's result (ONE for finished
   // edges), a_i = the factor / edge weight recorded at expansion
   uint32_t rn[2];
