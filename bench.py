@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the contract is ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
+os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "dd_gate_applies_per_s"
 UNIT = "gate-applies/s"
