@@ -483,7 +483,7 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
         uint32_t ch[2] = {nd_c0(nd), nd.c1};
         for (int k = 0; k < 2; k++)
           if (ch[k] != 0 && jatomic_cas(E->fwd + ch[k], 0u, 0xFFFFFFFFu) == 0) {
-            uint32_t pos = jatomic_add(&E->gc_count, 1u);
+            uint32_t pos = jagg_inc(&E->gc_count);
             list[pos] = ch[k];
             E->fwd[ch[k]] = pos + 1;
           }

@@ -157,6 +157,29 @@ struct Ctx {
   uint32_t ltid, lnth;
 };
 
+// Warp-aggregated increment of a counter that every lane of the warp may be bumping at this point: ONE atomic
+// per warp instead of up to 32 on the same address (the bump allocators and statistics of the grid path are
+// otherwise serialised by the L2 atomic unit).  Returns the lane's own slot.
+#ifdef JKQ_EMU
+JD uint32_t jagg_inc(uint32_t *p) { return (*p)++; }
+JD void jagg_stat(unsigned long long *p, uint32_t v) { *p += v; }
+#else
+JD uint32_t jagg_inc(uint32_t *p) {
+  const unsigned m = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)p);  // lanes bumping this very counter
+  const int leader = __ffs(m) - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(p, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+JD void jagg_stat(unsigned long long *p, uint32_t v) {
+  const unsigned m = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)p);
+  const uint32_t sum = __reduce_add_sync(m, v);
+  if ((int)(threadIdx.x & 31u) == __ffs(m) - 1) atomicAdd(p, (unsigned long long)sum);
+}
+#endif
+
 // counters nobody waits for: atomics whose result is unused compile to fire-and-forget RED instructions,
 // where a load-add-store would stall the (in-order) thread for an L2 round trip
 // (MODE_CTA counts in shared memory: a global memory operation in flight makes the next
@@ -173,7 +196,7 @@ template <int MODE> JD void jstat_max(JEng *E, CtaState *S, uint32_t v) {
 #else
 template <int MODE> JD void jstat(JEng *E, CtaState *S, int which, uint32_t v) {
   if (MODE == MODE_CTA) atomicAdd(&S->st[which], v);
-  else atomicAdd(&E->st[which], (unsigned long long)v);
+  else jagg_stat(&E->st[which], v);
 }
 template <int MODE> JD void jstat_max(JEng *E, CtaState *S, uint32_t v) {
   if (MODE == MODE_CTA) atomicMax(&S->st[JST_MAXF], v);
@@ -330,7 +353,7 @@ JD unsigned long long *vt_meta(JVSlot *s) { return reinterpret_cast<unsigned lon
 JD unsigned long long vt_meta_of(uint32_t keylo, uint32_t id1) { return (unsigned long long)keylo | ((unsigned long long)id1 << 32); }
 
 template <int MODE> JD void pend_push(JEng *E, CtaState *S, uint32_t ring, uint32_t slot) {
-  uint32_t i = jatomic_add(MODE == MODE_CTA ? &S->pend_n[ring] : &E->pend_n[ring], 1u);
+  uint32_t i = MODE == MODE_CTA ? jatomic_add(&S->pend_n[ring], 1u) : jagg_inc(&E->pend_n[ring]);
   if (MODE == MODE_CTA) {
     if (i < JKQ_SPEND) S->pend[i] = slot;
     else jwant_grid(S);
@@ -426,7 +449,7 @@ template <int MODE> JNI void vals_commit(JEng *E, CtaState *S, uint32_t par, uin
     }
     uint32_t id1 = JV_DROPPED;
     if (!drop) {
-      uint32_t idx = jatomic_add(MODE == MODE_CTA ? &S->val_count : &E->val_count, 1u);
+      uint32_t idx = MODE == MODE_CTA ? jatomic_add(&S->val_count, 1u) : jagg_inc(&E->val_count);
       if (MODE == MODE_CTA) {
         if (idx >= S->val_limit) jwant_grid(S);  // the shared table is full: grid path
         else { S->vals[idx] = v; id1 = idx + 1; jstat<MODE>(E, S, JST_VALS, 1u); }  // (copied to HBM by cta_flush)
@@ -612,7 +635,7 @@ template <int MODE> JD uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_t
     uint32_t s = ld_r<MODE>(E->utab + h);
     if (s == 0) {
       if (mine == 0) {
-        mine = jatomic_add(&E->node_count, 1u);
+        mine = jagg_inc(&E->node_count);
         if (mine >= E->node_cap) { jset_error<MODE>(E, S, JKQ_ERR_NODE_FULL); return 0; }
         E->nodes[mine] = rec;
         jfence<MODE>();
@@ -650,7 +673,7 @@ template <int MODE> JD uint32_t item_alloc(JEng *E, CtaState *S) {
     if (mine >= JKQ_SITEMS) { jwant_grid(S); return JI_FAIL; }
     return mine;
   }
-  uint32_t mine = jatomic_add(&E->item_count, 1u);
+  uint32_t mine = jagg_inc(&E->item_count);
   if (mine >= E->item_cap) { jset_error<MODE>(E, S, JKQ_ERR_ITEM_FULL); return JI_FAIL; }
   return mine;
 }
@@ -797,7 +820,16 @@ JD bool combine_sum(Ctx &c, int m, uint64_t al, uint32_t A, uint64_t be, uint32_
   }
   if (al == 0) { slot_pass(s, B, be); return true; }
   if (be == 0) { slot_pass(s, A, al); return true; }
-  if (A > B) { uint32_t t = A; A = B; B = t; uint64_t tw = al; al = be; be = tw; }
+  // Operand order of the memo key.  The reference orders by pointer value (QMDDpackage.cpp:1331-1335) and
+  // can afford any ratio y.w/x.w in 200-bit reals; here the operand with the larger weight comes first, so the
+  // ratio has magnitude <= 1 (a deep random circuit otherwise produces ratios beyond the value table's
+  // range); equal magnitudes fall back to the node order.
+  bool swap = A > B;
+  if (al != be && al != jneg(be)) {
+    const double ma = jmag2<MODE>(c, al), mb = jmag2<MODE>(c, be);
+    if (ma != mb) swap = mb > ma;
+  }
+  if (swap) { uint32_t t = A; A = B; B = t; uint64_t tw = al; al = be; be = tw; }
   uint64_t r;
   if (!cdiv<MODE>(c, be, al, &r)) return false;
   slot_ref(s, al, A, B, JW_ONE, r, 0, tag_level(JK_S, m));
@@ -814,7 +846,13 @@ JD bool combine(Ctx &c, int low, int m, uint64_t al, uint32_t A, uint64_t be, ui
   if (al == 0 && be == 0 && ga == 0) { slot_zero(s); return true; }
   if (sel == 0 && be == 0 && al == ga) { slot_pass(s, A, ga); return true; }  // gate row acts as identity
   if (sel == 1 && al == 0 && be == ga) { slot_pass(s, B, ga); return true; }
+  // common factor: the largest of the three weights (first one on ties), so the key weights have magnitude <= 1
   uint64_t f = al ? al : (be ? be : ga), wa, wb, wc;
+  {
+    double mf = jmag2<MODE>(c, f);
+    if (be != 0 && be != f) { const double mb = jmag2<MODE>(c, be); if (mb > mf) { f = be; mf = mb; } }
+    if (ga != 0 && ga != f) { const double mg = jmag2<MODE>(c, ga); if (mg > mf) { f = ga; mf = mg; } }
+  }
   bool o1 = cdiv<MODE>(c, al, f, &wa), o2 = cdiv<MODE>(c, be, f, &wb), o3 = cdiv<MODE>(c, ga, f, &wc);
   if (!(o1 && o2 && o3)) return false;
   uint32_t An = (wa != 0 || (sel == 0 && wc != 0)) ? A : 0;

@@ -9,7 +9,8 @@ from qiskit_jku_provider_b200.engine import Engine
 cases = [(18, 120), (18, 140), (18, 160), (20, 160), (20, 200), (22, 200)]
 if len(sys.argv) > 1:
     cases = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
-eng = Engine(device=0, node_capacity=1 << 25, value_capacity=1 << 22)
+import os
+eng = Engine(device=0, node_capacity=1 << int(os.environ.get('NODE_LOG2', '25')), value_capacity=1 << int(os.environ.get('VAL_LOG2', '22')))
 for n, ops in cases:
     circ = C.random_circuit(n, ops, 1)
     eng.load(circ)
