@@ -38,7 +38,7 @@ JD void block_sync() {}
 #else
 JD void block_sync() { __syncthreads(); }
 
-// MODE_CTA: one __syncthreads.  MODE_GRID: sense-reversing counter barrier in HBM; the kernel is
+// MODE_CTA: one __syncthreads.  MODE_GRID: single-word arrival counter in HBM (see below); the kernel is
 // launched cooperatively (all CTAs co-resident).
 template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
   const uint32_t slot = c.ring, nxt = slot == 2 ? 0 : slot + 1;
@@ -65,19 +65,19 @@ template <int MODE> JD uint32_t sync_or(Ctx &c, uint32_t flags) {
     if (threadIdx.x == 0) {
       if (blockIdx.x < 1024) E->dbg_phase[blockIdx.x] = c.phase;
       if (r) atomicOr(&E->bar_flags[slot], r);
-      unsigned int gen = *(volatile unsigned int *)&E->bar_gen;
+      // One atomic per CTA on one word (the scheme of cooperative groups' grid.sync): CTA 0 adds what is
+      // missing to flip the top bit once everybody has arrived; everybody spins until the bit differs from
+      // the value its own arrival saw.  2.3k cycles on B200 against 4.1k for a count + generation pair.
+      if (blockIdx.x == 0) { E->bar_flags[nxt] = 0; E->pend_n[nxt] = 0; }  // next phase's word and counter: nobody uses them now
+      const unsigned int add = blockIdx.x == 0 ? 0x80000000u - (gridDim.x - 1u) : 1u;
       __threadfence();
-      if (atomicAdd(&E->bar_count, 1u) == gridDim.x - 1) {
-        E->bar_count = 0;
-        E->bar_flags[nxt] = 0;  // next phase's word and counter: nobody reads or writes them now
-        E->pend_n[nxt] = 0;
-        __threadfence();
-        atomicAdd(&E->bar_gen, 1u);
-      } else {
-        long long t0 = clock64();
-        while (*(volatile unsigned int *)&E->bar_gen == gen) {
-          __nanosleep(32);
-          if (clock64() - t0 > 8000000000ll) {
+      const unsigned int old = atomicAdd(&E->bar_count, add);
+      long long t0 = 0;
+      unsigned int spins = 0;
+      while (((old ^ *(volatile unsigned int *)&E->bar_count) & 0x80000000u) == 0) {
+        if ((++spins & 1023u) == 0) {
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) {
             if (atomicCAS(&E->status, 0, JKQ_ERR_BARRIER_TIMEOUT) == 0) E->dbg_timeout_block = blockIdx.x;
             break;
           }
