@@ -56,7 +56,7 @@ typedef struct {
   uint32_t reserved;
 } jkq_config;
 
-enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER = 3 };
+enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER = 3, JKQ_OP_MEASURE_ONE = 4, JKQ_OP_RESET = 5 };
 
 /* One operation of a circuit.
  *  GATE      2x2 matrix m (row major, re/im pairs) on `target`, applied where every qubit in ctrl_pos
@@ -66,7 +66,12 @@ enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER 
  *  SNAPSHOT  record the full state vector in slot `arg` (QASMsimulator.cpp:973-1037).
  *  MEASURE   qubit `target` -> classical bit `arg`; counts are sampled from the final state
  *            (QASMsimulator.cpp:487-500).
- *  BARRIER   no-op (QASMsimulator.cpp:944-949). */
+ *  BARRIER   no-op (QASMsimulator.cpp:944-949).
+ *  MEASURE_ONE  measure qubit `target` NOW and collapse the state (Simulator::MeasureOne, Simulator.cpp:226-289):
+ *            outcome drawn with P(0) = AssignProbsOne from the Philox stream (option "measure_seed", op index),
+ *            state projected and rescaled by 1/sqrt(p); the outcome goes to classical bit `arg`
+ *            (jkq_get_mid_measurements).
+ *  RESET     Simulator::ResetQubit (Simulator.cpp:341-413): MEASURE_ONE, then X if the outcome was 1. */
 typedef struct {
   uint32_t kind;
   uint32_t target;
@@ -123,6 +128,10 @@ int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count, double *re
 int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n);              /* Active[v] */
 int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_written);
 int jkq_get_stats(jkq_handle *h, jkq_stats *out);
+/* P(qubit reads 0) in the current state (Simulator::AssignProbsOne / GetProbability, Simulator.cpp:291-339, 433-464) */
+int jkq_get_qubit_probability(jkq_handle *h, uint32_t qubit, double *p0);
+/* outcomes of the MEASURE_ONE ops of the last jkq_apply: bit c of *bits = classical bit c, *mask = bits written */
+int jkq_get_mid_measurements(jkq_handle *h, uint64_t *bits, uint64_t *mask);
 
 /* multi-GPU shot sharding: export the level-ordered sampling DD, import it on another handle */
 int jkq_dd_export(jkq_handle *h, jkq_snode *host_nodes, size_t cap, uint32_t *n_nodes, uint32_t *root);

@@ -50,6 +50,8 @@ SYMBOLS = [
     ("jkq_get_level_counts", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t]),
     ("jkq_get_level_log", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
     ("jkq_get_stats", C.c_int, [_H, C.POINTER(JkqStats)]),
+    ("jkq_get_qubit_probability", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double)]),
+    ("jkq_get_mid_measurements", C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("jkq_dd_import", C.c_int, [_H, C.c_uint32, C.POINTER(JkqSNode), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     ("jkq_get_measure_map", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_size_t]),

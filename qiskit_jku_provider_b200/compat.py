@@ -287,6 +287,14 @@ class QuantumCircuit:
             return gate
         raise AttributeError(name)
 
+    def reset(self, q):
+        if isinstance(q, _Register):
+            for k in range(q.size):
+                self.reset(q[k])
+            return self
+        self.data.append(('reset', [], [self._qindex(q)], []))
+        return self
+
     def measure(self, q, c):
         if isinstance(q, _Register):
             for k in range(q.size):

@@ -69,6 +69,37 @@ __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *o
   }
 }
 
+// Simulator::AssignProbsOne (Simulator.cpp:291-339): probability that the qubit on `level` reads 0.  The arena
+// is level-ordered and the sampling records hold every node's branch probability, so the path mass is pushed
+// down from the root one level at a time; at `level` the masses times q0 add up to P(0).  One CTA.
+__global__ void __launch_bounds__(256) k_marginal(const JEng *E, const JSNode *sn, double *mass, int level, double *out) {
+  __shared__ double s_sum;
+  const int n = (int)E->n;
+  const uint32_t total = E->node_count;
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) mass[i] = 0.0;
+  if (threadIdx.x == 0) s_sum = 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) mass[E->root] = 1.0;
+  __syncthreads();
+  for (int L = n - 1; L > level; L--) {
+    const uint32_t off = E->lvl_off[L], cnt = E->lvl_cnt[L];
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const JSNode s = sn[off + i];
+      const double m = mass[off + i];
+      if (m == 0.0) continue;
+      if (s.q0 > 0.0) atomicAdd(&mass[s.c0], m * s.q0);
+      if (s.q0 < 1.0) atomicAdd(&mass[s.c1], m * (1.0 - s.q0));
+    }
+    __syncthreads();
+  }
+  double acc = 0.0;
+  const uint32_t off = E->lvl_off[level], cnt = E->lvl_cnt[level];
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += mass[off + i] * sn[off + i].q0;
+  atomicAdd(&s_sum, acc);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_sum;
+}
+
 struct SampleParams {
   uint8_t bitpos[JKQ_MAXQ];
 };
@@ -189,6 +220,9 @@ struct jkq_handle {
   std::vector<jkq_op> ops;
   std::vector<JGate> gates;         // GATE ops only
   std::vector<int> gate_of_op;      // ops index -> number of gates before it
+  uint64_t measure_seed = 1;        // Philox key of the mid-circuit measurement outcomes
+  uint64_t mid_bits = 0, mid_mask = 0;  // outcomes of MEASURE_ONE ops by classical bit
+  double *scalar_dev = nullptr;
   uint32_t n = 0;
   bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
   SampleParams sp;
@@ -256,7 +290,7 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
   cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.mdir); cudaFree(E.thin_spill); cudaFree(E.fwd); cudaFree(E.vfwd);
   cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
-  cudaFree(h->mat_u); cudaFree(h->mat_epoch);
+  cudaFree(h->mat_u); cudaFree(h->mat_epoch); cudaFree(h->scalar_dev);
   cudaFree(h->n_out); cudaFree(h->overflow);
   if (h->gates_pin) cudaFreeHost(h->gates_pin);
   free_hist(h);
@@ -329,6 +363,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   CU(cudaMalloc(&h->prob, (size_t)E.node_cap * 8));
   CU(cudaMalloc(&h->n_out, 8));
   CU(cudaMalloc(&h->overflow, 4));
+  CU(cudaMalloc(&h->scalar_dev, 8));
   CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   // cooperative grid size: every CTA must be resident
@@ -345,6 +380,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!h || !name) return JKQ_E_ARGUMENT;
   if (!strcmp(name, "level_log")) { h->level_log = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "force_mode")) { h->cfg.force_mode = (int)value; return JKQ_E_OK; }
+  if (!strcmp(name, "measure_seed")) { h->measure_seed = (uint64_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
     if (value < 1 || value > JKQ_SITEMS / 2) value = JKQ_SITEMS / 2;
@@ -401,6 +437,25 @@ static int parse_ops(std::string *err, uint32_t n_qubits, const jkq_op *ops, siz
       any_measure = true;
     } else if (o.kind == JKQ_OP_SNAPSHOT) {
       if (has_snapshot) *has_snapshot = true;
+    } else if (o.kind == JKQ_OP_MEASURE_ONE || o.kind == JKQ_OP_RESET) {
+      // MeasureOne / ResetQubit (Simulator.cpp:226-289, 341-413): one (two) single-qubit gate slot(s) whose
+      // matrix the host fills in once the outcome is drawn -- the projector scaled by 1/sqrt(p), and for a
+      // reset the X that takes |1> back to |0>
+      if (o.target >= n_qubits || (o.kind == JKQ_OP_MEASURE_ONE && o.arg >= 64)) { snprintf(buf, sizeof(buf), "op %zu: bad measure/reset", i); *err = buf; return JKQ_E_ARGUMENT; }
+      if (has_snapshot) *has_snapshot = true;  // (not served by the batch path either)
+      for (int rep = 0; rep < (o.kind == JKQ_OP_RESET ? 2 : 1); rep++) {
+        JGate g;
+        memset(&g, 0, sizeof(g));
+        g.m[0] = 1.0; g.m[6] = 1.0;
+        g.target = (int)(n_qubits - 1 - o.target);
+        g.low = g.top = g.target;
+        g.role[g.target] = JR_TARGET;
+        std::array<double, 8> a;  // a matrix slot of its own: the entries change from run to run
+        for (int k = 0; k < 8; k++) a[k] = -1.0 - (double)mats.size() - 0.001 * k;
+        mats.push_back(a);
+        g.pad = (int32_t)(mats.size() - 1);
+        gates.push_back(g);
+      }
     } else if (o.kind != JKQ_OP_BARRIER) {
       snprintf(buf, sizeof(buf), "op %zu: unknown kind %u", i, o.kind); *err = buf;
       return JKQ_E_ARGUMENT;
@@ -488,6 +543,7 @@ static int launch_gates(jkq_handle *h, bool grid, int upto) {
 
 // run gates [host.next_gate, upto): single-CTA path until a frontier outgrows it, then the grid path
 static int run_segment(jkq_handle *h, int upto) {
+  if (h->host.next_gate >= upto && !h->host.cursor_saved) return JKQ_E_OK;  // nothing left to apply
   bool grid = h->cfg.force_mode == 2;
   for (;;) {
     int rc = launch_gates(h, grid, upto);
@@ -519,6 +575,71 @@ static int run_segment(jkq_handle *h, int upto) {
   }
 }
 
+// Philox-4x32-10 on the host: the same stream the device sampler uses (jkq_sample.cuh), for the outcomes of
+// mid-circuit measurements.
+static double philox_uniform(uint64_t seed, uint64_t counter) {
+  uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0x4D454153u /* "MEAS" */, 0};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+}
+
+static int build_sampling_now(jkq_handle *h);
+
+// P(qubit reads 0) in the state as it is now (AssignProbsOne, Simulator.cpp:291-339)
+static int qubit_probability(jkq_handle *h, uint32_t qubit, double *p0) {
+  int rc = build_sampling_now(h);
+  if (rc) return rc;
+  k_marginal<<<1, 256, 0, h->stream>>>(h->dev, h->snodes, h->prob, (int)(h->n - 1 - qubit), h->scalar_dev);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(p0, h->scalar_dev, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->sampling_ready = false;  // (k_marginal used the probability array as scratch)
+  return JKQ_E_OK;
+}
+
+// MeasureOne / ResetQubit at op i (Simulator.cpp:226-289, 341-413): apply what precedes, get P(0), draw the
+// outcome, fill the matrices of the op's gate slot(s): projector / sqrt(p), then (reset) X when the outcome was 1.
+static int measure_collapse(jkq_handle *h, size_t i) {
+  const jkq_op &o = h->ops[i];
+  const int g0 = h->gate_of_op[i];
+  int rc = run_segment(h, g0);
+  if (rc) return rc;
+  double p0 = 0;
+  rc = qubit_probability(h, o.target, &p0);
+  if (rc) return rc;
+  if (p0 < 0) p0 = 0;
+  if (p0 > 1) p0 = 1;
+  const double u = philox_uniform(h->measure_seed, (uint64_t)i);
+  const int outcome = u < p0 ? 0 : 1;
+  const double p = outcome ? 1.0 - p0 : p0;
+  if (!(p > 0)) return fail(h, JKQ_E_ZERO_STATE, "measurement of qubit %u: outcome %d has probability 0", o.target, outcome);
+  JGate &g = h->gates[g0];
+  memset(g.m, 0, sizeof(g.m));
+  g.m[outcome ? 6 : 0] = 1.0 / sqrt(p);
+  CU(cudaMemcpyAsync(h->gates_dev + g0, &g, sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  int n_slots = 1;
+  if (o.kind == JKQ_OP_RESET) {
+    JGate &x = h->gates[g0 + 1];
+    memset(x.m, 0, sizeof(x.m));
+    if (outcome) { x.m[2] = 1.0; x.m[4] = 1.0; }
+    else { x.m[0] = 1.0; x.m[6] = 1.0; }
+    CU(cudaMemcpyAsync(h->gates_dev + g0 + 1, &x, sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+    n_slots = 2;
+  } else {
+    h->mid_mask |= 1ull << o.arg;
+    if (outcome) h->mid_bits |= 1ull << o.arg;
+  }
+  CU(cudaStreamSynchronize(h->stream));  // (the host copies of the gates are pageable)
+  return run_segment(h, g0 + n_slots);
+}
+
 extern "C" int jkq_apply(jkq_handle *h) {
   if (!h) return JKQ_E_ARGUMENT;
   if (!h->loaded) return fail(h, JKQ_E_STATE, "jkq_apply before jkq_load_circuit");
@@ -542,16 +663,21 @@ extern "C" int jkq_apply(jkq_handle *h) {
   k_init<MODE_GRID><<<1, 32, 0, h->stream>>>(h->dev);
   CU(cudaGetLastError());
   const uint64_t cta0 = h->stats.cta_launches, grid0 = h->stats.grid_launches;
+  h->mid_bits = 0; h->mid_mask = 0;
   size_t i = 0;
+  auto boundary = [](uint32_t k) { return k == JKQ_OP_SNAPSHOT || k == JKQ_OP_MEASURE_ONE || k == JKQ_OP_RESET; };
   while (i < h->ops.size()) {
-    if (h->ops[i].kind == JKQ_OP_GATE) {
+    const uint32_t kind = h->ops[i].kind;
+    if (kind == JKQ_OP_GATE) {
       size_t j = i;
-      while (j < h->ops.size() && h->ops[j].kind != JKQ_OP_SNAPSHOT) j++;
+      while (j < h->ops.size() && !boundary(h->ops[j].kind)) j++;
       int upto = j < h->ops.size() ? h->gate_of_op[j] : (int)h->gates.size();
       int rc = run_segment(h, upto);
       if (rc) return rc;
       i = j;
-    } else if (h->ops[i].kind == JKQ_OP_SNAPSHOT) {
+    } else if (kind == JKQ_OP_SNAPSHOT) {
+      int rc0 = run_segment(h, h->gate_of_op[i]);
+      if (rc0) return rc0;
       if (h->n > 30) return fail(h, JKQ_E_CAPACITY, "state-vector snapshot needs 2^%u amplitudes", h->n);
       double2 *buf = nullptr;
       uint64_t len = 1ull << h->n;
@@ -563,6 +689,10 @@ extern "C" int jkq_apply(jkq_handle *h) {
       if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
       k_amplitudes<<<blocks, 256, 0, h->stream>>>(h->dev, 0, len, buf);
       CU(cudaGetLastError());
+      i++;
+    } else if (kind == JKQ_OP_MEASURE_ONE || kind == JKQ_OP_RESET) {
+      int rc = measure_collapse(h, i);
+      if (rc) return rc;
       i++;
     } else {
       i++;
@@ -580,9 +710,15 @@ extern "C" int jkq_apply(jkq_handle *h) {
   return JKQ_E_OK;
 }
 
+static int build_sampling_now(jkq_handle *h);
 static int ensure_sampling(jkq_handle *h) {
   if (h->sampling_ready) return JKQ_E_OK;
   if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply or jkq_dd_import first");
+  return build_sampling_now(h);
+}
+
+// level-ordered compaction + bottom-up probabilities of the CURRENT state (also between the segments of a circuit)
+static int build_sampling_now(jkq_handle *h) {
   // level-ordered compaction + bottom-up probabilities; the CTA path first unless the DD is clearly too big for it
   bool grid = h->cfg.force_mode == 2 || (h->cfg.force_mode != 1 && h->host.node_count > 8 * JKQ_SNODES);
   JEng *E = h->dev;
@@ -779,6 +915,20 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF];
   h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;
   *out = h->stats;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_get_qubit_probability(jkq_handle *h, uint32_t qubit, double *p0) {
+  if (!h || !p0) return JKQ_E_ARGUMENT;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  if (qubit >= h->n) return fail(h, JKQ_E_ARGUMENT, "qubit %u out of range", qubit);
+  CU(cudaSetDevice(h->device));
+  return qubit_probability(h, qubit, p0);
+}
+
+extern "C" int jkq_get_mid_measurements(jkq_handle *h, uint64_t *bits, uint64_t *mask) {
+  if (!h || !bits || !mask) return JKQ_E_ARGUMENT;
+  *bits = h->mid_bits; *mask = h->mid_mask;
   return JKQ_E_OK;
 }
 

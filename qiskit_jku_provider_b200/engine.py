@@ -7,7 +7,7 @@ import numpy as np
 from . import _native
 from .jkusimulatorerror import JKUSimulatorError
 
-OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER = 0, 1, 2, 3
+OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER, OP_MEASURE_ONE, OP_RESET = 0, 1, 2, 3, 4, 5
 FINAL_SLOT = 0xFFFFFFFF
 
 SNODE_DTYPE = np.dtype([("c0", "<u4"), ("c1", "<u4"), ("q0", "<f8")])
@@ -194,6 +194,18 @@ class Engine:
         w = C.c_size_t(0)
         self._check(self._lib.jkq_get_level_log(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size, C.byref(w)))
         return out[:w.value].reshape(n_gates, self.n).tolist()
+
+    def qubit_probability(self, qubit):
+        """P(qubit reads 0) in the current state (Simulator::AssignProbsOne)."""
+        p = C.c_double(0)
+        self._check(self._lib.jkq_get_qubit_probability(self._h, int(qubit), C.byref(p)))
+        return p.value
+
+    def mid_measurements(self):
+        """{classical bit: outcome} of the MEASURE_ONE ops of the last apply."""
+        bits, mask = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.jkq_get_mid_measurements(self._h, C.byref(bits), C.byref(mask)))
+        return {c: (bits.value >> c) & 1 for c in range(64) if (mask.value >> c) & 1}
 
     def stats(self):
         s = _native.JkqStats()

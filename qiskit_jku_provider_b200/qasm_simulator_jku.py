@@ -18,7 +18,7 @@ import numpy as np
 
 from . import circuits
 from .compat import BackendConfiguration, BackendStatus, BaseBackend, Result
-from .engine import OP_BARRIER, OP_DTYPE, OP_GATE, OP_MEASURE, OP_SNAPSHOT, Engine
+from .engine import OP_BARRIER, OP_DTYPE, OP_GATE, OP_MEASURE, OP_RESET, OP_SNAPSHOT, Engine
 from .jkujob import JKUJob
 from .jkusimulatorerror import JKUSimulatorError
 
@@ -106,6 +106,7 @@ class JKUSimulatorWrapper:
         (``circuits.expand`` restates qelib1) and stamped onto the instruction's qubits; the result is one
         numpy structured array with the memory layout of ``jkq_op`` (include/jkq.h)."""
         kinds, targets, cpos, cneg, mats, args = [], [], [], [], [], []
+        self.per_shot = False
         self.max_snapshot_index = 0
         snapshot_slots = []
         zero_m = (0.0,) * 8
@@ -122,6 +123,11 @@ class JKUSimulatorWrapper:
                 kinds.append(OP_SNAPSHOT); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(slot)
             elif name == 'barrier':
                 kinds.append(OP_BARRIER); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
+            elif name == 'reset':
+                # ResetQubit (Simulator.cpp:341-413): its outcome is random, so the circuit is re-simulated per
+                # shot like the reference does when the state is not reusable (QASMsimulator.cpp:501-522)
+                self.per_shot = True
+                kinds.append(OP_RESET); targets.append(op.qubits[0]); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
             else:
                 params = tuple(getattr(op, 'params', None) or ())
                 qubits = op.qubits
@@ -160,8 +166,18 @@ class JKUSimulatorWrapper:
             print(RUN_MESSAGE)
         eng = self.engine
         eng.load_ops(n, ops)
-        eng.run(self.shots, self.seed)
-        output_data = self.collect_output(eng, measurement_data, slots, want_sv)
+        if self.per_shot:
+            # every shot is its own run: a fresh draw for each reset, one sample of the final state
+            merged = {}
+            for shot in range(int(self.shots)):
+                eng.set_option("measure_seed", (int(self.seed) * 1000003 + shot) & 0x7FFFFFFFFFFFFFFF)
+                eng.run(1, int(self.seed) + shot)
+                for k, v in eng.counts().items():
+                    merged[k] = merged.get(k, 0) + v
+            output_data = self.collect_output(eng, measurement_data, slots, want_sv, counts_override=merged)
+        else:
+            eng.run(self.shots, self.seed)
+            output_data = self.collect_output(eng, measurement_data, slots, want_sv)
         self.end_time = time.time()
         stats = eng.stats()
         result_dict = {'header': {'name': experiment.header.name,
@@ -176,7 +192,7 @@ class JKUSimulatorWrapper:
                        }
         return result_dict
 
-    def collect_output(self, eng, measurement_data, slots, want_sv):
+    def collect_output(self, eng, measurement_data, slots, want_sv, counts_override=None):
         """Counts as hex keys over the classical bits (reference convert_counts/qubits_to_clbits,
         :219-235) and snapshots in Qiskit order (:190-211).  The engine already keys outcomes by
         classical bit and indexes amplitudes with bit q = qubit q, so no bit-reversal table is needed."""
@@ -184,8 +200,11 @@ class JKUSimulatorWrapper:
         clbits_num = measurement_data['clbits_num']
         if clbits_num > 0:
             if measurement_data['mapping']:
-                keys, vals = eng.counts_arrays()
-                result['counts'] = {hex(int(k)): int(v) for k, v in zip(keys, vals)}
+                if counts_override is not None:
+                    result['counts'] = {hex(int(k)): int(v) for k, v in counts_override.items()}
+                else:
+                    keys, vals = eng.counts_arrays()
+                    result['counts'] = {hex(int(k)): int(v) for k, v in zip(keys, vals)}
             else:  # nothing measured: every shot reads all-zero classical bits
                 result['counts'] = {hex(0): int(self.shots)}
         else:

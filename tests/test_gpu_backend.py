@@ -199,3 +199,21 @@ def test_probabilities_output(backend):
     assert np.allclose(snaps['3']['probabilities'], [0.5, 0.5, 0, 0])
     assert set(snaps['4']['probabilities_ket']) == {'00', '11'}
     assert res.data()['counts'] == {}
+
+
+def test_reset_is_resimulated_per_shot():
+    """h q0; cx q0,q1; reset q0; measure: q0 always reads 0, q1 keeps the branch the reset collapsed it to --
+    a 50/50 mixture over shots (the reference re-simulates per shot, QASMsimulator.cpp:501-522)."""
+    from qiskit_jku_provider_b200 import JKUProvider
+    from qiskit_jku_provider_b200.compat import ClassicalRegister, QuantumCircuit, QuantumRegister, assemble
+    qr, cr = QuantumRegister(2, "q"), ClassicalRegister(2, "c")
+    qc = QuantumCircuit(qr, cr, name="reset")
+    qc.h(qr[0])
+    qc.cx(qr[0], qr[1])
+    qc.reset(qr[0])
+    qc.measure(qr, cr)
+    backend = JKUProvider().get_backend("qasm_simulator")
+    backend.silent = True
+    counts = backend.run(assemble(qc, shots=300, seed=5)).result().get_counts()
+    assert set(counts) <= {"00", "10"} and sum(counts.values()) == 300
+    assert 100 <= counts.get("00", 0) <= 200
