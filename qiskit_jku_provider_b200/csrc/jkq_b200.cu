@@ -107,8 +107,11 @@ struct SampleParams {
 #define JH_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define JH_SMEM 2048
 
+// (the all-ones outcome of a 64-bit register collides with the empty marker: it is counted in the extra word
+// hc[slots] behind the table)
 __device__ __forceinline__ void hist_global_add(unsigned long long *hk, unsigned long long *hc, uint32_t hmask, uint64_t key,
                                                 unsigned long long cnt, int *overflow) {
+  if (key == JH_EMPTY) { atomicAdd(hc + (size_t)hmask + 1, cnt); return; }
   uint32_t h = (uint32_t)jmix(key) & hmask;
   for (uint32_t probes = 0; probes <= hmask; probes++) {
     unsigned long long old = hk[h];
@@ -139,9 +142,10 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < rounded; s += stride) {
     const bool active = s < nshots;
     uint64_t key = active ? sample_walk(sn, root, n, sp.bitpos, seed, shot0 + s) : JH_EMPTY;
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
     if (!active || lane != (uint32_t)(__ffs(peers) - 1)) continue;
     uint32_t cnt = __popc(peers);
+    if (key == JH_EMPTY) { hist_global_add(hk, hc, hmask, key, cnt, overflow); continue; }
     uint32_t h = (uint32_t)jmix(key) & (JH_SMEM - 1);
     bool done = false;
     for (int p = 0; p < 8 && !done; p++) {
@@ -165,6 +169,7 @@ __global__ void k_hist_fill(unsigned long long *hk, unsigned long long *hc, uint
     hk[i] = JH_EMPTY;
     hc[i] = 0;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) hc[slots] = 0;
 }
 
 __global__ void k_hist_compact(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, unsigned long long *ok,
@@ -174,6 +179,10 @@ __global__ void k_hist_compact(const unsigned long long *hk, const unsigned long
       unsigned long long p = atomicAdd(n_out, 1ull);
       if (p < cap) { ok[p] = hk[i]; oc[p] = hc[i]; }
     }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) {
+    unsigned long long p = atomicAdd(n_out, 1ull);
+    if (p < cap) { ok[p] = JH_EMPTY; oc[p] = hc[slots]; }
   }
 }
 
@@ -775,7 +784,7 @@ extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t
     if (slots > h->hslots) {
       free_hist(h);
       CU(cudaMalloc(&h->hk, slots * 8));
-      CU(cudaMalloc(&h->hc, slots * 8));
+      CU(cudaMalloc(&h->hc, (slots + 1) * 8));
       h->hslots = slots;
     }
     k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots);
@@ -1031,14 +1040,14 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
     if (!st) {
       // MeasureAll x shots (Simulator.cpp:148-224): this CTA's threads walk the shots of the circuit
       for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x) { be.hk[k] = JH_EMPTY; be.hc[k] = 0; }
-      if (threadIdx.x == 0) { s_cnt = 0; s_ovf = 0; }
+      if (threadIdx.x == 0) { s_cnt = 0; s_ovf = 0; be.hc[hslots] = 0; }
       __syncthreads();
       const uint64_t rounded = (shots + 31) & ~31ull;
       const uint32_t lane = threadIdx.x & 31;
       for (uint64_t s = threadIdx.x; s < rounded; s += blockDim.x) {
         const bool active = s < shots;
         const uint64_t key = active ? sample_walk(be.sn, 1u, (int)cd.n, cd.sp.bitpos, cd.seed, s) : JH_EMPTY;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
         if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hk, be.hc, hslots - 1, key, __popc(peers), &s_ovf);
       }
       __syncthreads();
@@ -1047,6 +1056,10 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
           const unsigned int p = atomicAdd(&s_cnt, 1u);
           if (p < cap) { keys[(size_t)i * cap + p] = be.hk[k]; counts[(size_t)i * cap + p] = be.hc[k]; }
         }
+      if (threadIdx.x == 0 && be.hc[hslots]) {
+        const unsigned int p = atomicAdd(&s_cnt, 1u);
+        if (p < cap) { keys[(size_t)i * cap + p] = JH_EMPTY; counts[(size_t)i * cap + p] = be.hc[hslots]; }
+      }
       __syncthreads();
       nd = s_cnt;
       if (s_ovf || nd > cap) st = 103;  // JKQ_E_CAPACITY
@@ -1194,7 +1207,7 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
     for (jkq_handle *h : b->eng) {
       free_hist(h);
       CU(cudaMalloc(&h->hk, hslots * 8));
-      CU(cudaMalloc(&h->hc, hslots * 8));
+      CU(cudaMalloc(&h->hc, (hslots + 1) * 8));
       h->hslots = hslots;
     }
     b->hslots = hslots;

@@ -251,3 +251,28 @@ def test_cursor_handed_to_the_grid_path_when_the_cta_pools_run_out(oracle_mod):
                     assert abs(sum(lc) - sum(o["level_counts"])) <= 0.01 * sum(o["level_counts"]), (circ.name, limit)
                 else:
                     assert lc == o["level_counts"], (circ.name, limit)
+
+
+def test_maximum_width_64_qubits(eng):
+    """JKQ_MAXQ = 64 levels: 64-bit outcome keys, a 63-control gate, amplitudes addressed by a 64-bit index."""
+    eng.set_option("force_mode", 0)
+    eng.set_option("level_log", 0)
+    n = 64
+    eng.load(C.ghz(n))
+    eng.run(2000, 5)
+    c = eng.counts()
+    assert set(c) <= {0, (1 << n) - 1} and sum(c.values()) == 2000 and abs(c[0] - 1000) < 120
+    assert eng.level_counts() == [2] * (n - 1) + [1]
+    assert abs(abs(eng.amplitudes((1 << n) - 1, 1)[0]) ** 2 - 0.5) < 1e-12
+    circ = C.Circuit(n, name="mcz64")
+    for q in range(n):
+        circ.add("h", [q])
+    circ.ops.append(C.MCG("z", n - 1, list(range(n - 1))))
+    eng.load(circ)
+    eng.apply()
+    a0, a1 = eng.amplitudes(0, 1)[0], eng.amplitudes((1 << n) - 1, 1)[0]
+    # only |1...1> changes sign; 2^-32 = 2.3e-10 sits at the table tolerance (Ctol = 1e-10 absolute,
+    # QMDDcomplexD.cpp:336): (1/sqrt2)^63 and (1/sqrt2)^64 are one table entry, in the reference as well
+    assert a1 == -a0 and abs(abs(a0) - 2.0 ** -32) < 1.01e-10
+    assert eng.level_counts() == [2] * (n - 1) + [1]
+    assert abs(eng.qubit_probability(17) - 0.5) < 1e-12
