@@ -56,7 +56,10 @@ typedef struct {
   uint32_t reserved;
 } jkq_config;
 
-enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER = 3, JKQ_OP_MEASURE_ONE = 4, JKQ_OP_RESET = 5 };
+enum {
+  JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER = 3, JKQ_OP_MEASURE_ONE = 4, JKQ_OP_RESET = 5,
+  JKQ_OP_IF = 6, JKQ_OP_PROBABILITIES = 7
+};
 
 /* One operation of a circuit.
  *  GATE      2x2 matrix m (row major, re/im pairs) on `target`, applied where every qubit in ctrl_pos
@@ -71,7 +74,15 @@ enum { JKQ_OP_GATE = 0, JKQ_OP_SNAPSHOT = 1, JKQ_OP_MEASURE = 2, JKQ_OP_BARRIER 
  *            outcome drawn with P(0) = AssignProbsOne from the Philox stream (option "measure_seed", op index),
  *            state projected and rescaled by 1/sqrt(p); the outcome goes to classical bit `arg`
  *            (jkq_get_mid_measurements).
- *  RESET     Simulator::ResetQubit (Simulator.cpp:341-413): MEASURE_ONE, then X if the outcome was 1. */
+ *  RESET     Simulator::ResetQubit (Simulator.cpp:291-339): the reference's reset is a PROJECTION, not a measurement --
+ *            the state is projected on |0> of `target` and rescaled by 1/sqrt(P(0)); only when P(0) = 0 an X comes
+ *            first.  No random number is drawn.  Option "physical_reset" = 1 selects measure-then-X instead.
+ *  IF        `if (creg == k) qop;` (QASMsimulator.cpp:952-971): the next `arg` ops (0 reads as 1; GATE, MEASURE_ONE,
+ *            RESET or BARRIER) are executed only when (classical bits & ctrl_pos) == ctrl_neg, the classical bits
+ *            being the MEASURE_ONE outcomes so far (unwritten bits read 0).  The condition is evaluated once.
+ *  PROBABILITIES  record, in slot `arg`, the probability of every assignment of the qubits in the mask ctrl_pos
+ *            (Simulator::GetProbability per assignment, QASMsimulator.cpp:990-1011): 2^k doubles, bit j of the index =
+ *            the j-th lowest qubit of the mask (jkq_get_probabilities). */
 typedef struct {
   uint32_t kind;
   uint32_t target;
@@ -130,6 +141,8 @@ int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_writte
 int jkq_get_stats(jkq_handle *h, jkq_stats *out);
 /* P(qubit reads 0) in the current state (Simulator::AssignProbsOne / GetProbability, Simulator.cpp:291-339, 433-464) */
 int jkq_get_qubit_probability(jkq_handle *h, uint32_t qubit, double *p0);
+/* the 2^k probabilities a PROBABILITIES op recorded in `slot`; *n = 2^k (also when out is NULL or cap too small) */
+int jkq_get_probabilities(jkq_handle *h, uint32_t slot, double *out, size_t cap, size_t *n);
 /* outcomes of the MEASURE_ONE ops of the last jkq_apply: bit c of *bits = classical bit c, *mask = bits written */
 int jkq_get_mid_measurements(jkq_handle *h, uint64_t *bits, uint64_t *mask);
 
@@ -153,6 +166,37 @@ const char *jkq_batch_last_error(const jkq_batch *b);
 int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_qubits, const jkq_op *ops, const uint64_t *op_offsets,
                   uint64_t shots, const uint64_t *seeds, size_t cap, uint64_t *keys, uint64_t *counts, uint32_t *n_distinct,
                   int32_t *status, uint64_t *gates_applied, double *apply_ms_sum);
+
+/* OpenQASM 2.0 front end (host code): text -> the op list jkq_load_circuit takes.  Replaces the executing parser
+ * of the reference (src/QASMsimulator.cpp:895-1060, src/QASMscanner.cpp); the semantics it keeps and the points where
+ * it deliberately differs are listed at the top of csrc/jkq_qasm.cpp.  `measure` becomes MEASURE_ONE, `reset` RESET,
+ * `if` IF, `snapshot(k) q...` a PROBABILITIES op (flag JKQ_QASM_PROBABILITIES, --display_probabilities of main.cpp:84)
+ * and, when it lists every qubit, a SNAPSHOT op (flag JKQ_QASM_STATEVECTOR, --display_statevector), both in slot k;
+ * `show_probabilities;` a PROBABILITIES op over all qubits in slot JKQ_SLOT_SHOW_PROBABILITIES + i.
+ * `include "f";` reads include_dir/f, then ./f; "qelib1.inc" falls back to the built-in standard header.
+ * jkq_qasm_parse always sets *out (free it with jkq_program_free); on a syntax error it returns JKQ_E_ARGUMENT and
+ * jkq_program_error() gives the message with line and column. */
+typedef struct jkq_program jkq_program;
+enum { JKQ_QASM_STATEVECTOR = 1, JKQ_QASM_PROBABILITIES = 2 };
+#define JKQ_SLOT_SHOW_PROBABILITIES 0x80000000u
+typedef struct {
+  uint32_t n_qubits, n_clbits;
+  size_t n_ops;
+  const jkq_op *ops;           /* owned by the program */
+  uint32_t n_qregs, n_cregs, n_snapshots;
+  int32_t gate_after_measure;  /* a gate follows a measure: the reference re-simulates per shot (QASMsimulator.cpp:501-522) */
+  int64_t first_measure;       /* index of the first MEASURE_ONE op, -1 = none */
+} jkq_program_info;
+int jkq_qasm_parse(const char *text, const char *include_dir, uint32_t flags, jkq_program **out);
+const char *jkq_program_error(const jkq_program *p);
+void jkq_program_free(jkq_program *p);
+int jkq_program_get_info(const jkq_program *p, jkq_program_info *info);
+/* register `index` of the qregs (creg = 0) or cregs (creg = 1), in declaration order */
+int jkq_program_get_register(const jkq_program *p, int creg, uint32_t index, char *name, size_t name_cap, uint32_t *offset,
+                             uint32_t *size);
+/* snapshot statement `index` in program order: its slot and its qubits in argument order (first argument = most
+ * significant bit of the reference's probability / state-vector index, QASMsimulator.cpp:993-1031) */
+int jkq_program_get_snapshot(const jkq_program *p, uint32_t index, uint32_t *slot, uint32_t *qubits, size_t cap, size_t *n_qubits);
 
 /* GPU-measured roofline denominators: uniform random 32-byte sector reads and 64-bit atomicCAS over
  * a `bytes`-sized buffer; returns giga-operations per second */

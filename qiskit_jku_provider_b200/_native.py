@@ -29,6 +29,12 @@ class JkqStats(C.Structure):
         ("distinct_outcomes", C.c_uint64)]
 
 
+class JkqProgramInfo(C.Structure):
+    _fields_ = [("n_qubits", C.c_uint32), ("n_clbits", C.c_uint32), ("n_ops", C.c_size_t), ("ops", C.POINTER(JkqOp)),
+                ("n_qregs", C.c_uint32), ("n_cregs", C.c_uint32), ("n_snapshots", C.c_uint32),
+                ("gate_after_measure", C.c_int32), ("first_measure", C.c_int64)]
+
+
 class JkqSNode(C.Structure):
     _fields_ = [("c0", C.c_uint32), ("c1", C.c_uint32), ("q0", C.c_double)]
 
@@ -50,6 +56,7 @@ SYMBOLS = [
     ("jkq_get_level_counts", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t]),
     ("jkq_get_level_log", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
     ("jkq_get_stats", C.c_int, [_H, C.POINTER(JkqStats)]),
+    ("jkq_get_probabilities", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_size_t)]),
     ("jkq_get_qubit_probability", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double)]),
     ("jkq_get_mid_measurements", C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -61,6 +68,12 @@ SYMBOLS = [
     ("jkq_batch_run", C.c_int, [_H, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(JkqOp), C.POINTER(C.c_uint64), C.c_uint64,
                                 C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    ("jkq_qasm_parse", C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(_H)]),
+    ("jkq_program_error", C.c_char_p, [_H]),
+    ("jkq_program_free", None, [_H]),
+    ("jkq_program_get_info", C.c_int, [_H, C.POINTER(JkqProgramInfo)]),
+    ("jkq_program_get_register", C.c_int, [_H, C.c_int, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("jkq_program_get_snapshot", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
     ("jkq_random_sector_bench", C.c_int, [_H, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 

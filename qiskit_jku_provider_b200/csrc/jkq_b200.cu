@@ -100,6 +100,67 @@ __global__ void __launch_bounds__(256) k_marginal(const JEng *E, const JSNode *s
   if (threadIdx.x == 0) *out = s_sum;
 }
 
+// Simulator::GetProbability for every assignment of a set of qubits (the "probabilities" of a snapshot,
+// QASMsimulator.cpp:990-1011).  bit_of_level[L] = index bit that fixes the qubit on level L, -1 = level not listed.
+struct ProbParams {
+  int8_t bit_of_level[JKQ_MAXQ];
+};
+// all qubits listed: one thread follows one path of conditional branch probabilities
+__global__ void __launch_bounds__(256) k_probs_full(const JEng *E, const JSNode *sn, ProbParams pp, uint64_t count, double *out) {
+  const int n = (int)E->n;
+  const double norm = E->norm;
+  const uint32_t root = E->root;
+  for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < count; a += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t node = root;
+    double p = norm;
+    for (int L = n - 1; L >= 0 && p != 0.0; L--) {
+      const JSNode s = sn[node];
+      const int b = (int)((a >> pp.bit_of_level[L]) & 1ull);
+      p *= b ? 1.0 - s.q0 : s.q0;
+      node = b ? s.c1 : s.c0;
+    }
+    out[a] = p;
+  }
+}
+// a subset: one CTA per assignment pushes the path mass down level by level (k_marginal with fixed branches on the
+// listed levels) and stops at the lowest listed level -- below it the conditional probabilities sum to one
+__global__ void __launch_bounds__(256) k_probs_subset(const JEng *E, const JSNode *sn, ProbParams pp, int low, uint64_t count,
+                                                      double *scratch, double *out) {
+  __shared__ double s_sum;
+  const int n = (int)E->n;
+  const uint32_t total = E->node_count;
+  double *mass = scratch + (size_t)blockIdx.x * total;
+  for (uint64_t a = blockIdx.x; a < count; a += gridDim.x) {
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) mass[i] = 0.0;
+    if (threadIdx.x == 0) s_sum = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) mass[E->root] = E->norm;
+    __syncthreads();
+    for (int L = n - 1; L > low; L--) {
+      const uint32_t off = E->lvl_off[L], cnt = E->lvl_cnt[L];
+      const int bl = pp.bit_of_level[L];
+      const int b = bl < 0 ? -1 : (int)((a >> bl) & 1ull);
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const JSNode s = sn[off + i];
+        const double m = mass[off + i];
+        if (m == 0.0) continue;
+        if (b != 1 && s.q0 > 0.0) atomicAdd(&mass[s.c0], m * s.q0);
+        if (b != 0 && s.q0 < 1.0) atomicAdd(&mass[s.c1], m * (1.0 - s.q0));
+      }
+      __syncthreads();
+    }
+    const uint32_t off = E->lvl_off[low], cnt = E->lvl_cnt[low];
+    const int b = (int)((a >> pp.bit_of_level[low]) & 1ull);
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += mass[off + i] * (b ? 1.0 - sn[off + i].q0 : sn[off + i].q0);
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) out[a] = s_sum;
+    __syncthreads();
+  }
+}
+
 struct SampleParams {
   uint8_t bitpos[JKQ_MAXQ];
 };
@@ -237,6 +298,9 @@ struct jkq_handle {
   SampleParams sp;
   uint32_t dd_root = 0, dd_nodes = 0;
   std::map<uint32_t, double2 *> snapshots;  // slot -> device buffer of 2^n amplitudes
+  std::map<uint32_t, std::pair<double *, uint32_t>> prob_slots;  // slot -> (device buffer of 2^k probabilities, k)
+  bool physical_reset = false;      // RESET = measure-then-X instead of the reference's projection
+  uint64_t placeholder_gates = 0;   // projector / X slots of MEASURE_ONE and RESET applied by the last jkq_apply
   // histogram
   unsigned long long *hk = nullptr, *hc = nullptr, *ok = nullptr, *oc = nullptr, *n_out = nullptr;
   int *overflow = nullptr;
@@ -290,6 +354,8 @@ static void free_hist(jkq_handle *h) {
 static void free_snapshots(jkq_handle *h) {
   for (auto &kv : h->snapshots) cudaFree(kv.second);
   h->snapshots.clear();
+  for (auto &kv : h->prob_slots) cudaFree(kv.second.first);
+  h->prob_slots.clear();
 }
 
 extern "C" void jkq_destroy(jkq_handle *h) {
@@ -390,6 +456,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "level_log")) { h->level_log = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "force_mode")) { h->cfg.force_mode = (int)value; return JKQ_E_OK; }
   if (!strcmp(name, "measure_seed")) { h->measure_seed = (uint64_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "physical_reset")) { h->physical_reset = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
     if (value < 1 || value > JKQ_SITEMS / 2) value = JKQ_SITEMS / 2;
@@ -465,6 +532,24 @@ static int parse_ops(std::string *err, uint32_t n_qubits, const jkq_op *ops, siz
         g.pad = (int32_t)(mats.size() - 1);
         gates.push_back(g);
       }
+    } else if (o.kind == JKQ_OP_IF) {
+      const size_t cnt = o.arg ? o.arg : 1;
+      bool ok = i + cnt < n_ops;
+      for (size_t j = 1; ok && j <= cnt; j++) {
+        const uint32_t nk = ops[i + j].kind;
+        ok = nk == JKQ_OP_GATE || nk == JKQ_OP_MEASURE_ONE || nk == JKQ_OP_RESET || nk == JKQ_OP_BARRIER;
+      }
+      if (!ok) {
+        snprintf(buf, sizeof(buf), "op %zu: IF must be followed by the gate, measure-one or reset ops it guards", i); *err = buf;
+        return JKQ_E_ARGUMENT;
+      }
+      if (has_snapshot) *has_snapshot = true;  // (needs the host between segments: not served by the batch path)
+    } else if (o.kind == JKQ_OP_PROBABILITIES) {
+      if (o.ctrl_pos == 0 || (o.ctrl_pos & ~qmask) || __builtin_popcountll(o.ctrl_pos) > 26) {
+        snprintf(buf, sizeof(buf), "op %zu: probabilities need 1..26 qubits of the circuit", i); *err = buf;
+        return JKQ_E_ARGUMENT;
+      }
+      if (has_snapshot) *has_snapshot = true;
     } else if (o.kind != JKQ_OP_BARRIER) {
       snprintf(buf, sizeof(buf), "op %zu: unknown kind %u", i, o.kind); *err = buf;
       return JKQ_E_ARGUMENT;
@@ -613,8 +698,13 @@ static int qubit_probability(jkq_handle *h, uint32_t qubit, double *p0) {
   return JKQ_E_OK;
 }
 
-// MeasureOne / ResetQubit at op i (Simulator.cpp:226-289, 341-413): apply what precedes, get P(0), draw the
-// outcome, fill the matrices of the op's gate slot(s): projector / sqrt(p), then (reset) X when the outcome was 1.
+// MeasureOne / ResetQubit at op i (Simulator.cpp:226-289, 291-339): apply what precedes, get P(0), then fill the
+// matrices of the op's gate slot(s).
+//   MEASURE_ONE            draw the outcome; slot 0 = projector on it / sqrt(p)
+//   RESET (reference)      no draw: slot 0 = X when P(0) = 0, else identity; slot 1 = |0><0| / sqrt(P(0))
+//   RESET (physical_reset) draw the outcome; slot 0 = projector / sqrt(p); slot 1 = X when the outcome was 1
+static void set_diag(JGate &g, double d0, double d1) { memset(g.m, 0, sizeof(g.m)); g.m[0] = d0; g.m[6] = d1; }
+static void set_x(JGate &g) { memset(g.m, 0, sizeof(g.m)); g.m[2] = 1.0; g.m[4] = 1.0; }
 static int measure_collapse(jkq_handle *h, size_t i) {
   const jkq_op &o = h->ops[i];
   const int g0 = h->gate_of_op[i];
@@ -625,28 +715,75 @@ static int measure_collapse(jkq_handle *h, size_t i) {
   if (rc) return rc;
   if (p0 < 0) p0 = 0;
   if (p0 > 1) p0 = 1;
-  const double u = philox_uniform(h->measure_seed, (uint64_t)i);
-  const int outcome = u < p0 ? 0 : 1;
-  const double p = outcome ? 1.0 - p0 : p0;
-  if (!(p > 0)) return fail(h, JKQ_E_ZERO_STATE, "measurement of qubit %u: outcome %d has probability 0", o.target, outcome);
-  JGate &g = h->gates[g0];
-  memset(g.m, 0, sizeof(g.m));
-  g.m[outcome ? 6 : 0] = 1.0 / sqrt(p);
-  CU(cudaMemcpyAsync(h->gates_dev + g0, &g, sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  const double norm = h->host.norm > 0 ? h->host.norm : 1.0;  // (k_marginal works on normalised records)
   int n_slots = 1;
-  if (o.kind == JKQ_OP_RESET) {
-    JGate &x = h->gates[g0 + 1];
-    memset(x.m, 0, sizeof(x.m));
-    if (outcome) { x.m[2] = 1.0; x.m[4] = 1.0; }
-    else { x.m[0] = 1.0; x.m[6] = 1.0; }
-    CU(cudaMemcpyAsync(h->gates_dev + g0 + 1, &x, sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  if (o.kind == JKQ_OP_RESET && !h->physical_reset) {
+    JGate &first = h->gates[g0], &proj = h->gates[g0 + 1];
+    double p = p0;
+    if (p0 <= 0.0) { set_x(first); p = 1.0; }
+    else set_diag(first, 1.0, 1.0);
+    set_diag(proj, 1.0 / sqrt(p * norm), 0.0);
     n_slots = 2;
   } else {
-    h->mid_mask |= 1ull << o.arg;
-    if (outcome) h->mid_bits |= 1ull << o.arg;
+    const double u = philox_uniform(h->measure_seed, (uint64_t)i);
+    const int outcome = u < p0 ? 0 : 1;
+    const double p = outcome ? 1.0 - p0 : p0;
+    if (!(p > 0)) return fail(h, JKQ_E_ZERO_STATE, "measurement of qubit %u: outcome %d has probability 0", o.target, outcome);
+    const double f = 1.0 / sqrt(p * norm);
+    set_diag(h->gates[g0], outcome ? 0.0 : f, outcome ? f : 0.0);
+    if (o.kind == JKQ_OP_RESET) {
+      if (outcome) set_x(h->gates[g0 + 1]);
+      else set_diag(h->gates[g0 + 1], 1.0, 1.0);
+      n_slots = 2;
+    } else {
+      h->mid_mask |= 1ull << o.arg;
+      if (outcome) h->mid_bits |= 1ull << o.arg;
+      else h->mid_bits &= ~(1ull << o.arg);
+    }
   }
+  h->placeholder_gates += (uint64_t)n_slots;
+  CU(cudaMemcpyAsync(h->gates_dev + g0, &h->gates[g0], n_slots * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // (the host copies of the gates are pageable)
   return run_segment(h, g0 + n_slots);
+}
+
+// the 2^k probabilities of a PROBABILITIES op, into its slot
+static int record_probabilities(jkq_handle *h, const jkq_op &o) {
+  int rc = build_sampling_now(h);
+  if (rc) return rc;
+  ProbParams pp;
+  int k = 0, low = -1;
+  for (int L = 0; L < JKQ_MAXQ; L++) pp.bit_of_level[L] = -1;
+  for (uint32_t q = 0; q < h->n; q++) {
+    if (!(o.ctrl_pos >> q & 1)) continue;
+    const int L = (int)(h->n - 1 - q);
+    pp.bit_of_level[L] = (int8_t)k++;
+    if (low < 0 || L < low) low = L;
+  }
+  const uint64_t count = 1ull << k;
+  double *buf = nullptr;
+  CU(cudaMalloc(&buf, count * sizeof(double)));
+  auto it = h->prob_slots.find(o.arg);
+  if (it != h->prob_slots.end()) { cudaFree(it->second.first); h->prob_slots.erase(it); }
+  h->prob_slots[o.arg] = std::make_pair(buf, (uint32_t)k);
+  if ((uint32_t)k == h->n) {
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    k_probs_full<<<blocks, 256, 0, h->stream>>>(h->dev, h->snodes, pp, count, buf);
+    CU(cudaGetLastError());
+  } else {
+    const uint64_t per = (uint64_t)h->host.node_count * sizeof(double);
+    uint64_t blocks = count < (uint64_t)h->sm_count * 4 ? count : (uint64_t)h->sm_count * 4;
+    while (blocks > 1 && blocks * per > (256ull << 20)) blocks /= 2;
+    double *scratch = nullptr;
+    CU(cudaMalloc(&scratch, blocks * per));
+    k_probs_subset<<<(int)blocks, 256, 0, h->stream>>>(h->dev, h->snodes, pp, low, count, scratch, buf);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(scratch);
+  }
+  h->sampling_ready = false;  // (gates may follow: the records are rebuilt when shots are asked for)
+  return JKQ_E_OK;
 }
 
 extern "C" int jkq_apply(jkq_handle *h) {
@@ -672,9 +809,11 @@ extern "C" int jkq_apply(jkq_handle *h) {
   k_init<MODE_GRID><<<1, 32, 0, h->stream>>>(h->dev);
   CU(cudaGetLastError());
   const uint64_t cta0 = h->stats.cta_launches, grid0 = h->stats.grid_launches;
-  h->mid_bits = 0; h->mid_mask = 0;
+  h->mid_bits = 0; h->mid_mask = 0; h->placeholder_gates = 0;
   size_t i = 0;
-  auto boundary = [](uint32_t k) { return k == JKQ_OP_SNAPSHOT || k == JKQ_OP_MEASURE_ONE || k == JKQ_OP_RESET; };
+  auto boundary = [](uint32_t k) {
+    return k == JKQ_OP_SNAPSHOT || k == JKQ_OP_MEASURE_ONE || k == JKQ_OP_RESET || k == JKQ_OP_IF || k == JKQ_OP_PROBABILITIES;
+  };
   while (i < h->ops.size()) {
     const uint32_t kind = h->ops[i].kind;
     if (kind == JKQ_OP_GATE) {
@@ -703,6 +842,22 @@ extern "C" int jkq_apply(jkq_handle *h) {
       int rc = measure_collapse(h, i);
       if (rc) return rc;
       i++;
+    } else if (kind == JKQ_OP_PROBABILITIES) {
+      int rc = run_segment(h, h->gate_of_op[i]);
+      if (!rc) rc = record_probabilities(h, h->ops[i]);
+      if (rc) return rc;
+      i++;
+    } else if (kind == JKQ_OP_IF) {
+      // every MEASURE_ONE before this op has been resolved: the condition is known on the host
+      if ((h->mid_bits & h->ops[i].ctrl_pos) == h->ops[i].ctrl_neg) { i++; continue; }
+      const size_t cnt = h->ops[i].arg ? h->ops[i].arg : 1;
+      int rc = run_segment(h, h->gate_of_op[i + 1]);
+      if (rc) return rc;
+      // skip the guarded ops: their gate slots are stepped over
+      h->host.next_gate = i + 1 + cnt < h->ops.size() ? h->gate_of_op[i + 1 + cnt] : (int)h->gates.size();
+      CU(cudaMemcpyAsync(&h->dev->next_gate, &h->host.next_gate, sizeof(h->host.next_gate), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      i += 1 + cnt;
     } else {
       i++;
     }
@@ -884,6 +1039,20 @@ extern "C" int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, 
   return JKQ_E_OK;
 }
 
+extern "C" int jkq_get_probabilities(jkq_handle *h, uint32_t slot, double *out, size_t cap, size_t *n) {
+  if (!h) return JKQ_E_ARGUMENT;
+  auto it = h->prob_slots.find(slot);
+  if (it == h->prob_slots.end()) return fail(h, JKQ_E_ARGUMENT, "no probabilities in slot %u", slot);
+  const size_t len = (size_t)1 << it->second.second;
+  if (n) *n = len;
+  if (!out) return JKQ_E_OK;
+  if (cap < len) return fail(h, JKQ_E_CAPACITY, "need room for %zu probabilities", len);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, it->second.first, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
 extern "C" int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n) {
   if (!h || !per_level) return JKQ_E_ARGUMENT;
   if (n < h->n) return fail(h, JKQ_E_CAPACITY, "need %u entries", h->n);
@@ -895,9 +1064,10 @@ extern "C" int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n
 }
 
 extern "C" int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_written) {
-  if (!h || !out || !n_written) return JKQ_E_ARGUMENT;
+  if (!h || !n_written) return JKQ_E_ARGUMENT;
   if (!h->applied || !h->lvl_log) return fail(h, JKQ_E_STATE, "level log not recorded (set option level_log=1 before jkq_apply)");
   size_t total = h->gates.size() * h->n;
+  if (!out) { *n_written = total; return JKQ_E_OK; }  // size query
   if (cap < total) return fail(h, JKQ_E_CAPACITY, "need %zu entries", total);
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(out, h->lvl_log, total * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -919,7 +1089,8 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
     fprintf(stderr, "  per gate: cursor_prepare %llu  solo expand %llu  solo reduce %llu  cursor_finish %llu | solo levels/gate %.2f  wide gates %llu\n",
             E.prof[11] / E.prof[6], E.prof[12] / E.prof[6], E.prof[13] / E.prof[6], E.prof[14] / E.prof[6], (double)E.prof[15] / E.prof[6], E.prof[10]);
 #endif
-  h->stats.gates = E.st[JST_GATES]; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
+  // (ApplyGate calls: MeasureOne / ResetQubit multiply their projectors in directly)
+  h->stats.gates = E.st[JST_GATES] - h->placeholder_gates; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
   h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];
   h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF];
   h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;

@@ -1,0 +1,395 @@
+// jku_simulator -- the executable interface of the reference on the B200 engine.
+//
+// The reference's Python backend talks to its simulator through exactly this program: argv flags plus OpenQASM on
+// stdin, JSON on stdout (qiskit_jku_provider/qasm_simulator_jku.py:82-97 -> src/main.cpp:75-150 ->
+// QASMsimulator::Simulate(int shots), src/QASMsimulator.cpp:479-566).  This file is main.cpp + the driver and
+// printing part of QASMsimulator::Simulate on top of the C ABI (include/jkq.h): same flags, same JSON schema,
+// same key conventions, so the reference package runs on the GPU engine by pointing its executable path here.
+//   counts       bitstring over ALL qubits, character i = qubit i (QASMsimulator.cpp:489-500)
+//   snapshots    per slot: "probabilities" [2^k], "probabilities_ket" {bits: p > 0}, "statevector" [2^n strings in
+//                the format of Cprint, QMDDcomplexD.cpp:100-135]; first snapshot argument = most significant bit
+//   --ps         the three SIMULATION STATS lines of main.cpp:142-147
+// Shots: when no gate follows a measurement the counts are sampled from the state before the first measurement
+// (Simulator::ResetBeforeMeasurement, QASMsimulator.cpp:487-500); otherwise the circuit is re-simulated for every
+// shot with fresh measurement outcomes (:501-522).  Random numbers are Philox streams of --seed, not glibc rand().
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/jkq.h"
+
+namespace {
+
+const char *USAGE =
+    "Allowed options:\n"
+    "  --help                      produce help message\n"
+    "  --seed arg                  seed for random number generator\n"
+    "  --simulate_qasm [=arg(=)]   simulate a quantum circuit given in QPENQASM 2.0 format (if no file is given, the\n"
+    "                              circuit is read from stdin)\n"
+    "  --shots arg                 number of shots\n"
+    "  --ps                        print simulation stats (applied gates, sim. time, and maximal size of the DD)\n"
+    "  --display_statevector       adds the state-vector to snapshots\n"
+    "  --display_probabilities     adds the probabilities of the basis states to snapshots\n"
+    "  --precision arg             two numbers are treated to be equal if their difference is smaller than this value\n"
+    "  --device arg                CUDA device ordinal (default 0)\n"
+    "  --dump_ops                  parse only: print the op list as JSON (no GPU needed)\n";
+
+struct Options {
+  bool help = false, simulate = false, ps = false, statevector = false, probabilities = false, dump_ops = false;
+  bool have_seed = false, have_shots = false, have_precision = false;
+  unsigned long seed = 0;
+  unsigned long shots = 1;
+  double precision = 0;
+  int device = 0;
+  std::string file;
+};
+
+bool parse_args(int argc, char **argv, Options &o, std::string &err) {
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i], val;
+    bool has_val = false;
+    const size_t eq = a.find('=');
+    if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_val = true; }
+    auto need = [&]() {
+      if (has_val) return true;
+      if (i + 1 < argc) { val = argv[++i]; return true; }
+      err = "the required argument for option '" + a + "' is missing";
+      return false;
+    };
+    if (a == "--help") o.help = true;
+    else if (a == "--ps") o.ps = true;
+    else if (a == "--display_statevector") o.statevector = true;
+    else if (a == "--display_probabilities") o.probabilities = true;
+    else if (a == "--dump_ops") o.dump_ops = true;
+    else if (a == "--simulate_qasm") {
+      o.simulate = true;
+      if (has_val) o.file = val;
+      else if (i + 1 < argc && strncmp(argv[i + 1], "--", 2) != 0) o.file = argv[++i];
+    } else if (a == "--seed") { if (!need()) return false; o.seed = strtoul(val.c_str(), nullptr, 10); o.have_seed = true; }
+    else if (a == "--shots") { if (!need()) return false; o.shots = strtoul(val.c_str(), nullptr, 10); o.have_shots = true; }
+    else if (a == "--precision") { if (!need()) return false; o.precision = strtod(val.c_str(), nullptr); o.have_precision = true; }
+    else if (a == "--device") { if (!need()) return false; o.device = atoi(val.c_str()); }
+    else { err = "unrecognised option '" + a + "'"; return false; }
+  }
+  return true;
+}
+
+struct SnapshotData {
+  std::vector<double> probabilities;             // reference index order (first argument = MSB); empty = not recorded
+  std::vector<std::string> statevector;          // empty = not recorded
+};
+
+// Cprint (QMDDcomplexD.cpp:100-135): parts that snap to zero are left out, "0" when both do
+std::string format_amplitude(double re, double im, double tol) {
+  const bool has_re = fabs(re) > tol, has_im = fabs(im) > tol;
+  if (!has_re && !has_im) return "0";
+  std::ostringstream os;
+  if (has_re) {
+    if (re < 0) os << "-";
+    os << fabs(re);
+  }
+  if (has_im) os << (im < 0 ? "-" : "+") << fabs(im) << "i";
+  return os.str();
+}
+
+struct Runner {
+  jkq_handle *h = nullptr;
+  const jkq_program *prog = nullptr;
+  jkq_program_info info;
+  double tol = 1e-10;
+  std::map<uint32_t, SnapshotData> snapshots;     // by slot, like the reference's std::map<int, Snapshot*>
+  std::vector<std::vector<double>> shown;         // show_probabilities statements, in order
+  uint64_t gates = 0, max_nodes = 0;
+  bool want_stats = false;
+
+  void die(const char *what, int rc) {
+    std::cerr << "ERROR: " << what << " failed (" << rc << "): " << (h ? jkq_last_error(h) : "") << std::endl;
+    exit(1);
+  }
+
+  // load ops[0, n_ops), apply
+  void apply(size_t n_ops, uint64_t measure_seed) {
+    int rc = jkq_load_circuit(h, info.n_qubits, info.ops, n_ops);
+    if (rc) die("jkq_load_circuit", rc);
+    jkq_set_option(h, "measure_seed", (int64_t)measure_seed);
+    rc = jkq_apply(h);
+    if (rc == JKQ_E_ZERO_STATE) {
+      std::cerr << "ERROR: numerical instabilities led to a 0-vector! Abort simulation!" << std::endl;  // Simulator.cpp:239
+      exit(1);
+    }
+    if (rc) die("jkq_apply", rc);
+    jkq_stats st;
+    if (!jkq_get_stats(h, &st)) gates = st.gates;
+    if (want_stats) {
+      size_t n = 0;
+      if (jkq_get_level_log(h, nullptr, 0, &n)) n = 0;
+      std::vector<uint32_t> log(n ? n : 1);
+      if (n && !jkq_get_level_log(h, log.data(), n, &n)) {
+        for (size_t g = 0; g + info.n_qubits <= n; g += info.n_qubits) {
+          uint64_t s = 0;
+          for (uint32_t v = 0; v < info.n_qubits; v++) s += log[g + v];
+          if (s > max_nodes) max_nodes = s;
+        }
+      }
+    }
+  }
+
+  // read back what the snapshot / show_probabilities statements among ops[0, n_ops) recorded
+  void collect(size_t n_ops, bool statevector, bool probabilities) {
+    std::vector<uint32_t> qubits(64);
+    for (uint32_t s = 0; s < info.n_snapshots; s++) {
+      uint32_t slot = 0;
+      size_t k = 0;
+      jkq_program_get_snapshot(prog, s, &slot, qubits.data(), qubits.size(), &k);
+      SnapshotData d;
+      if (probabilities) {
+        size_t len = 0;
+        if (jkq_get_probabilities(h, slot, nullptr, 0, &len)) continue;  // (the statement lies behind n_ops)
+        std::vector<double> raw(len);
+        int rc = jkq_get_probabilities(h, slot, raw.data(), len, &len);
+        if (rc) die("jkq_get_probabilities", rc);
+        // engine order: bit j = j-th lowest listed qubit; reference order: bit k-1-a = argument a
+        std::vector<uint32_t> rank(k);
+        for (size_t a = 0; a < k; a++) {
+          uint32_t r = 0;
+          for (size_t b = 0; b < k; b++) r += qubits[b] < qubits[a];
+          rank[a] = r;
+        }
+        d.probabilities.resize(len);
+        for (size_t i = 0; i < len; i++) {
+          size_t e = 0;
+          for (size_t a = 0; a < k; a++) e |= ((i >> (k - 1 - a)) & 1) << rank[a];
+          d.probabilities[i] = raw[e];
+        }
+      }
+      if (statevector && k == info.n_qubits) {
+        const size_t len = (size_t)1 << k;
+        std::vector<double> amps(2 * len);
+        if (jkq_get_statevector(h, slot, amps.data(), len) == 0) {
+          d.statevector.resize(len);
+          for (size_t i = 0; i < len; i++) {
+            size_t e = 0;  // engine index: bit q = qubit q
+            for (size_t a = 0; a < k; a++) e |= ((i >> (k - 1 - a)) & 1) << qubits[a];
+            d.statevector[i] = format_amplitude(amps[2 * e], amps[2 * e + 1], tol);
+          }
+        }
+      } else if (statevector && n_ops == info.n_ops) {
+        std::cerr << "Snapshot must contain all qubits when containing statevector!" << std::endl;  // QASMsimulator.cpp:1014
+      }
+      snapshots[slot] = d;  // (an entry per snapshot statement even when nothing was asked for, QASMsimulator.cpp:1036)
+    }
+    shown.clear();
+    for (uint32_t i = 0;; i++) {
+      size_t len = 0;
+      if (jkq_get_probabilities(h, JKQ_SLOT_SHOW_PROBABILITIES + i, nullptr, 0, &len)) break;
+      std::vector<double> raw(len);
+      if (jkq_get_probabilities(h, JKQ_SLOT_SHOW_PROBABILITIES + i, raw.data(), len, &len)) break;
+      shown.push_back(raw);
+    }
+  }
+};
+
+void dump_ops(const jkq_program_info &info) {
+  std::cout.precision(17);
+  std::cout << "{\"n_qubits\": " << info.n_qubits << ", \"n_clbits\": " << info.n_clbits << ", \"gate_after_measure\": " << info.gate_after_measure
+            << ", \"first_measure\": " << info.first_measure << ", \"ops\": [";
+  for (size_t i = 0; i < info.n_ops; i++) {
+    const jkq_op &o = info.ops[i];
+    std::cout << (i ? ",\n " : "\n ") << "{\"kind\": " << o.kind << ", \"target\": " << o.target << ", \"ctrl_pos\": " << o.ctrl_pos
+              << ", \"ctrl_neg\": " << o.ctrl_neg << ", \"arg\": " << o.arg << ", \"m\": [";
+    for (int k = 0; k < 8; k++) std::cout << (k ? ", " : "") << o.m[k];
+    std::cout << "]}";
+  }
+  std::cout << "\n]}" << std::endl;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Options opt;
+  std::string err;
+  if (!parse_args(argc, argv, opt, err)) {
+    std::cerr << err << std::endl;
+    return 1;
+  }
+  if (opt.help || !opt.simulate) {
+    std::cout << USAGE << "\n";
+    return 1;
+  }
+  const unsigned long seed = opt.have_seed ? opt.seed : (unsigned long)time(nullptr);
+  if (opt.shots < 1) std::cerr << "Shots have to be greater than 0!" << std::endl;  // QASMsimulator.cpp:480-482
+
+  std::string text;
+  {
+    std::stringstream ss;
+    if (opt.file.empty()) ss << std::cin.rdbuf();
+    else {
+      std::ifstream f(opt.file.c_str());
+      if (!f) { std::cerr << "Failed to open file '" << opt.file << "'!" << std::endl; return 1; }
+      ss << f.rdbuf();
+    }
+    text = ss.str();
+  }
+  std::string dir;
+  if (!opt.file.empty()) {
+    const size_t slash = opt.file.rfind('/');
+    if (slash != std::string::npos) dir = opt.file.substr(0, slash);
+  }
+
+  jkq_program *prog = nullptr;
+  const uint32_t flags = (opt.statevector ? JKQ_QASM_STATEVECTOR : 0) | (opt.probabilities ? JKQ_QASM_PROBABILITIES : 0);
+  if (jkq_qasm_parse(text.c_str(), dir.empty() ? nullptr : dir.c_str(), flags, &prog)) {
+    std::cerr << "ERROR: " << jkq_program_error(prog) << std::endl;
+    jkq_program_free(prog);
+    return 1;
+  }
+  Runner r;
+  r.prog = prog;
+  jkq_program_get_info(prog, &r.info);
+  if (opt.dump_ops) {
+    dump_ops(r.info);
+    jkq_program_free(prog);
+    return 0;
+  }
+
+  jkq_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.device = opt.device;
+  if (opt.have_precision) { cfg.tolerance = opt.precision; r.tol = opt.precision; }
+  int rc = jkq_create(&r.h, &cfg);
+  if (rc) {
+    std::cerr << "ERROR: no usable CUDA device (" << rc << "): this simulator has no CPU path" << std::endl;
+    return 1;
+  }
+  r.want_stats = opt.ps;
+  if (opt.ps) jkq_set_option(r.h, "level_log", 1);
+
+  const auto t1 = std::chrono::high_resolution_clock::now();
+  const jkq_program_info &info = r.info;
+  const unsigned long shots = opt.shots < 1 ? 1 : opt.shots;
+  std::map<std::string, unsigned long long> result;
+  auto add_counts = [&]() {
+    size_t n = 0;
+    jkq_get_counts(r.h, nullptr, nullptr, 0, &n);
+    std::vector<uint64_t> keys(n ? n : 1), cnts(n ? n : 1);
+    int rc2 = jkq_get_counts(r.h, keys.data(), cnts.data(), n, &n);
+    if (rc2) r.die("jkq_get_counts", rc2);
+    for (size_t i = 0; i < n; i++) {
+      std::string s(info.n_qubits, '0');
+      for (uint32_t q = 0; q < info.n_qubits; q++) s[q] = (char)('0' + ((keys[i] >> q) & 1));
+      result[s] += cnts[i];
+    }
+  };
+  if (!info.gate_after_measure) {
+    const size_t prefix = info.first_measure >= 0 ? (size_t)info.first_measure : info.n_ops;
+    if (prefix < info.n_ops) {
+      // statements behind the first measurement see the collapsed state (Simulate() runs to the end before the
+      // shots are drawn from `beforeMeasurement`)
+      r.apply(info.n_ops, seed);
+      r.collect(info.n_ops, opt.statevector, opt.probabilities);
+    }
+    r.apply(prefix, seed);
+    if (prefix == info.n_ops) r.collect(info.n_ops, opt.statevector, opt.probabilities);
+    rc = jkq_sample(r.h, shots, seed, 0, 0);
+    if (rc) r.die("jkq_sample", rc);
+    add_counts();
+  } else {
+    for (unsigned long s = 0; s < shots; s++) {
+      r.apply(info.n_ops, seed * 0x9E3779B97F4A7C15ull + s);
+      rc = jkq_sample(r.h, 1, seed, s, 0);
+      if (rc) r.die("jkq_sample", rc);
+      add_counts();
+    }
+    r.collect(info.n_ops, opt.statevector, opt.probabilities);
+  }
+  const auto t2 = std::chrono::high_resolution_clock::now();
+
+  // show_probabilities statements (QASMsimulator.cpp:1039-1055) print while the reference simulates: before the JSON
+  for (const std::vector<double> &p : r.shown) {
+    std::cout << "Probabilities of the states |";
+    for (int i = (int)info.n_qubits - 1; i >= 0; i--) {
+      char name[64] = "q";
+      uint32_t off = 0, size = 0;
+      for (uint32_t k = 0; k < info.n_qregs; k++) {
+        char nm[48];
+        jkq_program_get_register(prog, 0, k, nm, sizeof(nm), &off, &size);
+        if ((uint32_t)i >= off && (uint32_t)i < off + size) { snprintf(name, sizeof(name), "%s[%u]", nm, (uint32_t)i - off); break; }
+      }
+      std::cout << name << " ";
+    }
+    std::cout << ">:" << std::endl;
+    for (size_t i = 0; i < p.size(); i++) {
+      std::cout << "  |";
+      for (int j = (int)info.n_qubits - 1; j >= 0; j--) std::cout << ((i >> j) & 1);
+      std::cout << ">: " << p[i] << std::endl;
+    }
+  }
+
+  std::cout << "{" << std::endl << "  \"counts\": {" << std::endl;
+  {
+    bool first = true;
+    for (const auto &kv : result) {
+      if (!first) std::cout << ",\n";
+      std::cout << "    \"" << kv.first << "\": " << kv.second;
+      first = false;
+    }
+  }
+  std::cout << "  }";
+  if (!r.snapshots.empty()) {
+    std::cout << "," << std::endl;
+    std::cout << "  \"snapshots\": {" << std::endl;
+    for (auto it = r.snapshots.begin(); it != r.snapshots.end(); ++it) {
+      const SnapshotData &d = it->second;
+      std::cout << "    \"" << it->first << "\": {" << std::endl;
+      if (!d.probabilities.empty()) {
+        const size_t k = (size_t)llround(log2((double)d.probabilities.size()));
+        std::cout << "      \"probabilities\": [" << d.probabilities[0];
+        for (size_t i = 1; i < d.probabilities.size(); i++) std::cout << ", " << d.probabilities[i];
+        std::cout << "]," << std::endl;
+        std::cout << "      \"probabilities_ket\": {";
+        bool first = true;
+        std::map<std::string, double> ket;
+        for (size_t i = 0; i < d.probabilities.size(); i++) {
+          if (!(d.probabilities[i] > 0.0)) continue;
+          std::string s(k, '0');
+          for (size_t j = 0; j < k; j++) s[j] = (char)('0' + ((i >> (k - 1 - j)) & 1));
+          ket[s] = d.probabilities[i];
+        }
+        for (const auto &kv : ket) {
+          std::cout << (first ? "" : ", ") << "\"" << kv.first << "\": " << kv.second;
+          first = false;
+        }
+        std::cout << "}";
+      }
+      if (!d.statevector.empty()) {
+        if (!d.probabilities.empty()) std::cout << "," << std::endl;
+        std::cout << "      \"statevector\": [\"" << d.statevector[0];
+        for (size_t i = 1; i < d.statevector.size(); i++) std::cout << "\", \"" << d.statevector[i];
+        std::cout << "\"]";
+      }
+      std::cout << std::endl << "    }" << (std::next(it, 1) != r.snapshots.end() ? "," : "") << std::endl;
+    }
+    std::cout << "  }" << std::endl;
+  }
+  std::cout << "}" << std::endl;
+
+  if (opt.ps) {
+    const std::chrono::duration<float> diff = t2 - t1;
+    std::cout << std::endl << "SIMULATION STATS: " << std::endl;
+    std::cout << "  Number of applied gates: " << r.gates << std::endl;
+    std::cout << "  Simulation time: " << diff.count() << " seconds" << std::endl;
+    std::cout << "  Maximal size of DD (number of nodes) during simulation: " << r.max_nodes << std::endl;
+  }
+  jkq_destroy(r.h);
+  jkq_program_free(prog);
+  return 0;
+}

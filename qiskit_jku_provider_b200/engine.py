@@ -7,7 +7,7 @@ import numpy as np
 from . import _native
 from .jkusimulatorerror import JKUSimulatorError
 
-OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER, OP_MEASURE_ONE, OP_RESET = 0, 1, 2, 3, 4, 5
+OP_GATE, OP_SNAPSHOT, OP_MEASURE, OP_BARRIER, OP_MEASURE_ONE, OP_RESET, OP_IF, OP_PROBABILITIES = 0, 1, 2, 3, 4, 5, 6, 7
 FINAL_SLOT = 0xFFFFFFFF
 
 SNODE_DTYPE = np.dtype([("c0", "<u4"), ("c1", "<u4"), ("q0", "<f8")])
@@ -194,6 +194,14 @@ class Engine:
         w = C.c_size_t(0)
         self._check(self._lib.jkq_get_level_log(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size, C.byref(w)))
         return out[:w.value].reshape(n_gates, self.n).tolist()
+
+    def probabilities(self, slot):
+        """The 2^k probabilities a PROBABILITIES op recorded in ``slot`` (bit j of the index = j-th lowest listed qubit)."""
+        n = C.c_size_t(0)
+        self._check(self._lib.jkq_get_probabilities(self._h, int(slot), None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float64)
+        self._check(self._lib.jkq_get_probabilities(self._h, int(slot), out.ctypes.data_as(C.POINTER(C.c_double)), out.size, C.byref(n)))
+        return out
 
     def qubit_probability(self, qubit):
         """P(qubit reads 0) in the current state (Simulator::AssignProbsOne)."""

@@ -63,7 +63,8 @@ def _gate_template(name, n_qubits, params):
 class JKUSimulatorWrapper:
     """Converter between Qobj experiments and the engine."""
 
-    def __init__(self, engine=None, silent=False):
+    def __init__(self, engine=None, silent=False, physical_reset=False):
+        self.physical_reset = bool(physical_reset)
         self.seed = 0
         self.shots = 1
         self.engine = engine
@@ -124,9 +125,12 @@ class JKUSimulatorWrapper:
             elif name == 'barrier':
                 kinds.append(OP_BARRIER); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
             elif name == 'reset':
-                # ResetQubit (Simulator.cpp:341-413): its outcome is random, so the circuit is re-simulated per
-                # shot like the reference does when the state is not reusable (QASMsimulator.cpp:501-522)
-                self.per_shot = True
+                # ResetQubit (Simulator.cpp:291-339) PROJECTS on |0> and rescales -- deterministic, so the shots are
+                # drawn from the one final state.  With ``physical_reset`` the qubit is measured and flipped back
+                # instead; that outcome is random, and the circuit is re-simulated per shot like the reference does
+                # when a state is not reusable (QASMsimulator.cpp:501-522).
+                if self.physical_reset:
+                    self.per_shot = True
                 kinds.append(OP_RESET); targets.append(op.qubits[0]); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
             else:
                 params = tuple(getattr(op, 'params', None) or ())
@@ -165,6 +169,7 @@ class JKUSimulatorWrapper:
         if not self.silent:
             print(RUN_MESSAGE)
         eng = self.engine
+        eng.set_option("physical_reset", int(self.physical_reset))
         eng.load_ops(n, ops)
         if self.per_shot:
             # every shot is its own run: a fresh draw for each reset, one sample of the final state
@@ -253,11 +258,13 @@ class QasmSimulator(BaseBackend):
         ]
     }
 
-    def __init__(self, configuration=None, provider=None, silent=False, device=0, **engine_options):
+    def __init__(self, configuration=None, provider=None, silent=False, device=0, physical_reset=False, **engine_options):
         """
         Args:
             configuration (dict): backend configuration
             device (int): CUDA ordinal the engine runs on
+            physical_reset (bool): ``reset`` = measure and flip back (per-shot re-simulation) instead of the
+                                   reference's projection on |0> (Simulator.cpp:291-339)
             engine_options: forwarded to ``jkq_config`` (node_capacity, tolerance, ...)
         Raises:
             ImportError: if libjkq_b200.so was not built (the reference raises FileNotFoundError when
@@ -269,6 +276,7 @@ class QasmSimulator(BaseBackend):
         from . import _native
         _native.load()  # fail early and loudly, like the reference's executable check
         self.silent = silent
+        self.physical_reset = physical_reset
         self._device = device
         self._engine_options = engine_options
         self._engine = None
@@ -288,7 +296,7 @@ class QasmSimulator(BaseBackend):
         """Run circuits in q_job"""
         result_list = []
         self._validate(qobj)
-        s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent)
+        s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset)
         s.shots = qobj.config.shots
         start = time.time()
         for experiment in qobj.experiments:

@@ -201,9 +201,9 @@ def test_probabilities_output(backend):
     assert res.data()['counts'] == {}
 
 
-def test_reset_is_resimulated_per_shot():
-    """h q0; cx q0,q1; reset q0; measure: q0 always reads 0, q1 keeps the branch the reset collapsed it to --
-    a 50/50 mixture over shots (the reference re-simulates per shot, QASMsimulator.cpp:501-522)."""
+def test_reset_projects_like_the_reference():
+    """h q0; cx q0,q1; reset q0; measure: the reference's ResetQubit projects on q0 = 0 (Simulator.cpp:291-339),
+    which leaves |00> -- every shot reads 00."""
     from qiskit_jku_provider_b200 import JKUProvider
     from qiskit_jku_provider_b200.compat import ClassicalRegister, QuantumCircuit, QuantumRegister, assemble
     qr, cr = QuantumRegister(2, "q"), ClassicalRegister(2, "c")
@@ -214,6 +214,26 @@ def test_reset_is_resimulated_per_shot():
     qc.measure(qr, cr)
     backend = JKUProvider().get_backend("qasm_simulator")
     backend.silent = True
-    counts = backend.run(assemble(qc, shots=300, seed=5)).result().get_counts()
+    assert backend.run(assemble(qc, shots=300, seed=5)).result().get_counts() == {"00": 300}
+
+
+def test_physical_reset_is_resimulated_per_shot():
+    """With physical_reset: q0 always reads 0, q1 keeps the branch the measurement collapsed it to -- a 50/50 mixture
+    over shots (re-simulated per shot, as the reference does for non-reusable states, QASMsimulator.cpp:501-522)."""
+    from qiskit_jku_provider_b200 import JKUProvider
+    from qiskit_jku_provider_b200.compat import ClassicalRegister, QuantumCircuit, QuantumRegister, assemble
+    qr, cr = QuantumRegister(2, "q"), ClassicalRegister(2, "c")
+    qc = QuantumCircuit(qr, cr, name="reset")
+    qc.h(qr[0])
+    qc.cx(qr[0], qr[1])
+    qc.reset(qr[0])
+    qc.measure(qr, cr)
+    backend = JKUProvider().get_backend("qasm_simulator")
+    backend.silent = True
+    backend.physical_reset = True
+    try:
+        counts = backend.run(assemble(qc, shots=300, seed=5)).result().get_counts()
+    finally:
+        backend.physical_reset = False
     assert set(counts) <= {"00", "10"} and sum(counts.values()) == 300
     assert 100 <= counts.get("00", 0) <= 200

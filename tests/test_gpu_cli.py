@@ -1,0 +1,213 @@
+"""GPU: the jku_simulator executable (csrc/jku_simulator.cpp) against what the UNMODIFIED reference executable printed
+for the same QASM programs and flags (tests/golden/cli/*.json, see tests/golden/make_cli_golden.py) -- the exact
+boundary the reference's Python backend crosses (qasm_simulator_jku.py:82-97) -- and the engine ops behind it
+(IF, PROBABILITIES) through the C ABI."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_qasm_frontend import CLI_DIR, HEADER, PROGRAMS, dense_run, load_case, parse_amplitude, reference_order
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from qiskit_jku_provider_b200 import _build
+    assert os.path.exists(_build.CLI), "jku_simulator was not built (python -c 'import __graft_entry__ as g; g.build()')"
+    return _build.CLI
+
+
+def run_cli(cli, qasm, shots, seed, flags, cwd=None):
+    out = subprocess.run([cli, "--simulate_qasm", "--shots=%d" % shots, "--seed=%d" % seed, "--ps"] + list(flags), input=qasm,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=600, cwd=cwd)
+    assert out.returncode == 0, out.stderr
+    text = out.stdout
+    body = json.loads(text[text.index("{"):text.index("SIMULATION STATS")])
+    stats = {}
+    for line in text[text.index("SIMULATION STATS"):].splitlines():
+        if ":" in line and not line.startswith("SIMULATION"):
+            k, v = line.split(":", 1)
+            stats[k.strip()] = v.strip()
+    return body, stats, out
+
+
+def ref_stats(rec):
+    stats = {}
+    text = rec["stdout"]
+    for line in text[text.index("SIMULATION STATS"):].splitlines():
+        if ":" in line and not line.startswith("SIMULATION"):
+            k, v = line.split(":", 1)
+            stats[k.strip()] = v.strip()
+    return stats
+
+
+def total_variation(a, b, shots_a, shots_b):
+    keys = set(a) | set(b)
+    return 0.5 * sum(abs(a.get(k, 0) / shots_a - b.get(k, 0) / shots_b) for k in keys)
+
+
+@pytest.mark.parametrize("name", PROGRAMS)
+def test_cli_matches_the_reference_executable(cli, name):
+    qasm, rec, ref = load_case(name)
+    got, stats, out = run_cli(cli, qasm, rec["shots"], rec["seed"], rec["flags"])
+    # counts: same keys over all qubits (character i = qubit i); the RNG differs (Philox vs glibc rand), so the
+    # histograms agree statistically.  Two samples of `shots` draws over k outcomes: TV distance ~ sqrt(k / shots).
+    assert sum(got["counts"].values()) == rec["shots"]
+    assert all(len(k) == len(next(iter(ref["counts"]))) for k in got["counts"])
+    k = len(set(got["counts"]) | set(ref["counts"]))
+    tv = total_variation(got["counts"], ref["counts"], rec["shots"], rec["shots"])
+    assert tv < 2.5 * np.sqrt(k / rec["shots"]) + 1e-12, (tv, got["counts"], ref["counts"])
+    if len(ref["counts"]) == 1:
+        assert got["counts"] == ref["counts"]
+    # an outcome the reference can never produce must not appear: supports agree up to rare outcomes
+    rare = 5.0 / rec["shots"]
+    for key, c in got["counts"].items():
+        assert key in ref["counts"] or c / rec["shots"] < 10 * rare, key
+    # snapshots
+    assert set(got.get("snapshots", {})) == set(ref.get("snapshots", {}))
+    for slot, want in ref.get("snapshots", {}).items():
+        mine = got["snapshots"][slot]
+        assert set(mine) == set(want), slot
+        if "probabilities" in want:
+            np.testing.assert_allclose(np.array(mine["probabilities"]), np.array(want["probabilities"]), rtol=2e-5, atol=2e-6)
+            assert set(mine["probabilities_ket"]) == set(want["probabilities_ket"])
+            for key, v in want["probabilities_ket"].items():
+                assert abs(mine["probabilities_ket"][key] - v) <= 2e-5 * v + 2e-6
+        if "statevector" in want:
+            a = np.array([parse_amplitude(s) for s in mine["statevector"]])
+            b = np.array([parse_amplitude(s) for s in want["statevector"]])
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-6)
+            same = sum(x == y for x, y in zip(mine["statevector"], want["statevector"]))
+            assert same >= 0.9 * len(b), (mine["statevector"], want["statevector"])  # the printed strings themselves
+    # --ps: ApplyGate calls of the (last) run and the largest DD
+    rs = ref_stats(rec)
+    if name != "teleport":  # (there the count depends on the last shot's measurement outcomes)
+        assert stats["Number of applied gates"] == rs["Number of applied gates"]
+        assert stats["Maximal size of DD (number of nodes) during simulation"] == rs["Maximal size of DD (number of nodes) during simulation"]
+    else:
+        assert 5 <= int(stats["Number of applied gates"]) <= 7
+    # the reference complains on stderr about partial snapshots with --display_statevector; so do we
+    assert ("Snapshot must contain all qubits" in out.stderr) == ("Snapshot must contain all qubits" in rec["stderr"])
+
+
+def test_cli_teleport_conditionals_fire(cli):
+    """teleportation of |1>: q[2] reads 1 in every shot only if both `if` corrections are applied on the right outcomes"""
+    qasm, rec, ref = load_case("teleport")
+    got, _, _ = run_cli(cli, qasm, 300, 21, [])
+    assert set(got["counts"]) == {"001", "011", "101", "111"}
+    assert all(40 <= c <= 110 for c in got["counts"].values())
+
+
+def test_cli_is_reproducible_and_seed_dependent(cli):
+    qasm, rec, _ = load_case("qelib_all")
+    a, _, _ = run_cli(cli, qasm, 500, 5, [])
+    b, _, _ = run_cli(cli, qasm, 500, 5, [])
+    c, _, _ = run_cli(cli, qasm, 500, 6, [])
+    assert a["counts"] == b["counts"] and a["counts"] != c["counts"]
+
+
+def test_cli_show_probabilities_and_include_file(cli, tmp_path):
+    (tmp_path / "qelib1.inc").write_text("gate h a { U(pi/2,0,pi) a; }\ngate cx c,t { CX c,t; }\n")
+    out = subprocess.run([cli, "--simulate_qasm", "--shots=10", "--seed=1"], input=HEADER + "qreg q[2];\nh q[0];\ncx q[0],q[1];\nshow_probabilities;\n",
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=600, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0].startswith("Probabilities of the states |q[1] q[0] >:")
+    assert [l.strip() for l in lines[1:5]] == ["|00>: 0.5", "|01>: 0", "|10>: 0", "|11>: 0.5"]
+    assert set(json.loads(out.stdout[out.stdout.index("{"):])["counts"]) <= {"00", "11"}
+
+
+def test_cli_precision_flag_reaches_the_engine(cli):
+    # with a tolerance of 0.2 the tiny rotation snaps to the identity: one outcome; with the default it does not
+    prog = HEADER + "qreg q[1];\nry(0.2) q[0];\n"
+    coarse, _, _ = run_cli(cli, prog, 2000, 3, ["--precision=0.2"])
+    fine, _, _ = run_cli(cli, prog, 2000, 3, [])
+    assert set(coarse["counts"]) == {"0"} and set(fine["counts"]) == {"0", "1"}
+
+
+# ---- the engine ops behind the front end, through the C ABI
+@pytest.fixture(scope="module")
+def eng():
+    from qiskit_jku_provider_b200.engine import Engine
+    e = Engine(device=0, node_capacity=1 << 18)
+    yield e
+    e.close()
+
+
+def test_probabilities_op_matches_a_dense_simulation(eng):
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import OP_DTYPE, OP_PROBABILITIES, circuit_ops
+    for circ, masks in ((C.random_circuit(7, 40, 3), (0b1111111, 0b0010110, 0b1000000, 0b0000001, 0b1100011)),
+                        (C.qft(9), (0b111111111, 0b101010101)), (C.ghz(12), (0b100000000001, 0xFFF))):
+        base = circuit_ops(circ)
+        ops = np.zeros(len(base) + len(masks), dtype=OP_DTYPE)
+        ops[:len(base)] = base
+        for j, m in enumerate(masks):
+            ops[len(base) + j]["kind"] = OP_PROBABILITIES
+            ops[len(base) + j]["ctrl_pos"] = m
+            ops[len(base) + j]["arg"] = 10 + j
+        eng.load_ops(circ.n, ops)
+        eng.apply()
+        p = np.abs(eng.statevector()) ** 2
+        for j, m in enumerate(masks):
+            qubits = [q for q in range(circ.n) if (m >> q) & 1]
+            want = np.zeros(1 << len(qubits))
+            for basis, v in enumerate(p):
+                i = sum(((basis >> q) & 1) << r for r, q in enumerate(qubits))
+                want[i] += v
+            got = eng.probabilities(10 + j)
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-9, err_msg="%s mask %x" % (circ.name, m))
+
+
+def test_probabilities_op_on_a_large_dd_uses_the_grid_sampling_records(eng):
+    """a DD of tens of thousands of nodes: subset probabilities still add up and match single-qubit marginals"""
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import OP_DTYPE, OP_PROBABILITIES, circuit_ops
+    circ = C.random_circuit(16, 110, 1)
+    base = circuit_ops(circ)
+    ops = np.zeros(len(base) + 1, dtype=OP_DTYPE)
+    ops[:len(base)] = base
+    ops[-1]["kind"] = OP_PROBABILITIES
+    ops[-1]["ctrl_pos"] = 0b1000000000100101
+    ops[-1]["arg"] = 1
+    eng.load_ops(circ.n, ops)
+    eng.apply()
+    got = eng.probabilities(1)
+    assert abs(got.sum() - 1.0) < 1e-8
+    qubits = [0, 2, 5, 15]
+    for r, q in enumerate(qubits):
+        p0 = sum(v for i, v in enumerate(got) if not (i >> r) & 1)
+        assert abs(p0 - eng.qubit_probability(q)) < 1e-8
+
+
+def test_if_op_follows_the_measured_bits(eng):
+    from qiskit_jku_provider_b200.engine import OP_IF, OP_MEASURE_ONE, gate_op, simple_op
+    from qiskit_jku_provider_b200 import circuits as C
+    h = C.Circuit(1).add("h", [0]).ops[0].matrix()
+    x = [[0, 1], [1, 0]]
+    fired = 0
+    for seed in range(30):
+        cond = simple_op(OP_IF, 0, 2)          # guards the next two ops
+        cond.ctrl_pos, cond.ctrl_neg = 0b1000, 0b1000
+        ops = [gate_op(0, h), simple_op(OP_MEASURE_ONE, 0, 3), cond, gate_op(1, x), gate_op(2, x), gate_op(3, x)]
+        eng.set_option("measure_seed", 300 + seed)
+        eng.load_ops(4, ops)
+        eng.apply()
+        bit = eng.mid_measurements()[3]
+        fired += bit
+        p = np.abs(eng.statevector()) ** 2
+        want = 0b1000 | (0b0111 if bit else 0)   # q3 always flipped; q1, q2 only when the measured bit is 1; q0 = the outcome
+        assert abs(p[want] - 1.0) < 1e-9, (seed, bit, np.argmax(p))
+        assert eng.stats()["gates"] == (4 if bit else 2)
+    assert 6 <= fired <= 24
+
+
+def test_if_op_needs_something_to_guard(eng):
+    from qiskit_jku_provider_b200.engine import OP_IF, simple_op
+    from qiskit_jku_provider_b200.jkusimulatorerror import JKUSimulatorError
+    with pytest.raises(JKUSimulatorError):
+        eng.load_ops(2, [simple_op(OP_IF, 0, 1)])

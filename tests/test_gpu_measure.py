@@ -64,13 +64,40 @@ def test_measure_then_gates_continue_on_the_collapsed_state(eng):
     assert abs(p[base] - 0.5) < 1e-9 and abs(p[base | 2] - 0.5) < 1e-9 and abs(p.sum() - 1.0) < 1e-9
 
 
-def test_reset_returns_the_qubit_to_zero(eng):
+def test_reset_projects_on_zero_like_the_reference(eng):
+    """Simulator::ResetQubit (Simulator.cpp:291-339): projection on |0> of the qubit, rescaled; X first when P(0) = 0."""
     from qiskit_jku_provider_b200.engine import OP_RESET, simple_op
-    for seed in range(12):
-        ops = _ops(C.ghz(3)) + [simple_op(OP_RESET, 0, 0)]
-        eng.set_option("measure_seed", 50 + seed)
-        eng.load_ops(3, ops)
-        eng.apply()
-        p = np.abs(eng.statevector()) ** 2
-        assert abs(eng.qubit_probability(0) - 1.0) < 1e-12           # qubit 0 is |0> again
-        assert min(abs(p[0b000] - 1.0), abs(p[0b110] - 1.0)) < 1e-9  # the other two keep the collapsed branch
+    eng.set_option("physical_reset", 0)
+    eng.load_ops(3, _ops(C.ghz(3)) + [simple_op(OP_RESET, 0, 0)])
+    eng.apply()
+    p = np.abs(eng.statevector()) ** 2
+    assert abs(p[0b000] - 1.0) < 1e-9 and abs(eng.qubit_probability(0) - 1.0) < 1e-12
+    # |1> on the qubit: P(0) = 0, the reference flips it
+    c = C.Circuit(2)
+    c.add("x", [0])
+    c.add("h", [1])
+    eng.load_ops(2, _ops(c) + [simple_op(OP_RESET, 0, 0)])
+    eng.apply()
+    p = np.abs(eng.statevector()) ** 2
+    assert abs(p[0b00] - 0.5) < 1e-9 and abs(p[0b10] - 0.5) < 1e-9
+    assert eng.stats()["gates"] == 2  # the projector / X slots are not ApplyGate calls
+
+
+def test_physical_reset_measures_and_flips(eng):
+    from qiskit_jku_provider_b200.engine import OP_RESET, simple_op
+    eng.set_option("physical_reset", 1)
+    seen = set()
+    try:
+        for seed in range(12):
+            ops = _ops(C.ghz(3)) + [simple_op(OP_RESET, 0, 0)]
+            eng.set_option("measure_seed", 50 + seed)
+            eng.load_ops(3, ops)
+            eng.apply()
+            p = np.abs(eng.statevector()) ** 2
+            assert abs(eng.qubit_probability(0) - 1.0) < 1e-12           # qubit 0 is |0> again
+            assert min(abs(p[0b000] - 1.0), abs(p[0b110] - 1.0)) < 1e-9  # the other two keep the collapsed branch
+            seen.add(int(np.argmax(p)))
+    finally:
+        eng.set_option("physical_reset", 0)
+    assert seen == {0b000, 0b110}
+
