@@ -103,6 +103,40 @@ def cpu_reference_run(circ, runs):
     return kind, times
 
 
+def executable_legs(device):
+    """The process boundary the reference's Python backend crosses (qasm_simulator_jku.py:82-97): wall time of one
+    `jku_simulator --simulate_qasm=FILE --shots=1024 --seed=1` process, ours (CUDA context creation included) and the
+    unmodified reference executable (oracle/_ref/jku_simulator) on the same QASM text.  Best of 3 (reference: 1 run of
+    the slow program)."""
+    import subprocess
+    import tempfile
+    from qiskit_jku_provider_b200 import _build
+    from qiskit_jku_provider_b200 import circuits as C
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "jku_simulator")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for c, ref_runs in ((C.qft(32), 3), (C.random_circuit(18, 100, 1), 1)):
+            path = os.path.join(tmp, c.name + ".qasm")
+            with open(path, "w") as f:
+                f.write(c.qasm())
+            leg = {"applies": len(c)}
+            for key, cmd, runs in (("b200", [_build.CLI, "--simulate_qasm=" + path, "--shots=1024", "--seed=1", "--device=%d" % device], 3),
+                                   ("reference_cpu", [ref_exe, "--simulate_qasm=" + path, "--shots=1024", "--seed=1"], ref_runs)):
+                if not os.path.exists(cmd[0]):
+                    leg[key + "_wall_s"] = None
+                    continue
+                best = None
+                for _ in range(runs):
+                    t0 = time.perf_counter()
+                    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+                    dt = time.perf_counter() - t0
+                    if r.returncode == 0 and (best is None or dt < best):
+                        best = dt
+                leg[key + "_wall_s"] = best
+            out[c.name] = leg
+    return out
+
+
 def run_reference_arm(args):
     """bench.py --impl reference: the reference's own CPU engine on the host cores, same metric and config.
     The reference is single-threaded and gate application does not shard, so N GPUs are mirrored the way our
@@ -340,6 +374,9 @@ def main():
                                              "nodes_created": s3["nodes_created"],
                                              "nodes_created_per_s": s3["nodes_created"] / (s3["apply_ms"] * 1e-3),
                                              "cta_launches_total": s3["cta_launches"], "grid_launches_total": s3["grid_launches"]}
+
+        if rank == 0:
+            extra["executable"] = executable_legs(local)
 
     if rank == 0:
         peaks, peaks_src = measured_peaks()

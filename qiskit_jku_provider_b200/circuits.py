@@ -113,6 +113,14 @@ class Op:
             return "cx %d %d" % (self.controls[0][0], self.target)
         return ("mcg %s %d %d %s" % (self.name, self.target, len(self.controls), ctl)).rstrip()
 
+    def qasm(self):
+        """OpenQASM 2.0 statement (builtin U / CX only); ValueError for a primitive QASM cannot express."""
+        if self.kind == "u" and not self.controls:
+            return "U(%s,%s,%s) q[%d];" % (self.theta.token(), self.phi.token(), self.lam.token(), self.target)
+        if self.kind == "g" and self.name == "x" and len(self.controls) == 1 and self.controls[0][1] == 1:
+            return "CX q[%d],q[%d];" % (self.controls[0][0], self.target)
+        raise ValueError("no OpenQASM 2.0 form for %s" % self.line())
+
     def matrix(self):
         """2x2 complex matrix in FP64.  U follows the SU(2) phase convention of
         src/QASMsimulator.cpp:295-298 (x = U(pi,0,pi) = -iX, u1(l) = diag(e^{-il/2}, e^{il/2}))."""
@@ -281,6 +289,17 @@ class Circuit:
         with open(path, "w") as f:
             f.write(self.text())
         return path
+
+    def qasm(self, measure=False):
+        """The circuit as an OpenQASM 2.0 program of builtin U / CX statements (what the reference's front end
+        reduces every program to, QASMsimulator.cpp:281-357)."""
+        lines = ["OPENQASM 2.0;", "qreg q[%d];" % self.n]
+        if measure:
+            lines.append("creg c[%d];" % self.n)
+        lines += [op.qasm() for op in self.ops]
+        if measure:
+            lines.append("measure q -> c;")
+        return "\n".join(lines) + "\n"
 
     def __len__(self):
         return len(self.ops)

@@ -110,6 +110,17 @@ def test_cli_is_reproducible_and_seed_dependent(cli):
     assert a["counts"] == b["counts"] and a["counts"] != c["counts"]
 
 
+def test_cli_counts_equal_the_in_process_engine(cli, eng):
+    """same circuit as QASM text through the executable and as ops through the C ABI: identical histograms
+    (same DD, same Philox stream)"""
+    from qiskit_jku_provider_b200 import circuits as C
+    for circ in (C.qft(10), C.random_circuit(9, 50, 4)):
+        got, _, _ = run_cli(cli, circ.qasm(measure=True), 3000, 17, [])
+        eng.load(circ)
+        eng.run(3000, 17)
+        assert got["counts"] == eng.counts_bitstrings()
+
+
 def test_cli_show_probabilities_and_include_file(cli, tmp_path):
     (tmp_path / "qelib1.inc").write_text("gate h a { U(pi/2,0,pi) a; }\ngate cx c,t { CX c,t; }\n")
     out = subprocess.run([cli, "--simulate_qasm", "--shots=10", "--seed=1"], input=HEADER + "qreg q[2];\nh q[0];\ncx q[0],q[1];\nshow_probabilities;\n",
