@@ -167,6 +167,18 @@ int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_qubits, con
                   uint64_t shots, const uint64_t *seeds, size_t cap, uint64_t *keys, uint64_t *counts, uint32_t *n_distinct,
                   int32_t *status, uint64_t *gates_applied, double *apply_ms_sum);
 
+/* Per-shot re-simulation (QASMsimulator.cpp:501-522: a circuit with a gate behind a measurement is simulated again
+ * for every shot) as ONE kernel: `shots` instances of the same op list run side by side, one CTA per SM, each
+ * handling its MEASURE_ONE / RESET / IF ops on the device.  Instance s draws its measurement outcomes from the
+ * Philox stream (measure_seed0 + s, op index) -- what jkq_apply draws with option "measure_seed" = measure_seed0 + s --
+ * and its final read-out of all measured qubits (MeasureAll) as shot (shot_offset + s) of stream `seed` -- what
+ * jkq_sample(1, seed, shot_offset + s) draws.  keys[s] = the outcome, mid_bits[s] (may be NULL) = the classical bits
+ * of the MEASURE_ONE ops; status[s] != 0: the instance outgrew the single-CTA path and is left to a full jkq_handle.
+ * SNAPSHOT / PROBABILITIES ops record nothing here. */
+int jkq_batch_run_shots(jkq_batch *b, uint32_t n_qubits, const jkq_op *ops, size_t n_ops, uint64_t shots, uint64_t seed,
+                        uint64_t shot_offset, uint64_t measure_seed0, int physical_reset, uint64_t *keys, uint64_t *mid_bits,
+                        int32_t *status, uint64_t *gates_applied, double *kernel_ms);
+
 /* OpenQASM 2.0 front end (host code): text -> the op list jkq_load_circuit takes.  Replaces the executing parser
  * of the reference (src/QASMsimulator.cpp:895-1060, src/QASMscanner.cpp); the semantics it keeps and the points where
  * it deliberately differs are listed at the top of csrc/jkq_qasm.cpp.  `measure` becomes MEASURE_ONE, `reset` RESET,

@@ -68,6 +68,9 @@ SYMBOLS = [
     ("jkq_batch_run", C.c_int, [_H, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(JkqOp), C.POINTER(C.c_uint64), C.c_uint64,
                                 C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    ("jkq_batch_run_shots", C.c_int, [_H, C.c_uint32, C.POINTER(JkqOp), C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_double)]),
     ("jkq_qasm_parse", C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(_H)]),
     ("jkq_program_error", C.c_char_p, [_H]),
     ("jkq_program_free", None, [_H]),

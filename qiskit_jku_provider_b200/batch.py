@@ -97,6 +97,28 @@ class BatchRunner:
             dev_ms += st["apply_ms"]
         return out, total_gates, dev_ms
 
+    def run_shots(self, n_qubits, ops, shots, seed=1, shot_offset=0, measure_seed0=None, physical_reset=False):
+        """Per-shot re-simulation of ONE circuit with mid-circuit measure / reset / if ops (``jkq_batch_run_shots``):
+        ``shots`` instances side by side, instance s drawing its measurement outcomes from the stream
+        ``measure_seed0 + s``.  Returns (keys[shots], mid_bits[shots], status[shots], gate applies, kernel ms);
+        status != 0 marks an instance that outgrew the single-CTA path."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        shots = int(shots)
+        keys = np.zeros(max(1, shots), dtype=np.uint64)
+        bits = np.zeros(max(1, shots), dtype=np.uint64)
+        status = np.zeros(max(1, shots), dtype=np.int32)
+        gates, ms = C.c_uint64(0), C.c_double(0)
+        u64p = C.POINTER(C.c_uint64)
+        if measure_seed0 is None:
+            measure_seed0 = (int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        rc = self._lib.jkq_batch_run_shots(self._b, int(n_qubits), ops.ctypes.data_as(C.POINTER(_native.JkqOp)) if len(ops) else None, len(ops),
+                                           shots, int(seed), int(shot_offset), int(measure_seed0) & 0xFFFFFFFFFFFFFFFF, int(bool(physical_reset)),
+                                           keys.ctypes.data_as(u64p), bits.ctypes.data_as(u64p), status.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           C.byref(gates), C.byref(ms))
+        if rc != 0:
+            raise JKUSimulatorError("jkq_batch_run_shots failed (%d): %s" % (rc, self._lib.jkq_batch_last_error(self._b).decode()))
+        return keys[:shots], bits[:shots], status[:shots], int(gates.value), float(ms.value)
+
     def close(self):
         if getattr(self, "_b", None):
             self._lib.jkq_batch_destroy(self._b)

@@ -72,7 +72,7 @@ __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *o
 // Simulator::AssignProbsOne (Simulator.cpp:291-339): probability that the qubit on `level` reads 0.  The arena
 // is level-ordered and the sampling records hold every node's branch probability, so the path mass is pushed
 // down from the root one level at a time; at `level` the masses times q0 add up to P(0).  One CTA.
-__global__ void __launch_bounds__(256) k_marginal(const JEng *E, const JSNode *sn, double *mass, int level, double *out) {
+__device__ double marginal_block(const JEng *E, const JSNode *sn, double *mass, int level) {
   __shared__ double s_sum;
   const int n = (int)E->n;
   const uint32_t total = E->node_count;
@@ -97,7 +97,13 @@ __global__ void __launch_bounds__(256) k_marginal(const JEng *E, const JSNode *s
   for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += mass[off + i] * sn[off + i].q0;
   atomicAdd(&s_sum, acc);
   __syncthreads();
-  if (threadIdx.x == 0) *out = s_sum;
+  const double r = s_sum;
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(256) k_marginal(const JEng *E, const JSNode *sn, double *mass, int level, double *out) {
+  const double p0 = marginal_block(E, sn, mass, level);
+  if (threadIdx.x == 0) *out = p0;
 }
 
 // Simulator::GetProbability for every assignment of a set of qubits (the "probabilities" of a snapshot,
@@ -1245,6 +1251,162 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
   }
 }
 
+// ---- per-shot re-simulation as one kernel ------------------------------------------------------------------
+// A circuit with a gate behind a measurement cannot reuse its final state: the reference parses and simulates it
+// again for every shot (QASMsimulator.cpp:501-522).  Here `n_shots` instances of the SAME gate list go through the
+// queue of k_batch's scheme, one CTA per SM; an instance handles MeasureOne / ResetQubit / `if` itself: it stops
+// before the op's gate slot, builds the sampling records, takes the qubit's marginal (marginal_block), draws the
+// outcome from the Philox stream (measure seed of the instance, index of the op) -- the same numbers the host path
+// of jkq_apply draws -- writes the projector (and X) into two private gate slots and runs them as ordinary gates.
+struct JShotSlot {   // one per gate slot of the circuit
+  uint32_t kind;     // 0 gate | 1 measure projector | 2,3 reset (reference: X-or-identity, projector) | 4,5 reset (physical: projector, X-or-identity)
+  uint32_t clbit;
+  uint32_t op_index; // Philox counter of the draw
+  uint32_t if_skip;  // > 0: an `if` guards the if_skip slots starting here
+  uint64_t if_mask, if_value;
+};
+
+__device__ double philox_uniform_dev(uint64_t seed, uint64_t counter) {  // twin of philox_uniform (host)
+  uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0x4D454153u, 0};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+}
+
+__global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, JBatchCirc cd, const JGate *gates, const JShotSlot *slots,
+                                                       JGate *priv_all, unsigned int n_shots, unsigned int *next, uint64_t measure_seed0,
+                                                       uint64_t shot_offset, JBatchOut *out, unsigned long long *keys,
+                                                       unsigned long long *mid_bits) {
+  __shared__ unsigned int s_i;
+  __shared__ unsigned long long s_bits;
+  __shared__ int s_g, s_h;
+  const JBatchEng be = engs[blockIdx.x];
+  JEng *E = be.E;
+  JGate *priv = priv_all + 2 * blockIdx.x;
+  const int n_gates = (int)cd.n_gates;
+  for (;;) {
+    if (threadIdx.x == 0) s_i = atomicAdd(next, 1u);
+    __syncthreads();
+    const unsigned int inst = s_i;
+    __syncthreads();
+    if (inst >= n_shots) break;
+    if (threadIdx.x == 0) { E->n = cd.n; E->lvl_log = nullptr; E->mat_u = nullptr; E->mat_epoch = nullptr; E->cursor_saved = 0; s_bits = 0; }
+    {
+      Ctx c = make_ctx<MODE_CTA>(E);
+      init_state<MODE_CTA>(c);
+    }
+    __threadfence();
+    __syncthreads();
+    int st = 0, g = 0;
+    uint64_t placeholders = 0;
+    // after a segment: did the single-CTA path finish it?
+    auto segment_status = [&](int upto) {
+      __threadfence();
+      __syncthreads();
+      int r = *(volatile int *)&E->status;
+      if (!r && (*(volatile int *)&E->next_gate < upto || *(volatile int *)&E->want_grid || *(volatile unsigned int *)&E->cursor_saved))
+        r = JKQ_ERR_ITEM_FULL;  // outgrew the single-CTA path
+      return r;
+    };
+    while (!st && g < n_gates) {
+      const JShotSlot sl = slots[g];
+      if (sl.if_skip && (s_bits & sl.if_mask) != sl.if_value) {  // `if` is false: step over the guarded slots
+        g += (int)sl.if_skip;
+        __syncthreads();
+        if (threadIdx.x == 0) E->next_gate = g;
+        __threadfence();
+        __syncthreads();
+        continue;
+      }
+      if (sl.kind == 0) {
+        // plain gates up to the next slot that needs a decision
+        if (threadIdx.x == 0) {
+          int h = g + 1;
+          while (h < n_gates && slots[h].kind == 0 && slots[h].if_skip == 0) h++;
+          s_h = h;
+        }
+        __syncthreads();
+        const int h = s_h;
+        __syncthreads();
+        Ctx c = make_ctx<MODE_CTA>(E);
+        run_gates<MODE_CTA>(c, gates, h);
+        st = segment_status(h);
+        g = h;
+        continue;
+      }
+      // MeasureOne / ResetQubit: P(qubit reads 0) in the state as it is now
+      {
+        Ctx c = make_ctx<MODE_CTA>(E);
+        build_sampling<MODE_CTA>(c, be.sn, be.prob);
+      }
+      __threadfence();
+      __syncthreads();
+      st = *(volatile int *)&E->status;
+      if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
+      if (st) break;
+      const int level = gates[g].target;
+      double p0 = marginal_block(E, be.sn, be.prob, level);
+      if (p0 < 0.0) p0 = 0.0;
+      if (p0 > 1.0) p0 = 1.0;
+      const double norm = E->norm > 0.0 ? E->norm : 1.0;
+      if (threadIdx.x == 0) {
+        JGate a = gates[g], b = gates[g + (sl.kind == 1 ? 0 : 1)];
+        for (int k = 0; k < 8; k++) { a.m[k] = 0.0; b.m[k] = 0.0; }
+        if (sl.kind == 2) {  // the reference's reset: projection on |0>, X first when P(0) = 0
+          double p = p0;
+          if (p0 <= 0.0) { a.m[2] = 1.0; a.m[4] = 1.0; p = 1.0; }
+          else { a.m[0] = 1.0; a.m[6] = 1.0; }
+          b.m[0] = 1.0 / sqrt(p * norm);
+        } else {
+          const double u = philox_uniform_dev(measure_seed0 + inst, (uint64_t)sl.op_index);
+          const int outcome = u < p0 ? 0 : 1;
+          const double p = outcome ? 1.0 - p0 : p0;
+          if (!(p > 0.0)) E->status = JKQ_ERR_ZERO_STATE;
+          else a.m[outcome ? 6 : 0] = 1.0 / sqrt(p * norm);
+          if (sl.kind == 1) {
+            if (outcome) s_bits |= 1ull << sl.clbit;
+            else s_bits &= ~(1ull << sl.clbit);
+          } else if (outcome) { b.m[2] = 1.0; b.m[4] = 1.0; }
+          else { b.m[0] = 1.0; b.m[6] = 1.0; }
+        }
+        priv[0] = a;
+        priv[1] = b;
+      }
+      __threadfence();
+      __syncthreads();
+      st = *(volatile int *)&E->status;
+      if (st) break;
+      const int n_slots = sl.kind == 1 ? 1 : 2;
+      {
+        Ctx c = make_ctx<MODE_CTA>(E);
+        run_gates<MODE_CTA>(c, priv - g, g + n_slots);  // gate index g is priv[0]
+      }
+      st = segment_status(g + n_slots);
+      g += n_slots;
+      placeholders += (uint64_t)n_slots;
+    }
+    unsigned long long key = 0;
+    if (!st) {
+      Ctx c = make_ctx<MODE_CTA>(E);
+      build_sampling<MODE_CTA>(c, be.sn, be.prob);
+      __threadfence();
+      __syncthreads();
+      st = *(volatile int *)&E->status;
+      if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
+      // MeasureAll once (Simulator.cpp:148-224): shot (shot_offset + inst) of the sampling stream
+      if (!st && threadIdx.x == 0) key = sample_walk(be.sn, E->root, (int)cd.n, cd.sp.bitpos, cd.seed, shot_offset + inst);
+    }
+    if (threadIdx.x == 0) {
+      JBatchOut o;
+      o.status = st; o.n_distinct = st ? 0u : 1u; o.gates = (uint64_t)E->st[JST_GATES] - placeholders;
+      out[inst] = o;
+      keys[inst] = key;
+      if (mid_bits) mid_bits[inst] = s_bits;
+      E->status = 0; E->want_grid = 0; E->cursor_saved = 0;
+    }
+    __syncthreads();
+  }
+}
+
 struct jkq_batch {
   int device = 0, sm_count = 0;
   jkq_config cfg;
@@ -1263,6 +1425,10 @@ struct jkq_batch {
   unsigned long long *res_dev = nullptr, *res_pin = nullptr;  // keys then counts
   size_t res_cap = 0;
   uint64_t hslots = 0;
+  JGate *priv_dev = nullptr;          // two private gate slots per engine (k_batch_shots)
+  JShotSlot *slots_dev = nullptr;
+  size_t slots_cap = 0;
+  bool engs_uploaded = false;
 };
 
 extern "C" const char *jkq_batch_last_error(const jkq_batch *b) { return b ? b->err.c_str() : "null batch"; }
@@ -1272,6 +1438,7 @@ extern "C" void jkq_batch_destroy(jkq_batch *b) {
   cudaSetDevice(b->device);
   for (jkq_handle *h : b->eng) jkq_destroy(h);
   cudaFree(b->engs_dev); cudaFree(b->next_dev); cudaFree(b->gates_dev); cudaFree(b->circ_dev); cudaFree(b->out_dev); cudaFree(b->res_dev);
+  cudaFree(b->priv_dev); cudaFree(b->slots_dev);
   if (b->gates_pin) cudaFreeHost(b->gates_pin);
   if (b->circ_pin) cudaFreeHost(b->circ_pin);
   if (b->out_pin) cudaFreeHost(b->out_pin);
@@ -1326,6 +1493,8 @@ extern "C" int jkq_batch_create(jkq_batch **out, int device, int n_engines, cons
   BCU(cudaMalloc(&b->engs_dev, b->eng.size() * sizeof(JBatchEng)));
   BCU(cudaMalloc(&b->next_dev, 4));
   BCU(cudaFuncSetAttribute(k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  BCU(cudaFuncSetAttribute(k_batch_shots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  BCU(cudaMalloc(&b->priv_dev, b->eng.size() * 2 * sizeof(JGate)));
   // the control blocks of the engines: written once (the kernel initialises the per-circuit part itself)
   for (jkq_handle *h : b->eng) {
     JEng &E = h->host;
@@ -1382,6 +1551,7 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
       h->hslots = hslots;
     }
     b->hslots = hslots;
+    b->engs_uploaded = true;
     std::vector<JBatchEng> be(b->eng.size());
     for (size_t e = 0; e < b->eng.size(); e++) {
       jkq_handle *h = b->eng[e];
@@ -1447,6 +1617,120 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
   if (gates_applied) *gates_applied = total;
   float ms = 0;
   if (apply_ms_sum && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *apply_ms_sum = ms;
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_batch_run_shots(jkq_batch *b, uint32_t n_qubits, const jkq_op *ops, size_t n_ops, uint64_t shots, uint64_t seed,
+                                   uint64_t shot_offset, uint64_t measure_seed0, int physical_reset, uint64_t *keys, uint64_t *mid_bits,
+                                   int32_t *status, uint64_t *gates_applied, double *kernel_ms) {
+  if (!b || (n_ops && !ops) || !keys || !status) return JKQ_E_ARGUMENT;
+  BCU(cudaSetDevice(b->device));
+  b->err.clear();
+  if (gates_applied) *gates_applied = 0;
+  if (kernel_ms) *kernel_ms = 0;
+  if (shots == 0) return JKQ_E_OK;
+  if (shots > 0xFFFFFFF0ull) { b->err = "too many shots for one launch"; return JKQ_E_ARGUMENT; }
+  // ---- host: gate descriptors (placeholder slots for measure / reset) and what each slot is
+  std::vector<JGate> gates;
+  std::vector<int> gate_of_op;
+  JBatchCirc cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.n = n_qubits; cd.seed = seed;
+  {
+    std::string err;
+    int rc = parse_ops(&err, n_qubits, ops, n_ops, gates, &gate_of_op, cd.sp, nullptr, nullptr);
+    if (rc) { b->err = err; return rc; }
+  }
+  cd.n_gates = (uint32_t)gates.size();
+  gate_of_op.push_back((int)gates.size());
+  std::vector<JShotSlot> slots(gates.size() + 1);
+  memset(slots.data(), 0, slots.size() * sizeof(JShotSlot));
+  for (size_t i = 0; i < n_ops; i++) {
+    const jkq_op &o = ops[i];
+    const int g = gate_of_op[i];
+    if (o.kind == JKQ_OP_MEASURE_ONE) {
+      slots[g].kind = 1; slots[g].clbit = o.arg; slots[g].op_index = (uint32_t)i;
+    } else if (o.kind == JKQ_OP_RESET) {
+      slots[g].kind = physical_reset ? 4 : 2; slots[g + 1].kind = physical_reset ? 5 : 3;
+      slots[g].op_index = (uint32_t)i;
+    } else if (o.kind == JKQ_OP_IF) {
+      const size_t cnt = o.arg ? o.arg : 1;
+      const int first = gate_of_op[i + 1], last = gate_of_op[i + 1 + cnt];
+      if (last > first) { slots[first].if_skip = (uint32_t)(last - first); slots[first].if_mask = o.ctrl_pos; slots[first].if_value = o.ctrl_neg; }
+    }  // (SNAPSHOT / PROBABILITIES ops record nothing on this path)
+  }
+  // ---- buffers (grow-only)
+  if (!b->engs_uploaded) {
+    std::vector<JBatchEng> be(b->eng.size());
+    for (size_t e = 0; e < b->eng.size(); e++) {
+      jkq_handle *h = b->eng[e];
+      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hk = h->hk; be[e].hc = h->hc;
+    }
+    BCU(cudaMemcpy(b->engs_dev, be.data(), be.size() * sizeof(JBatchEng), cudaMemcpyHostToDevice));
+    b->engs_uploaded = true;
+  }
+  if (gates.size() + 1 > b->gates_cap) {
+    cudaFree(b->gates_dev);
+    if (b->gates_pin) cudaFreeHost(b->gates_pin);
+    b->gates_cap = pow2_at_least(gates.size() + 1, 1024);
+    BCU(cudaMalloc(&b->gates_dev, b->gates_cap * sizeof(JGate)));
+    BCU(cudaMallocHost(&b->gates_pin, b->gates_cap * sizeof(JGate)));
+  }
+  if (slots.size() > b->slots_cap) {
+    cudaFree(b->slots_dev);
+    b->slots_cap = pow2_at_least(slots.size(), 1024);
+    BCU(cudaMalloc(&b->slots_dev, b->slots_cap * sizeof(JShotSlot)));
+  }
+  if (shots > b->circ_cap) {
+    cudaFree(b->circ_dev); cudaFree(b->out_dev);
+    if (b->circ_pin) cudaFreeHost(b->circ_pin);
+    if (b->out_pin) cudaFreeHost(b->out_pin);
+    b->circ_cap = pow2_at_least(shots, 64);
+    BCU(cudaMalloc(&b->circ_dev, b->circ_cap * sizeof(JBatchCirc)));
+    BCU(cudaMalloc(&b->out_dev, b->circ_cap * sizeof(JBatchOut)));
+    BCU(cudaMallocHost(&b->circ_pin, b->circ_cap * sizeof(JBatchCirc)));
+    BCU(cudaMallocHost(&b->out_pin, b->circ_cap * sizeof(JBatchOut)));
+  }
+  const size_t res_words = 2 * (size_t)shots;
+  if (res_words > b->res_cap) {
+    cudaFree(b->res_dev);
+    if (b->res_pin) cudaFreeHost(b->res_pin);
+    b->res_cap = res_words;
+    BCU(cudaMalloc(&b->res_dev, res_words * 8));
+    BCU(cudaMallocHost(&b->res_pin, res_words * 8));
+  }
+  // ---- one launch
+  if (!gates.empty()) {
+    memcpy(b->gates_pin, gates.data(), gates.size() * sizeof(JGate));
+    BCU(cudaMemcpyAsync(b->gates_dev, b->gates_pin, gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, b->stream));
+  }
+  BCU(cudaMemcpyAsync(b->slots_dev, slots.data(), slots.size() * sizeof(JShotSlot), cudaMemcpyHostToDevice, b->stream));
+  BCU(cudaMemsetAsync(b->next_dev, 0, 4, b->stream));
+  const unsigned int blocks = (unsigned int)(shots < b->eng.size() ? shots : b->eng.size());
+  BCU(cudaEventRecord(b->ev0, b->stream));
+  k_batch_shots<<<blocks, b->cfg.cta_threads, sizeof(CtaSmem), b->stream>>>(b->engs_dev, cd, b->gates_dev, b->slots_dev, b->priv_dev, (unsigned int)shots,
+                                                                           b->next_dev, measure_seed0, shot_offset, b->out_dev, b->res_dev,
+                                                                           b->res_dev + shots);
+  BCU(cudaGetLastError());
+  BCU(cudaEventRecord(b->ev1, b->stream));
+  BCU(cudaMemcpyAsync(b->out_pin, b->out_dev, shots * sizeof(JBatchOut), cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaMemcpyAsync(b->res_pin, b->res_dev, res_words * 8, cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaStreamSynchronize(b->stream));  // (also covers the pageable copy of `slots`)
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < shots; i++) {
+    const JBatchOut &o = b->out_pin[i];
+    status[i] = o.status;
+    keys[i] = b->res_pin[i];
+    if (mid_bits) mid_bits[i] = b->res_pin[shots + i];
+    if (o.status) {
+      if (b->err.empty()) b->err = "shot " + std::to_string(i) + ": " + status_text(o.status);
+      continue;
+    }
+    total += o.gates;
+  }
+  if (gates_applied) *gates_applied = total;
+  float ms = 0;
+  if (kernel_ms && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *kernel_ms = ms;
   return JKQ_E_OK;
 }
 
