@@ -284,6 +284,7 @@ struct jkq_handle {
   std::string err;
   JEng host;       // host mirror of the control block
   JEng *dev = nullptr;
+  void *slab = nullptr;  // the one device allocation behind the arenas, tables, control block and sampling records
   JSNode *snodes = nullptr;
   double *prob = nullptr;
   uint32_t *lvl_log = nullptr;
@@ -368,11 +369,10 @@ extern "C" void jkq_destroy(jkq_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   JEng &E = h->host;
-  cudaFree(E.nodes); cudaFree(E.nodes_alt); cudaFree(E.utab); cudaFree(E.vals); cudaFree(E.vals_alt); cudaFree(E.vtab);
-  cudaFree(E.pend); cudaFree(E.items); cudaFree(E.dtab); cudaFree(E.mdir); cudaFree(E.thin_spill); cudaFree(E.fwd); cudaFree(E.vfwd);
-  cudaFree(h->dev); cudaFree(h->snodes); cudaFree(h->prob); cudaFree(h->lvl_log); cudaFree(h->gates_dev);
-  cudaFree(h->mat_u); cudaFree(h->mat_epoch); cudaFree(h->scalar_dev);
-  cudaFree(h->n_out); cudaFree(h->overflow);
+  (void)E;
+  cudaFree(h->slab);  // arenas, tables, control block, sampling records: one allocation (jkq_create)
+  cudaFree(h->lvl_log); cudaFree(h->gates_dev);
+  cudaFree(h->mat_u); cudaFree(h->mat_epoch);
   if (h->gates_pin) cudaFreeHost(h->gates_pin);
   free_hist(h);
   free_snapshots(h);
@@ -423,28 +423,27 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   E.pend_cap = cfg.value_capacity;
   E.item_cap = cfg.item_capacity; E.dtab_mask = cfg.item_capacity * 2 - 1;
   E.cta_item_limit = cfg.cta_item_limit; E.gc_min = cfg.gc_min;
-  CU(cudaMalloc(&E.nodes, (size_t)E.node_cap * sizeof(JNode)));
-  CU(cudaMalloc(&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)));
-  CU(cudaMalloc(&E.utab, ((size_t)E.utab_mask + 1) * 4));
-  CU(cudaMalloc(&E.vals, (size_t)E.val_cap * 8));
-  CU(cudaMalloc(&E.vals_alt, (size_t)E.val_cap * 8));
-  CU(cudaMalloc(&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)));
-  CU(cudaMalloc(&E.pend, (size_t)E.pend_cap * 4));
-  CU(cudaMalloc(&E.items, (size_t)E.item_cap * sizeof(JItem)));
-  CU(cudaMalloc(&E.dtab, ((size_t)E.dtab_mask + 1) * 8));
-  CU(cudaMalloc(&E.mdir, (size_t)E.node_cap * 8));
-  CU(cudaMalloc(&E.thin_spill, sizeof(ThinState)));
+  // One slab per handle, carved into the arenas and tables (a pool of 148 small engines would otherwise spend
+  // most of its creation time in ~25 driver allocations each).
+  {
+    struct Part { void **ptr; size_t bytes; };
+    const Part parts[] = {
+        {(void **)&E.nodes, (size_t)E.node_cap * sizeof(JNode)}, {(void **)&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)},
+        {(void **)&E.utab, ((size_t)E.utab_mask + 1) * 4}, {(void **)&E.vals, (size_t)E.val_cap * 8}, {(void **)&E.vals_alt, (size_t)E.val_cap * 8},
+        {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.pend, (size_t)E.pend_cap * 4},
+        {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
+        {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
+        {(void **)&E.vfwd, (size_t)E.val_cap * 4}, {(void **)&h->dev, sizeof(JEng)}, {(void **)&h->snodes, (size_t)E.node_cap * sizeof(JSNode)},
+        {(void **)&h->prob, (size_t)E.node_cap * 8}, {(void **)&h->n_out, 8}, {(void **)&h->overflow, 4}, {(void **)&h->scalar_dev, 8}};
+    size_t total = 0;
+    for (const Part &p : parts) total += (p.bytes + 255) & ~(size_t)255;
+    CU(cudaMalloc(&h->slab, total));
+    size_t off = 0;
+    for (const Part &p : parts) { *p.ptr = (char *)h->slab + off; off += (p.bytes + 255) & ~(size_t)255; }
+  }
   // generation-tagged de-dup tables: zeroed once, never cleared again (the generation counts across circuits)
   CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
   CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
-  CU(cudaMalloc(&E.fwd, (size_t)E.node_cap * 4));
-  CU(cudaMalloc(&E.vfwd, (size_t)E.val_cap * 4));
-  CU(cudaMalloc(&h->dev, sizeof(JEng)));
-  CU(cudaMalloc(&h->snodes, (size_t)E.node_cap * sizeof(JSNode)));
-  CU(cudaMalloc(&h->prob, (size_t)E.node_cap * 8));
-  CU(cudaMalloc(&h->n_out, 8));
-  CU(cudaMalloc(&h->overflow, 4));
-  CU(cudaMalloc(&h->scalar_dev, 8));
   CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   // cooperative grid size: every CTA must be resident

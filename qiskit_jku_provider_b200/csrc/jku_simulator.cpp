@@ -303,12 +303,39 @@ int main(int argc, char **argv) {
     if (rc) r.die("jkq_sample", rc);
     add_counts();
   } else {
+    // Per-shot re-simulation (QASMsimulator.cpp:501-522) as one kernel launch: every shot is an instance of the
+    // circuit on its own SM with its own measurement outcomes.  Shot s: measurement stream `mseed + s`, final
+    // MeasureAll = shot s of stream `seed` -- the same draws as the sequential loop below, which serves the shots
+    // the single-CTA path could not finish.
+    const uint64_t mseed = (uint64_t)seed * 0x9E3779B97F4A7C15ull;
+    std::vector<uint64_t> keys(shots);
+    std::vector<int32_t> status(shots, 1);
+    jkq_batch *batch = nullptr;
+    uint64_t batch_gates = 0;
+    if (jkq_batch_create(&batch, opt.device, 1 << 16, &cfg) == 0) {
+      if (jkq_batch_run_shots(batch, info.n_qubits, info.ops, info.n_ops, shots, seed, 0, mseed, 0, keys.data(), nullptr, status.data(),
+                              &batch_gates, nullptr) != 0)
+        std::fill(status.begin(), status.end(), 1);
+    }
+    if (batch) jkq_batch_destroy(batch);
+    unsigned long left = 0;
     for (unsigned long s = 0; s < shots; s++) {
-      r.apply(info.n_ops, seed * 0x9E3779B97F4A7C15ull + s);
+      if (status[s]) { left++; continue; }
+      std::string str(info.n_qubits, '0');
+      for (uint32_t q = 0; q < info.n_qubits; q++) str[q] = (char)('0' + ((keys[s] >> q) & 1));
+      result[str] += 1;
+    }
+    bool want_last = info.n_snapshots > 0 || opt.ps;  // snapshots, show_probabilities and stats come from the last shot's run
+    for (size_t i = 0; i < info.n_ops; i++) want_last = want_last || info.ops[i].kind == JKQ_OP_PROBABILITIES;
+    for (unsigned long s = 0; s < shots; s++) {
+      if (!status[s] && !(want_last && s == shots - 1)) continue;
+      r.apply(info.n_ops, mseed + s);
+      if (!status[s]) continue;  // (only re-run for its snapshots)
       rc = jkq_sample(r.h, 1, seed, s, 0);
       if (rc) r.die("jkq_sample", rc);
       add_counts();
     }
+    (void)left;
     r.collect(info.n_ops, opt.statevector, opt.probabilities);
   }
   const auto t2 = std::chrono::high_resolution_clock::now();
