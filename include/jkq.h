@@ -152,6 +152,15 @@ int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *host_nodes,
                   const uint8_t *clbit_of_level);
 int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n);
 
+/* Sparse histogram exchange between GPUs: every outcome key has an owner rank (a hash of the key).
+ * jkq_counts_partition sorts this handle's (key, count) pairs by owner into DEVICE buffers of the caller (`cap` entries
+ * each; NULL = only count) and reports per_owner[world] -- the split sizes of the all-to-all the caller runs (NCCL);
+ * jkq_counts_merge adds received pairs (DEVICE buffers) into the handle's histogram (reset = 1: start an empty one
+ * with room for `expect` keys), after which jkq_get_counts returns the keys this rank owns.  The caller makes sure
+ * the buffers are complete before the call (synchronise the producing stream); both calls return synchronised. */
+int jkq_counts_partition(jkq_handle *h, uint32_t world, uint64_t *dev_keys, uint64_t *dev_counts, size_t cap, uint64_t *per_owner);
+int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const uint64_t *dev_counts, size_t n, size_t expect, int reset);
+
 /* Batches of independent circuits (the reference runs one `jku_simulator` process per experiment,
  * sequentially: qasm_simulator_jku.py:340-359).  A pool of `n_engines` small engines; each circuit runs as one
  * persistent single-CTA kernel chain on its own stream, so circuits of the batch occupy different SMs.

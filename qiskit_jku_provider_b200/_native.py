@@ -62,6 +62,8 @@ SYMBOLS = [
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("jkq_dd_import", C.c_int, [_H, C.c_uint32, C.POINTER(JkqSNode), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     ("jkq_get_measure_map", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_size_t]),
+    ("jkq_counts_partition", C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
+    ("jkq_counts_merge", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     ("jkq_batch_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.POINTER(JkqConfig)]),
     ("jkq_batch_destroy", None, [_H]),
     ("jkq_batch_last_error", C.c_char_p, [_H]),

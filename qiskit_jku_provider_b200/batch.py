@@ -110,7 +110,7 @@ class BatchRunner:
         gates, ms = C.c_uint64(0), C.c_double(0)
         u64p = C.POINTER(C.c_uint64)
         if measure_seed0 is None:
-            measure_seed0 = (int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+            measure_seed0 = (int(seed) * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF  # (same default as multi_gpu.run_shots_sharded)
         rc = self._lib.jkq_batch_run_shots(self._b, int(n_qubits), ops.ctypes.data_as(C.POINTER(_native.JkqOp)) if len(ops) else None, len(ops),
                                            shots, int(seed), int(shot_offset), int(measure_seed0) & 0xFFFFFFFFFFFFFFFF, int(bool(physical_reset)),
                                            keys.ctypes.data_as(u64p), bits.ctypes.data_as(u64p), status.ctypes.data_as(C.POINTER(C.c_int32)),

@@ -253,6 +253,46 @@ __global__ void k_hist_compact(const unsigned long long *hk, const unsigned long
   }
 }
 
+// ---- sparse histogram exchange between GPUs ---------------------------------------------------
+// A histogram with up to 10^9 distinct outcomes does not fit a dense all-reduce: every outcome key has an OWNER rank
+// (hash of the key, independent of the slot hash), each rank sorts its (key, count) pairs by owner into one send
+// buffer (count pass, prefix on the host, scatter pass), the pairs travel in one all-to-all, and the owner adds what
+// it received into its histogram with the same insert the sampler uses.
+__device__ __forceinline__ uint32_t hist_owner(uint64_t key, uint32_t world) { return (uint32_t)((jmix(key ^ 0x5851F42D4C957F2Dull) >> 32) % world); }
+
+__global__ void __launch_bounds__(256) k_hist_owner_count(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, uint32_t world,
+                                                          unsigned long long *per_owner) {
+  __shared__ unsigned int s_cnt[64];
+  for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x)
+    if (hk[i] != JH_EMPTY) atomicAdd(&s_cnt[hist_owner(hk[i], world)], 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) atomicAdd(&s_cnt[hist_owner(JH_EMPTY, world)], 1u);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(per_owner + i, (unsigned long long)s_cnt[i]);
+}
+
+__global__ void __launch_bounds__(256) k_hist_owner_scatter(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, uint32_t world,
+                                                            unsigned long long *cursor, unsigned long long *out_keys, unsigned long long *out_counts) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = hk[i];
+    if (key == JH_EMPTY) continue;
+    const unsigned long long p = atomicAdd(cursor + hist_owner(key, world), 1ull);
+    out_keys[p] = key; out_counts[p] = hc[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) {
+    const unsigned long long p = atomicAdd(cursor + hist_owner(JH_EMPTY, world), 1ull);
+    out_keys[p] = JH_EMPTY; out_counts[p] = hc[slots];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_hist_merge(unsigned long long *hk, unsigned long long *hc, uint32_t hmask, const unsigned long long *in_keys,
+                                                    const unsigned long long *in_counts, uint64_t n, int *overflow) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    if (in_counts[i]) hist_global_add(hk, hc, hmask, in_keys[i], in_counts[i], overflow);
+}
+
 // Roofline denominators measured on the device in use: uniform random 32-byte sector reads
 // (ld.global.cg, one sector per load) and random 64-bit atomicCAS.
 __global__ void k_random_sector(const uint4 *buf, uint64_t n_sectors2, int per_thread, uint64_t seed, unsigned long long *sink) {
@@ -1008,6 +1048,67 @@ extern "C" int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, s
     CU(cudaMemcpyAsync(counts, h->oc, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
+  return JKQ_E_OK;
+}
+
+// sort this handle's histogram by owner rank into caller-provided DEVICE buffers (sparse exchange)
+extern "C" int jkq_counts_partition(jkq_handle *h, uint32_t world, uint64_t *dev_keys, uint64_t *dev_counts, size_t cap, uint64_t *per_owner) {
+  if (!h || !per_owner || world < 1 || world > 64) return JKQ_E_ARGUMENT;
+  if (!h->hist_valid) return fail(h, JKQ_E_STATE, "no histogram: call jkq_sample first");
+  CU(cudaSetDevice(h->device));
+  unsigned long long *cnt = nullptr;
+  CU(cudaMalloc(&cnt, 64 * 8));
+  CU(cudaMemsetAsync(cnt, 0, 64 * 8, h->stream));
+  k_hist_owner_count<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, world, cnt);
+  unsigned long long host_cnt[64];
+  cudaError_t e = cudaMemcpyAsync(host_cnt, cnt, 64 * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { cudaFree(cnt); return fail(h, JKQ_E_CUDA, "jkq_counts_partition: %s", cudaGetErrorString(e)); }
+  uint64_t total = 0;
+  unsigned long long offs[64];
+  for (uint32_t r = 0; r < world; r++) { per_owner[r] = host_cnt[r]; offs[r] = total; total += host_cnt[r]; }
+  h->stats.distinct_outcomes = total;
+  if (!dev_keys || !dev_counts) { cudaFree(cnt); return JKQ_E_OK; }  // size query
+  if (cap < total) { cudaFree(cnt); return fail(h, JKQ_E_CAPACITY, "%llu distinct outcomes, buffers hold %zu", (unsigned long long)total, cap); }
+  e = cudaMemcpyAsync(cnt, offs, world * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    k_hist_owner_scatter<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, world, cnt, (unsigned long long *)dev_keys,
+                                                                  (unsigned long long *)dev_counts);
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(cnt);
+  if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "jkq_counts_partition: %s", cudaGetErrorString(e));
+  return JKQ_E_OK;
+}
+
+// add (key, count) pairs from DEVICE buffers into the histogram; reset = 1 starts an empty one sized for `expect` keys
+extern "C" int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const uint64_t *dev_counts, size_t n, size_t expect, int reset) {
+  if (!h || (n && (!dev_keys || !dev_counts))) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  if (reset || !h->hist_valid) {
+    const uint64_t slots = pow2_at_least((uint64_t)(expect > n ? expect : n) * 2, 1u << 12);
+    if (slots > h->hslots) {
+      free_hist(h);
+      CU(cudaMalloc(&h->hk, slots * 8));
+      CU(cudaMalloc(&h->hc, (slots + 1) * 8));
+      h->hslots = slots;
+    }
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
+    h->hist_valid = true;
+  }
+  if (n) {
+    uint64_t want = (n + 255) / 256;
+    int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
+    k_hist_merge<<<blocks, 256, 0, h->stream>>>(h->hk, h->hc, (uint32_t)(h->hslots - 1), (const unsigned long long *)dev_keys,
+                                                (const unsigned long long *)dev_counts, n, h->overflow);
+    CU(cudaGetLastError());
+  }
+  int ovf = 0;
+  CU(cudaMemcpyAsync(&ovf, h->overflow, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (ovf) return fail(h, JKQ_E_CAPACITY, "count histogram overflow while merging (raise `expect`)");
   return JKQ_E_OK;
 }
 

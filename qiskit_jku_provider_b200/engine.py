@@ -163,6 +163,12 @@ class Engine:
                                              v.ctypes.data_as(C.POINTER(C.c_uint64)), k.size, C.byref(n)))
         return k[:n.value], v[:n.value]
 
+    def distinct_outcomes(self):
+        """number of distinct outcomes in the histogram (no copy)"""
+        n = C.c_size_t(0)
+        self._check(self._lib.jkq_get_counts(self._h, None, None, 0, C.byref(n)))
+        return int(n.value)
+
     def counts(self):
         """{outcome as int (bit c = classical bit c): count}"""
         k, v = self.counts_arrays()
@@ -240,6 +246,17 @@ class Engine:
         self._check(self._lib.jkq_dd_import(self._h, int(n_qubits), nodes.ctypes.data_as(C.POINTER(_native.JkqSNode)),
                                             nodes.size, int(root), m.ctypes.data_as(C.POINTER(C.c_uint8))))
         self.n = int(n_qubits)
+
+    def counts_partition(self, world, dev_keys=0, dev_counts=0, cap=0):
+        """Sort the histogram by owner rank into device buffers (raw pointers; 0 = only count): per-owner sizes."""
+        per = (C.c_uint64 * 64)()
+        self._check(self._lib.jkq_counts_partition(self._h, int(world), C.c_void_p(dev_keys or None), C.c_void_p(dev_counts or None),
+                                                   int(cap), per))
+        return [int(per[r]) for r in range(world)]
+
+    def counts_merge(self, dev_keys, dev_counts, n, expect=0, reset=True):
+        self._check(self._lib.jkq_counts_merge(self._h, C.c_void_p(dev_keys or None), C.c_void_p(dev_counts or None), int(n), int(expect),
+                                               int(bool(reset))))
 
     def random_sector_bench(self, nbytes=1 << 32, iters=3):
         a, b = C.c_double(0), C.c_double(0)

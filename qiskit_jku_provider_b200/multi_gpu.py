@@ -4,8 +4,12 @@ The canonical DD is built on rank 0 only (hash-consing does not shard).  The fin
 sampling DD -- 16 bytes per node -- is broadcast (NCCL over NVLink on GPUs, gloo in the CPU tests),
 every rank samples the contiguous shot range ``shard(total, rank, world)`` with the Philox counter =
 GLOBAL shot index, and the count histograms are merged: dense all-reduce when the outcome space is
-small, otherwise an all-gather of (key, count) pairs reduced on every rank.  Because the stream of a
-shot depends only on (seed, global shot index), counts are identical for every world size.
+small; otherwise the sparse exchange -- every key has an owner rank, each rank sorts its (key, count)
+pairs by owner on the device (``jkq_counts_partition``), one all-to-all moves them (NCCL over NVLink), the
+owner adds them into its histogram (``jkq_counts_merge``) and the result stays distributed by owner
+(``merge_counts_by_owner``).  ``merge_counts`` (all-gather, dict on every rank) remains for small histograms.
+Because the stream of a shot depends only on (seed, global shot index), counts are identical for every
+world size.
 """
 
 import numpy as np
@@ -81,6 +85,44 @@ def merge_counts(dist, keys, counts, n_bits):
     return merged
 
 
+def exchange_by_owner(dist, keys, counts, per_owner):
+    """The one exchange step of the sparse merge: ``keys`` / ``counts`` (int64 tensors on the backend's device, sorted
+    by owner rank, ``per_owner[r]`` entries for rank r) go out in an all-to-all; returns what this rank owns."""
+    import torch
+    dev = keys.device
+    send_sizes = torch.tensor([int(x) for x in per_owner], dtype=torch.int64, device=dev)
+    recv_sizes = torch.empty_like(send_sizes)
+    dist.all_to_all_single(recv_sizes, send_sizes)
+    rs = [int(x) for x in recv_sizes.tolist()]
+    ss = [int(x) for x in per_owner]
+    got_k = torch.empty(sum(rs), dtype=torch.int64, device=dev)
+    got_c = torch.empty(sum(rs), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(got_k, keys, output_split_sizes=rs, input_split_sizes=ss)
+    dist.all_to_all_single(got_c, counts, output_split_sizes=rs, input_split_sizes=ss)
+    return got_k, got_c
+
+
+def merge_counts_by_owner(dist, engine):
+    """Sparse histogram merge on the GPUs: partition by owner -> all-to-all -> merge into the owner's histogram.
+    Afterwards ``engine.counts_arrays()`` holds the outcomes THIS rank owns with their global counts.  Returns
+    (distinct outcomes owned here, distinct outcomes in total, pairs sent, pairs received)."""
+    import torch
+    world = dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    total = sum(engine.counts_partition(world))
+    keys = torch.empty(max(1, total), dtype=torch.int64, device=dev)
+    counts = torch.empty(max(1, total), dtype=torch.int64, device=dev)
+    per = engine.counts_partition(world, keys.data_ptr(), counts.data_ptr(), total)
+    got_k, got_c = exchange_by_owner(dist, keys[:total], counts[:total], per)
+    torch.cuda.synchronize()  # the library merges on its own stream
+    engine.counts_merge(got_k.data_ptr() if got_k.numel() else 0, got_c.data_ptr() if got_c.numel() else 0, got_k.numel(),
+                        expect=got_k.numel(), reset=True)
+    owned = engine.distinct_outcomes()
+    t = torch.tensor([owned], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    return owned, int(t[0]), total, int(got_k.numel())
+
+
 def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None):
     """Run ``circuit`` on rank 0, broadcast its sampling DD, sample ``total_shots`` split over the
     ranks, return (merged counts dict, local engine stats).  ``engine``: this rank's Engine."""
@@ -102,3 +144,23 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None):
     if world > 1:
         return merge_counts(dist, keys, vals, n_bits), engine.stats()
     return {int(k): int(v) for k, v in zip(keys, vals)}, engine.stats()
+
+
+def run_shots_sharded(dist, runner, n_qubits, ops, total_shots, seed, measure_seed0=None, physical_reset=False, n_bits=None):
+    """Per-shot re-simulation of a measured circuit (``BatchRunner.run_shots``) with the shots split over the ranks:
+    rank r runs the contiguous range ``shard(total, r, world)``; shot s uses the measurement stream
+    ``measure_seed0 + s`` and read-out shot s of stream ``seed`` on whichever rank it lands, so the merged histogram
+    does not depend on the world size.  Returns (counts dict on every rank, shots this rank could not finish on
+    the single-CTA path, kernel ms of this rank)."""
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    if measure_seed0 is None:
+        measure_seed0 = (int(seed) * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
+    lo, hi = shard(total_shots, rank, world)
+    keys, _, status, _, ms = runner.run_shots(n_qubits, ops, hi - lo, seed=seed, shot_offset=lo, measure_seed0=measure_seed0 + lo,
+                                              physical_reset=physical_reset)
+    good = np.asarray(keys)[np.asarray(status) == 0]
+    uniq, cnt = np.unique(good, return_counts=True) if len(good) else (np.zeros(0, np.uint64), np.zeros(0, np.int64))
+    failed = [lo + int(i) for i in np.nonzero(np.asarray(status))[0]]
+    if world > 1:
+        return merge_counts(dist, uniq.astype(np.uint64), cnt.astype(np.uint64), n_bits if n_bits is not None else int(n_qubits)), failed, ms
+    return {int(k): int(v) for k, v in zip(uniq, cnt)}, failed, ms

@@ -63,8 +63,9 @@ def _gate_template(name, n_qubits, params):
 class JKUSimulatorWrapper:
     """Converter between Qobj experiments and the engine."""
 
-    def __init__(self, engine=None, silent=False, physical_reset=False):
+    def __init__(self, engine=None, silent=False, physical_reset=False, shots_runner=None):
         self.physical_reset = bool(physical_reset)
+        self.shots_runner = shots_runner  # batch.BatchRunner for per-shot re-simulation, or None: sequential
         self.seed = 0
         self.shots = 1
         self.engine = engine
@@ -172,13 +173,27 @@ class JKUSimulatorWrapper:
         eng.set_option("physical_reset", int(self.physical_reset))
         eng.load_ops(n, ops)
         if self.per_shot:
-            # every shot is its own run: a fresh draw for each reset, one sample of the final state
+            # Every shot is its own run with fresh measurement outcomes (QASMsimulator.cpp:501-522).  All shots go
+            # through one launch of the shots kernel (jkq_batch_run_shots: one instance per SM at a time); a shot the
+            # single-CTA path cannot finish is redone on the full engine with the same Philox streams.
+            shots = int(self.shots)
+            mseed0 = (int(self.seed) * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
             merged = {}
-            for shot in range(int(self.shots)):
-                eng.set_option("measure_seed", (int(self.seed) * 1000003 + shot) & 0x7FFFFFFFFFFFFFFF)
-                eng.run(1, int(self.seed) + shot)
+            status = np.ones(shots, dtype=np.int32)
+            if self.shots_runner is not None:
+                keys, _, status, _, _ = self.shots_runner.run_shots(n, ops, shots, seed=int(self.seed), measure_seed0=mseed0,
+                                                                    physical_reset=self.physical_reset)
+                for k in keys[status == 0].tolist():
+                    merged[k] = merged.get(k, 0) + 1
+            for shot in np.nonzero(status)[0].tolist():
+                eng.set_option("measure_seed", mseed0 + shot)
+                eng.apply()
+                eng.sample(1, seed=int(self.seed), shot_offset=shot)
                 for k, v in eng.counts().items():
                     merged[k] = merged.get(k, 0) + v
+            if not np.any(status):  # the final state of the last shot, for the snapshots
+                eng.set_option("measure_seed", mseed0 + shots - 1)
+                eng.apply()
             output_data = self.collect_output(eng, measurement_data, slots, want_sv, counts_override=merged)
         else:
             eng.run(self.shots, self.seed)
@@ -280,11 +295,19 @@ class QasmSimulator(BaseBackend):
         self._device = device
         self._engine_options = engine_options
         self._engine = None
+        self._shots_runner = None
 
     def _get_engine(self):
         if self._engine is None:  # lazy: creating the CUDA context is deferred to the first job
             self._engine = Engine(device=self._device, **self._engine_options)
         return self._engine
+
+    def _get_shots_runner(self):
+        if self._shots_runner is None:  # pool of small engines, one per SM, for per-shot re-simulation
+            from .batch import BatchRunner
+            small = {"tolerance": self._engine_options["tolerance"]} if "tolerance" in self._engine_options else None
+            self._shots_runner = BatchRunner(workers=1 << 16, device=self._device, small=small)
+        return self._shots_runner
 
     def run(self, qobj):
         job_id = str(uuid.uuid4())
@@ -296,7 +319,8 @@ class QasmSimulator(BaseBackend):
         """Run circuits in q_job"""
         result_list = []
         self._validate(qobj)
-        s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset)
+        s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset,
+                                shots_runner=self._get_shots_runner() if self.physical_reset else None)
         s.shots = qobj.config.shots
         start = time.time()
         for experiment in qobj.experiments:

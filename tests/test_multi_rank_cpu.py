@@ -65,3 +65,49 @@ def test_sharded_counts_equal_single_rank(oracle_mod, world):
         assert p.exitcode == 0
     assert dense == expect
     assert sparse == expect
+
+
+def _owner(keys, world):
+    return (keys * np.uint64(0x9E3779B97F4A7C15) >> np.uint64(40)) % np.uint64(world)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qiskit_jku_provider_b200.multi_gpu import exchange_by_owner
+    rng = np.random.default_rng(100 + rank)
+    keys = np.unique(rng.integers(0, 5000, size=3000 + 500 * rank).astype(np.uint64))
+    counts = rng.integers(1, 9, size=len(keys)).astype(np.int64)
+    own = _owner(keys, world).astype(np.int64)
+    order = np.argsort(own, kind="stable")          # what jkq_counts_partition does on the device
+    per = np.bincount(own, minlength=world).tolist()
+    got_k, got_c = exchange_by_owner(dist, torch.from_numpy(keys[order].view(np.int64).copy()), torch.from_numpy(counts[order].copy()), per)
+    gk = got_k.numpy().view(np.uint64)
+    assert (_owner(gk, world) == rank).all()       # only keys this rank owns arrive
+    merged = {}
+    for k, c in zip(gk.tolist(), got_c.tolist()):   # what jkq_counts_merge does on the device
+        merged[k] = merged.get(k, 0) + c
+    q.put((rank, dict(zip(keys.tolist(), counts.tolist())), merged))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sparse_exchange_delivers_every_pair_to_its_owner(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, have = {}, {}
+    for rank, local, merged in got:
+        for k, c in local.items():
+            want[k] = want.get(k, 0) + c
+        assert not (set(merged) & set(have))        # owners are disjoint
+        have.update(merged)
+    assert have == want
