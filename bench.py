@@ -21,8 +21,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# the contract is ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
-os.environ["NCCL_DEBUG"] = "WARN"
+# The contract is ONE JSON line on stdout.  NCCL prints its version banner to the C-level stdout at any debug level
+# from VERSION up, so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate
+# of the original stdout (emit()).
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 METRIC = "dd_gate_applies_per_s"
 UNIT = "gate-applies/s"
@@ -137,6 +147,28 @@ def executable_legs(device):
     return out
 
 
+def reference_per_shot(qasm, shots):
+    """shots/s of the unmodified reference executable on a program it re-simulates per shot (needs qelib1.inc: the
+    program is fed with the include replaced by the standard header text of the front end's built-in copy)"""
+    import subprocess
+    import tempfile
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "jku_simulator")
+    if not os.path.exists(ref_exe):
+        return None
+    header = ("gate u3(theta,phi,lambda) q { U(theta,phi,lambda) q; }\ngate u2(phi,lambda) q { U(pi/2,phi,lambda) q; }\n"
+              "gate u1(lambda) q { U(0,0,lambda) q; }\ngate cx c,t { CX c,t; }\ngate x a { u3(pi,0,pi) a; }\ngate z a { u1(pi) a; }\n"
+              "gate h a { u2(0,pi) a; }\n")
+    text = qasm.replace('include "qelib1.inc";\n', header)
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        r = subprocess.run([ref_exe, "--simulate_qasm", "--shots=%d" % shots, "--seed=1"], input=text, cwd=tmp, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, universal_newlines=True, timeout=600)
+        dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        return None
+    return {"shots": shots, "wall_s": dt, "shots_per_s": shots / dt}
+
+
 def run_reference_arm(args):
     """bench.py --impl reference: the reference's own CPU engine on the host cores, same metric and config.
     The reference is single-threaded and gate application does not shard, so N GPUs are mirrored the way our
@@ -166,14 +198,14 @@ def run_reference_arm(args):
     value = replicas * len(circ) / t
     sample = "%s: full QFT-32 circuit (2528 applies) x %d steps x %d concurrent replica process(es), apply loop timed inside the engine (std::chrono), 1 thread each" % (
         "oracle/_ref/jku_ref = unmodified reference engine, MPFR 200-bit" if kind == "reference" else "oracle/qmdd_oracle.c FP64 port", args.steps, replicas)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "mpfr200" if kind == "reference" else "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "host_threads": replicas, "note": "the reference engine is single-threaded; one replica process per GPU of our arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": wall}))
+        "wall_s": wall})
 
 
 def main():
@@ -316,7 +348,7 @@ def main():
             for _ in range(3):
                 barrier()
                 t2 = time.perf_counter()
-                counts, sst = multi_gpu.sample_sharded(dist, eng, shots, 7, circuit=c2) if dist is not None else (None, None)
+                counts, sst = multi_gpu.sample_sharded(dist, eng, shots, 7, circuit=c2, sparse="owner") if dist is not None else (None, None)
                 if dist is None:
                     eng.load(c2)
                     eng.apply()
@@ -331,6 +363,9 @@ def main():
                     k_ms = float(t[0])
                 cur = {"shots": shots, "kernel_ms_max_over_ranks": k_ms, "shots_per_s_kernel": shots / (k_ms * 1e-3),
                        "wall_s_apply_broadcast_sample_merge": w, "shots_per_s_wall": shots / w}
+                if isinstance(counts, dict) and "distinct_total" in counts:
+                    cur["merge"] = "owner exchange (jkq_counts_partition -> NCCL all-to-all -> jkq_counts_merge)"
+                    cur["distinct_total"] = counts["distinct_total"]
                 if best is None or cur["shots_per_s_kernel"] > best["shots_per_s_kernel"]:
                     best = cur
             best["algorithmic_bytes_per_shot"] = (c2.n + 1) * 32
@@ -375,7 +410,28 @@ def main():
                                              "nodes_created_per_s": s3["nodes_created"] / (s3["apply_ms"] * 1e-3),
                                              "cta_launches_total": s3["cta_launches"], "grid_launches_total": s3["grid_launches"]}
 
+        # per-shot re-simulation of a circuit with gates behind measurements: every shot is an
+        # instance of the circuit on its own SM (k_batch_shots), shots split over the ranks
+        from qiskit_jku_provider_b200.qasm import parse_qasm
+        prog = parse_qasm(C.teleport_qasm())
+        ps_shots = 200000
+        with BatchRunner(workers=1 << 16, device=local) as br:
+            multi_gpu.run_shots_sharded(dist, br, prog.n_qubits, prog.ops, 2000, 3)
+            barrier()
+            t2 = time.perf_counter()
+            merged, failed, ps_ms = multi_gpu.run_shots_sharded(dist, br, prog.n_qubits, prog.ops, ps_shots, 3)
+            barrier()
+            ps_wall = time.perf_counter() - t2
+        if dist is not None:
+            tt = torch.tensor([ps_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ps_ms = float(tt[0])
+        extra["per_shot_teleport"] = {"shots": ps_shots, "kernel_ms_max_over_ranks": ps_ms, "shots_per_s_kernel": ps_shots / (ps_ms * 1e-3),
+                                      "wall_s_ops_in_counts_out": ps_wall, "shots_per_s_wall": ps_shots / ps_wall,
+                                      "q2_always_one": all((k >> 2) & 1 for k in merged), "shots_left_to_full_engine": len(failed),
+                                      "note": "3 mid-circuit measurements + 2 conditioned gates per shot, handled on the device"}
         if rank == 0:
+            extra["per_shot_teleport"]["reference_cpu"] = reference_per_shot(C.teleport_qasm(), 400)
             extra["executable"] = executable_legs(local)
 
     if rank == 0:
@@ -416,7 +472,7 @@ def main():
                "engine_stats": {k: st[k] for k in ("gates", "items", "nodes_created", "value_inserts", "gc_runs", "retry_rounds",
                                                    "max_frontier", "live_nodes")},
                "extra": extra}
-        print(json.dumps(out))
+        emit(out)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

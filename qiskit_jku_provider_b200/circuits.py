@@ -405,3 +405,11 @@ def dense_statevector(circ):
         psi[i0] = m[0][0] * a0 + m[0][1] * a1
         psi[i1] = m[1][0] * a0 + m[1][1] * a1
     return psi
+
+
+def teleport_qasm():
+    """Teleportation of |1> from q[0] to q[2] with measured corrections: the smallest program with gates behind
+    measurements, i.e. the per-shot re-simulation workload (QASMsimulator.cpp:501-522).  q[2] reads 1 in every shot."""
+    return ('OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[3];\ncreg c0[1];\ncreg c1[1];\ncreg out[1];\n'
+            'x q[0];\nh q[1];\ncx q[1], q[2];\ncx q[0], q[1];\nh q[0];\nmeasure q[0] -> c0[0];\nmeasure q[1] -> c1[0];\n'
+            'if (c0 == 1) z q[2];\nif (c1 == 1) x q[2];\nmeasure q[2] -> out[0];\n')

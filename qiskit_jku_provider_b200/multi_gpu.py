@@ -123,9 +123,12 @@ def merge_counts_by_owner(dist, engine):
     return owned, int(t[0]), total, int(got_k.numel())
 
 
-def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None):
+def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None, sparse="gather"):
     """Run ``circuit`` on rank 0, broadcast its sampling DD, sample ``total_shots`` split over the
-    ranks, return (merged counts dict, local engine stats).  ``engine``: this rank's Engine."""
+    ranks, return (merged counts dict, local engine stats).  ``engine``: this rank's Engine.
+    ``sparse="owner"`` (NCCL only): an outcome space too large for the dense all-reduce is merged by the
+    owner exchange and stays distributed -- the first return value is then
+    {"owned": distinct outcomes in this rank's histogram, "distinct_total": ..., "pairs_sent": ...}."""
     rank, world = dist.get_rank(), dist.get_world_size()
     nodes = root = n = mm = None
     if rank == 0:
@@ -139,8 +142,11 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None):
             engine.dd_import(n, nodes, root, mm)
     lo, hi = shard(total_shots, rank, world)
     engine.sample(hi - lo, seed=seed, shot_offset=lo)
-    keys, vals = engine.counts_arrays()
     n_bits = int(sum(1 for b in mm if b < 64))
+    if world > 1 and sparse == "owner" and n_bits > DENSE_MAX_BITS and dist.get_backend() == "nccl":
+        owned, total, sent, _ = merge_counts_by_owner(dist, engine)
+        return {"owned": owned, "distinct_total": total, "pairs_sent": sent}, engine.stats()
+    keys, vals = engine.counts_arrays()
     if world > 1:
         return merge_counts(dist, keys, vals, n_bits), engine.stats()
     return {int(k): int(v) for k, v in zip(keys, vals)}, engine.stats()
