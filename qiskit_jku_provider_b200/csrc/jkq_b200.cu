@@ -275,10 +275,20 @@ __global__ void __launch_bounds__(256) k_hist_owner_count(const unsigned long lo
 
 __global__ void __launch_bounds__(256) k_hist_owner_scatter(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, uint32_t world,
                                                             unsigned long long *cursor, unsigned long long *out_keys, unsigned long long *out_counts) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-    const unsigned long long key = hk[i];
-    if (key == JH_EMPTY) continue;
-    const unsigned long long p = atomicAdd(cursor + hist_owner(key, world), 1ull);
+  // one atomic per (warp, owner) instead of one per pair: the `world` cursors are the only contended words
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, rounded = (slots + 31) & ~31ull;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    const unsigned long long key = i < slots ? hk[i] : JH_EMPTY;
+    const bool live = key != JH_EMPTY;
+    const uint32_t owner = live ? hist_owner(key, world) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, owner);
+    if (!live) continue;
+    const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long p = base + __popc(peers & ((1u << lane) - 1u));
     out_keys[p] = key; out_counts[p] = hc[i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) {
@@ -1372,6 +1382,14 @@ __device__ double philox_uniform_dev(uint64_t seed, uint64_t counter) {  // twin
   return ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
 }
 
+#ifdef JKQ_PROFILE
+__device__ unsigned long long g_shot_prof[8];  // cycles: 0 plain gates 1 build_sampling 2 marginal 3 projector gates 4 final sampling 5 init; 6 shots
+#define SPROF_T(v) long long v = clock64()
+#define SPROF_ADD(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_shot_prof[slot], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define SPROF_T(v) do {} while (0)
+#define SPROF_ADD(slot, a, b) do {} while (0)
+#endif
 __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, JBatchCirc cd, const JGate *gates, const JShotSlot *slots,
                                                        JGate *priv_all, unsigned int n_shots, unsigned int *next, uint64_t measure_seed0,
                                                        uint64_t shot_offset, JBatchOut *out, unsigned long long *keys,
@@ -1389,6 +1407,7 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
     const unsigned int inst = s_i;
     __syncthreads();
     if (inst >= n_shots) break;
+    SPROF_T(q0);
     if (threadIdx.x == 0) { E->n = cd.n; E->lvl_log = nullptr; E->mat_u = nullptr; E->mat_epoch = nullptr; E->cursor_saved = 0; s_bits = 0; }
     {
       Ctx c = make_ctx<MODE_CTA>(E);
@@ -1396,6 +1415,9 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
     }
     __threadfence();
     __syncthreads();
+    SPROF_T(q1);
+    SPROF_ADD(5, q0, q1);
+    SPROF_ADD(6, 0, 1);
     int st = 0, g = 0;
     uint64_t placeholders = 0;
     // after a segment: did the single-CTA path finish it?
@@ -1427,24 +1449,32 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
         __syncthreads();
         const int h = s_h;
         __syncthreads();
+        SPROF_T(a0);
         Ctx c = make_ctx<MODE_CTA>(E);
         run_gates<MODE_CTA>(c, gates, h);
         st = segment_status(h);
+        SPROF_T(a1);
+        SPROF_ADD(0, a0, a1);
         g = h;
         continue;
       }
       // MeasureOne / ResetQubit: P(qubit reads 0) in the state as it is now
+      SPROF_T(b0);
       {
         Ctx c = make_ctx<MODE_CTA>(E);
         build_sampling<MODE_CTA>(c, be.sn, be.prob);
       }
       __threadfence();
       __syncthreads();
+      SPROF_T(b1);
+      SPROF_ADD(1, b0, b1);
       st = *(volatile int *)&E->status;
       if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
       if (st) break;
       const int level = gates[g].target;
       double p0 = marginal_block(E, be.sn, be.prob, level);
+      SPROF_T(b2);
+      SPROF_ADD(2, b1, b2);
       if (p0 < 0.0) p0 = 0.0;
       if (p0 > 1.0) p0 = 1.0;
       const double norm = E->norm > 0.0 ? E->norm : 1.0;
@@ -1481,10 +1511,13 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
         run_gates<MODE_CTA>(c, priv - g, g + n_slots);  // gate index g is priv[0]
       }
       st = segment_status(g + n_slots);
+      SPROF_T(b3);
+      SPROF_ADD(3, b2, b3);
       g += n_slots;
       placeholders += (uint64_t)n_slots;
     }
     unsigned long long key = 0;
+    SPROF_T(f0);
     if (!st) {
       Ctx c = make_ctx<MODE_CTA>(E);
       build_sampling<MODE_CTA>(c, be.sn, be.prob);
@@ -1495,6 +1528,8 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
       // MeasureAll once (Simulator.cpp:148-224): shot (shot_offset + inst) of the sampling stream
       if (!st && threadIdx.x == 0) key = sample_walk(be.sn, E->root, (int)cd.n, cd.sp.bitpos, cd.seed, shot_offset + inst);
     }
+    SPROF_T(f1);
+    SPROF_ADD(4, f0, f1);
     if (threadIdx.x == 0) {
       JBatchOut o;
       o.status = st; o.n_distinct = st ? 0u : 1u; o.gates = (uint64_t)E->st[JST_GATES] - placeholders;
@@ -1831,6 +1866,16 @@ extern "C" int jkq_batch_run_shots(jkq_batch *b, uint32_t n_qubits, const jkq_op
   if (gates_applied) *gates_applied = total;
   float ms = 0;
   if (kernel_ms && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *kernel_ms = ms;
+#ifdef JKQ_PROFILE
+  {
+    unsigned long long p[8], z[8] = {0};
+    cudaMemcpyFromSymbol(p, g_shot_prof, sizeof(p));
+    cudaMemcpyToSymbol(g_shot_prof, z, sizeof(z));
+    if (p[6])
+      fprintf(stderr, "k_batch_shots cycles/shot over %llu shots: init %llu  plain gates %llu  build_sampling %llu  marginal %llu  projector gates %llu  final sampling %llu\n",
+              p[6], p[5] / p[6], p[0] / p[6], p[1] / p[6], p[2] / p[6], p[3] / p[6], p[4] / p[6]);
+  }
+#endif
   return JKQ_E_OK;
 }
 

@@ -518,7 +518,25 @@ template <int MODE> JD uint64_t cx_lookup(JEng *E, CtaState *S, uint32_t ring, d
 #define JOP_MUL 0u
 #define JOP_ADD 1u
 #define JOP_DIV 2u
+#ifdef JKQ_EMU_MEMOSTAT
+#include <unordered_map>
+#include <string>
+struct JMemoStat { std::unordered_map<std::string, int> seen; unsigned long long calls = 0, repeats = 0, recent_hits = 0; std::string ring[256]; unsigned pos = 0; };
+inline JMemoStat &jmemostat() { static JMemoStat m; return m; }
+#endif
 template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, uint32_t op, uint64_t a, uint64_t b) {
+#ifdef JKQ_EMU_MEMOSTAT
+  {
+    JMemoStat &m = jmemostat();
+    char key[64];
+    snprintf(key, sizeof(key), "%u:%llx:%llx", op, (unsigned long long)a, (unsigned long long)b);
+    m.calls++;
+    if (m.seen[key]++) m.repeats++;
+    // direct-mapped 256-entry cache model
+    unsigned h = (unsigned)((a * 0x9E3779B97F4A7C15ull ^ b * 0xC2B2AE3D27D4EB4Full ^ op) >> 56);
+    if (m.ring[h] == key) m.recent_hits++; else m.ring[h] = key;
+  }
+#endif
   double ar = jval2<MODE>(E, S, (uint32_t)(a >> 32)), ai = jval2<MODE>(E, S, (uint32_t)a);
   double br = jval2<MODE>(E, S, (uint32_t)(b >> 32)), bi = jval2<MODE>(E, S, (uint32_t)b);
   if (a >> 63) ar = -ar;

@@ -318,9 +318,8 @@ int main(int argc, char **argv) {
         std::fill(status.begin(), status.end(), 1);
     }
     if (batch) jkq_batch_destroy(batch);
-    unsigned long left = 0;
     for (unsigned long s = 0; s < shots; s++) {
-      if (status[s]) { left++; continue; }
+      if (status[s]) continue;  // (redone below on the full engine)
       std::string str(info.n_qubits, '0');
       for (uint32_t q = 0; q < info.n_qubits; q++) str[q] = (char)('0' + ((keys[s] >> q) & 1));
       result[str] += 1;
@@ -335,7 +334,6 @@ int main(int argc, char **argv) {
       if (rc) r.die("jkq_sample", rc);
       add_counts();
     }
-    (void)left;
     r.collect(info.n_ops, opt.statevector, opt.probabilities);
   }
   const auto t2 = std::chrono::high_resolution_clock::now();

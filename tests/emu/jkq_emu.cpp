@@ -180,6 +180,9 @@ int main(int argc, char **argv) {
               jre<MODE_GRID>(gctx, nd.w), jim<MODE_GRID>(gctx, nd.w), (unsigned long long)nd.w);
     }
   }
+#ifdef JKQ_EMU_MEMOSTAT
+  fprintf(stderr, "cx_arith calls %llu  repeats (unbounded memo) %llu  hits (256-entry direct-mapped) %llu\n", jmemostat().calls, jmemostat().repeats, jmemostat().recent_hits);
+#endif
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n", n, gates.size());
   printf(" \"items\": %llu,\n \"nodes_created\": %llu,\n \"val_inserts\": %llu,\n \"gc_runs\": %llu,\n \"retry_rounds\": %llu,\n \"max_frontier\": %llu,\n",
          E->st[JST_ITEMS], E->st[JST_NODES], E->st[JST_VALS], E->st[JST_GC_RUNS], E->st[JST_RETRY], E->st[JST_MAXF]);
