@@ -720,11 +720,22 @@ template <int MODE> JD void mode_leave(Ctx &c) {
 // ------------------------------------------------------------------------------------ circuit driver
 // Applies gates [E->next_gate, n_gates).  Collects when the arena passed its limit, or after every
 // gate when a level log was requested (parity tests: reference Active[v], QMDDpackage.h:199-201).
-template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
+// MODE_CTA, enter = false: the state of the previous call is still in this CTA's shared memory (same kernel, same
+// CTA, left with leave = false) -- no reload, no collection; leave = false: nothing is written back to the arena.
+template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, bool enter = true, bool leave = true) {
   JEng *E = c.E;
   const int n = (int)E->n;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
-  uint32_t f = mode_enter<MODE>(c);
+  uint32_t f = 0;
+  if (MODE != MODE_CTA || enter) f = mode_enter<MODE>(c);
+  else {
+    if (c.ltid == 0) {  // the barrier ring starts over with the fresh context of this call
+      c.sh->pend_n[0] = c.sh->pend_n[1] = c.sh->pend_n[2] = 0;
+      c.sh->bflags[0] = c.sh->bflags[1] = c.sh->bflags[2] = c.sh->bflags[3] = 0;
+      c.sh->want_grid = 0;
+    }
+    block_sync();
+  }
   int g = MODE == MODE_CTA ? c.sh->next_gate : ld_s<MODE>(&E->next_gate);
   if (MODE == MODE_CTA && !f && g < n_gates) {  // stage the first gate descriptor
     uint32_t *dst = reinterpret_cast<uint32_t *>(&c.sh->gate[g & 1]);
@@ -783,8 +794,108 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates) {
   }
   if ((f & JF_GRID) && c.block0 && c.ltid == 0) { E->want_grid = 1; if (MODE == MODE_GRID) E->gen++; }
   sync_or<MODE>(c, 0);
-  mode_leave<MODE>(c);
+  if (MODE != MODE_CTA || leave) mode_leave<MODE>(c);
 }
+
+// ------------------------------------------------------------------------------------ measurement in shared memory
+// MODE_CTA, state rooted in shared memory (after run_gates(..., leave = false)): squared norms bottom-up, the marginal
+// of one qubit and one MeasureAll walk WITHOUT going through the arena -- the same arithmetic as build_sampling /
+// marginal_block / sample_walk (q0 = p0 / (p0 + p1) from the same products in the same order), on a discovery-ordered
+// list of the live nodes.  Scratch lives in the item pool, which is idle between gates.  All threads call.
+struct ShotScratch {
+  uint32_t pos[JKQ_SNODES];  // node id -> 1 + index in list, 0 = not reached
+  uint32_t list[1024];
+  double prob[1024];         // squared norm of the sub-vector below list[i]
+  double q0[1024];           // P(branch 0 | node)
+  double mass[1024];
+  uint32_t lvl_b[JKQ_MAXQ + 1];
+  uint32_t cnt;
+  int fail;
+  double sum, norm;
+};
+static_assert(sizeof(ShotScratch) <= sizeof(JItem) * JKQ_SITEMS, "scratch must fit the shared item pool");
+
+#ifndef JKQ_EMU
+// returns false when the live DD has more than 1024 nodes (the caller goes through build_sampling instead)
+JD bool cta_norms(Ctx &c, ShotScratch *X) {
+  CtaState *S = c.sh;
+  const int n = (int)c.E->n;
+  const uint32_t nn = S->node_count < JKQ_SNODES ? S->node_count : JKQ_SNODES;
+  for (uint32_t i = c.ltid; i < nn; i += c.lnth) X->pos[i] = 0;
+  block_sync();
+  if (c.ltid == 0) { X->list[0] = S->root; X->pos[S->root] = 1; X->cnt = 1; X->fail = 0; }
+  block_sync();
+  uint32_t b = 0, e = 1;
+  for (int L = n - 1; L >= 0; L--) {
+    if (c.ltid == 0) X->lvl_b[L] = b;
+    if (L > 0)
+      for (uint32_t i = b + c.ltid; i < e; i += c.lnth) {
+        const JNode nd = S->nodes[X->list[i]];
+        const uint32_t ch[2] = {nd_c0(nd), nd.c1};
+        for (int k = 0; k < 2; k++)
+          if (ch[k] != 0 && atomicCAS(&X->pos[ch[k]], 0u, 0xFFFFFFFFu) == 0u) {
+            const uint32_t p = atomicAdd(&X->cnt, 1u);
+            if (p < 1024u) { X->list[p] = ch[k]; X->pos[ch[k]] = p + 1u; }
+            else X->fail = 1;
+          }
+      }
+    block_sync();
+    b = e;
+    e = X->cnt < 1024u ? X->cnt : 1024u;
+    if (X->fail) return false;
+  }
+  // level L occupies [lvl_b[L], lvl_b[L - 1]) (level 0 ends at cnt); bottom-up like build_sampling
+  for (int L = 0; L < n; L++) {
+    const uint32_t lo = X->lvl_b[L], hi = L == 0 ? X->cnt : X->lvl_b[L - 1];
+    for (uint32_t i = lo + c.ltid; i < hi; i += c.lnth) {
+      const JNode nd = S->nodes[X->list[i]];
+      const uint64_t w0 = nd_w0(nd), w1 = nd_w1(nd);
+      const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
+      const double p0 = w0 ? JKQ_DMUL(c0 ? X->prob[X->pos[c0] - 1u] : 1.0, jmag2<MODE_CTA>(c, w0)) : 0.0;
+      const double p1 = w1 ? JKQ_DMUL(c1 ? X->prob[X->pos[c1] - 1u] : 1.0, jmag2<MODE_CTA>(c, w1)) : 0.0;
+      const double tot = JKQ_DADD(p0, p1);
+      X->prob[i] = tot;
+      X->q0[i] = JKQ_DDIV(p0, tot);
+    }
+    block_sync();
+  }
+  if (c.ltid == 0) X->norm = JKQ_DMUL(X->prob[0], jmag2<MODE_CTA>(c, S->rootw));
+  block_sync();
+  return true;
+}
+
+// P(the qubit on `level` reads 0): AssignProbsOne (Simulator.cpp:341-413) on the lists of cta_norms
+JD double cta_marginal(Ctx &c, ShotScratch *X, int level) {
+  CtaState *S = c.sh;
+  const int n = (int)c.E->n;
+  const uint32_t total = X->cnt;
+  for (uint32_t i = c.ltid; i < total; i += c.lnth) X->mass[i] = 0.0;
+  if (c.ltid == 0) X->sum = 0.0;
+  block_sync();
+  if (c.ltid == 0) X->mass[0] = 1.0;
+  block_sync();
+  for (int L = n - 1; L > level; L--) {
+    const uint32_t lo = X->lvl_b[L], hi = X->lvl_b[L - 1];
+    for (uint32_t i = lo + c.ltid; i < hi; i += c.lnth) {
+      const double m = X->mass[i];
+      if (m == 0.0) continue;
+      const JNode nd = S->nodes[X->list[i]];
+      const double q = X->q0[i];
+      if (q > 0.0) atomicAdd(&X->mass[X->pos[nd_c0(nd)] - 1u], m * q);
+      if (q < 1.0) atomicAdd(&X->mass[X->pos[nd.c1] - 1u], m * (1.0 - q));
+    }
+    block_sync();
+  }
+  const uint32_t lo = X->lvl_b[level], hi = level == 0 ? X->cnt : X->lvl_b[level - 1];
+  double acc = 0.0;
+  for (uint32_t i = lo + c.ltid; i < hi; i += c.lnth) acc += X->mass[i] * X->q0[i];
+  if (acc != 0.0) atomicAdd(&X->sum, acc);
+  block_sync();
+  const double r = X->sum;
+  block_sync();
+  return r;
+}
+#endif
 
 // ------------------------------------------------------------------------------------ sampling prep
 // Simulator::AssignProbs (Simulator.cpp:127-146) once per DD instead of once per shot: after a

@@ -1396,7 +1396,7 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
                                                        unsigned long long *mid_bits) {
   __shared__ unsigned int s_i;
   __shared__ unsigned long long s_bits;
-  __shared__ int s_g, s_h;
+  __shared__ int s_h;
   const JBatchEng be = engs[blockIdx.x];
   JEng *E = be.E;
   JGate *priv = priv_all + 2 * blockIdx.x;
@@ -1409,32 +1409,41 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
     if (inst >= n_shots) break;
     SPROF_T(q0);
     if (threadIdx.x == 0) { E->n = cd.n; E->lvl_log = nullptr; E->mat_u = nullptr; E->mat_epoch = nullptr; E->cursor_saved = 0; s_bits = 0; }
-    {
-      Ctx c = make_ctx<MODE_CTA>(E);
-      init_state<MODE_CTA>(c);
-    }
+    Ctx c = make_ctx<MODE_CTA>(E);
+    init_state<MODE_CTA>(c);
     __threadfence();
     __syncthreads();
     SPROF_T(q1);
     SPROF_ADD(5, q0, q1);
     SPROF_ADD(6, 0, 1);
+    // The whole shot runs on this CTA's shared memory: the first segment loads the state (mode_enter), the later
+    // ones find it where the previous one left it (run_gates enter = false / leave = false), and the measurements
+    // work on the shared-memory DD (cta_norms / cta_marginal).  Nothing goes back to the arena.
+    ShotScratch *X = reinterpret_cast<ShotScratch *>(c.sh->items);
     int st = 0, g = 0;
-    uint64_t placeholders = 0;
+    bool resident = false;
+    uint64_t placeholders = 0;  // projector / X slots applied: not ApplyGate calls
     // after a segment: did the single-CTA path finish it?
     auto segment_status = [&](int upto) {
       __threadfence();
       __syncthreads();
       int r = *(volatile int *)&E->status;
-      if (!r && (*(volatile int *)&E->next_gate < upto || *(volatile int *)&E->want_grid || *(volatile unsigned int *)&E->cursor_saved))
+      if (!r && (c.sh->next_gate < upto || *(volatile int *)&E->want_grid || *(volatile unsigned int *)&E->cursor_saved))
         r = JKQ_ERR_ITEM_FULL;  // outgrew the single-CTA path
       return r;
+    };
+    auto segment = [&](const JGate *gl, int upto) {
+      c = make_ctx<MODE_CTA>(E);
+      run_gates<MODE_CTA>(c, gl, upto, !resident, false);
+      resident = true;
+      return segment_status(upto);
     };
     while (!st && g < n_gates) {
       const JShotSlot sl = slots[g];
       if (sl.if_skip && (s_bits & sl.if_mask) != sl.if_value) {  // `if` is false: step over the guarded slots
         g += (int)sl.if_skip;
         __syncthreads();
-        if (threadIdx.x == 0) E->next_gate = g;
+        if (threadIdx.x == 0) { if (resident) c.sh->next_gate = g; else E->next_gate = g; }
         __threadfence();
         __syncthreads();
         continue;
@@ -1450,9 +1459,7 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
         const int h = s_h;
         __syncthreads();
         SPROF_T(a0);
-        Ctx c = make_ctx<MODE_CTA>(E);
-        run_gates<MODE_CTA>(c, gates, h);
-        st = segment_status(h);
+        st = segment(gates, h);
         SPROF_T(a1);
         SPROF_ADD(0, a0, a1);
         g = h;
@@ -1460,57 +1467,51 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
       }
       // MeasureOne / ResetQubit: P(qubit reads 0) in the state as it is now
       SPROF_T(b0);
-      {
-        Ctx c = make_ctx<MODE_CTA>(E);
-        build_sampling<MODE_CTA>(c, be.sn, be.prob);
+      if (!resident) {  // a measurement before any gate: only load the state
+        c = make_ctx<MODE_CTA>(E);
+        const uint32_t f = mode_enter<MODE_CTA>(c);
+        resident = true;
+        if (f) { st = (f & JF_ERROR) ? *(volatile int *)&E->status : JKQ_ERR_NODE_FULL; if (!st) st = JKQ_ERR_INTERNAL; break; }
       }
-      __threadfence();
-      __syncthreads();
+      if (!cta_norms(c, X)) { st = JKQ_ERR_NODE_FULL; break; }  // (more than 1024 live nodes: left to the full engine)
       SPROF_T(b1);
       SPROF_ADD(1, b0, b1);
-      st = *(volatile int *)&E->status;
-      if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
-      if (st) break;
       const int level = gates[g].target;
-      double p0 = marginal_block(E, be.sn, be.prob, level);
+      double p0 = cta_marginal(c, X, level);
       SPROF_T(b2);
       SPROF_ADD(2, b1, b2);
       if (p0 < 0.0) p0 = 0.0;
       if (p0 > 1.0) p0 = 1.0;
-      const double norm = E->norm > 0.0 ? E->norm : 1.0;
+      const double norm = X->norm > 0.0 ? X->norm : 1.0;
       if (threadIdx.x == 0) {
-        JGate a = gates[g], b = gates[g + (sl.kind == 1 ? 0 : 1)];
-        for (int k = 0; k < 8; k++) { a.m[k] = 0.0; b.m[k] = 0.0; }
+        JGate ga = gates[g], gb = gates[g + (sl.kind == 1 ? 0 : 1)];
+        for (int k = 0; k < 8; k++) { ga.m[k] = 0.0; gb.m[k] = 0.0; }
         if (sl.kind == 2) {  // the reference's reset: projection on |0>, X first when P(0) = 0
           double p = p0;
-          if (p0 <= 0.0) { a.m[2] = 1.0; a.m[4] = 1.0; p = 1.0; }
-          else { a.m[0] = 1.0; a.m[6] = 1.0; }
-          b.m[0] = 1.0 / sqrt(p * norm);
+          if (p0 <= 0.0) { ga.m[2] = 1.0; ga.m[4] = 1.0; p = 1.0; }
+          else { ga.m[0] = 1.0; ga.m[6] = 1.0; }
+          gb.m[0] = 1.0 / sqrt(p * norm);
         } else {
           const double u = philox_uniform_dev(measure_seed0 + inst, (uint64_t)sl.op_index);
           const int outcome = u < p0 ? 0 : 1;
           const double p = outcome ? 1.0 - p0 : p0;
           if (!(p > 0.0)) E->status = JKQ_ERR_ZERO_STATE;
-          else a.m[outcome ? 6 : 0] = 1.0 / sqrt(p * norm);
+          else ga.m[outcome ? 6 : 0] = 1.0 / sqrt(p * norm);
           if (sl.kind == 1) {
             if (outcome) s_bits |= 1ull << sl.clbit;
             else s_bits &= ~(1ull << sl.clbit);
-          } else if (outcome) { b.m[2] = 1.0; b.m[4] = 1.0; }
-          else { b.m[0] = 1.0; b.m[6] = 1.0; }
+          } else if (outcome) { gb.m[2] = 1.0; gb.m[4] = 1.0; }
+          else { gb.m[0] = 1.0; gb.m[6] = 1.0; }
         }
-        priv[0] = a;
-        priv[1] = b;
+        priv[0] = ga;
+        priv[1] = gb;
       }
       __threadfence();
       __syncthreads();
       st = *(volatile int *)&E->status;
       if (st) break;
       const int n_slots = sl.kind == 1 ? 1 : 2;
-      {
-        Ctx c = make_ctx<MODE_CTA>(E);
-        run_gates<MODE_CTA>(c, priv - g, g + n_slots);  // gate index g is priv[0]
-      }
-      st = segment_status(g + n_slots);
+      st = segment(priv - g, g + n_slots);  // gate index g is priv[0]
       SPROF_T(b3);
       SPROF_ADD(3, b2, b3);
       g += n_slots;
@@ -1519,20 +1520,42 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
     unsigned long long key = 0;
     SPROF_T(f0);
     if (!st) {
-      Ctx c = make_ctx<MODE_CTA>(E);
-      build_sampling<MODE_CTA>(c, be.sn, be.prob);
-      __threadfence();
-      __syncthreads();
-      st = *(volatile int *)&E->status;
-      if (!st && *(volatile int *)&E->want_grid) st = JKQ_ERR_NODE_FULL;
-      // MeasureAll once (Simulator.cpp:148-224): shot (shot_offset + inst) of the sampling stream
-      if (!st && threadIdx.x == 0) key = sample_walk(be.sn, E->root, (int)cd.n, cd.sp.bitpos, cd.seed, shot_offset + inst);
+      if (!resident) {
+        c = make_ctx<MODE_CTA>(E);
+        const uint32_t f = mode_enter<MODE_CTA>(c);
+        resident = true;
+        if (f) st = (f & JF_ERROR) ? JKQ_ERR_INTERNAL : JKQ_ERR_NODE_FULL;
+      }
+      if (!st && !cta_norms(c, X)) st = JKQ_ERR_NODE_FULL;
+      // MeasureAll once (Simulator.cpp:148-224): shot (shot_offset + inst) of the sampling stream, the walk of
+      // sample_walk on the shared-memory lists
+      if (!st && threadIdx.x == 0) {
+        const uint64_t shot = shot_offset + inst;
+        const int n = (int)cd.n;
+        uint32_t idx = 0, pc[4] = {0, 0, 0, 0};
+        for (int step = 0; step < n; step++) {
+          if ((step & 3) == 0) {
+            pc[0] = (uint32_t)shot; pc[1] = (uint32_t)(shot >> 32); pc[2] = (uint32_t)(step >> 2); pc[3] = 0;
+            philox4x32(pc, (uint32_t)cd.seed, (uint32_t)(cd.seed >> 32));
+          }
+          const uint32_t word = (step & 3) == 0 ? pc[0] : (step & 3) == 1 ? pc[1] : (step & 3) == 2 ? pc[2] : pc[3];
+          const double u = ((double)word + 0.5) * (1.0 / 4294967296.0);
+          const JNode nd = c.sh->nodes[X->list[idx]];
+          const uint32_t bit = !(u < X->q0[idx]);
+          const uint32_t bp = cd.sp.bitpos[n - 1 - step];
+          if (bit && bp < 64) key |= 1ull << bp;
+          const uint32_t ch = bit ? nd.c1 : nd_c0(nd);
+          if (step + 1 < n) idx = X->pos[ch] - 1u;
+        }
+      }
     }
     SPROF_T(f1);
     SPROF_ADD(4, f0, f1);
+    __syncthreads();
     if (threadIdx.x == 0) {
       JBatchOut o;
-      o.status = st; o.n_distinct = st ? 0u : 1u; o.gates = (uint64_t)E->st[JST_GATES] - placeholders;
+      o.status = st; o.n_distinct = st ? 0u : 1u;
+      o.gates = (uint64_t)E->st[JST_GATES] + (resident ? (uint64_t)c.sh->st[JST_GATES] : 0ull) - placeholders;
       out[inst] = o;
       keys[inst] = key;
       if (mid_bits) mid_bits[inst] = s_bits;
