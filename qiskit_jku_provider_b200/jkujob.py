@@ -1,67 +1,58 @@
-"""Job class of the backend (mirror of the reference's ``qiskit_jku_provider/jkujob.py:21-131``).
+"""``JKUJob``: the future-like handle ``QasmSimulator.run`` returns (surface of ``qiskit_jku_provider/jkujob.py:21-131``:
+``submit / result(timeout) / cancel / status / backend / qobj``, ``JobError`` on a second submit or on use before
+submit).
 
-The one deliberate difference: the executor is a ThreadPoolExecutor on every platform.  The reference
-uses a ProcessPoolExecutor on Linux (``jkujob.py:47-50``), i.e. fork -- which is unsafe once a CUDA
-context exists in the parent; ctypes releases the GIL during the engine call, so a thread suffices.
+One deliberate difference: the work runs on a single worker THREAD on every platform.  The reference forks a
+process pool on Linux (``jkujob.py:47-50``), which is not an option once the parent holds a CUDA context; ctypes
+releases the GIL for the duration of the engine call, so a thread gives the same concurrency.
 """
 
-import functools
-from concurrent import futures
+from concurrent.futures import ThreadPoolExecutor
 
 from .compat import BaseJob, JobError, JobStatus, validate_qobj_against_schema
 
-
-def requires_submit(func):
-    """Decorator to ensure that a submit has been performed before calling the method."""
-    @functools.wraps(func)
-    def _wrapper(self, *args, **kwargs):
-        if self._future is None:
-            raise JobError("Job not submitted yet!. You have to .submit() first!")
-        return func(self, *args, **kwargs)
-    return _wrapper
+_WORKER = ThreadPoolExecutor(max_workers=1, thread_name_prefix="jkq-job")
 
 
 class JKUJob(BaseJob):
-    """JKU Job class."""
+    """One submitted Qobj."""
 
-    _executor = futures.ThreadPoolExecutor(max_workers=1)
+    _executor = _WORKER  # (class attribute kept for code that swaps the executor, as with the reference)
 
     def __init__(self, backend, job_id, fn, qobj):
         super().__init__(backend, job_id)
-        self._fn = fn
-        self._qobj = qobj
-        self._future = None
+        self._fn, self._qobj, self._future = fn, qobj, None
 
+    # -- life cycle
     def submit(self):
-        """Submit the job to the backend for execution.  Raises JobError on a second submit."""
         if self._future is not None:
             raise JobError("We have already submitted the job!")
         validate_qobj_against_schema(self._qobj)
         self._future = self._executor.submit(self._fn, self._job_id, self._qobj)
 
-    @requires_submit
+    def _submitted(self):
+        if self._future is None:
+            raise JobError("Job not submitted yet!. You have to .submit() first!")
+        return self._future
+
     def result(self, timeout=None):
-        return self._future.result(timeout=timeout)
+        return self._submitted().result(timeout=timeout)
 
-    @requires_submit
     def cancel(self):
-        return self._future.cancel()
+        return self._submitted().cancel()
 
-    @requires_submit
     def status(self):
-        # The order is important here
-        if self._future.running():
-            _status = JobStatus.RUNNING
-        elif self._future.cancelled():
-            _status = JobStatus.CANCELLED
-        elif self._future.done():
-            _status = JobStatus.DONE if self._future.exception() is None else JobStatus.ERROR
-        elif self._future._state == 'PENDING':
-            _status = JobStatus.QUEUED
-        else:
-            raise JobError('Unexpected behavior of {0}'.format(self.__class__.__name__))
-        return _status
+        future = self._submitted()
+        # running / cancelled / done are tested in this order: a finished future also answers False to running()
+        if future.running():
+            return JobStatus.RUNNING
+        if future.cancelled():
+            return JobStatus.CANCELLED
+        if future.done():
+            return JobStatus.ERROR if future.exception() is not None else JobStatus.DONE
+        return JobStatus.QUEUED  # accepted by the executor, not started yet
 
+    # -- accessors
     def backend(self):
         return self._backend
 

@@ -1,20 +1,20 @@
-"""Exception for errors raised by the JKU simulator (mirror of the reference's
-``qiskit_jku_provider/jkusimulatorerror.py:16-26``; derives from QiskitError when qiskit is there)."""
+"""``JKUSimulatorError``: what the backend raises for anything the engine or the front end rejects.
 
-try:  # pragma: no cover - qiskit is optional
-    from qiskit import QiskitError as _Base
-except Exception:  # qiskit absent: plain Exception keeps the same surface
-    _Base = Exception
+Surface of ``qiskit_jku_provider/jkusimulatorerror.py:16-26``: built from message parts, ``.message`` is their
+space-joined text and ``str()`` is its ``repr``.  A subclass of ``QiskitError`` when qiskit is importable, so
+existing ``except QiskitError`` clauses keep catching it.
+"""
+
+try:  # pragma: no cover - qiskit is optional in this image
+    from qiskit import QiskitError as _Parent
+except Exception:
+    _Parent = Exception
 
 
-class JKUSimulatorError(_Base):
-    """Class for errors raised by the JKU simulator."""
-
-    def __init__(self, *message):
-        """Set the error message."""
-        super().__init__(*message)
-        self.message = ' '.join(str(m) for m in message)
+class JKUSimulatorError(_Parent):
+    def __init__(self, *parts):
+        super().__init__(*parts)
+        self.message = ' '.join(map(str, parts))
 
     def __str__(self):
-        """Return the message."""
         return repr(self.message)
