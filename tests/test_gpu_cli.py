@@ -121,6 +121,49 @@ def test_cli_counts_equal_the_in_process_engine(cli, eng):
         assert got["counts"] == eng.counts_bitstrings()
 
 
+def random_program(seed, n_qubits=6, n_statements=40):
+    """random OpenQASM 2.0 text over the qelib1 vocabulary, two registers, a user gate, a full snapshot at the end"""
+    import random
+    rng = random.Random(seed)
+    one = [("h", 0), ("x", 0), ("y", 0), ("z", 0), ("s", 0), ("sdg", 0), ("t", 0), ("tdg", 0), ("id", 0), ("rx", 1), ("ry", 1), ("rz", 1),
+           ("u1", 1), ("u2", 2), ("u3", 3)]
+    two = [("cx", 0), ("cz", 0), ("cy", 0), ("ch", 0), ("swap", 0), ("crz", 1), ("cu1", 1), ("cu3", 3), ("rzz", 1), ("pair", 2)]
+    three = [("ccx", 0), ("cswap", 0)]
+    na = n_qubits // 2
+    names = ["a[%d]" % i for i in range(na)] + ["b[%d]" % i for i in range(n_qubits - na)]
+    lines = ["OPENQASM 2.0;", 'include "qelib1.inc";',
+             "gate pair(x, y) p, q { ry(x) p; cx p, q; rz(y - x/2) q; cu1(x*y) q, p; }",
+             "qreg a[%d];" % na, "qreg b[%d];" % (n_qubits - na)]
+    for _ in range(n_statements):
+        r = rng.random()
+        gates, k = (one, 1) if r < 0.5 else (two, 2) if r < 0.9 else (three, 3)
+        name, n_par = rng.choice(gates)
+        args = rng.sample(names, k)
+        par = "(%s)" % ",".join(rng.choice(["%.6f" % rng.uniform(-3, 3), "pi/%d" % rng.randint(1, 8), "-pi*%d/%d" % (rng.randint(1, 5), rng.randint(2, 9))])
+                                for _ in range(n_par)) if n_par else ""
+        lines.append("%s%s %s;" % (name, par, ",".join(args)))
+    if rng.random() < 0.5:
+        lines.append("h a;")          # a whole-register statement
+    lines.append("snapshot(0) %s;" % ",".join(names))
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_cli_statevector_of_random_programs_equals_a_dense_simulation(cli, seed):
+    from qiskit_jku_provider_b200.qasm import parse_qasm
+    text = random_program(seed)
+    prog = parse_qasm(text, statevector=True)
+    _, states = dense_run(prog)
+    want = reference_order(states[0], prog.snapshots[0][1])
+    got, _, _ = run_cli(cli, text, 64, seed, ["--display_statevector"])
+    mine = np.array([parse_amplitude(a) for a in got["snapshots"]["0"]["statevector"]])
+    np.testing.assert_allclose(mine, want, rtol=0, atol=2e-6)  # six printed digits
+    assert abs(np.vdot(mine, mine).real - 1.0) < 1e-4
+    p = np.abs(want) ** 2
+    # counts keys: character i = qubit i; the snapshot lists the qubits in order, so int(key, 2) is its index
+    assert all(p[int(k, 2)] > 1e-7 for k in got["counts"])
+
+
 def test_cli_show_probabilities_and_include_file(cli, tmp_path):
     (tmp_path / "qelib1.inc").write_text("gate h a { U(pi/2,0,pi) a; }\ngate cx c,t { CX c,t; }\n")
     out = subprocess.run([cli, "--simulate_qasm", "--shots=10", "--seed=1"], input=HEADER + "qreg q[2];\nh q[0];\ncx q[0],q[1];\nshow_probabilities;\n",
