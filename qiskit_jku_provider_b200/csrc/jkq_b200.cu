@@ -1205,6 +1205,21 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
     fprintf(stderr, "  per gate: cursor_prepare %llu  solo expand %llu  solo reduce %llu  cursor_finish %llu | solo levels/gate %.2f  wide gates %llu\n",
             E.prof[11] / E.prof[6], E.prof[12] / E.prof[6], E.prof[13] / E.prof[6], E.prof[14] / E.prof[6], (double)E.prof[15] / E.prof[6], E.prof[10]);
 #endif
+#ifdef JKQ_PROFILE2
+  {
+    unsigned long long p[16], z[16] = {0};
+    cudaMemcpyFromSymbol(p, g_fine, sizeof(p));
+    cudaMemcpyToSymbol(g_fine, z, sizeof(z));
+    if (p[1])
+      fprintf(stderr, "JKQ_PROFILE2 lane 0: expand_item %llu calls, %llu cycles each | chain path %llu times: %llu cycles each, %.1f levels each | expand_child x2 %llu cycles/plain call, de-dup %llu | reduce_item %llu calls, %llu cycles each; chain rebuild %llu cycles per chain item\n",
+              p[1], p[0] / p[1], p[10], p[10] ? p[2] / p[10] : 0, p[10] ? (double)p[3] / p[10] : 0.0, (p[1] - p[10]) ? p[4] / (p[1] - p[10]) : 0,
+              (p[1] - p[10]) ? p[5] / (p[1] - p[10]) : 0, p[7], p[7] ? p[6] / p[7] : 0, p[10] ? p[8] / p[10] : 0);
+    if (p[11])
+      fprintf(stderr, "  plain expand_child pairs: %llu (avg %llu cycles) | M at target %llu (avg %llu) | F same-node %llu (avg %llu) | other %llu (avg %llu); de-dup per pair %llu\n",
+              p[11], p[4] / p[11], p[13], p[13] ? p[12] / p[13] : 0, p[15], p[15] ? p[14] / p[15] : 0, p[11] - p[13] - p[15],
+              (p[11] - p[13] - p[15]) ? (p[4] - p[12] - p[14]) / (p[11] - p[13] - p[15]) : 0, p[5] / p[11]);
+  }
+#endif
   // (ApplyGate calls: MeasureOne / ResetQubit multiply their projectors in directly)
   h->stats.gates = E.st[JST_GATES] - h->placeholder_gates; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
   h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];

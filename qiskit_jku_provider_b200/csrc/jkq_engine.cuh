@@ -955,8 +955,25 @@ JD bool chain_node(const JNode &n, uint32_t *child) {
   return true;
 }
 
+#if defined(JKQ_PROFILE2) && !defined(JKQ_EMU)
+__device__ unsigned long long g_fine[16];
+#define JFINE_T(v) long long v = clock64()
+#define JFINE_ADD(c, slot, a, b) do { if (MODE == MODE_CTA && (c).tid == 0) g_fine[slot] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define JFINE_T(v) do {} while (0)
+#define JFINE_ADD(c, slot, a, b) do {} while (0)
+#endif
+template <int MODE> JD uint32_t expand_item_impl(Ctx &c, const JGate &g, uint32_t idx, int L);
 // returns the new flags word of the item (state JS_DONE or JS_RETRY)
 template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
+  JFINE_T(t0);
+  const uint32_t r = expand_item_impl<MODE>(c, g, idx, L);
+  JFINE_T(t1);
+  JFINE_ADD(c, 0, t0, t1);
+  JFINE_ADD(c, 1, 0, 1);
+  return r;
+}
+template <int MODE> JD uint32_t expand_item_impl(Ctx &c, const JGate &g, uint32_t idx, int L) {
   JItem *it = c.items + idx;
   const uint32_t tag = ld_i<MODE>(&it->tag), ia = ld_i<MODE>(&it->a);
   const uint32_t kind = tag & 15u, sel = (tag >> 4) & 1u;
@@ -1003,6 +1020,7 @@ template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx
     // reduce_item rebuilds the chain in one go.  The skipped levels cost a node load and a unique-table
     // insert each instead of two phases.
     CtaState *S = c.sh;
+    JFINE_T(w0);
     uint32_t cur = chain_c, k = 0;
     int Lc = L - 1;
     while (Lc > g.low && g.role[Lc] == JR_IDLE && k < 60) {
@@ -1034,19 +1052,31 @@ template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx
         if (Lc < S->min_def) S->min_def = Lc;
 #endif
         it->ch[0] = child; it->ch[1] = k | (off << 8); it->chw[0] = nd_w0(na); it->chw[1] = nd_w1(na);
+        JFINE_T(w1);
+        JFINE_ADD(c, 2, w0, w1);
+        JFINE_ADD(c, 3, 0, k);
+        JFINE_ADD(c, 10, 0, 1);
         return item_flags(JS_DONE, JC_REF, JC_REF, 1u + nd_flag(na)) | JFLAG_CHAIN;
       }
       // (scratch or waiting list full: the plain path below; readers clamp defer_n to JKQ_SDEFER)
     }
   }
   Slot s0, s1;
+  JFINE_T(x0);
   bool e0 = expand_child<MODE>(c, g, L, 0, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s0);
   bool e1 = expand_child<MODE>(c, g, L, 1, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s1);
+  JFINE_T(x1);
+  JFINE_ADD(c, 4, x0, x1);
+  JFINE_ADD(c, 11, 0, 1);
+  if (kind == JK_M) { JFINE_ADD(c, 12, x0, x1); JFINE_ADD(c, 13, 0, 1); }
+  else if (kind == JK_F && ia == ib) { JFINE_ADD(c, 14, x0, x1); JFINE_ADD(c, 15, 0, 1); }
   if (!(e0 && e1)) return JS_RETRY;  // both children were tried: all their missing values are proposed
   bool ok = true;
   if (s0.kind == JC_REF) { s0.target = dt_find_or_insert<MODE>(c.E, c.sh, c.items, s0.ia, s0.ib, s0.iwa, s0.iwb, s0.iwc, s0.itag); ok = s0.target != JI_FAIL; }
   if (ok && s1.kind == JC_REF) { s1.target = dt_find_or_insert<MODE>(c.E, c.sh, c.items, s1.ia, s1.ib, s1.iwa, s1.iwb, s1.iwc, s1.itag); ok = s1.target != JI_FAIL; }
   if (!ok) return JS_DONE;  // error / want_grid already flagged; the gate is abandoned
+  JFINE_T(x2);
+  JFINE_ADD(c, 5, x1, x2);
   it->ch[0] = s0.target; it->ch[1] = s1.target; it->chw[0] = s0.w; it->chw[1] = s1.w;
   // same-node fused item whose two children carry the node's own weights: normalised pair again
   uint32_t hint = 0;
@@ -1109,7 +1139,16 @@ JD bool reduce_core(Ctx &c, uint32_t rn[2], const uint64_t f[2], const uint64_t 
   return true;
 }
 
+template <int MODE> JD bool reduce_item_impl(Ctx &c, uint32_t idx, uint32_t flags);
 template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx, uint32_t flags) {
+  JFINE_T(t0);
+  const bool r = reduce_item_impl<MODE>(c, idx, flags);
+  JFINE_T(t1);
+  JFINE_ADD(c, 6, t0, t1);
+  JFINE_ADD(c, 7, 0, 1);
+  return r;
+}
+template <int MODE> JD bool reduce_item_impl(Ctx &c, uint32_t idx, uint32_t flags) {
   JItem *it = c.items + idx;
   if (MODE == MODE_CTA && (flags & JFLAG_CHAIN)) {
     // compressed chain (expand_item): rebuild the skipped nodes over the child's result, bottom-up
@@ -1119,11 +1158,14 @@ template <int MODE> JD bool reduce_item(Ctx &c, uint32_t idx, uint32_t flags) {
     if (f0 == 0) { it->rw = 0; it->rnode = 0; return true; }
     const uint32_t info = ld_i<MODE>(&it->ch[1]), k = info & 0xFFu, off = info >> 8;
     const unsigned long long mask = c.sh->chain[off];
+    JFINE_T(y0);
     for (uint32_t j = k; j-- > 0 && r != 0;) {
       const uint32_t fl = (uint32_t)((mask >> j) & 1ull);
       const uint64_t w = c.sh->chain[off + 1 + j];  // 0: the node's other edge is the zero edge
       r = ut_find_or_insert<MODE>(c.E, c.sh, ((fl == 1 && w == 0) ? 0u : r) | (fl << 31), (fl == 0 && w == 0) ? 0u : r, w);
     }
+    JFINE_T(y1);
+    JFINE_ADD(c, 8, y0, y1);
     uint32_t rn[2] = {r, r};
     const uint64_t f[2] = {f0, f0}, a[2] = {ld_i<MODE>(&it->chw[0]), ld_i<MODE>(&it->chw[1])};
     uint32_t rnode;
