@@ -164,6 +164,24 @@ def test_cli_statevector_of_random_programs_equals_a_dense_simulation(cli, seed)
     assert all(p[int(k, 2)] > 1e-7 for k in got["counts"])
 
 
+def test_cli_measured_circuit_too_large_for_one_sm_falls_back_to_the_full_engine(cli):
+    """a measured circuit whose DD outgrows the shared-memory pools: the shots kernel reports every shot as unfinished
+    and the executable redoes them on the full engine (grid path) -- same counts layout, every shot accounted for"""
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.batch import BatchRunner
+    from qiskit_jku_provider_b200.qasm import parse_qasm
+    body = C.random_circuit(14, 90, 2).qasm().replace("OPENQASM 2.0;\n", "").replace("qreg q[14];\n", "")
+    text = HEADER + "qreg q[14];\ncreg c[1];\n" + body + "measure q[3] -> c[0];\nif (c == 1) x q[0];\nh q[5];\n"
+    prog = parse_qasm(text)
+    assert prog.gate_after_measure
+    with BatchRunner(workers=8, device=0) as br:
+        _, _, status, _, _ = br.run_shots(prog.n_qubits, prog.ops, 4, seed=2)
+    assert status.all()                                   # none of them fits one SM
+    got, stats, _ = run_cli(cli, text, 4, 2, [])
+    assert sum(got["counts"].values()) == 4 and all(len(k) == 14 for k in got["counts"])
+    assert int(stats["Maximal size of DD (number of nodes) during simulation"]) > 2048
+
+
 def test_cli_show_probabilities_and_include_file(cli, tmp_path):
     (tmp_path / "qelib1.inc").write_text("gate h a { U(pi/2,0,pi) a; }\ngate cx c,t { CX c,t; }\n")
     out = subprocess.run([cli, "--simulate_qasm", "--shots=10", "--seed=1"], input=HEADER + "qreg q[2];\nh q[0];\ncx q[0],q[1];\nshow_probabilities;\n",
