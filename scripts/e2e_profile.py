@@ -22,7 +22,7 @@ t0 = time.perf_counter()
 for _ in range(10):
     r = backend.run(qobj).result()
     r.get_counts()
-print("ms per call: %.3f   engine apply_ms %.3f sample_ms %.3f" % (1e2 * (time.perf_counter() - t0), r.results[0].metadata["engine"]["apply_ms"] if hasattr(r.results[0], "metadata") else -1, 0))
+print("ms per call: %.3f" % (1e2 * (time.perf_counter() - t0)))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(10):
