@@ -467,6 +467,7 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   if (MODE == MODE_CTA && (clean_vals || reload)) {
     for (uint32_t i = c.ltid; i < JKQ_SVT_SLOTS; i += c.lnth) vt_clear_slot(c.sh->vtab + i);
     for (uint32_t i = c.ltid; i < JKQ_SMATS; i += c.lnth) c.sh->mtag[i] = 0;  // cached matrix ids are void
+    for (uint32_t i = c.ltid; i < JKQ_SMEMO; i += c.lnth) c.sh->memo[i][0] = 0;  // and so are memoised results
   }
   if (c.block0 && c.ltid == 0) {
     list[0] = E->root;

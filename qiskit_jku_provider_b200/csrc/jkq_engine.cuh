@@ -87,6 +87,7 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SVT_SLOTS 2048u  // value-table slots
 #define JKQ_SPEND 512u       // value-table slots claimed in one phase
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
+#define JKQ_SMEMO 512u       // entries of the complex-operation memo (16 bytes each)
 #define JKQ_SCHAIN 1024u     // scratch words of compressed chains (per gate)
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
@@ -113,6 +114,7 @@ struct CtaState {
   JGate gate[2];
   uint32_t mtag[JKQ_SMATS];
   uint64_t mu[JKQ_SMATS][4];
+  unsigned long long memo[JKQ_SMEMO][2];    // (op, a, b) -> result id of cx_arith, see there
   uint32_t pend[JKQ_SPEND];
   uint32_t mdir[JKQ_SNODES];
   uint32_t dtab[JKQ_SDT_SLOTS];
@@ -518,10 +520,14 @@ template <int MODE> JD uint64_t cx_lookup(JEng *E, CtaState *S, uint32_t ring, d
 #define JOP_MUL 0u
 #define JOP_ADD 1u
 #define JOP_DIV 2u
+static_assert(JKQ_SVALS <= 1024u, "jpack22 holds 10-bit value indices");
+// weight id <-> 22 bits (value indices below 1024: single-CTA path)
+JD uint64_t jpack22(uint64_t w) { return ((w >> 63) << 21) | (((w >> 32) & 0x3FFull) << 11) | (((w >> 31) & 1ull) << 10) | (w & 0x3FFull); }
+JD uint64_t junpack22(uint64_t p) { return ((p >> 21) << 63) | (((p >> 11) & 0x3FFull) << 32) | (((p >> 10) & 1ull) << 31) | (p & 0x3FFull); }
 #ifdef JKQ_EMU_MEMOSTAT
 #include <unordered_map>
 #include <string>
-struct JMemoStat { std::unordered_map<std::string, int> seen; unsigned long long calls = 0, repeats = 0, recent_hits = 0; std::string ring[256]; unsigned pos = 0; };
+struct JMemoStat { std::unordered_map<std::string, int> seen; unsigned long long calls = 0, repeats = 0, recent_hits = 0; std::string ring[1024]; unsigned pos = 0; };
 inline JMemoStat &jmemostat() { static JMemoStat m; return m; }
 #endif
 template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, uint32_t op, uint64_t a, uint64_t b) {
@@ -533,10 +539,26 @@ template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, u
     m.calls++;
     if (m.seen[key]++) m.repeats++;
     // direct-mapped 256-entry cache model
-    unsigned h = (unsigned)((a * 0x9E3779B97F4A7C15ull ^ b * 0xC2B2AE3D27D4EB4Full ^ op) >> 56);
+    unsigned h = (unsigned)((a * 0x9E3779B97F4A7C15ull ^ b * 0xC2B2AE3D27D4EB4Full ^ op) >> MEMO_SHIFT);
     if (m.ring[h] == key) m.recent_hits++; else m.ring[h] = key;
   }
 #endif
+  // Operation memo of the single-CTA path (the reference's ctm / cta / ctd caches, QMDDcomplexD.cpp:498-777, as a
+  // direct-mapped table in shared memory): 9 of 10 calls repeat an earlier (op, a, b).  Value indices are below
+  // 1024 there, so a weight id packs into 22 bits and (op, a, b) into 46; an entry is two words,
+  //   word 0 = VALID | key,  word 1 = key[45:4] << 22 | result,
+  // and the slot index is hash(key[45:4]) ^ key[3:0]: two entries that agree on key[45:4] never share a slot,
+  // so a reader that catches the two words of different writers cannot take them for one entry.
+  uint64_t memo_key = 0;
+  uint32_t memo_slot = 0;
+  if (MODE == MODE_CTA) {
+    const uint64_t pa = jpack22(a), pb = jpack22(b);
+    memo_key = ((uint64_t)op << 44) | (pa << 22) | pb;
+    const uint64_t top = memo_key >> 4;
+    memo_slot = (hfin((uint32_t)top * 0x9E3779B1u + (uint32_t)(top >> 32) * 0x85EBCA6Bu) ^ (uint32_t)(memo_key & 15u)) & (JKQ_SMEMO - 1u);
+    const unsigned long long w0 = ld_r<MODE>(&S->memo[memo_slot][0]), w1 = ld_r<MODE>(&S->memo[memo_slot][1]);
+    if (w0 == (memo_key | (1ull << 63)) && (w1 >> 22) == top) return junpack22(w1 & 0x3FFFFFull);
+  }
   double ar = jval2<MODE>(E, S, (uint32_t)(a >> 32)), ai = jval2<MODE>(E, S, (uint32_t)a);
   double br = jval2<MODE>(E, S, (uint32_t)(b >> 32)), bi = jval2<MODE>(E, S, (uint32_t)b);
   if (a >> 63) ar = -ar;
@@ -558,7 +580,12 @@ template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, u
     re = JKQ_DDIV(JKQ_DADD(JKQ_DMUL(ar, br), JKQ_DMUL(ai, bi)), d);
     im = JKQ_DDIV(JKQ_DSUB(JKQ_DMUL(ai, br), JKQ_DMUL(ar, bi)), d);
   }
-  return cx_lookup<MODE>(E, S, ring, re, im);
+  const uint64_t r = cx_lookup<MODE>(E, S, ring, re, im);
+  if (MODE == MODE_CTA && r != JW_MISS) {
+    S->memo[memo_slot][0] = memo_key | (1ull << 63);
+    S->memo[memo_slot][1] = ((memo_key >> 4) << 22) | jpack22(r);
+  }
+  return r;
 }
 template <int MODE> JD bool cmul(Ctx &c, uint64_t a, uint64_t b, uint64_t *out) {
   if (a == JW_ONE) { *out = b; return true; }
