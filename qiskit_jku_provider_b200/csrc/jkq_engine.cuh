@@ -87,7 +87,7 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SVT_SLOTS 2048u  // value-table slots
 #define JKQ_SPEND 512u       // value-table slots claimed in one phase
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
-#define JKQ_SMEMO 512u       // entries of the complex-operation memo (16 bytes each)
+#define JKQ_SMEMO 1024u      // entries of the complex-operation memo (16 bytes each)
 #define JKQ_SCHAIN 1024u     // scratch words of compressed chains (per gate)
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
