@@ -385,6 +385,7 @@ def main():
             barrier()
             b_wall = time.perf_counter() - t2
             fb = br.fallbacks
+            b_kernel_only, b_fallback = br.last_kernel_ms, br.last_fallback_ms
         tt = torch.tensor([float(b_gates), b_ms], dtype=torch.float64, device="cuda")
         if dist is not None:
             g_all = tt.clone()
@@ -397,7 +398,9 @@ def main():
             "gate_applies_per_s_kernel": b_gates / (b_ms * 1e-3), "wall_s_host_ops_in_counts_out": b_wall,
             "gate_applies_per_s_wall": b_gates / b_wall, "circuits_per_s_wall": n_batch / b_wall, "engines_per_gpu": 148,
             "full_engine_fallbacks_rank0": fb,
-            "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue; circuits split i % world == rank"}
+            "k_batch_ms_rank0": b_kernel_only, "fallback_apply_ms_rank0": b_fallback,
+            "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue (longest gate list first); circuits split "
+                    "i % world == rank; kernel_ms = k_batch + the circuits that outgrew one SM, redone one after the other on the full engine"}
         if rank == 0:
             for c3 in (C.ghz(24), C.grover(20, 20), C.random_circuit(18, 100, 1), C.random_circuit(18, 120, 1)):
                 eng.load(c3)

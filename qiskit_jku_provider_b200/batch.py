@@ -77,6 +77,7 @@ class BatchRunner:
             raise JKUSimulatorError("jkq_batch_run failed (%d): %s" % (rc, self._lib.jkq_batch_last_error(self._b).decode()))
         self.last_fast_path_error = self._lib.jkq_batch_last_error(self._b).decode() if status.any() else ""
         out, total_gates, dev_ms = {}, int(gates.value), float(ms.value)
+        self.last_kernel_ms, self.last_fallback_ms = dev_ms, 0.0  # k_batch alone / circuits redone on the full engine
         for j, i in enumerate(mine):
             if status[j] == 0:
                 k = int(nd[j])
@@ -95,6 +96,7 @@ class BatchRunner:
             st = self._big.stats()
             total_gates += st["gates"]
             dev_ms += st["apply_ms"]
+            self.last_fallback_ms += st["apply_ms"]
         return out, total_gates, dev_ms
 
     def run_shots(self, n_qubits, ops, shots, seed=1, shot_offset=0, measure_seed0=None, physical_reset=False):

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <array>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -1301,11 +1302,21 @@ struct JBatchOut {
   int32_t status;
   uint32_t n_distinct;
   uint64_t gates;
+  uint64_t t0_ns, t1_ns;  // JKQ_PROFILE: %globaltimer when the instance started / ended (else 0)
 };
+__device__ __forceinline__ uint64_t jglobaltimer() {
+#ifdef JKQ_PROFILE
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#else
+  return 0;
+#endif
+}
 
 __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const JBatchCirc *circ, const JGate *gates, unsigned int n_circ,
-                                                 unsigned int *next, uint64_t shots, uint32_t hslots, uint32_t cap, JBatchOut *out,
-                                                 unsigned long long *keys, unsigned long long *counts) {
+                                                 const unsigned int *order, unsigned int *next, uint64_t shots, uint32_t hslots, uint32_t cap,
+                                                 JBatchOut *out, unsigned long long *keys, unsigned long long *counts) {
   __shared__ unsigned int s_i, s_cnt;
   __shared__ int s_ovf;
   const JBatchEng be = engs[blockIdx.x];
@@ -1313,9 +1324,11 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
   for (;;) {
     if (threadIdx.x == 0) s_i = atomicAdd(next, 1u);
     __syncthreads();
-    const unsigned int i = s_i;
+    const unsigned int q = s_i;
     __syncthreads();
-    if (i >= n_circ) break;
+    if (q >= n_circ) break;
+    const unsigned int i = order[q];  // longest gate lists first: a heavy circuit must not be the last one to start
+    const uint64_t t_begin = jglobaltimer();
     const JBatchCirc cd = circ[i];
     if (threadIdx.x == 0) { E->n = cd.n; E->lvl_log = nullptr; E->mat_u = nullptr; E->mat_epoch = nullptr; E->cursor_saved = 0; }
     {
@@ -1369,6 +1382,7 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
     if (threadIdx.x == 0) {
       JBatchOut o;
       o.status = st; o.n_distinct = nd; o.gates = (uint64_t)E->st[JST_GATES];
+      o.t0_ns = t_begin; o.t1_ns = jglobaltimer();
       out[i] = o;
       E->status = 0; E->want_grid = 0; E->cursor_saved = 0;
     }
@@ -1569,6 +1583,7 @@ __global__ void __launch_bounds__(256, 1) k_batch_shots(const JBatchEng *engs, J
     __syncthreads();
     if (threadIdx.x == 0) {
       JBatchOut o;
+      o.t0_ns = 0; o.t1_ns = 0;
       o.status = st; o.n_distinct = st ? 0u : 1u;
       o.gates = (uint64_t)E->st[JST_GATES] + (resident ? (uint64_t)c.sh->st[JST_GATES] : 0ull) - placeholders;
       out[inst] = o;
@@ -1593,6 +1608,7 @@ struct jkq_batch {
   JGate *gates_dev = nullptr, *gates_pin = nullptr;
   size_t gates_cap = 0;
   JBatchCirc *circ_dev = nullptr, *circ_pin = nullptr;
+  unsigned int *order_dev = nullptr, *order_pin = nullptr;  // queue order of k_batch (same capacity as circ_*)
   JBatchOut *out_dev = nullptr, *out_pin = nullptr;
   size_t circ_cap = 0;
   unsigned long long *res_dev = nullptr, *res_pin = nullptr;  // keys then counts
@@ -1611,7 +1627,8 @@ extern "C" void jkq_batch_destroy(jkq_batch *b) {
   cudaSetDevice(b->device);
   for (jkq_handle *h : b->eng) jkq_destroy(h);
   cudaFree(b->engs_dev); cudaFree(b->next_dev); cudaFree(b->gates_dev); cudaFree(b->circ_dev); cudaFree(b->out_dev); cudaFree(b->res_dev);
-  cudaFree(b->priv_dev); cudaFree(b->slots_dev);
+  cudaFree(b->priv_dev); cudaFree(b->slots_dev); cudaFree(b->order_dev);
+  if (b->order_pin) cudaFreeHost(b->order_pin);
   if (b->gates_pin) cudaFreeHost(b->gates_pin);
   if (b->circ_pin) cudaFreeHost(b->circ_pin);
   if (b->out_pin) cudaFreeHost(b->out_pin);
@@ -1744,6 +1761,10 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
     if (b->circ_pin) cudaFreeHost(b->circ_pin);
     if (b->out_pin) cudaFreeHost(b->out_pin);
     b->circ_cap = pow2_at_least(n_circuits, 64);
+    cudaFree(b->order_dev);
+    if (b->order_pin) cudaFreeHost(b->order_pin);
+    BCU(cudaMalloc(&b->order_dev, b->circ_cap * sizeof(unsigned int)));
+    BCU(cudaMallocHost(&b->order_pin, b->circ_cap * sizeof(unsigned int)));
     BCU(cudaMalloc(&b->circ_dev, b->circ_cap * sizeof(JBatchCirc)));
     BCU(cudaMalloc(&b->out_dev, b->circ_cap * sizeof(JBatchOut)));
     BCU(cudaMallocHost(&b->circ_pin, b->circ_cap * sizeof(JBatchCirc)));
@@ -1760,13 +1781,23 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
   // ---- one launch
   memcpy(b->gates_pin, gates.data(), gates.size() * sizeof(JGate));
   memcpy(b->circ_pin, cd.data(), n_circuits * sizeof(JBatchCirc));
+  {
+    // queue order: longest gate list first.  The gate count is the only cost known up front; it keeps the circuits
+    // most likely to be slow (large DDs come with long gate lists) away from the end of the queue, where one late
+    // starter would leave 147 SMs idle.
+    std::vector<unsigned int> ord(n_circuits);
+    for (size_t i = 0; i < n_circuits; i++) ord[i] = (unsigned int)i;
+    std::stable_sort(ord.begin(), ord.end(), [&](unsigned int x, unsigned int y) { return cd[x].n_gates > cd[y].n_gates; });
+    memcpy(b->order_pin, ord.data(), n_circuits * sizeof(unsigned int));
+  }
+  BCU(cudaMemcpyAsync(b->order_dev, b->order_pin, n_circuits * sizeof(unsigned int), cudaMemcpyHostToDevice, b->stream));
   BCU(cudaMemcpyAsync(b->gates_dev, b->gates_pin, gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, b->stream));
   BCU(cudaMemcpyAsync(b->circ_dev, b->circ_pin, n_circuits * sizeof(JBatchCirc), cudaMemcpyHostToDevice, b->stream));
   BCU(cudaMemsetAsync(b->next_dev, 0, 4, b->stream));
   const unsigned int blocks = (unsigned int)(n_circuits < b->eng.size() ? n_circuits : b->eng.size());
   BCU(cudaEventRecord(b->ev0, b->stream));
-  k_batch<<<blocks, b->cfg.cta_threads, sizeof(CtaSmem), b->stream>>>(b->engs_dev, b->circ_dev, b->gates_dev, (unsigned int)n_circuits, b->next_dev,
-                                                                     shots, (uint32_t)hslots, (uint32_t)cap, b->out_dev, b->res_dev,
+  k_batch<<<blocks, b->cfg.cta_threads, sizeof(CtaSmem), b->stream>>>(b->engs_dev, b->circ_dev, b->gates_dev, (unsigned int)n_circuits, b->order_dev,
+                                                                     b->next_dev, shots, (uint32_t)hslots, (uint32_t)cap, b->out_dev, b->res_dev,
                                                                      b->res_dev + n_circuits * cap);
   BCU(cudaGetLastError());
   BCU(cudaEventRecord(b->ev1, b->stream));
@@ -1790,6 +1821,24 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
   if (gates_applied) *gates_applied = total;
   float ms = 0;
   if (apply_ms_sum && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *apply_ms_sum = ms;
+#ifdef JKQ_PROFILE
+  {
+    uint64_t first = ~0ull, last = 0, sum = 0, longest = 0, late = 0;
+    size_t longest_i = 0;
+    for (size_t i = 0; i < n_circuits; i++) {
+      const JBatchOut &o = b->out_pin[i];
+      if (!o.t1_ns) continue;
+      if (o.t0_ns < first) first = o.t0_ns;
+      if (o.t1_ns > last) { last = o.t1_ns; late = i; }
+      sum += o.t1_ns - o.t0_ns;
+      if (o.t1_ns - o.t0_ns > longest) { longest = o.t1_ns - o.t0_ns; longest_i = i; }
+    }
+    if (last > first)
+      fprintf(stderr, "k_batch: span %.2f ms, sum of circuit times %.2f ms (/%u CTAs = %.2f ms), longest circuit %zu: %.2f ms (status %d, %u gates), last to finish %zu: started at %.2f ms, took %.2f ms\n",
+              (last - first) * 1e-6, sum * 1e-6, blocks, sum * 1e-6 / blocks, longest_i, longest * 1e-6, b->out_pin[longest_i].status, cd[longest_i].n_gates,
+              (size_t)late, (b->out_pin[late].t0_ns - first) * 1e-6, (b->out_pin[late].t1_ns - b->out_pin[late].t0_ns) * 1e-6);
+  }
+#endif
   return JKQ_E_OK;
 }
 
@@ -1859,6 +1908,10 @@ extern "C" int jkq_batch_run_shots(jkq_batch *b, uint32_t n_qubits, const jkq_op
     if (b->circ_pin) cudaFreeHost(b->circ_pin);
     if (b->out_pin) cudaFreeHost(b->out_pin);
     b->circ_cap = pow2_at_least(shots, 64);
+    cudaFree(b->order_dev);
+    if (b->order_pin) cudaFreeHost(b->order_pin);
+    BCU(cudaMalloc(&b->order_dev, b->circ_cap * sizeof(unsigned int)));
+    BCU(cudaMallocHost(&b->order_pin, b->circ_cap * sizeof(unsigned int)));
     BCU(cudaMalloc(&b->circ_dev, b->circ_cap * sizeof(JBatchCirc)));
     BCU(cudaMalloc(&b->out_dev, b->circ_cap * sizeof(JBatchOut)));
     BCU(cudaMallocHost(&b->circ_pin, b->circ_cap * sizeof(JBatchCirc)));
