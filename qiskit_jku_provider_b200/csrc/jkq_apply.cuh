@@ -168,9 +168,37 @@ template <int MODE> JD uint32_t lr_end(const Ctx &c, int L) { return MODE == MOD
 
 // One level run by the cursor warp alone (at most one item per lane): no CTA / grid barrier, values are
 // committed warp-locally.  Returns 0 or barrier flags.
+#ifndef JKQ_EMU
+// expansion of a level of at most 16 items: two lanes per item, one per child slot (expand_item_pair)
+template <int MODE>
+JD uint32_t solo_expand_pairs(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L, uint32_t nwork) {
+  const uint32_t lane = c.ltid, slot = lane >> 1, child = lane & 1u, pm = 3u << (lane & ~1u);
+  const uint32_t i = slot < nwork ? level_item<MODE>(c, L, b, e, slot) : JI_FAIL;
+  JItem *it = c.items + (i == JI_FAIL ? 0 : i);
+  bool need = i != JI_FAIL;
+  if (need) need = (ld_i<MODE>(&it->flags) & 3u) != JS_DEAD;
+  for (;;) {
+    if (need) {
+      const uint32_t fl = expand_item_pair<MODE>(c, g, i, L, child, pm);
+      if (child == 0) it->flags = fl;
+      need = (fl & 3u) == JS_RETRY;
+    }
+    const uint32_t bad = jballot(need);
+    jsyncwarp();
+    const uint32_t tr = thin_trouble<MODE>(c);  // pools exhausted / errors are sticky words
+    if (tr) return tr;
+    if (!bad) return 0;
+    thin_commit<MODE>(c);
+  }
+}
+#endif
+
 template <int MODE, bool expand>
 JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   const uint32_t nwork = e - b + defer_count<MODE>(c, L);
+#ifndef JKQ_EMU
+  if (expand && nwork <= JKQ_WARP / 2) return solo_expand_pairs<MODE>(c, g, b, e, L, nwork);
+#endif
   const uint32_t i = c.ltid < nwork ? level_item<MODE>(c, L, b, e, c.ltid) : JI_FAIL;
   JItem *it = c.items + (i == JI_FAIL ? 0 : i);
   bool need = i != JI_FAIL;

@@ -990,6 +990,62 @@ __device__ unsigned long long g_fine[16];
 #define JFINE_T(v) do {} while (0)
 #define JFINE_ADD(c, slot, a, b) do {} while (0)
 #endif
+// Chain compression of a same-node fused item whose node `na` has all its non-zero edges on one child `chain_c`
+// (see the comment inside).  Returns 0 when the plain path has to be taken, else the item's new flags | 1 << 31.
+template <int MODE>
+JD uint32_t chain_try(Ctx &c, const JGate &g, JItem *it, uint32_t tag, uint64_t iwa, uint64_t iwb, uint64_t iwc, const JNode &na, int L, uint32_t chain_c) {
+  // Chain compression.  Both operands are the same node, all its non-zero edges go to the same child c
+  // (a basis-state node with one zero edge, or a product-state node with two edges to one child), and the
+  // level carries no control: the item's only child is the same key on c, and the result is the old node
+  // over that child's result with the top weight passed through.  For the states of QFT / GHZ-like
+  // circuits that repeats level after level down to the next control: walk the chain of such
+  // nodes once, keep their (norm flag, weight) in scratch, and refer directly to the item at its end --
+  // reduce_item rebuilds the chain in one go.  The skipped levels cost a node load and a unique-table
+  // insert each instead of two phases.
+  CtaState *S = c.sh;
+  JFINE_T(w0);
+  uint32_t cur = chain_c, k = 0;
+  int Lc = L - 1;
+  while (Lc > g.low && g.role[Lc] == JR_IDLE && k < 60) {
+    const JNode nd = node_load<MODE>(c, cur);
+    uint32_t nxt;
+    if (!chain_node(nd, &nxt)) break;
+    cur = nxt; k++; Lc--;
+  }
+  if (k >= 1) {
+    const uint32_t off = jatomic_add(&S->chain_n, k + 1u);
+    const uint32_t dn = off + k + 1u <= JKQ_SCHAIN ? jatomic_add(&S->defer_n[Lc], 1u) : JKQ_SDEFER;
+    if (dn < JKQ_SDEFER) {
+      unsigned long long mask = 0;
+      uint32_t cur2 = chain_c;
+      for (uint32_t j = 0; j < k; j++) {
+        const JNode nd = node_load<MODE>(c, cur2);
+        S->chain[off + 1 + j] = nd.w;
+        mask |= (unsigned long long)nd_flag(nd) << j;
+        chain_node(nd, &cur2);
+      }
+      S->chain[off] = mask;
+      bool created = false;
+      const uint32_t child = dt_find_or_insert<MODE>(c.E, S, c.items, cur, cur, iwa, iwb, iwc, tag_level(tag, Lc), &created);
+      S->defer[Lc][dn] = (child != JI_FAIL && created) ? (uint16_t)child : (uint16_t)0xFFFFu;
+      if (child == JI_FAIL) return JS_DONE | 0x80000000u;  // want_grid flagged; the gate is abandoned
+#ifndef JKQ_EMU
+      atomicMin(&S->min_def, Lc);
+#else
+      if (Lc < S->min_def) S->min_def = Lc;
+#endif
+      it->ch[0] = child; it->ch[1] = k | (off << 8); it->chw[0] = nd_w0(na); it->chw[1] = nd_w1(na);
+      JFINE_T(w1);
+      JFINE_ADD(c, 2, w0, w1);
+      JFINE_ADD(c, 3, 0, k);
+      JFINE_ADD(c, 10, 0, 1);
+      return item_flags(JS_DONE, JC_REF, JC_REF, 1u + nd_flag(na)) | JFLAG_CHAIN | 0x80000000u;
+    }
+    // (scratch or waiting list full: the plain path below; readers clamp defer_n to JKQ_SDEFER)
+  }
+  return 0;
+}
+
 template <int MODE> JD uint32_t expand_item_impl(Ctx &c, const JGate &g, uint32_t idx, int L);
 // returns the new flags word of the item (state JS_DONE or JS_RETRY)
 template <int MODE> JD uint32_t expand_item(Ctx &c, const JGate &g, uint32_t idx, int L) {
@@ -1038,55 +1094,8 @@ template <int MODE> JD uint32_t expand_item_impl(Ctx &c, const JGate &g, uint32_
   }
   uint32_t chain_c = 0;
   if (MODE == MODE_CTA && kind == JK_F && ia == ib && ia != 0 && role == JR_IDLE && L - 1 >= g.low && chain_node(na, &chain_c)) {
-    // Chain compression.  Both operands are the same node, all its non-zero edges go to the same child c
-    // (a basis-state node with one zero edge, or a product-state node with two edges to one child), and the
-    // level carries no control: the item's only child is the same key on c, and the result is the old node
-    // over that child's result with the top weight passed through.  For the states of QFT / GHZ-like
-    // circuits that repeats level after level down to the next control: walk the chain of such
-    // nodes once, keep their (norm flag, weight) in scratch, and refer directly to the item at its end --
-    // reduce_item rebuilds the chain in one go.  The skipped levels cost a node load and a unique-table
-    // insert each instead of two phases.
-    CtaState *S = c.sh;
-    JFINE_T(w0);
-    uint32_t cur = chain_c, k = 0;
-    int Lc = L - 1;
-    while (Lc > g.low && g.role[Lc] == JR_IDLE && k < 60) {
-      const JNode nd = node_load<MODE>(c, cur);
-      uint32_t nxt;
-      if (!chain_node(nd, &nxt)) break;
-      cur = nxt; k++; Lc--;
-    }
-    if (k >= 1) {
-      const uint32_t off = jatomic_add(&S->chain_n, k + 1u);
-      const uint32_t dn = off + k + 1u <= JKQ_SCHAIN ? jatomic_add(&S->defer_n[Lc], 1u) : JKQ_SDEFER;
-      if (dn < JKQ_SDEFER) {
-        unsigned long long mask = 0;
-        uint32_t cur2 = chain_c;
-        for (uint32_t j = 0; j < k; j++) {
-          const JNode nd = node_load<MODE>(c, cur2);
-          S->chain[off + 1 + j] = nd.w;
-          mask |= (unsigned long long)nd_flag(nd) << j;
-          chain_node(nd, &cur2);
-        }
-        S->chain[off] = mask;
-        bool created = false;
-        const uint32_t child = dt_find_or_insert<MODE>(c.E, S, c.items, cur, cur, iwa, iwb, iwc, tag_level(tag, Lc), &created);
-        S->defer[Lc][dn] = (child != JI_FAIL && created) ? (uint16_t)child : (uint16_t)0xFFFFu;
-        if (child == JI_FAIL) return JS_DONE;  // want_grid flagged; the gate is abandoned
-#ifndef JKQ_EMU
-        atomicMin(&S->min_def, Lc);
-#else
-        if (Lc < S->min_def) S->min_def = Lc;
-#endif
-        it->ch[0] = child; it->ch[1] = k | (off << 8); it->chw[0] = nd_w0(na); it->chw[1] = nd_w1(na);
-        JFINE_T(w1);
-        JFINE_ADD(c, 2, w0, w1);
-        JFINE_ADD(c, 3, 0, k);
-        JFINE_ADD(c, 10, 0, 1);
-        return item_flags(JS_DONE, JC_REF, JC_REF, 1u + nd_flag(na)) | JFLAG_CHAIN;
-      }
-      // (scratch or waiting list full: the plain path below; readers clamp defer_n to JKQ_SDEFER)
-    }
+    const uint32_t cr = chain_try<MODE>(c, g, it, tag, iwa, iwb, iwc, na, L, chain_c);
+    if (cr) return cr & 0x7FFFFFFFu;
   }
   Slot s0, s1;
   JFINE_T(x0);
@@ -1110,6 +1119,65 @@ template <int MODE> JD uint32_t expand_item_impl(Ctx &c, const JGate &g, uint32_
   if (kind == JK_F && ia == ib && s0.w == nd_w0(na) && s1.w == nd_w1(na) && s0.kind != JC_ZERO && s1.kind != JC_ZERO) hint = 1u + nd_flag(na);
   return item_flags(JS_DONE, s0.kind, s1.kind, hint);
 }
+
+#ifndef JKQ_EMU
+// expand_item for a PAIR of lanes: lane `child` (0 / 1) of the pair computes child slot `child` of the item -- the
+// two slots are independent (own arithmetic, own de-dup insert), which halves the dependent chain of a level that
+// holds at most 16 items (the usual case on the single-warp path).  `pm` = mask of the two lanes; both lanes take
+// every branch below together (the branches depend on the item only) and return the same flags word.
+template <int MODE> JD uint32_t expand_item_pair(Ctx &c, const JGate &g, uint32_t idx, int L, uint32_t child, uint32_t pm) {
+  JItem *it = c.items + idx;
+  const uint32_t tag = ld_i<MODE>(&it->tag), ia = ld_i<MODE>(&it->a);
+  const uint32_t kind = tag & 15u, sel = (tag >> 4) & 1u;
+  const uint32_t role = g.role[L];
+  if (kind == JK_M && L > g.target) {  // a level above the target forwards the node's two edges: one edge per lane
+    const JNode p = node_load<MODE>(c, ia);
+    const uint32_t ch = child ? p.c1 : nd_c0(p);
+    const uint64_t w = child ? nd_w1(p) : nd_w0(p);
+    uint32_t k, t = ch;
+    bool ok = true;
+    if (w == 0) { k = JC_ZERO; t = 0; }
+    else if (role_satisfied(role, (int)child)) { k = JC_REF; t = dt_find_or_insert_m<MODE>(c.E, c.sh, c.items, ch); ok = t != JI_FAIL; }
+    else k = JC_PASS;
+    const uint32_t ko = __shfl_xor_sync(pm, k, 1);
+    const bool oko = __shfl_xor_sync(pm, (uint32_t)ok, 1) != 0;
+    if (!(ok && oko)) return JS_DONE;  // error / want_grid flagged; the gate is abandoned
+    it->ch[child] = t; it->chw[child] = w;
+    return item_flags(JS_DONE, child ? ko : k, child ? k : ko, 1u + nd_flag(p));
+  }
+  const uint32_t ib = ld_i<MODE>(&it->b);
+  uint64_t iwa = 0, iwb = 0, iwc = 0;
+  JNode na, nb;
+  na.c0 = na.c1 = 0; na.w = 0; nb = na;
+  if (ia) na = node_load<MODE>(c, ia);
+  if (kind != JK_M) {
+    iwa = ld_i<MODE>(&it->wa); iwb = ld_i<MODE>(&it->wb); iwc = ld_i<MODE>(&it->wc);
+    if (ib) nb = (ib == ia) ? na : node_load<MODE>(c, ib);
+  }
+  uint32_t chain_c = 0;
+  if (MODE == MODE_CTA && kind == JK_F && ia == ib && ia != 0 && role == JR_IDLE && L - 1 >= g.low && chain_node(na, &chain_c)) {
+    uint32_t cr = 0;  // the chain walk has nothing to split: lane 0 of the pair does it
+    if (child == 0) cr = chain_try<MODE>(c, g, it, tag, iwa, iwb, iwc, na, L, chain_c);
+    cr = __shfl_sync(pm, cr, (threadIdx.x & 31u) & ~1u);
+    if (cr) return cr & 0x7FFFFFFFu;
+  }
+  Slot s;
+  const bool e = expand_child<MODE>(c, g, L, (int)child, kind, sel, tag, role, ia, ib, iwa, iwb, iwc, na, nb, s);
+  const bool eo = __shfl_xor_sync(pm, (uint32_t)e, 1) != 0;
+  if (!(e && eo)) return JS_RETRY;  // both children were tried: all their missing values are proposed
+  bool ok = true;
+  if (s.kind == JC_REF) { s.target = dt_find_or_insert<MODE>(c.E, c.sh, c.items, s.ia, s.ib, s.iwa, s.iwb, s.iwc, s.itag); ok = s.target != JI_FAIL; }
+  const bool oko = __shfl_xor_sync(pm, (uint32_t)ok, 1) != 0;
+  if (!(ok && oko)) return JS_DONE;  // error / want_grid already flagged; the gate is abandoned
+  it->ch[child] = s.target; it->chw[child] = s.w;
+  // same-node fused item whose two children carry the node's own weights: normalised pair again
+  const bool keeps = s.kind != JC_ZERO && s.w == (child ? nd_w1(na) : nd_w0(na));
+  const bool keeps_o = __shfl_xor_sync(pm, (uint32_t)keeps, 1) != 0;
+  const uint32_t ko = __shfl_xor_sync(pm, s.kind, 1);
+  const uint32_t hint = (kind == JK_F && ia == ib && keeps && keeps_o) ? 1u + nd_flag(na) : 0u;
+  return item_flags(JS_DONE, child ? ko : s.kind, child ? s.kind : ko, hint);
+}
+#endif
 
 // ------------------------------------------------------------------------------------ reduce
 // Bottom-up step: QMDDmakeNonterminal (QMDDpackage.cpp:1204-1233) = zero test, NormC normalisation
