@@ -492,6 +492,8 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
     if (MODE == MODE_GRID)
       for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
   }
+  if (MODE == MODE_CTA)  // node ids are about to change: memoised chain rebuilds are void
+    for (uint32_t i = c.ltid; i < JKQ_SCMEMO; i += c.lnth) c.sh->cmemo[i] = 0;
   if (MODE == MODE_CTA && (clean_vals || reload)) {
     for (uint32_t i = c.ltid; i < JKQ_SVT_SLOTS; i += c.lnth) vt_clear_slot(c.sh->vtab + i);
     for (uint32_t i = c.ltid; i < JKQ_SMATS; i += c.lnth) c.sh->mtag[i] = 0;  // cached matrix ids are void

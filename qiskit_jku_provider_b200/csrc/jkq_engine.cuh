@@ -88,7 +88,8 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SPEND 512u       // value-table slots claimed in one phase
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
 #define JKQ_SMEMO 1024u      // entries of the complex-operation memo (16 bytes each)
-#define JKQ_SCHAIN 1024u     // scratch words of compressed chains (per gate)
+#define JKQ_SCHAIN 512u      // words of chain-compression scratch per gate (a chain of k nodes takes k + 1)
+#define JKQ_SCMEMO 512u      // entries of the chain-rebuild memo (8 bytes each)
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
@@ -115,6 +116,7 @@ struct CtaState {
   uint32_t mtag[JKQ_SMATS];
   uint64_t mu[JKQ_SMATS][4];
   unsigned long long memo[JKQ_SMEMO][2];    // (op, a, b) -> result id of cx_arith, see there
+  unsigned long long cmemo[JKQ_SCMEMO];     // (item node, skipped levels, result below) -> rebuilt chain top, see reduce_item
   uint32_t pend[JKQ_SPEND];
   uint32_t mdir[JKQ_SNODES];
   uint32_t dtab[JKQ_SDT_SLOTS];
@@ -521,6 +523,7 @@ template <int MODE> JD uint64_t cx_lookup(JEng *E, CtaState *S, uint32_t ring, d
 #define JOP_ADD 1u
 #define JOP_DIV 2u
 static_assert(JKQ_SVALS <= 1024u, "jpack22 holds 10-bit value indices");
+static_assert(JKQ_SNODES <= 2048u, "the chain-rebuild memo holds 11-bit node ids");
 // weight id <-> 22 bits (value indices below 1024: single-CTA path)
 JD uint64_t jpack22(uint64_t w) { return ((w >> 63) << 21) | (((w >> 32) & 0x3FFull) << 11) | (((w >> 31) & 1ull) << 10) | (w & 0x3FFull); }
 JD uint64_t junpack22(uint64_t p) { return ((p >> 21) << 63) | (((p >> 11) & 0x3FFull) << 32) | (((p >> 10) & 1ull) << 31) | (p & 0x3FFull); }
@@ -1254,10 +1257,21 @@ template <int MODE> JD bool reduce_item_impl(Ctx &c, uint32_t idx, uint32_t flag
     const uint32_t info = ld_i<MODE>(&it->ch[1]), k = info & 0xFFu, off = info >> 8;
     const unsigned long long mask = c.sh->chain[off];
     JFINE_T(y0);
-    for (uint32_t j = k; j-- > 0 && r != 0;) {
-      const uint32_t fl = (uint32_t)((mask >> j) & 1ull);
-      const uint64_t w = c.sh->chain[off + 1 + j];  // 0: the node's other edge is the zero edge
-      r = ut_find_or_insert<MODE>(c.E, c.sh, ((fl == 1 && w == 0) ? 0u : r) | (fl << 31), (fl == 0 && w == 0) ? 0u : r, w);
+    // The rebuilt chain is a function of (the item's node, which fixes the chain below it; the number of skipped
+    // levels; the result node under the chain) -- and three rebuilds out of four repeat an earlier one (QFT-32), so
+    // they are memoised until the collector renumbers the nodes: ids are below 2048 on this path, key and value
+    // share one 64-bit word.
+    const unsigned long long ckey = (1ull << 28) | ((unsigned long long)ld_i<MODE>(&it->a) << 17) | ((unsigned long long)k << 11) | r;
+    const uint32_t cslot = hfin((uint32_t)ckey * 0x9E3779B1u) & (JKQ_SCMEMO - 1u);
+    const unsigned long long cw = ld_r<MODE>(&c.sh->cmemo[cslot]);
+    if ((cw >> 11) == ckey) r = (uint32_t)(cw & 0x7FFull);
+    else {
+      for (uint32_t j = k; j-- > 0 && r != 0;) {
+        const uint32_t fl = (uint32_t)((mask >> j) & 1ull);
+        const uint64_t w = c.sh->chain[off + 1 + j];  // 0: the node's other edge is the zero edge
+        r = ut_find_or_insert<MODE>(c.E, c.sh, ((fl == 1 && w == 0) ? 0u : r) | (fl << 31), (fl == 0 && w == 0) ? 0u : r, w);
+      }
+      if (r != 0) c.sh->cmemo[cslot] = (ckey << 11) | r;
     }
     JFINE_T(y1);
     JFINE_ADD(c, 8, y0, y1);
