@@ -24,6 +24,9 @@ struct CtaSmem {
   ThinState t;
 };
 
+// 227 KB of shared memory per CTA on sm_100; the kernels add up to ~200 bytes of static shared memory on top
+static_assert(sizeof(CtaSmem) + 512 <= 227 * 1024, "CtaState + ThinState no longer fit one SM's shared memory");
+
 template <int MODE> __device__ __forceinline__ Ctx make_ctx(JEng *E) {
   Ctx c;
   c.E = E;
