@@ -1211,9 +1211,12 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
 #endif
 #ifdef JKQ_PROFILE2
   {
-    unsigned long long p[16], z[16] = {0};
+    unsigned long long p[32], z[32] = {0};
     cudaMemcpyFromSymbol(p, g_fine, sizeof(p));
     cudaMemcpyToSymbol(g_fine, z, sizeof(z));
+    if (p[17] || p[19])
+      fprintf(stderr, "  cursor_prepare: %llu up-steps, %llu cycles each | %llu levels down, %llu cycles each\n", p[17], p[17] ? p[16] / p[17] : 0, p[19],
+              p[19] ? p[18] / p[19] : 0);
     if (p[1])
       fprintf(stderr, "JKQ_PROFILE2 lane 0: expand_item %llu calls, %llu cycles each | chain path %llu times: %llu cycles each, %.1f levels each | expand_child x2 %llu cycles/plain call, de-dup %llu | reduce_item %llu calls, %llu cycles each; chain rebuild %llu cycles per chain item\n",
               p[1], p[0] / p[1], p[10], p[10] ? p[2] / p[10] : 0, p[10] ? (double)p[3] / p[10] : 0.0, (p[1] - p[10]) ? p[4] / (p[1] - p[10]) : 0,

@@ -986,7 +986,7 @@ JD bool chain_node(const JNode &n, uint32_t *child) {
 }
 
 #if defined(JKQ_PROFILE2) && !defined(JKQ_EMU)
-__device__ unsigned long long g_fine[16];
+__device__ unsigned long long g_fine[32];
 #define JFINE_T(v) long long v = clock64()
 #define JFINE_ADD(c, slot, a, b) do { if (MODE == MODE_CTA && (c).tid == 0) g_fine[slot] += (unsigned long long)((b) - (a)); } while (0)
 #else

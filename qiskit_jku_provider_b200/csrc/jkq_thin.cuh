@@ -217,12 +217,17 @@ template <int MODE> JD uint32_t cursor_prepare(Ctx &c, int top, int *lsw, uint32
   int M = T->M;
   uint32_t walked = 0;
   *blocked = 0; *lsw = M; *icount = 0;
+  JFINE_T(u0);
   for (; M < top; M++) {
     const uint32_t f = cursor_up_step<MODE>(c, M + 1, false);
+    JFINE_ADD(c, 17, 0, 1);
     if (f) { if (lane == 0) T->M = M; jsyncwarp(); return f; }
   }
+  JFINE_T(u1);
+  JFINE_ADD(c, 16, u0, u1);
   uint32_t cnt = T->cnt[M];
   while (M > top) {
+    JFINE_ADD(c, 19, 0, 1);
     const ThinKids k = thin_children<MODE>(c, M, cnt);
     if (lane < cnt) T->ent[M][lane] = k.ent;
     walked += cnt;
@@ -243,6 +248,8 @@ template <int MODE> JD uint32_t cursor_prepare(Ctx &c, int top, int *lsw, uint32
     if (lane == 0) T->cnt[M] = cnt;
     jsyncwarp();
   }
+  JFINE_T(u2);
+  JFINE_ADD(c, 18, u1, u2);
   // the cursor is at the gate's top level: one M item per cursor edge (a zero edge gets a dead item)
   if (lane < cnt) {
     const ThinRes r = T->res[M & 1][lane];
