@@ -6,7 +6,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libjkq_b200.so")
+LIB = os.environ.get("JKQ_LIB") or os.path.join(HERE, "libjkq_b200.so")  # (JKQ_LIB: A/B runs of two builds on one box)
 SOURCES = ["jkq_b200.cu", "jkq_qasm.cpp"]
 CLI = os.path.join(HERE, "jku_simulator")  # the executable interface of the reference (src/main.cpp) on this engine
 CLI_SOURCES = ["jku_simulator.cpp"]
