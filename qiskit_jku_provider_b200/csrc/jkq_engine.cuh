@@ -87,7 +87,9 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SVT_SLOTS 2048u  // value-table slots
 #define JKQ_SPEND 512u       // value-table slots claimed in one phase
 #define JKQ_SMATS 128u       // cached canonical ids of gate matrices
+#ifndef JKQ_SMEMO
 #define JKQ_SMEMO 1024u      // entries of the complex-operation memo (16 bytes each)
+#endif
 #define JKQ_SCHAIN 512u      // words of chain-compression scratch per gate (a chain of k nodes takes k + 1)
 #define JKQ_SCMEMO 512u      // entries of the chain-rebuild memo (8 bytes each)
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
@@ -1264,7 +1266,11 @@ template <int MODE> JD bool reduce_item_impl(Ctx &c, uint32_t idx, uint32_t flag
     const unsigned long long ckey = (1ull << 28) | ((unsigned long long)ld_i<MODE>(&it->a) << 17) | ((unsigned long long)k << 11) | r;
     const uint32_t cslot = hfin((uint32_t)ckey * 0x9E3779B1u) & (JKQ_SCMEMO - 1u);
     const unsigned long long cw = ld_r<MODE>(&c.sh->cmemo[cslot]);
+#ifdef JKQ_NO_CMEMO
+    if (false) r = 0;
+#else
     if ((cw >> 11) == ckey) r = (uint32_t)(cw & 0x7FFull);
+#endif
     else {
       for (uint32_t j = k; j-- > 0 && r != 0;) {
         const uint32_t fl = (uint32_t)((mask >> j) & 1ull);
