@@ -147,6 +147,7 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
     if (flags & JF_ERROR) return JF_ERROR;
     if (flags & JF_GRID) return JF_GRID;
     if (!(flags & JF_RETRY)) return 0;
+    if (round > JKQ_RETRY_LIMIT && c.tid == 0) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);  // (seen at the next barrier)
     vals_commit<MODE>(c.E, c.sh, c.ring == 0 ? 2u : c.ring - 1u, c.tid, c.nth);  // the candidates of the phase just ended
     if (c.tid == 0) jstat<MODE>(c.E, c.sh, JST_RETRY, 1u);
     flags = sync_or<MODE>(c, 0);
@@ -177,6 +178,7 @@ JD uint32_t solo_expand_pairs(Ctx &c, const JGate &g, uint32_t b, uint32_t e, in
   JItem *it = c.items + (i == JI_FAIL ? 0 : i);
   bool need = i != JI_FAIL;
   if (need) need = (ld_i<MODE>(&it->flags) & 3u) != JS_DEAD;
+  uint32_t rounds = 0;
   for (;;) {
     if (need) {
       const uint32_t fl = expand_item_pair<MODE>(c, g, i, L, child, pm);
@@ -188,6 +190,7 @@ JD uint32_t solo_expand_pairs(Ctx &c, const JGate &g, uint32_t b, uint32_t e, in
     const uint32_t tr = thin_trouble<MODE>(c);  // pools exhausted / errors are sticky words
     if (tr) return tr;
     if (!bad) return 0;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);  // (seen by thin_trouble next round)
     thin_commit<MODE>(c);
   }
 }
@@ -196,7 +199,7 @@ JD uint32_t solo_expand_pairs(Ctx &c, const JGate &g, uint32_t b, uint32_t e, in
 template <int MODE, bool expand>
 JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   const uint32_t nwork = e - b + defer_count<MODE>(c, L);
-#ifndef JKQ_EMU
+#if !defined(JKQ_EMU) && !defined(JKQ_NO_PAIRS)
   if (expand && nwork <= JKQ_WARP / 2) return solo_expand_pairs<MODE>(c, g, b, e, L, nwork);
 #endif
   const uint32_t i = c.ltid < nwork ? level_item<MODE>(c, L, b, e, c.ltid) : JI_FAIL;
@@ -204,6 +207,7 @@ JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   bool need = i != JI_FAIL;
   uint32_t fl = 0;
   if (need) { fl = ld_i<MODE>(&it->flags); need = (fl & 3u) != JS_DEAD; }
+  uint32_t rounds = 0;
   for (;;) {
     if (need) {
       if (expand) fl = expand_item<MODE>(c, g, i, L);
@@ -216,6 +220,7 @@ JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
     const uint32_t tr = thin_trouble<MODE>(c);  // pools exhausted / errors are sticky words
     if (tr) return tr;
     if (!bad) return 0;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);  // (seen by thin_trouble next round)
     thin_commit<MODE>(c);
   }
 }
@@ -600,6 +605,7 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   sync_or<MODE>(c, 0);  // (a JF_GRID raised here is picked up below through sh->want_grid)
   const uint32_t nv = rd_vals<MODE>(c);
   const bool fits = MODE != MODE_CTA || !c.sh->want_grid;
+  if (MODE == MODE_CTA && !fits && c.ltid == 0) c.sh->nofit = 1;
   // copy back with remapped weights, rebuild the unique table
   for (uint32_t i = c.tid; i < live; i += c.nth) {
     JNode nn = ld_s<MODE_GRID>(E->nodes_alt + i + 1);
@@ -695,12 +701,14 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       S->node_hard = E->node_cap < JKQ_SNODES ? E->node_cap : JKQ_SNODES;
       if (E->cta_node_limit && E->cta_node_limit < S->node_hard) S->node_hard = E->cta_node_limit;
       S->val_hard = E->val_cap < JKQ_SVALS ? E->val_cap : JKQ_SVALS;
+      if (E->cta_val_limit && E->cta_val_limit < S->val_hard) S->val_hard = E->cta_val_limit;
       S->node_soft = S->node_hard - S->node_hard / 8;  // the rest is the reserve of cursor_to_root
       S->val_soft = S->val_hard - S->val_hard / 16;
+      if (E->cta_no_reserve) { S->node_soft = S->node_hard; S->val_soft = S->val_hard; }
       S->node_limit = S->node_soft; S->val_limit = S->val_soft;
       S->pend_n[0] = S->pend_n[1] = S->pend_n[2] = 0;
       S->bflags[0] = S->bflags[1] = S->bflags[2] = S->bflags[3] = 0;
-      S->err = (uint32_t)E->status; S->want_grid = 0;
+      S->err = (uint32_t)E->status; S->want_grid = 0; S->nofit = 0;
       S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw;
       S->flushed_nodes = S->node_count; S->flushed_vals = S->val_count;  // shared memory holds nothing yet
       S->next_gate = E->next_gate;
@@ -743,8 +751,17 @@ template <int MODE> JD void mode_leave(Ctx &c) {
   if (c.ltid == 0) {
     CtaState *S = c.sh;
     c.E->item_count = S->item_count;
-    c.E->node_count = S->node_count < S->node_hard ? S->node_count : S->node_hard;
-    c.E->val_count = S->val_count < S->val_hard ? S->val_count : S->val_hard;
+    // The shared counters are the truth on this path (the arena's are only refreshed here and by the collector).
+    // After a failed allocation they overshoot the pools: clamp.  Not when the collector found the state too large
+    // for the pools (nofit): nothing was allocated since, and the counts may legitimately exceed the pool sizes (a
+    // state that was built on the grid path) -- clamping them cut live reals / nodes off.
+    if (S->nofit) {
+      c.E->node_count = S->node_count;
+      c.E->val_count = S->val_count;
+    } else {
+      c.E->node_count = S->node_count < S->node_hard ? S->node_count : S->node_hard;
+      c.E->val_count = S->val_count < S->val_hard ? S->val_count : S->val_hard;
+    }
   }
 }
 
@@ -786,6 +803,9 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, b
   for (; !f && g < n_gates; g++) {
     f = apply_gate<MODE>(c, gates, g, n_gates, n, log);
     if (f) break;
+    // Gate g is applied from here on, whatever happens to the collection below: if the rebuild up to the root runs out
+    // of the shared pools (JF_GRID), the grid path must continue AFTER this gate (it used to redo it: gate applied twice).
+    if (c.block0 && c.ltid == 0) { if (MODE == MODE_CTA) c.sh->next_gate = g + 1; else E->next_gate = g + 1; }
     const bool collect = ld_s<MODE>(MODE == MODE_CTA ? &c.sh->hand[g & 1].collect : &E->hand[g & 1].collect) != 0;
     uint32_t gcf = 0;
     if (collect) {
@@ -798,7 +818,6 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, b
       if (log && c.block0 && c.ltid == 0)
         for (uint32_t L = 0; L < E->n; L++) E->lvl_log[(size_t)g * E->n + L] = E->lvl_cnt[L];
     }
-    if (c.block0 && c.ltid == 0) { if (MODE == MODE_CTA) c.sh->next_gate = g + 1; else E->next_gate = g + 1; }
     if (gcf & JF_GRID) { f = JF_GRID; g++; break; }  // MODE_CTA: the live DD outgrew the shared-memory pools
   }
   // The state goes back to the arena as a DD with a root: rebuild the levels above the cursor.  An
@@ -806,11 +825,18 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, b
   // word is cleared first, or the first value miss of the rebuild would give up.
   if (!(f & JF_ERROR)) {
     if (MODE == MODE_CTA && (f & JF_GRID)) {
-      if (c.ltid == 0) c.sh->want_grid = 0;
+      // The abandoned gate may have stopped in the middle of a phase: value candidates that were claimed (PENDING)
+      // but never committed would sit in the shared value table for good -- a later value within tol above one is
+      // dropped at every commit in favour of a neighbour that never becomes an entry, and a value of the same bucket
+      // is never even put on the commit list (the retry loop of cursor_to_root then never ends).  Drop them.
+      for (uint32_t i = c.ltid; i < JKQ_SVT_SLOTS; i += c.lnth)
+        if (c.sh->vtab[i].id1 == JV_PENDING) { c.sh->vtab[i].vbits = JV_INF; c.sh->vtab[i].id1 = JV_DROPPED; }
+      if (c.ltid == 0) { c.sh->want_grid = 0; c.sh->pend_n[0] = c.sh->pend_n[1] = c.sh->pend_n[2] = 0; }
       block_sync();
     }
-    if (thin_warp) cursor_to_root<MODE>(c, n);
-    const uint32_t r = sync_or<MODE>(c, 0);
+    const bool force_spill = MODE == MODE_CTA && (f & JF_GRID) && E->cta_no_reserve == 2;  // testing aid
+    if (thin_warp && !force_spill) cursor_to_root<MODE>(c, n);
+    const uint32_t r = sync_or<MODE>(c, 0) | (force_spill ? JF_GRID : 0u);
     f |= r & JF_ERROR;
     if (MODE == MODE_CTA && !(r & JF_ERROR) && (r & JF_GRID)) {
       // Not even the reserve of the shared pools was enough to rebuild up to the root: hand the cursor

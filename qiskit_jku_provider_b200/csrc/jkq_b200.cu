@@ -362,6 +362,7 @@ struct jkq_handle {
   std::map<uint32_t, std::pair<double *, uint32_t>> prob_slots;  // slot -> (device buffer of 2^k probabilities, k)
   bool physical_reset = false;      // RESET = measure-then-X instead of the reference's projection
   uint64_t placeholder_gates = 0;   // projector / X slots of MEASURE_ONE and RESET applied by the last jkq_apply
+  bool debug_stop_at_handover = false;  // testing aid: jkq_apply returns where the single-CTA path would hand over
   // histogram
   unsigned long long *hk = nullptr, *hc = nullptr, *ok = nullptr, *oc = nullptr, *n_out = nullptr;
   int *overflow = nullptr;
@@ -401,6 +402,7 @@ static const char *status_text(int s) {
     case JKQ_ERR_PEND_FULL: return "pending-value buffer full";
     case JKQ_ERR_BARRIER_TIMEOUT: return "grid barrier timeout";
     case JKQ_ERR_ZERO_STATE: return "numerical instabilities led to a 0-vector";
+    case JKQ_ERR_RETRY_LIMIT: return "a level kept producing new values (retry limit of the value table reached)";
     default: return "internal error";
   }
 }
@@ -517,6 +519,9 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "measure_seed")) { h->measure_seed = (uint64_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "physical_reset")) { h->physical_reset = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_no_reserve")) { h->host.cta_no_reserve = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_val_limit")) { h->host.cta_val_limit = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "debug_stop_at_handover")) { h->debug_stop_at_handover = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
     if (value < 1 || value > JKQ_SITEMS / 2) value = JKQ_SITEMS / 2;
     h->cfg.cta_item_limit = (uint32_t)value; h->host.cta_item_limit = (uint32_t)value;
@@ -718,6 +723,11 @@ static int run_segment(jkq_handle *h, int upto) {
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
     if (h->host.next_gate >= upto && !h->host.cursor_saved) return JKQ_E_OK;
     if ((h->host.want_grid || h->host.cursor_saved) && !grid) {
+      if (h->debug_stop_at_handover) {
+        fprintf(stderr, "debug_stop_at_handover: next_gate %d cursor_saved %u nodes %u vals %u\n", h->host.next_gate, h->host.cursor_saved, h->host.node_count,
+                h->host.val_count);
+        return JKQ_E_OK;
+      }
       if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: state or frontier exceeds the single-CTA path and force_mode=1", h->host.next_gate);
       grid = true;
       h->host.want_grid = 0;
@@ -1172,6 +1182,7 @@ extern "C" int jkq_get_probabilities(jkq_handle *h, uint32_t slot, double *out, 
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }
+
 
 extern "C" int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n) {
   if (!h || !per_level) return JKQ_E_ARGUMENT;

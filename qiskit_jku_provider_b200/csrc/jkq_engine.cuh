@@ -101,6 +101,7 @@ struct CtaState {
   uint32_t pend_n[3], err;
   uint32_t want_grid, gen, pad2, pad3;
   uint32_t lsw, root, flushed_nodes, flushed_vals;  // [flushed, count): not yet copied to the HBM arena
+  uint32_t nofit;  // the collector found the state too large for the shared pools: it lives in the arena only
   uint64_t rootw;
   uint32_t st[JST_N + 1];
   int32_t next_gate, pad0;
@@ -487,9 +488,16 @@ template <int MODE> JNI uint32_t real_insert_direct(JEng *E, CtaState *S, double
   const uint32_t mask = vt_mask2<MODE>(E);
   JVSlot *tab = vt_tab2<MODE>(E, S);
   uint32_t h = vt_slot0(k, mask);
-  for (;;) {
+  for (uint32_t probes = 0;; probes++) {
     JVSlot sl = ld_s<MODE>(tab + h);
     if (sl.id1 == 0 || (sl.id1 == JV_DROPPED && sl.keylo == (uint32_t)k)) break;
+    if (probes > (mask >> 3)) {
+      // every slot this bucket can probe is taken (entries plus the tombstones of dropped candidates): the real is
+      // in the array but cannot be hashed -- give the gate up; the next collection rebuilds the table from the array
+      if (MODE == MODE_CTA) jwant_grid(S);
+      else jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+      return idx;
+    }
     h = vt_next(h, mask);
   }
   JVSlot sl;
@@ -503,7 +511,13 @@ template <int MODE> JD void vt_put(JEng *E, CtaState *S, uint32_t idx, double x)
   const uint32_t mask = vt_mask2<MODE>(E);
   JVSlot *tab = vt_tab2<MODE>(E, S);
   uint32_t h = vt_slot0(k, mask);
-  while (jatomic_cas(&tab[h].id1, 0u, idx + 1) != 0) h = vt_next(h, mask);
+  for (uint32_t probes = 0; jatomic_cas(&tab[h].id1, 0u, idx + 1) != 0; probes++) {
+    if (probes > (mask >> 3)) {  // (cannot happen in a table that was just cleared and is twice the size of the array)
+      jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+      return;
+    }
+    h = vt_next(h, mask);
+  }
   tab[h].vbits = jd2u(x);
   tab[h].keylo = (uint32_t)k;
 }
@@ -562,7 +576,9 @@ template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, u
     const uint64_t top = memo_key >> 4;
     memo_slot = (hfin((uint32_t)top * 0x9E3779B1u + (uint32_t)(top >> 32) * 0x85EBCA6Bu) ^ (uint32_t)(memo_key & 15u)) & (JKQ_SMEMO - 1u);
     const unsigned long long w0 = ld_r<MODE>(&S->memo[memo_slot][0]), w1 = ld_r<MODE>(&S->memo[memo_slot][1]);
+#ifndef JKQ_NO_MEMO
     if (w0 == (memo_key | (1ull << 63)) && (w1 >> 22) == top) return junpack22(w1 & 0x3FFFFFull);
+#endif
   }
   double ar = jval2<MODE>(E, S, (uint32_t)(a >> 32)), ai = jval2<MODE>(E, S, (uint32_t)a);
   double br = jval2<MODE>(E, S, (uint32_t)(b >> 32)), bi = jval2<MODE>(E, S, (uint32_t)b);

@@ -38,11 +38,18 @@ template <int MODE> JD void prof_add(JEng *E, CtaState *S, int slot, unsigned lo
 
 JD uint32_t lanes_below(uint32_t lane) { return (1u << lane) - 1u; }
 
-// sticky error / want_grid words as barrier flags (uniform over the warp)
+// sticky error / want_grid words as barrier flags.  Every lane of the cursor warp calls this (always from uniform
+// control flow) and every lane gets the SAME answer: the words are written by whichever lane ran out of a pool, and a
+// ballot orders nothing in memory -- two lanes reading the word right after one could disagree, part of the warp
+// would leave through the error path while the rest waited at the next __syncwarp (seen on B200 as a hang when the
+// shared value table filled up inside cursor_to_root).  The OR over the warp makes the decision collective.
 template <int MODE> JD uint32_t thin_trouble(const Ctx &c) {
   uint32_t fl = 0;
   if (MODE == MODE_CTA ? ld_r<MODE>(&c.sh->err) != 0 : ld_r<MODE>(&c.E->status) != 0) fl |= JF_ERROR;
   if (MODE == MODE_CTA && ld_r<MODE>(&c.sh->want_grid)) fl |= JF_GRID;
+#ifndef JKQ_EMU
+  fl = __reduce_or_sync(0xFFFFFFFFu, fl);
+#endif
   return fl;
 }
 // some lane met a value that is not in the table yet: commit the candidates (warp-local: nobody else runs)
@@ -150,7 +157,7 @@ template <int MODE> JD uint32_t cursor_up_step(Ctx &c, int L, bool from_items) {
     }
     hint = 1u + flag;
   }
-  uint32_t rnode = 0;
+  uint32_t rnode = 0, rounds = 0;
   uint64_t rw = 0;
   for (;;) {
     bool ok = true;
@@ -164,6 +171,7 @@ template <int MODE> JD uint32_t cursor_up_step(Ctx &c, int L, bool from_items) {
       if (fl) return fl;
     }
     if (!bad) break;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
     thin_commit<MODE>(c);
   }
   if (act) {
@@ -278,6 +286,7 @@ template <int MODE> JD uint32_t cursor_finish(Ctx &c, int lsw, uint32_t blocked)
     if (r.rw != 0) { irw = ld_i<MODE>(&c.items[lane].rw); irn = ld_i<MODE>(&c.items[lane].rnode); }
   }
   uint64_t nw = 0;
+  uint32_t rounds = 0;
   for (;;) {
     bool ok = true;
     if (act && irw != 0) ok = cmul<MODE>(c, r.rw, irw, &nw);
@@ -285,6 +294,7 @@ template <int MODE> JD uint32_t cursor_finish(Ctx &c, int lsw, uint32_t blocked)
     if (!bad) break;
     const uint32_t fl = thin_trouble<MODE>(c);
     if (fl) return fl;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
     thin_commit<MODE>(c);
   }
   if (act) {

@@ -110,7 +110,8 @@ typedef struct {
   uint32_t cta_item_limit;  // CTA mode bails out to grid mode above this frontier size
   uint32_t gc_min;          // never collect below this many allocated nodes
   uint32_t cta_node_limit;  // testing aid: cap on the shared-memory node pool of the CTA path (0 = its real size)
-  uint32_t pad_c;
+  uint32_t cta_val_limit;   // testing aid: the same for the shared-memory value table
+  uint32_t cta_no_reserve; // testing aid: no reserve in the shared pools, so the root rebuild of an abandoned gate fails too (saved-cursor hand-over)
   double tol;
   double inv_tol;
   // ---- arrays ----
@@ -188,5 +189,7 @@ typedef struct {
 #define JKQ_ERR_BARRIER_TIMEOUT 7
 #define JKQ_ERR_ZERO_STATE 8
 #define JKQ_ERR_INTERNAL 9
+#define JKQ_ERR_RETRY_LIMIT 10  // a level kept meeting new values for JKQ_RETRY_LIMIT rounds (watchdog)
+#define JKQ_RETRY_LIMIT 512u
 
 #endif

@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
   long shots = 0, amp_limit = 0;
   int levels = 0, amps = 0;
   uint64_t seed = 1;
-  uint32_t node_cap = 1u << 22, gc_min = 1u << 16;
+  uint32_t node_cap = 1u << 22, gc_min = 1u << 16, cta_node_limit = 0, cta_val_limit = 0, cta_no_reserve = 0;
   int dump_level = -1;
   bool force_grid = false;
   for (int i = 1; i < argc; i++) {
@@ -75,6 +75,9 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--node-cap") && i + 1 < argc) node_cap = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--gc-min") && i + 1 < argc) gc_min = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--dump-level") && i + 1 < argc) dump_level = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--cta-node-limit") && i + 1 < argc) cta_node_limit = (uint32_t)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--cta-val-limit") && i + 1 < argc) cta_val_limit = (uint32_t)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--cta-no-reserve") && i + 1 < argc) cta_no_reserve = (uint32_t)atol(argv[++i]);
     else if (!strcmp(argv[i], "--grid")) force_grid = true;
   }
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
@@ -125,6 +128,9 @@ int main(int argc, char **argv) {
   E->val_cap = 1u << 20; E->vtab_mask = (1u << 22) - 1;
   E->pend_cap = 1u << 20; E->item_cap = node_cap; E->dtab_mask = node_cap * 2 - 1;
   E->cta_item_limit = JKQ_SITEMS / 2; E->gc_min = gc_min;
+  E->cta_node_limit = cta_node_limit;
+  E->cta_val_limit = cta_val_limit;
+  E->cta_no_reserve = cta_no_reserve;
   E->nodes = (JNode *)calloc(E->node_cap, sizeof(JNode));
   E->nodes_alt = (JNode *)calloc(E->node_cap, sizeof(JNode));
   E->utab = (uint32_t *)calloc((size_t)E->utab_mask + 1, 4);

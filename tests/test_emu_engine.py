@@ -56,3 +56,41 @@ def test_emu_collector_keeps_state(emu_bin, oracle_mod):
     o = oracle_mod.run_oracle(circ, amps=True)
     assert e["gc_runs"] >= 3
     assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("circ", [C.random_circuit(10, 90, 11), C.random_circuit(12, 100, 5)], ids=lambda c: c.name)
+def test_emu_state_too_large_for_the_single_cta_pools_survives_a_failed_attempt(emu_bin, oracle_mod, circ):
+    """Regression: a single-CTA attempt that finds the state too large to load (more reals than the shared value table,
+    or more nodes than the shared arena) must leave the arena's counters alone -- mode_leave used to clamp them to the
+    pool sizes, which cut off live reals / nodes before the grid path took over (random10_90_s11: norm 9143)."""
+    o = oracle_mod.run_oracle(circ, amps=True)
+    e = run_emu(emu_bin, circ.text(), amps=True, extra=["--node-cap", str(1 << 20), "--gc-min", str(1 << 14)])
+    oa = np.array([complex(*a) for a in o["amps"]])
+    ea = np.array([complex(*a) for a in e["amps"]])
+    assert e["grid_switches"] >= 1
+    assert abs(e["norm"] - 1.0) < 1e-9
+    assert np.abs(oa - ea).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("limit", [96, 160])
+@pytest.mark.parametrize("circ", [C.grover(10, 4, marked=0x155), C.random_circuit(12, 70, 3)], ids=lambda c: c.name)
+def test_emu_tiny_shared_node_pool_hands_over_without_losing_counts(emu_bin, oracle_mod, circ, limit):
+    """A collection in the middle of a single-CTA run that finds the DD too large for a (here artificially tiny) shared
+    node pool: the value count lives in shared memory on that path and must reach the arena before the grid path
+    takes over."""
+    o = oracle_mod.run_oracle(circ, amps=True)
+    e = run_emu(emu_bin, circ.text(), amps=True, extra=["--node-cap", str(1 << 18), "--gc-min", str(1 << 15), "--cta-node-limit", str(limit)])
+    assert abs(e["norm"] - 1.0) < 1e-9
+    assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("limit", [0, 512, 300, 200])
+def test_emu_saved_cursor_hand_over(emu_bin, oracle_mod, limit):
+    """The single-CTA path abandons a gate and (testing aid --cta-no-reserve 2) does not rebuild up to the root: the
+    cursor itself is handed to the grid path, which re-hashes the arena as it is and continues from the cursor."""
+    circ = C.random_circuit(6, 90, 35)
+    o = oracle_mod.run_oracle(circ, amps=True)
+    e = run_emu(emu_bin, circ.text(), amps=True, extra=["--node-cap", str(1 << 18), "--gc-min", str(1 << 14), "--cta-val-limit", str(limit), "--cta-no-reserve", "2"])
+    assert e["grid_switches"] == 1
+    assert abs(e["norm"] - 1.0) < 1e-9
+    assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL

@@ -276,3 +276,45 @@ def test_maximum_width_64_qubits(eng):
     assert a1 == -a0 and abs(abs(a0) - 2.0 ** -32) < 1.01e-10
     assert eng.level_counts() == [2] * (n - 1) + [1]
     assert abs(eng.qubit_probability(17) - 0.5) < 1e-12
+
+
+def test_failed_single_cta_attempt_leaves_the_arena_counters_alone():
+    """Regression (found by scripts/parity_sweep.py): the state of random10_90_s11 has more reals than the shared
+    value table by the time shots are asked for; the single-CTA attempt of build_sampling finds it too large to load,
+    and used to clamp the arena's value count to the pool size on its way out -- every amplitude came out wrong."""
+    import numpy as np
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import Engine
+    import oracle
+    circ = C.random_circuit(10, 90, 11)
+    ref = oracle.run_oracle(circ, amps=True)
+    want = np.array([complex(*a) for a in ref["amps"]])
+    with Engine(device=0, node_capacity=1 << 18) as eng:
+        for mode in (0, 2):
+            eng.set_option("force_mode", mode)
+            eng.load(circ)
+            eng.run(4000, 3)
+            assert abs(eng.stats()["norm"] - 1.0) < 1e-9, mode
+            assert np.abs(eng.statevector() - want).max() < 1e-9, mode
+
+
+def test_gate_is_not_redone_when_the_collection_after_it_runs_out_of_the_shared_pools():
+    """Regression (scripts/parity_sweep.py, seed 35): gate 183 of random6_90_s35 completes on the single-CTA path, the
+    rebuild up to the root for the collection after it exhausts the shared value table, and the grid path used to
+    start over AT that gate (next_gate was only advanced after the collection) -- the gate was applied twice."""
+    import numpy as np
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import Engine
+    import oracle
+    circ = C.random_circuit(6, 90, 35)
+    ref = oracle.run_oracle(circ, amps=True)
+    want = np.array([complex(*a) for a in ref["amps"]])
+    with Engine(device=0, node_capacity=1 << 18) as eng:
+        for mode in (0, 2):
+            eng.set_option("force_mode", mode)
+            eng.load(circ)
+            eng.apply()
+            st = eng.stats()
+            assert np.abs(eng.statevector() - want).max() < 1e-9, mode
+            if mode == 0:
+                assert st["cta_launches"] >= 1 and st["grid_launches"] >= 1  # the hand-over did happen
