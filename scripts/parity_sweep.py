@@ -1,4 +1,5 @@
-"""Wider parity sweep than the test suite: random circuits through the single-CTA path, the grid path and the automatic
+"""usage: parity_sweep.py [n_seeds [n_min [n_span [first_seed]]]]
+Wider parity sweep than the test suite: random circuits through the single-CTA path, the grid path and the automatic
 mode against a dense NumPy simulation of the same ops (amplitudes to 1e-9), plus run-to-run determinism of the counts."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -27,8 +28,11 @@ def dense(circ):
 worst = 0.0
 n_checked = 0
 with Engine(device=0, node_capacity=1 << 20) as eng:
-    for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 40):
-        n = 6 + seed % 7
+    n_min = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    n_span = int(sys.argv[3]) if len(sys.argv) > 3 else 7
+    seed0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    for seed in range(seed0, seed0 + (int(sys.argv[1]) if len(sys.argv) > 1 else 40)):
+        n = n_min + seed % n_span
         circ = C.random_circuit(n, 40 + 10 * (seed % 6), seed)
         want = dense(circ)
         for mode in (0, 1, 2):

@@ -318,3 +318,13 @@ def test_gate_is_not_redone_when_the_collection_after_it_runs_out_of_the_shared_
             assert np.abs(eng.statevector() - want).max() < 1e-9, mode
             if mode == 0:
                 assert st["cta_launches"] >= 1 and st["grid_launches"] >= 1  # the hand-over did happen
+
+
+def test_parity_sweep_subset():
+    """scripts/parity_sweep.py on a slice of its seeds: random circuits through the single-CTA path, the grid path and
+    the automatic mode against a dense simulation (1e-9), counts identical between two runs."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "parity_sweep.py"), "14", "6", "7", "28"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "parity sweep ok" in out.stdout
