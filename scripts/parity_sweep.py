@@ -28,6 +28,9 @@ def dense(circ):
 worst = 0.0
 n_checked = 0
 with Engine(device=0, node_capacity=1 << 20) as eng:
+    for kv in filter(None, os.environ.get("SWEEP_OPTS", "").split(",")):  # e.g. SWEEP_OPTS=cta_val_limit=300,cta_node_limit=200
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     n_min = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     n_span = int(sys.argv[3]) if len(sys.argv) > 3 else 7
     seed0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
