@@ -800,6 +800,21 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, b
   sync_or<MODE>(c, 0);
   if (MODE == MODE_GRID && c.block0 && c.ltid == 0) E->cursor_saved = 0;
   const bool log = E->lvl_log != 0;
+  if (MODE == MODE_GRID && log && !f && g > 0 && g < n_gates) {
+    // Level log and a start in the middle of the circuit (hand-over from the single-CTA kernel): that kernel may have
+    // applied gate g - 1 without getting to the collection that counts its levels (the rebuild up to the root ran out
+    // of the shared pools).  Count them here; a row that was already written comes out the same.
+    if (thin_warp) cursor_to_root<MODE>(c, n);
+    f = sync_or<MODE>(c, 0) & JF_ERROR;
+    if (!f) {
+      if (gc_call<MODE>(c, false, false) & JF_ERROR) f = JF_ERROR;
+      else {
+        if (thin_warp) cursor_reset<MODE>(c, n);
+        if (c.block0 && c.ltid == 0)
+          for (uint32_t L = 0; L < E->n; L++) E->lvl_log[(size_t)(g - 1) * E->n + L] = E->lvl_cnt[L];
+      }
+    }
+  }
   for (; !f && g < n_gates; g++) {
     f = apply_gate<MODE>(c, gates, g, n_gates, n, log);
     if (f) break;

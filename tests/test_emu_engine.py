@@ -94,3 +94,16 @@ def test_emu_saved_cursor_hand_over(emu_bin, oracle_mod, limit):
     assert e["grid_switches"] == 1
     assert abs(e["norm"] - 1.0) < 1e-9
     assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("extra", [["--cta-val-limit", "60", "--cta-no-reserve", "2"], ["--cta-node-limit", "96"], ["--cta-val-limit", "48"]],
+                         ids=["saved_cursor", "tiny_node_pool", "tiny_value_table"])
+def test_emu_level_log_survives_the_hand_over(emu_bin, oracle_mod, extra):
+    """Per-gate level counts when the single-CTA kernel hands over in the middle of the circuit: the grid kernel counts
+    the levels of the last applied gate again on entry, every row equals the oracle's."""
+    circ = C.random_circuit(8, 60, 9)
+    o = oracle_mod.run_oracle(circ, levels=True, amps=True, extra=TIE)
+    e = run_emu(emu_bin, circ.text(), levels=True, amps=True, extra=["--node-cap", str(1 << 18), "--gc-min", str(1 << 14)] + extra)
+    assert e["grid_switches"] == 1
+    assert e["level_counts_per_gate"] == o["level_counts_per_gate"]
+    assert np.abs(np.array([complex(*a) for a in o["amps"]]) - np.array([complex(*a) for a in e["amps"]])).max() < AMP_TOL
