@@ -105,3 +105,14 @@ def test_circuit_without_measurements_is_just_sampled(runner, eng):
     for k in keys:
         got[int(k)] = got.get(int(k), 0) + 1
     assert not status.any() and got == want
+
+
+def test_shots_sweep_subset():
+    """scripts/shots_sweep.py on a slice of its seeds: random programs with mid-circuit measure / reset / if -- the
+    per-shot kernel equals the sequential path shot for shot, and the final state of a shot is one of the trajectories
+    of an independent dense NumPy simulation (1e-9)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "shots_sweep.py"), "10", "100"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "shots sweep ok" in out.stdout
