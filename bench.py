@@ -400,7 +400,7 @@ def main():
             "full_engine_fallbacks_rank0": fb,
             "k_batch_ms_rank0": b_kernel_only, "fallback_apply_ms_rank0": b_fallback,
             "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue (longest gate list first); circuits split "
-                    "i % world == rank; kernel_ms = k_batch + the circuits that outgrew one SM, redone one after the other on the full engine"}
+                    "i % world == rank; kernel_ms = k_batch + the circuits that outgrew one SM, redone from gate 0 on up to 4 full engines side by side (that part by the host clock: an upper bound)"}
         if rank == 0:
             for c3 in (C.ghz(24), C.grover(20, 20), C.random_circuit(18, 100, 1), C.random_circuit(18, 120, 1)):
                 eng.load(c3)
