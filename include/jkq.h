@@ -111,6 +111,7 @@ typedef struct {
   double sample_kernel_ms;   /* ... of the sampling kernel alone                               */
   double norm;               /* squared norm of the final state                                */
   uint64_t distinct_outcomes;
+  uint64_t thin_gates;       /* gates applied below the cursor edges without work items (thin_gate) */
 } jkq_stats;
 
 /* sampling record exported for multi-GPU shot sharding (16 bytes) */

@@ -26,7 +26,7 @@ class JkqStats(C.Structure):
         "gates", "items", "nodes_created", "value_inserts", "gc_runs", "gc_nodes_copied", "retry_rounds",
         "max_frontier", "live_nodes", "live_values", "cta_launches", "grid_launches", "sample_launches")] + [
         ("apply_ms", C.c_double), ("sample_ms", C.c_double), ("sample_kernel_ms", C.c_double), ("norm", C.c_double),
-        ("distinct_outcomes", C.c_uint64)]
+        ("distinct_outcomes", C.c_uint64), ("thin_gates", C.c_uint64)]
 
 
 class JkqProgramInfo(C.Structure):

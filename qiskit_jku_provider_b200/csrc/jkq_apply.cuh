@@ -309,7 +309,12 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     JPROF_ADD(c, 11, sp0, sp1);
     uint32_t b = 0, e = icount;
     int lowest = lsw + 1;
-    if (!f) {
+    uint32_t thin_done = 0, thin_entries = 0;
+#ifndef JKQ_NO_THIN_GATES
+    if (!f && !blocked) f = thin_gate<MODE>(c, g, &thin_done, &thin_entries);  // the whole gate below the cursor edges, if it is local
+#endif
+    if (!f && !thin_done && !blocked) cursor_items<MODE>(c, lsw, icount);
+    if (!f && !thin_done) {
       if (c.ltid == 0) *cnt_items<MODE>(c) = icount;
       jsyncwarp();
       for (int L = lsw; L >= 0 && (e > b || (MODE == MODE_CTA && ld_r<MODE>(&c.sh->min_def) <= L)); L--) {
@@ -326,7 +331,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     }
     JPROF_T(sp2);
     JPROF_ADD(c, 12, sp1, sp2);
-    if (!f && wide_L < 0) {
+    if (!f && wide_L < 0 && !thin_done) {
       for (int L = lowest; L <= lsw && !f; L++) {
         const uint32_t lb = lr_begin<MODE>(c, L), le = lr_end<MODE>(c, L);
         if (le - lb + defer_count<MODE>(c, L) == 0) continue;
@@ -342,11 +347,12 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       hand->lsw = (uint32_t)lsw; hand->blocked = blocked; hand->wide_L = wide_L; hand->wide_b = b; hand->wide_low = lowest;
       hand->collect = want_collect<MODE>(c, log);
       if (!f && wide_L < 0) {
-        const uint32_t cnt = rd_items<MODE>(c);
+        const uint32_t cnt = thin_done ? thin_entries : rd_items<MODE>(c);
         jstat<MODE>(E, c.sh, JST_ITEMS, cnt);
         jstat_max<MODE>(E, c.sh, cnt);
         jstat<MODE>(E, c.sh, JST_GATES, 1u);
-        if (MODE == MODE_CTA) c.sh->gen++;  // read by everybody only after the barrier below
+        if (thin_done) jstat<MODE>(E, c.sh, JST_THIN, 1u);
+        if (MODE == MODE_CTA && !thin_done) c.sh->gen++;  // read by everybody only after the barrier below
       }
     }
   }

@@ -520,6 +520,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "physical_reset")) { h->physical_reset = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_no_reserve")) { h->host.cta_no_reserve = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "thin_off")) { h->host.thin_off = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_val_limit")) { h->host.cta_val_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "debug_stop_at_handover")) { h->debug_stop_at_handover = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
@@ -1241,7 +1242,7 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   // (ApplyGate calls: MeasureOne / ResetQubit multiply their projectors in directly)
   h->stats.gates = E.st[JST_GATES] - h->placeholder_gates; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
   h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];
-  h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF];
+  h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF]; h->stats.thin_gates = E.st[JST_THIN];
   h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;
   *out = h->stats;
   return JKQ_E_OK;

@@ -48,6 +48,8 @@ static inline double ju2d(unsigned long long u) { double x; memcpy(&x, &u, 8); r
 static inline uint32_t jballot(bool p) { return p ? 1u : 0u; }
 static inline uint32_t jshfl(uint32_t v, uint32_t) { return v; }
 static inline uint32_t jmatch(uint32_t) { return 1u; }
+static inline uint32_t jmatch64(unsigned long long) { return 1u; }
+static inline unsigned long long jshfl64(unsigned long long v, uint32_t) { return v; }
 static inline void jsyncwarp() {}
 static inline uint32_t jpopc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
 static inline uint32_t jffs(uint32_t x) { return (uint32_t)__builtin_ffs((int)x); }
@@ -73,6 +75,8 @@ JD double ju2d(unsigned long long u) { return __longlong_as_double((long long)u)
 JD uint32_t jballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 JD uint32_t jshfl(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
 JD uint32_t jmatch(uint32_t v) { return __match_any_sync(0xFFFFFFFFu, v); }
+JD uint32_t jmatch64(unsigned long long v) { return __match_any_sync(0xFFFFFFFFu, v); }
+JD unsigned long long jshfl64(unsigned long long v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
 JD void jsyncwarp() { __syncwarp(); }
 JD uint32_t jpopc(uint32_t x) { return (uint32_t)__popc(x); }
 JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
@@ -91,7 +95,7 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SMEMO 1024u      // entries of the complex-operation memo (16 bytes each)
 #endif
 #define JKQ_SCHAIN 512u      // words of chain-compression scratch per gate (a chain of k nodes takes k + 1)
-#define JKQ_SCMEMO 512u      // entries of the chain-rebuild memo (8 bytes each)
+#define JKQ_SCMEMO 256u      // entries of the chain-rebuild memo (8 bytes each)
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
@@ -146,10 +150,14 @@ struct __attribute__((aligned(16))) ThinRes {
 };
 struct ThinState {
   ThinRes res[2][JKQ_WARP];          // the cursor edges (level parity)
-  ThinEnt ent[JKQ_MAXQ][JKQ_WARP];   // levels above the cursor
+  ThinEnt ent[JKQ_MAXQ][JKQ_WARP];   // levels above the cursor (levels at and below it: scratch records of thin_gate)
   uint32_t cnt[JKQ_MAXQ + 1];
   int32_t M;                         // cursor level
   uint32_t walked;                   // nodes passed on the way down since the last cursor_to_root (statistics)
+  // thin_gate (jkq_thin.cuh): a gate applied below the cursor edges without work items
+  ThinRes sres[2][JKQ_WARP];         // on the way down: the entries of the next level; on the way up: the results of a level
+  uint64_t vp[2 * JKQ_WARP];         // variants created at the target level: factor on the subspace "all controls
+  uint64_t vq[2 * JKQ_WARP];         //   below satisfied" (vp) and on its complement (vq), normalised by the larger one
 };
 
 struct Ctx {

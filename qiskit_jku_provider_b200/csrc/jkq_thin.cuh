@@ -258,16 +258,22 @@ template <int MODE> JD uint32_t cursor_prepare(Ctx &c, int top, int *lsw, uint32
   }
   JFINE_T(u2);
   JFINE_ADD(c, 18, u1, u2);
-  // the cursor is at the gate's top level: one M item per cursor edge (a zero edge gets a dead item)
+  // the cursor is at the gate's top level (cursor_items makes the work items if thin_gate does not take the gate)
+  *lsw = M; *icount = cnt;
+  if (lane == 0) { T->M = M; T->walked += walked; }
+  jsyncwarp();
+  return 0;
+}
+// cursor on the gate's top level: one M item per cursor edge (a zero edge gets a dead item)
+template <int MODE> JD void cursor_items(Ctx &c, int M, uint32_t cnt) {
+  ThinState *T = c.T;
+  const uint32_t lane = c.ltid;
   if (lane < cnt) {
     const ThinRes r = T->res[M & 1][lane];
     item_init_m(c.items + lane, r.rnode);
     if (r.rw == 0) c.items[lane].flags = JS_DEAD;
   }
-  *lsw = M; *icount = cnt;
-  if (lane == 0) { T->M = M; T->walked += walked; }
   jsyncwarp();
-  return 0;
 }
 
 // After the generic phases of a gate: the new edges at the cursor level.
@@ -302,6 +308,305 @@ template <int MODE> JD uint32_t cursor_finish(Ctx &c, int lsw, uint32_t blocked)
     T->res[lsw & 1][lane] = r;
   }
   jsyncwarp();
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------ thin gates
+// A gate applied directly below the cursor edges, without work items, hash de-duplication or barriers.
+//
+// With the cursor on the gate's top level, QMDDmultiply2 (QMDDpackage.cpp:1416-1517) only ever meets pairs
+// (gate node, ONE state node) as long as, at the target level, every product u_ij * w_j * [c_j] that is not zero
+// refers to one and the same child: a diagonal or anti-diagonal matrix (u1, rz, z, s, t, x, cx, controlled phases),
+// any matrix on a node whose two edges share their child or that has a zero edge (product and basis-like states: every
+// gate of QFT / GHZ).  QMDDadd (:1319-1414) then never has two different operands -- it adds weights.  Such a gate is a
+// PARTIAL DESCENT: from the cursor edges down to the gate's lowest level, following only the edges that satisfy the
+// controls, one lane per (node, variant), duplicates removed with match/shuffle exactly like the cursor does, then back
+// up through reduce_core (same normalisation, same unique table as everything else).
+//   above the target   entry = node; a control level forwards only its satisfied edge, the other edge is kept as it is
+//   target level       child i = P (u_i0 w0 + u_i1 w1) [c] + (I - P) w_i [c_i]   with P = "all controls below satisfied";
+//                      no control below: a finished edge.  Otherwise the pair (p, q) of factors on P and I - P,
+//                      divided by the larger one, is a VARIANT (T->vp / T->vq), the child an entry (c, variant)
+//   below the target   entry = (node, variant); idle level: both edges forward; control level: the unsatisfied edge
+//                      takes q, the satisfied one forwards (or takes p on the gate's lowest level)
+// A result that has the children and the weight ratio of the node it came from IS that node (no table access): on a
+// basis-state control the whole way up costs a compare per level.
+// Anything else (two different operands at the target: H on an entangled node; more than a warp of entries on a
+// level) is left to the generic item phases: *handled = 0 and nothing has changed.
+#define TGK_S1 5
+#define TGK_K0 10
+#define TGK_K1 12
+#define TGK_PC 14
+#define TGK_VALID (1u << 16)
+#define TGK_SKIP (1u << 17)  // fast-forwarded level: the entry's child is the entry of the same lane one level down
+#define TG_VAR_NONE 0xFFu
+
+// ranks of the distinct REF children of a level (key = node | variant << 32); same scheme as thin_children
+struct ThinDedup {
+  bool own0, own1;
+  uint32_t s0, s1, newcnt;
+};
+template <int MODE>
+JD ThinDedup thin_dedup(const Ctx &c, uint32_t cnt, bool v0ok, unsigned long long key0, bool v1ok, unsigned long long key1) {
+  const uint32_t lane = c.ltid;
+  ThinDedup d;
+  if (cnt == 1) {
+    const bool same = v0ok && v1ok && key0 == key1;
+    d.own0 = v0ok; d.own1 = v1ok && !same;
+    d.s0 = 0; d.s1 = (v0ok && !same) ? 1u : 0u;
+    d.newcnt = jshfl((d.own0 ? 1u : 0u) + (d.own1 ? 1u : 0u), 0);
+    return d;
+  }
+  const unsigned long long v0 = v0ok ? key0 : (0x8000000000000000ull | lane);
+  const uint32_t lead0 = jffs(jmatch64(v0)) - 1u;
+  d.own0 = v0ok && lead0 == lane;
+  bool dup1 = false;
+  uint32_t src = 0;
+  for (uint32_t j = 0; j < cnt; j++) {
+    const unsigned long long vj = jshfl64(v0, j);
+    if (v1ok && vj == key1) { dup1 = true; src = j; }
+  }
+  const uint32_t ldsrc = jshfl(lead0, src);
+  const unsigned long long v1 = (v1ok && !dup1) ? key1 : (0xC000000000000000ull | lane);
+  const uint32_t lead1 = jffs(jmatch64(v1)) - 1u;
+  d.own1 = v1ok && !dup1 && lead1 == lane;
+  const uint32_t b0 = jballot(d.own0), b1 = jballot(d.own1), n0 = jpopc(b0);
+  d.newcnt = n0 + jpopc(b1);
+  d.s0 = jpopc(b0 & lanes_below(lead0));
+  d.s1 = dup1 ? jpopc(b0 & lanes_below(ldsrc)) : n0 + jpopc(b1 & lanes_below(lead1));
+  return d;
+}
+
+// reduce_core with the "this is the node it came from" short-cut: `nd` / `node` = the node the two child edges
+// (rn, f * a) were derived from
+template <int MODE>
+JD bool thin_reduce(Ctx &c, uint32_t node, const JNode &nd, uint32_t rn[2], const uint64_t f[2], const uint64_t a[2], uint32_t *out_node,
+                    uint64_t *out_w) {
+  const uint32_t flag = nd_flag(nd);
+  // (a0, a1) still the node's own normalised pair (or its ONE next to a child that became zero)?
+  const uint32_t hint = (a[flag] == JW_ONE && (a[1u - flag] == nd.w || a[1u - flag] == 0)) ? 1u + flag : 0u;
+  if (rn[0] == nd_c0(nd) && rn[1] == nd.c1) {
+    if (hint && a[1u - flag] == nd.w && (f[0] == f[1] || nd.w == 0)) { *out_node = node; *out_w = f[flag]; return true; }
+    if (nd.w == 0 && a[1u - flag] == 0 && a[flag] != 0) {  // one edge before and after: the node stays, its factor moves up
+      *out_node = node;
+      return cmul<MODE>(c, f[flag], a[flag], out_w);
+    }
+  }
+  return reduce_core<MODE>(c, rn, f, a, hint, out_node, out_w);
+}
+
+template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *handled, uint32_t *entries) {
+  ThinState *T = c.T;
+  const uint32_t lane = c.ltid;
+  const int top = g.top, tgt = g.target, low = g.low;
+  *handled = 0; *entries = 0;
+  const uint32_t off = c.E->thin_off;
+  if (off && ((off & 8u) || ((off & 1u) && top > tgt) || ((off & 2u) && low < tgt))) return 0;
+  uint32_t cnt = T->cnt[top], total = 0;
+  if ((off & 4u) && cnt > 1) return 0;
+  ThinRes edge;
+  edge.rw = 0; edge.rnode = 0; edge.pad = 0;
+  if (lane < cnt) edge = T->res[top & 1][lane];
+  bool act = lane < cnt && edge.rw != 0;
+  uint32_t node = edge.rnode, var = TG_VAR_NONE;
+  int L = top, lowest = top;
+  // ---- down.  Every lane leaves a record on every level (pk = 0: no entry), so the way up needs no counts.
+  for (;; L--) {
+    JNode nd;
+    nd.c0 = 0; nd.c1 = 0; nd.w = 0;
+    if (act) nd = node_load<MODE>(c, node);
+    const uint32_t role = g.role[L];
+    if (role == JR_IDLE) {
+      // Fast-forward: an idle level (it lies strictly between the gate's top and lowest level) where the non-zero
+      // edges of EVERY entry's node lead to one child -- product and basis-like states, level after level between a
+      // target and its control.  Every entry steps to that child in its own lane: no arithmetic, no de-duplication
+      // (entries that meet are merged on the next regular level), the record is just the node id.
+      uint32_t only = 0;
+      const bool chain = !act || chain_node(nd, &only);
+      if (jballot(!chain) == 0) {
+        T->ent[L][lane].pk = act ? (TGK_VALID | TGK_SKIP) : 0u;
+        if (act) T->ent[L][lane].pad = node;
+        total += jpopc(jballot(act));
+        node = only;
+        continue;
+      }
+    }
+    const uint64_t w0 = nd_w0(nd), w1 = nd_w1(nd);
+    const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
+    uint32_t k[2], cn[2] = {0, 0}, cv[2] = {TG_VAR_NONE, TG_VAR_NONE}, pc = 0, rounds = 0;
+    uint64_t cw[2];
+    bool nonlocal = false;
+    for (;;) {
+      bool ok = true;
+      k[0] = k[1] = JC_ZERO; cw[0] = cw[1] = 0; pc = 0;
+      if (act && L > tgt) {
+        JKQ_UNROLL
+        for (int i = 0; i < 2; i++) {
+          const uint64_t wi = i ? w1 : w0;
+          if (wi == 0) continue;
+          cw[i] = wi;
+          if (role_satisfied(role, i)) { k[i] = JC_REF; cn[i] = i ? c1 : c0; }
+          else { k[i] = JC_PASS; pc |= (uint32_t)i << i; }
+        }
+      } else if (act && L == tgt) {
+        JKQ_UNROLL
+        for (int i = 0; i < 2; i++) {
+          uint64_t al, be, p = 0;
+          const bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), w0, &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), w1, &be);
+          if (!(o1 && o2)) { ok = false; continue; }
+          if (al != 0 && be != 0 && c0 != c1) { nonlocal = true; continue; }  // a sum of two different sub-diagrams
+          if (!cadd<MODE>(c, al, be, &p)) { ok = false; continue; }
+          const uint32_t xi = al != 0 ? 0u : 1u;  // the child p sits on
+          if (low == tgt) {
+            if (p != 0) { k[i] = JC_PASS; pc |= xi << i; cw[i] = p; }
+            continue;
+          }
+          const uint64_t q = i ? w1 : w0;  // on child i
+          if (p != 0 && q != 0 && (xi ? c1 : c0) != (i ? c1 : c0)) { nonlocal = true; continue; }
+          if (p == 0 && q == 0) continue;
+          if (p == q) { k[i] = JC_PASS; pc |= (uint32_t)i << i; cw[i] = q; continue; }  // this row acts as the identity
+          uint64_t fac = p, kp, kq;  // common factor: the larger magnitude, p on ties
+          if (p == 0 || (q != 0 && q != jneg(p) && jmag2<MODE>(c, q) > jmag2<MODE>(c, p))) fac = q;
+          const bool o3 = cdiv<MODE>(c, p, fac, &kp), o4 = cdiv<MODE>(c, q, fac, &kq);
+          if (!(o3 && o4)) { ok = false; continue; }
+          k[i] = JC_REF; cn[i] = p != 0 ? (xi ? c1 : c0) : (i ? c1 : c0); cv[i] = 2u * lane + (uint32_t)i; cw[i] = fac;
+          T->vp[cv[i]] = kp; T->vq[cv[i]] = kq;
+        }
+      } else if (act) {
+        if (role == JR_IDLE) {
+          if (w0 != 0) { k[0] = JC_REF; cn[0] = c0; cv[0] = var; cw[0] = w0; }
+          if (w1 != 0) { k[1] = JC_REF; cn[1] = c1; cv[1] = var; cw[1] = w1; }
+        } else {
+          const uint32_t si = role == JR_CPOS ? 1u : 0u, ui = 1u - si;
+          const uint64_t ws = si ? w1 : w0, wu = si ? w0 : w1;
+          if (wu != 0) {
+            uint64_t t;
+            if (!cmul<MODE>(c, T->vq[var], wu, &t)) ok = false;
+            else if (t != 0) { k[ui] = JC_PASS; pc |= ui << ui; cw[ui] = t; }
+          }
+          if (ws != 0) {
+            if (L > low) { k[si] = JC_REF; cn[si] = si ? c1 : c0; cv[si] = var; cw[si] = ws; }
+            else {
+              uint64_t t;
+              if (!cmul<MODE>(c, T->vp[var], ws, &t)) ok = false;
+              else if (t != 0) { k[si] = JC_PASS; pc |= si << si; cw[si] = t; }
+            }
+          }
+        }
+      }
+      const uint32_t bad = jballot(!ok);
+      if (!bad) break;
+      const uint32_t fl = thin_trouble<MODE>(c);
+      if (fl) return fl;
+      if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
+      thin_commit<MODE>(c);
+    }
+    if (jballot(nonlocal)) return 0;  // the generic phases take the gate; nothing has been changed
+    const ThinDedup d = thin_dedup<MODE>(c, cnt, act && k[0] == JC_REF, (unsigned long long)cn[0] | ((unsigned long long)cv[0] << 32),
+                                         act && k[1] == JC_REF, (unsigned long long)cn[1] | ((unsigned long long)cv[1] << 32));
+    if (d.newcnt > JKQ_WARP || ((off & 4u) && d.newcnt > 1)) return 0;
+    if (act) {
+      ThinEnt e;
+      // (the ranks of children that are not entries are meaningless and may exceed five bits)
+      e.pk = (k[0] == JC_REF ? d.s0 : 0u) | ((k[1] == JC_REF ? d.s1 : 0u) << TGK_S1) | (k[0] << TGK_K0) | (k[1] << TGK_K1) | (pc << TGK_PC) | TGK_VALID;
+      e.pad = node; e.w = cw[0]; e.f = cw[1];
+      T->ent[L][lane] = e;
+    } else T->ent[L][lane].pk = 0;
+    total += jpopc(jballot(act));
+    if (d.newcnt == 0) { lowest = L; break; }
+    ThinRes nx;
+    nx.rw = 0;
+    if (d.own0) { nx.rnode = cn[0]; nx.pad = cv[0]; T->sres[(L - 1) & 1][d.s0] = nx; }
+    if (d.own1) { nx.rnode = cn[1]; nx.pad = cv[1]; T->sres[(L - 1) & 1][d.s1] = nx; }
+    jsyncwarp();
+    cnt = d.newcnt;
+    act = lane < cnt;
+    if (act) { nx = T->sres[(L - 1) & 1][lane]; node = nx.rnode; var = nx.pad; }
+    jsyncwarp();
+  }
+  // ---- up.  (my_node, my_w) = this lane's result one level down; my_same: it is the node the lane's entry there started from
+  uint32_t my_node = 0;
+  uint64_t my_w = 0;
+  bool my_same = false, unpublished = false;
+  for (L = lowest; L <= top; L++) {
+    const uint32_t pk = T->ent[L][lane].pk;
+    const bool on = (pk & TGK_VALID) != 0;
+    if (jballot(on && !(pk & TGK_SKIP)) == 0) {
+      // fast-forwarded level: the lane's own result from below under the old node -- which stays the old node while
+      // nothing below it changed; otherwise the node is rebuilt over the new child (both edges take the same factor,
+      // so the normal form is the node's own and the factor moves up)
+      if (on) {
+        const uint32_t old = T->ent[L][lane].pad;
+        if (my_w == 0) my_node = 0;
+        else if (my_same) my_node = old;
+        else {
+          const JNode od = node_load<MODE>(c, old);
+          const uint32_t fl = nd_flag(od);
+          my_node = ut_find_or_insert<MODE>(c.E, c.sh, ((fl == 1 && od.w == 0) ? 0u : my_node) | (fl << 31), (fl == 0 && od.w == 0) ? 0u : my_node, od.w);
+          my_same = my_node == old;
+        }
+      }
+      if (jballot(on && my_w != 0 && my_node == 0)) {  // a pool ran out
+        const uint32_t fl = thin_trouble<MODE>(c);
+        if (fl) return fl;
+      }
+      unpublished = true;
+      continue;
+    }
+    if (unpublished) {  // the results of the fast-forwarded level below go through the ring like those of any level
+      ThinRes r;
+      r.rw = my_w; r.rnode = my_node; r.pad = 0;
+      T->sres[(L - 1) & 1][lane] = r;
+      jsyncwarp();
+      unpublished = false;
+    }
+    ThinEnt e;
+    e.pk = pk; e.pad = 0; e.w = 0; e.f = 0;
+    JNode nd;
+    nd.c0 = 0; nd.c1 = 0; nd.w = 0;
+    uint32_t rn[2] = {0, 0};
+    uint64_t f[2] = {JW_ONE, JW_ONE}, a[2] = {0, 0};
+    if (on) {
+      e = T->ent[L][lane];
+      nd = node_load<MODE>(c, e.pad);
+      JKQ_UNROLL
+      for (int i = 0; i < 2; i++) {
+        const uint32_t kind = (e.pk >> (TGK_K0 + 2 * i)) & 3u;
+        const uint64_t cwi = i ? e.f : e.w;
+        if (kind == JC_PASS) { rn[i] = ((e.pk >> (TGK_PC + i)) & 1u) ? nd.c1 : nd_c0(nd); a[i] = cwi; }
+        else if (kind == JC_REF) {
+          const ThinRes r = T->sres[(L - 1) & 1][(e.pk >> (TGK_S1 * i)) & 31u];
+          f[i] = r.rw; rn[i] = r.rnode;
+          a[i] = f[i] ? cwi : 0;
+        }
+        if (a[i] == 0) rn[i] = 0;
+      }
+    }
+    uint32_t rnode = 0, rounds = 0;
+    uint64_t rw = 0;
+    for (;;) {
+      bool ok = true;
+      if (on) {
+        ok = thin_reduce<MODE>(c, e.pad, nd, rn, f, a, &rnode, &rw);
+        if (ok && L == top && rw != 0 && rnode != 0) ok = cmul<MODE>(c, edge.rw, rw, &rw);
+      }
+      const uint32_t bad = jballot(!ok);
+      if (bad || jballot(on && ok && rw != 0 && rnode == 0)) {  // (a node of 0 under a weight: a pool ran out)
+        const uint32_t fl = thin_trouble<MODE>(c);
+        if (fl) return fl;
+      }
+      if (!bad) break;
+      if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
+      thin_commit<MODE>(c);
+    }
+    ThinRes r;
+    r.rw = rw; r.rnode = rw ? rnode : 0; r.pad = 0;
+    my_node = r.rnode; my_w = rw; my_same = on && r.rnode == e.pad;
+    if (L == top) { if (on) T->res[top & 1][lane] = r; }
+    else T->sres[L & 1][lane] = r;
+    jsyncwarp();
+  }
+  *handled = 1; *entries = total;
   return 0;
 }
 

@@ -111,6 +111,7 @@ typedef struct {
   uint32_t gc_min;          // never collect below this many allocated nodes
   uint32_t cta_node_limit;  // testing aid: cap on the shared-memory node pool of the CTA path (0 = its real size)
   uint32_t cta_val_limit;   // testing aid: the same for the shared-memory value table
+  uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all
   uint32_t cta_no_reserve; // testing aid: no reserve in the shared pools, so the root rebuild of an abandoned gate fails too (saved-cursor hand-over)
   double tol;
   double inv_tol;
@@ -171,7 +172,7 @@ typedef struct {
 #define JST_NODES 1      // unique-table inserts
 #define JST_VALS 2       // reals appended to the value table
 #define JST_RETRY 3      // value-commit rounds
-#define JST_THIN 4       // levels walked by the thin path
+#define JST_THIN 4       // gates applied by thin_gate (no work items)
 #define JST_GATES 5
 #define JST_MAXF 6       // largest per-gate item count (max, not sum)
 #define JST_GC_RUNS 7

@@ -192,7 +192,7 @@ int main(int argc, char **argv) {
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n", n, gates.size());
   printf(" \"items\": %llu,\n \"nodes_created\": %llu,\n \"val_inserts\": %llu,\n \"gc_runs\": %llu,\n \"retry_rounds\": %llu,\n \"max_frontier\": %llu,\n",
          E->st[JST_ITEMS], E->st[JST_NODES], E->st[JST_VALS], E->st[JST_GC_RUNS], E->st[JST_RETRY], E->st[JST_MAXF]);
-  printf(" \"grid_switches\": %d,\n", grid_switches);
+  printf(" \"grid_switches\": %d,\n \"thin_gates\": %llu,\n", grid_switches, E->st[JST_THIN]);
   printf(" \"ctable_size\": %u,\n \"norm\": %.17g,\n", E->val_count, E->norm);
   printf(" \"level_counts\": [");
   for (int v = 0; v < n; v++) printf("%s%u", v ? "," : "", E->lvl_cnt[v]);
