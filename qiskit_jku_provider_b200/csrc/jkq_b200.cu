@@ -533,9 +533,28 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
 
 // ops -> gate descriptors (level roles, index of the matrix among the distinct matrices of the circuit) and the
 // measurement map.  Returns 0 or JKQ_E_ARGUMENT with a message in *err.
+// idle-level mask and parking level of the gates [first, gates.size()) of one circuit (JGate.idle / JGate.park)
+static void finish_gates(std::vector<JGate> &gates, size_t first) {
+  for (size_t i = first; i < gates.size(); i++) {
+    JGate &g = gates[i];
+    g.idle = 0;
+    for (int L = 0; L < JKQ_MAXQ; L++)
+      if (g.role[L] == JR_IDLE) g.idle |= 1ull << L;
+    g.park = g.top;
+    for (size_t j = i + 1; j < gates.size() && j <= i + JKQ_PARK_WINDOW; j++)
+      if (gates[j].top > g.park) g.park = gates[j].top;
+    // diagonal or anti-diagonal: local on any node (thin_gate).  (The projector / X slots of MEASURE_ONE and RESET
+    // are filled in later with matrices of the same two shapes.)
+    const bool diag = g.m[2] == 0.0 && g.m[3] == 0.0 && g.m[4] == 0.0 && g.m[5] == 0.0;
+    const bool anti = g.m[0] == 0.0 && g.m[1] == 0.0 && g.m[6] == 0.0 && g.m[7] == 0.0;
+    g.rsv = (diag || anti) ? 1 : 0;
+  }
+}
+
 static int parse_ops(std::string *err, uint32_t n_qubits, const jkq_op *ops, size_t n_ops, std::vector<JGate> &gates, std::vector<int> *gate_of_op,
                      SampleParams &sp, uint32_t *n_mats, bool *has_snapshot) {
   char buf[128];
+  const size_t first_gate = gates.size();
   if (n_qubits < 1 || n_qubits > JKQ_MAXQ) { snprintf(buf, sizeof(buf), "n_qubits must be 1..%d", JKQ_MAXQ); *err = buf; return JKQ_E_ARGUMENT; }
   bool any_measure = false;
   if (has_snapshot) *has_snapshot = false;
@@ -623,6 +642,7 @@ static int parse_ops(std::string *err, uint32_t n_qubits, const jkq_op *ops, siz
   if (!any_measure)  // engine-level default: every qubit, key bit q = qubit q
     for (uint32_t q = 0; q < n_qubits && q < 64; q++) sp.bitpos[n_qubits - 1 - q] = (uint8_t)q;
   if (n_mats) *n_mats = (uint32_t)mats.size();
+  finish_gates(gates, first_gate);
   return JKQ_E_OK;
 }
 

@@ -339,6 +339,7 @@ template <int MODE> JD uint32_t cursor_finish(Ctx &c, int lsw, uint32_t blocked)
 #define TGK_PC 14
 #define TGK_VALID (1u << 16)
 #define TGK_SKIP (1u << 17)  // fast-forwarded level: the entry's child is the entry of the same lane one level down
+#define TGK_RUN 18           // ... and the level its run of fast-forwarded levels started on (6 bits)
 #define TG_VAR_NONE 0xFFu
 
 // ranks of the distinct REF children of a level (key = node | variant << 32); same scheme as thin_children
@@ -398,39 +399,44 @@ JD bool thin_reduce(Ctx &c, uint32_t node, const JNode &nd, uint32_t rn[2], cons
 template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *handled, uint32_t *entries) {
   ThinState *T = c.T;
   const uint32_t lane = c.ltid;
-  const int top = g.top, tgt = g.target, low = g.low;
+  const int start = T->M, top = g.top, tgt = g.target, low = g.low;  // the cursor may be parked above the gate: start >= top
+  const uint64_t idle = g.idle;
   *handled = 0; *entries = 0;
   const uint32_t off = c.E->thin_off;
   if (off && ((off & 8u) || ((off & 1u) && top > tgt) || ((off & 2u) && low < tgt))) return 0;
-  uint32_t cnt = T->cnt[top], total = 0;
+  uint32_t cnt = T->cnt[start], total = 0;
   if ((off & 4u) && cnt > 1) return 0;
   ThinRes edge;
   edge.rw = 0; edge.rnode = 0; edge.pad = 0;
-  if (lane < cnt) edge = T->res[top & 1][lane];
+  if (lane < cnt) edge = T->res[start & 1][lane];
   bool act = lane < cnt && edge.rw != 0;
   uint32_t node = edge.rnode, var = TG_VAR_NONE;
-  int L = top, lowest = top;
-  // ---- down.  Every lane leaves a record on every level (pk = 0: no entry), so the way up needs no counts.
-  for (;; L--) {
-    JNode nd;
-    nd.c0 = 0; nd.c1 = 0; nd.w = 0;
-    if (act) nd = node_load<MODE>(c, node);
-    const uint32_t role = g.role[L];
-    if (role == JR_IDLE) {
-      // Fast-forward: an idle level (it lies strictly between the gate's top and lowest level) where the non-zero
-      // edges of EVERY entry's node lead to one child -- product and basis-like states, level after level between a
-      // target and its control.  Every entry steps to that child in its own lane: no arithmetic, no de-duplication
-      // (entries that meet are merged on the next regular level), the record is just the node id.
-      uint32_t only = 0;
-      const bool chain = !act || chain_node(nd, &only);
-      if (jballot(!chain) == 0) {
-        T->ent[L][lane].pk = act ? (TGK_VALID | TGK_SKIP) : 0u;
-        if (act) T->ent[L][lane].pad = node;
-        total += jpopc(jballot(act));
-        node = only;
-        continue;
+  int L = start, lowest = start;
+  JNode nd;
+  nd.c0 = 0; nd.c1 = 0; nd.w = 0;
+  if (act) nd = node_load<MODE>(c, node);
+  // ---- down.  Every lane leaves a record on every level (no VALID bit: no entry), so the way up needs no counts.
+  for (;;) {  // nd = the node of this lane's entry on level L
+    if (L < start && ((idle >> L) & 1ull)) {
+      // Fast-forward over idle levels (uninvolved levels between the cursor, the gate's top and its lowest level)
+      // where the non-zero edges of EVERY entry's node lead to one child -- product and basis-like states, level
+      // after level between a target and its control.  Every entry steps to that child in its own lane: no
+      // arithmetic, no de-duplication (entries that meet are merged on the next regular level); the record is the
+      // node id and the level the run started on.
+      const int Lt = L;
+      for (;;) {
+        uint32_t only = 0;
+        const bool chain = !act || chain_node(nd, &only);
+        if (jballot(!chain)) break;
+        T->ent[L][lane].pk = (act ? (TGK_VALID | TGK_SKIP) : 0u) | ((uint32_t)Lt << TGK_RUN);
+        if (act) { T->ent[L][lane].pad = node; node = only; }
+        L--;
+        if (act) nd = node_load<MODE>(c, node);
+        if (!((idle >> L) & 1ull)) break;
       }
+      total += (uint32_t)(Lt - L) * jpopc(jballot(act));
     }
+    const uint32_t role = g.role[L];
     const uint64_t w0 = nd_w0(nd), w1 = nd_w1(nd);
     const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
     uint32_t k[2], cn[2] = {0, 0}, cv[2] = {TG_VAR_NONE, TG_VAR_NONE}, pc = 0, rounds = 0;
@@ -521,20 +527,28 @@ template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *hand
     jsyncwarp();
     cnt = d.newcnt;
     act = lane < cnt;
-    if (act) { nx = T->sres[(L - 1) & 1][lane]; node = nx.rnode; var = nx.pad; }
+    L--;
+    if (act) { nx = T->sres[L & 1][lane]; node = nx.rnode; var = nx.pad; nd = node_load<MODE>(c, node); }
     jsyncwarp();
   }
   // ---- up.  (my_node, my_w) = this lane's result one level down; my_same: it is the node the lane's entry there started from
   uint32_t my_node = 0;
   uint64_t my_w = 0;
   bool my_same = false, unpublished = false;
-  for (L = lowest; L <= top; L++) {
+  for (L = lowest; L <= start; L++) {
     const uint32_t pk = T->ent[L][lane].pk;
     const bool on = (pk & TGK_VALID) != 0;
     if (jballot(on && !(pk & TGK_SKIP)) == 0) {
-      // fast-forwarded level: the lane's own result from below under the old node -- which stays the old node while
-      // nothing below it changed; otherwise the node is rebuilt over the new child (both edges take the same factor,
-      // so the normal form is the node's own and the factor moves up)
+      // Fast-forwarded level: the lane's own result from below under the old node -- which stays the old node while
+      // nothing below it changed: then the whole run is stepped over at once.  Otherwise the node is rebuilt over the
+      // new child (both edges take the same factor, so the normal form is the node's own and the factor moves up).
+      unpublished = true;
+      if (jballot(on && my_w != 0 && !my_same) == 0) {
+        const int Lt = (int)((pk >> TGK_RUN) & 63u);  // (every lane holds it, entry or not)
+        if (on) my_node = my_w ? T->ent[Lt][lane].pad : 0;
+        L = Lt;
+        continue;
+      }
       if (on) {
         const uint32_t old = T->ent[L][lane].pad;
         if (my_w == 0) my_node = 0;
@@ -550,7 +564,6 @@ template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *hand
         const uint32_t fl = thin_trouble<MODE>(c);
         if (fl) return fl;
       }
-      unpublished = true;
       continue;
     }
     if (unpublished) {  // the results of the fast-forwarded level below go through the ring like those of any level
@@ -562,7 +575,6 @@ template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *hand
     }
     ThinEnt e;
     e.pk = pk; e.pad = 0; e.w = 0; e.f = 0;
-    JNode nd;
     nd.c0 = 0; nd.c1 = 0; nd.w = 0;
     uint32_t rn[2] = {0, 0};
     uint64_t f[2] = {JW_ONE, JW_ONE}, a[2] = {0, 0};
@@ -588,7 +600,7 @@ template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *hand
       bool ok = true;
       if (on) {
         ok = thin_reduce<MODE>(c, e.pad, nd, rn, f, a, &rnode, &rw);
-        if (ok && L == top && rw != 0 && rnode != 0) ok = cmul<MODE>(c, edge.rw, rw, &rw);
+        if (ok && L == start && rw != 0 && rnode != 0) ok = cmul<MODE>(c, edge.rw, rw, &rw);
       }
       const uint32_t bad = jballot(!ok);
       if (bad || jballot(on && ok && rw != 0 && rnode == 0)) {  // (a node of 0 under a weight: a pool ran out)
@@ -602,7 +614,7 @@ template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *hand
     ThinRes r;
     r.rw = rw; r.rnode = rw ? rnode : 0; r.pad = 0;
     my_node = r.rnode; my_w = rw; my_same = on && r.rnode == e.pad;
-    if (L == top) { if (on) T->res[top & 1][lane] = r; }
+    if (L == start) { if (on) T->res[start & 1][lane] = r; }
     else T->sres[L & 1][lane] = r;
     jsyncwarp();
   }

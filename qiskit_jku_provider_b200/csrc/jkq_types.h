@@ -75,6 +75,7 @@ typedef struct __attribute__((aligned(16))) {
 #define JR_CPOS 1
 #define JR_CNEG 2
 #define JR_TARGET 3
+#define JKQ_PARK_WINDOW 4  // gates looked ahead for JGate.park
 
 typedef struct __attribute__((aligned(16))) {
   double m[8];  // 2x2 matrix, row major, (re, im) pairs -- FP64 entries from the host
@@ -82,8 +83,11 @@ typedef struct __attribute__((aligned(16))) {
   int32_t low;     // lowest level carrying a control or the target
   int32_t top;     // highest such level
   int32_t pad;     // index of this gate's matrix among the distinct matrices of the circuit
+  int32_t park;    // highest `top` among this gate and the next few: the cursor does not go below it for this gate
+  int32_t rsv;
+  uint64_t idle;   // bit L: level L carries neither a control nor the target
   uint8_t role[JKQ_MAXQ];
-} JGate;  // 144 bytes
+} JGate;  // 160 bytes
 
 // What the cursor warp tells everybody else about the gate it just prepared (or finished).  Two copies,
 // indexed by gate parity: the warp may already be writing the next gate's while the others read this one's.

@@ -121,6 +121,18 @@ int main(int argc, char **argv) {
     gates.push_back(g);
   }
   fclose(f);
+  for (size_t i = 0; i < gates.size(); i++) {  // as finish_gates in jkq_b200.cu
+    JGate &g = gates[i];
+    g.idle = 0;
+    for (int L = 0; L < JKQ_MAXQ; L++)
+      if (g.role[L] == JR_IDLE) g.idle |= 1ull << L;
+    g.park = g.top;
+    for (size_t j = i + 1; j < gates.size() && j <= i + JKQ_PARK_WINDOW; j++)
+      if (gates[j].top > g.park) g.park = gates[j].top;
+    const bool diag = g.m[2] == 0.0 && g.m[3] == 0.0 && g.m[4] == 0.0 && g.m[5] == 0.0;
+    const bool anti = g.m[0] == 0.0 && g.m[1] == 0.0 && g.m[6] == 0.0 && g.m[7] == 0.0;
+    g.rsv = (diag || anti) ? 1 : 0;
+  }
 
   JEng *E = (JEng *)calloc(1, sizeof(JEng));
   E->n = n; E->tol = 1e-10; E->inv_tol = 1.0 / E->tol;
