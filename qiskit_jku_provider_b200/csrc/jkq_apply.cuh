@@ -308,7 +308,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     // few gates need it (JGate.park) when the gate is one thin_gate is bound to take (diagonal / anti-diagonal matrix):
     // u1 on a control far below, then cx back up at the target -- the cursor stays at the target.
     int goal = g.top;
-    if ((g.rsv & 1) && !(E->thin_off & 16u)) {
+    if ((g.rsv & 1) && !(c.T->thin_off & 16u)) {
       const int M0 = c.T->M;
       if (M0 > goal) goal = M0 < g.park ? M0 : g.park;
     }
@@ -317,7 +317,8 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     JPROF_ADD(c, 11, sp0, sp1);
     uint32_t thin_done = 0, thin_entries = 0;
 #ifndef JKQ_NO_THIN_GATES
-    if (!f && !blocked) f = thin_gate<MODE>(c, g, &thin_done, &thin_entries);  // the whole gate below the cursor edges, if it is local
+    if (!f && !blocked) f = thin_probe<MODE>(c, g, &thin_done, &thin_entries);  // single-child paths, controls on basis-like nodes: no records
+    if (!f && !blocked && !thin_done) f = thin_gate<MODE>(c, g, &thin_done, &thin_entries);  // the whole gate below the cursor edges, if it is local
 #endif
     if (!f && !thin_done && !blocked && goal > g.top) f = cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);  // the item phases start at the top level
     uint32_t b = 0, e = icount;

@@ -158,6 +158,7 @@ struct ThinState {
   ThinRes sres[2][JKQ_WARP];         // on the way down: the entries of the next level; on the way up: the results of a level
   uint64_t vp[2 * JKQ_WARP];         // variants created at the target level: factor on the subspace "all controls
   uint64_t vq[2 * JKQ_WARP];         //   below satisfied" (vp) and on its complement (vq), normalised by the larger one
+  uint32_t thin_off, pad_t;          // copy of JEng.thin_off (testing aid), set by cursor_reset
 };
 
 struct Ctx {

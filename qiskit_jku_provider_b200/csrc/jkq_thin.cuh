@@ -73,6 +73,7 @@ template <int MODE> JD void cursor_reset(Ctx &c, int n) {
     T->cnt[n - 1] = 1;
     T->M = n - 1;
     T->walked = 0;
+    T->thin_off = c.E->thin_off;
   }
   jsyncwarp();
 }
@@ -396,13 +397,146 @@ JD bool thin_reduce(Ctx &c, uint32_t node, const JNode &nd, uint32_t rn[2], cons
   return reduce_core<MODE>(c, rn, f, a, hint, out_node, out_w);
 }
 
+// thin_probe: the cases of thin_gate that need no records at all, every cursor edge in its own lane with nothing
+// exchanged between lanes:
+//   * no control above the target, and from the cursor edge down to the target only nodes whose non-zero edges lead
+//     to one child (or the cursor already sits on the target level);
+//   * the target node local as in thin_gate;
+//   * every control below the target on a node with ONE non-zero edge, reached through single-child nodes: the
+//     sub-diagram under the target is then multiplied by p (all controls read "satisfied") or q (some control does
+//     not) and stays the node it is -- child i of the target becomes (c, p_i) or (c, q_i), no division, no table access.
+// The new target node comes from thin_reduce.  With the cursor parked above the target the edge only takes the new top
+// weight, which needs the target node to come out unchanged (a phase on a basis-state qubit); otherwise, and whenever
+// a condition above fails for any lane, nothing is written and thin_gate / the item phases take the gate.
+template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *handled, uint32_t *entries) {
+  ThinState *T = c.T;
+  const uint32_t lane = c.ltid;
+  const int start = T->M, tgt = g.target, low = g.low;
+  *handled = 0; *entries = 0;
+  if (g.top != tgt || (T->thin_off & 32u)) return 0;
+  const uint64_t idle = g.idle;
+  const uint32_t cnt = T->cnt[start];
+  ThinRes edge;
+  edge.rw = 0; edge.rnode = 0; edge.pad = 0;
+  if (lane < cnt) edge = T->res[start & 1][lane];
+  const bool act = lane < cnt && edge.rw != 0;
+  bool fail = false;
+  uint32_t node = edge.rnode;
+  JNode nd;
+  nd.c0 = 0; nd.c1 = 0; nd.w = 0;
+  if (act) nd = node_load<MODE>(c, node);
+  for (int L = start; L > tgt; L--) {  // down to the target through single-child nodes
+    uint32_t only = 0;
+    if (act && !fail) {
+      if (!chain_node(nd, &only)) fail = true;
+      else { node = only; nd = node_load<MODE>(c, node); }
+    }
+  }
+  if (jballot(fail)) return 0;
+  const uint64_t w0 = nd_w0(nd), w1 = nd_w1(nd);
+  const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
+  uint32_t rn[2] = {0, 0}, rounds = 0;
+  uint64_t p[2] = {0, 0}, a[2] = {0, 0};
+  const uint64_t f[2] = {JW_ONE, JW_ONE};
+  for (;;) {  // the target node's two rows
+    bool ok = true;
+    if (act) {
+      JKQ_UNROLL
+      for (int i = 0; i < 2; i++) {
+        uint64_t al, be;
+        const bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), w0, &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), w1, &be);
+        if (!(o1 && o2)) { ok = false; continue; }
+        if (al != 0 && be != 0 && c0 != c1) { fail = true; continue; }  // a sum of two different sub-diagrams
+        if (!cadd<MODE>(c, al, be, &p[i])) { ok = false; continue; }
+        rn[i] = al != 0 ? c0 : c1;  // the child p sits on
+      }
+    }
+    const uint32_t bad = jballot(!ok);
+    if (!bad) break;
+    const uint32_t fl = thin_trouble<MODE>(c);
+    if (fl) return fl;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
+    thin_commit<MODE>(c);
+  }
+  if (act && !fail) {
+    if (low == tgt) { a[0] = p[0]; a[1] = p[1]; }
+    else {
+      uint32_t seen = 0, seen_sat = 0;  // the walk below child 0, reused for child 1 when it is the same node
+      JKQ_UNROLL
+      for (int i = 0; i < 2; i++) {
+        const uint64_t q = i ? w1 : w0;
+        const uint32_t ci = i ? c1 : c0;
+        if (p[i] != 0 && q != 0 && rn[i] != ci) { fail = true; continue; }
+        if (p[i] == 0) rn[i] = ci;
+        if (p[i] == q) { a[i] = q; continue; }  // (also both zero)
+        bool sat = true;
+        if (i == 1 && seen == rn[1]) sat = seen_sat != 0;
+        else {
+          uint32_t z = rn[i];
+          for (int Lc = tgt - 1; Lc >= low && !fail; Lc--) {
+            const JNode zd = node_load<MODE>(c, z);
+            if ((idle >> Lc) & 1ull) {
+              uint32_t only = 0;
+              if (!chain_node(zd, &only)) fail = true;
+              z = only;
+              continue;
+            }
+            const uint32_t si = g.role[Lc] == JR_CPOS ? 1u : 0u;
+            const uint64_t ws = si ? nd_w1(zd) : nd_w0(zd), wu = si ? nd_w0(zd) : nd_w1(zd);
+            if (ws != 0 && wu != 0) { fail = true; break; }  // a control in superposition splits the sub-diagram
+            if (ws == 0) { sat = false; break; }
+            z = si ? zd.c1 : nd_c0(zd);
+          }
+          seen = rn[i]; seen_sat = sat ? 1u : 0u;
+        }
+        a[i] = sat ? p[i] : q;
+      }
+    }
+    if (a[0] == 0) rn[0] = 0;
+    if (a[1] == 0) rn[1] = 0;
+  }
+  if (jballot(fail)) return 0;
+  uint32_t rnode = 0;
+  uint64_t rw = 0;
+  rounds = 0;
+  for (;;) {
+    bool ok = true;
+    if (act && !fail) {
+      ok = thin_reduce<MODE>(c, node, nd, rn, f, a, &rnode, &rw);
+      if (ok && rw != 0) {
+        if (rnode == 0) {}  // (a pool ran out: seen below)
+        else if (start > tgt && rnode != node) fail = true;
+        else ok = cmul<MODE>(c, edge.rw, rw, &rw);
+      }
+    }
+    const uint32_t bad = jballot(!ok);
+    if (bad || jballot(act && ok && !fail && rw != 0 && rnode == 0)) {
+      const uint32_t fl = thin_trouble<MODE>(c);
+      if (fl) return fl;
+    }
+    if (!bad) break;
+    if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
+    thin_commit<MODE>(c);
+  }
+  if (jballot(fail)) return 0;
+  if (act) {
+    ThinRes r;
+    r.rw = rw; r.pad = 0;
+    r.rnode = rw == 0 ? 0u : (start > tgt ? edge.rnode : rnode);
+    T->res[start & 1][lane] = r;
+  }
+  jsyncwarp();
+  *handled = 1; *entries = jpopc(jballot(act)) * (uint32_t)(start - low + 1);
+  return 0;
+}
+
 template <int MODE> JD uint32_t thin_gate(Ctx &c, const JGate &g, uint32_t *handled, uint32_t *entries) {
   ThinState *T = c.T;
   const uint32_t lane = c.ltid;
   const int start = T->M, top = g.top, tgt = g.target, low = g.low;  // the cursor may be parked above the gate: start >= top
   const uint64_t idle = g.idle;
   *handled = 0; *entries = 0;
-  const uint32_t off = c.E->thin_off;
+  const uint32_t off = T->thin_off;
   if (off && ((off & 8u) || ((off & 1u) && top > tgt) || ((off & 2u) && low < tgt))) return 0;
   uint32_t cnt = T->cnt[start], total = 0;
   if ((off & 4u) && cnt > 1) return 0;
