@@ -50,11 +50,12 @@ typedef struct {
   uint32_t node_capacity;   /* nodes per arena (power of two)                 default 1<<22   */
   uint32_t value_capacity;  /* distinct reals (power of two)                  default 1<<20   */
   uint32_t item_capacity;   /* frontier work items (power of two)             default = nodes */
-  uint32_t cta_threads;     /* threads of the single-CTA path                 default 256     */
+  uint32_t cta_threads;     /* threads of the wide single-CTA launch          default 256     */
   uint32_t cta_item_limit;  /* frontier size that escalates to the grid path  default 4096    */
   uint32_t gc_min;          /* never collect below this many allocated nodes  default 1<<15   */
   uint32_t grid_blocks_per_sm; /* grid path CTAs per SM                       default 2       */
-  uint32_t reserved;
+  uint32_t reserved;        /* 1: always launch the single-CTA path with cta_threads (default: one warp until a
+                               level of a gate outgrows it, then cta_threads)                              */
 } jkq_config;
 
 enum {

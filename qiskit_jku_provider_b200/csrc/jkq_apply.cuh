@@ -275,12 +275,22 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
   JPROF_T(gt0);
   if (MODE == MODE_CTA) {
     CtaState *S = c.sh;
-    // stage the NEXT gate's descriptor while this one runs (warps other than the thin one when there are any)
-    if (gi + 1 < n_gates && (c.lnth <= JKQ_WARP || c.ltid >= JKQ_WARP)) {
-      const uint32_t first = c.lnth <= JKQ_WARP ? c.ltid : c.ltid - JKQ_WARP, step = c.lnth <= JKQ_WARP ? c.lnth : c.lnth - JKQ_WARP;
+    // stage the NEXT gate's descriptor while this one runs: the warps other than the cursor warp when there are any;
+    // a single warp issues asynchronous 16-byte copies (cp.async: no register, no stall) and waits for them at the end
+    // of the gate
+    if (gi + 1 < n_gates) {
       uint32_t *dst = reinterpret_cast<uint32_t *>(&S->gate[(gi + 1) & 1]);
       const uint32_t *src = reinterpret_cast<const uint32_t *>(gates + gi + 1);
-      for (uint32_t i = first; i < sizeof(JGate) / 4; i += step) dst[i] = src[i];
+#ifndef JKQ_EMU
+      if (c.lnth <= JKQ_WARP) {
+        if (c.ltid < sizeof(JGate) / 16)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * c.ltid)), "l"(src + 4 * c.ltid) : "memory");
+      } else
+#endif
+      if (c.lnth <= JKQ_WARP || c.ltid >= JKQ_WARP) {
+        const uint32_t first = c.lnth <= JKQ_WARP ? c.ltid : c.ltid - JKQ_WARP, step = c.lnth <= JKQ_WARP ? c.lnth : c.lnth - JKQ_WARP;
+        for (uint32_t i = first; i < sizeof(JGate) / 4; i += step) dst[i] = src[i];
+      }
     }
   }
   const JGate &g = MODE == MODE_CTA ? c.sh->gate[gi & 1] : gates[gi];
@@ -295,9 +305,9 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       if (c.ltid == 0) c.sh->gen = 1;
       jsyncwarp();
     }
-    if (MODE == MODE_CTA) {  // chain-compression scratch of the previous gate
+    if (MODE == MODE_CTA && c.sh->chain_dirty) {  // chain-compression scratch of the last gate that went through the item phases
       for (uint32_t L = c.ltid; L < (uint32_t)n; L += JKQ_WARP) c.sh->defer_n[L] = 0;
-      if (c.ltid == 0) { c.sh->chain_n = 0; c.sh->min_def = 0x7FFFFFFF; }
+      if (c.ltid == 0) { c.sh->chain_n = 0; c.sh->min_def = 0x7FFFFFFF; c.sh->chain_dirty = 0; }
     }
     if (c.ltid == 0) gate_setup<MODE>(c, g);
     jsyncwarp();
@@ -325,11 +335,22 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     int lowest = lsw + 1;
     if (!f && !thin_done && !blocked) cursor_items<MODE>(c, lsw, icount);
     if (!f && !thin_done) {
-      if (c.ltid == 0) *cnt_items<MODE>(c) = icount;
+      if (c.ltid == 0) { *cnt_items<MODE>(c) = icount; if (MODE == MODE_CTA) c.sh->chain_dirty = 1; }
       jsyncwarp();
       for (int L = lsw; L >= 0 && (e > b || (MODE == MODE_CTA && ld_r<MODE>(&c.sh->min_def) <= L)); L--) {
         const uint32_t nwork = e - b + defer_count<MODE>(c, L);
-        if (nwork > JKQ_WARP) { wide_L = L; break; }
+        if (nwork > JKQ_WARP) {
+          if (MODE == MODE_CTA && c.lnth <= JKQ_WARP && E->cta_wide_ok) {
+            // launched with the cursor warp alone (all a narrow diagram ever needs): give the gate up like one that
+            // does not fit, and let the host launch the wide shape from here
+            if (c.ltid == 0) { E->want_wide = 1; jwant_grid(c.sh); }
+            jsyncwarp();
+            f = JF_GRID;
+            break;
+          }
+          wide_L = L;
+          break;
+        }
         if (c.ltid == 0) lr_set<MODE>(c, L, b, e);
         lowest = L;
         if (nwork == 0) continue;  // a level skipped by chain compression
@@ -367,6 +388,9 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     }
   }
   {
+#ifndef JKQ_EMU
+    if (MODE == MODE_CTA && c.lnth <= JKQ_WARP) asm volatile("cp.async.wait_all;" ::: "memory");  // the next gate's descriptor
+#endif
     uint32_t fl = sync_or<MODE>(c, 0);
     JPROF_T(gt1);
     JPROF_ADD(c, 0, gt0, gt1);
@@ -725,7 +749,7 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       S->pend_n[0] = S->pend_n[1] = S->pend_n[2] = 0;
       S->bflags[0] = S->bflags[1] = S->bflags[2] = S->bflags[3] = 0;
       S->err = (uint32_t)E->status; S->want_grid = 0; S->nofit = 0;
-      S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw;
+      S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw; S->chain_dirty = 1;
       S->flushed_nodes = S->node_count; S->flushed_vals = S->val_count;  // shared memory holds nothing yet
       S->next_gate = E->next_gate;
       for (int k = 0; k <= JST_N; k++) S->st[k] = 0;

@@ -356,6 +356,7 @@ struct jkq_handle {
   double *scalar_dev = nullptr;
   uint32_t n = 0;
   bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
+  bool wide_now = false;            // the single-CTA kernel of this circuit is launched with cfg.cta_threads (it asked for them)
   SampleParams sp;
   uint32_t dd_root = 0, dd_nodes = 0;
   std::map<uint32_t, double2 *> snapshots;  // slot -> device buffer of 2^n amplitudes
@@ -713,7 +714,10 @@ static int launch_gates(jkq_handle *h, bool grid, int upto) {
     CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, sizeof(ThinState), h->stream));
     h->stats.grid_launches++;
   } else {
-    k_run_gates<MODE_CTA><<<1, h->cfg.cta_threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
+    // one warp while every level of every gate fits it (QFT, GHZ, Grover ...: the other warps would only wait at the
+    // gate barrier); the wide shape once the kernel asked for it (want_wide)
+    const unsigned threads = (h->wide_now || h->cfg.reserved == 1) ? h->cfg.cta_threads : 32u;
+    k_run_gates<MODE_CTA><<<1, threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
     CU(cudaGetLastError());
     h->stats.cta_launches++;
   }
@@ -743,6 +747,13 @@ static int run_segment(jkq_handle *h, int upto) {
     }
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
     if (h->host.next_gate >= upto && !h->host.cursor_saved) return JKQ_E_OK;
+    if (h->host.want_grid && h->host.want_wide && !h->host.cursor_saved && !grid && !h->wide_now) {
+      h->wide_now = true;
+      h->host.want_grid = 0; h->host.want_wide = 0;
+      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(&h->dev->want_wide, &h->host.want_wide, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+      continue;
+    }
     if ((h->host.want_grid || h->host.cursor_saved) && !grid) {
       if (h->debug_stop_at_handover) {
         fprintf(stderr, "debug_stop_at_handover: next_gate %d cursor_saved %u nodes %u vals %u\n", h->host.next_gate, h->host.cursor_saved, h->host.node_count,
@@ -891,7 +902,9 @@ extern "C" int jkq_apply(jkq_handle *h) {
   }
   E.lvl_log = h->lvl_log;
   E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
-  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0;
+  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0; E.want_wide = 0;
+  E.cta_wide_ok = (h->cfg.cta_threads > 32 && h->cfg.reserved != 1) ? 1u : 0u;
+  h->wide_now = false;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));

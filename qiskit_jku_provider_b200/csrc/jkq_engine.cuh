@@ -99,7 +99,7 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
-  uint32_t node_limit, val_limit, pad4, pad5;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
+  uint32_t node_limit, val_limit, chain_dirty, pad5;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
   uint32_t node_hard, val_hard, node_soft, val_soft;
   JHand hand[2];
   uint32_t pend_n[3], err;

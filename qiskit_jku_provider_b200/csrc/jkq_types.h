@@ -115,6 +115,7 @@ typedef struct {
   uint32_t gc_min;          // never collect below this many allocated nodes
   uint32_t cta_node_limit;  // testing aid: cap on the shared-memory node pool of the CTA path (0 = its real size)
   uint32_t cta_val_limit;   // testing aid: the same for the shared-memory value table
+  uint32_t cta_wide_ok;     // a one-warp single-CTA launch may ask for the wide one (want_wide) when a level outgrows the warp
   uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all
   uint32_t cta_no_reserve; // testing aid: no reserve in the shared pools, so the root rebuild of an abandoned gate fails too (saved-cursor hand-over)
   double tol;
@@ -158,7 +159,7 @@ typedef struct {
   int32_t want_grid;    // CTA mode asked for the grid path
   uint32_t tables_valid;  // HBM unique / value hash tables match the arena (MODE_CTA lets them go stale)
   uint32_t cursor_saved;  // thin_spill holds the state; root / rootw are stale; only the grid path may continue
-  uint32_t pad_s;
+  uint32_t want_wide;     // raised together with want_grid by a one-warp launch: the wide single-CTA launch is enough
   // ---- counters ----
   unsigned long long st[12];  // JST_* below
   // ---- grid barrier ----

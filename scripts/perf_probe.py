@@ -23,7 +23,7 @@ for th in threads:
             if best is None or st["apply_ms"] < best["apply_ms"]:
                 best = st
         print(json.dumps({"threads": th, "name": c.name, "applies": len(c), "apply_ms": round(best["apply_ms"], 3),
-                          "us_per_gate": round(1e3 * best["apply_ms"] / len(c), 2), "items": best["items"],
+                          "us_per_gate": round(1e3 * best["apply_ms"] / len(c), 2), "items": best["items"], "thin": best["thin_gates"],
                           "retry": best["retry_rounds"], "nodes_created": best["nodes_created"], "gc": best["gc_runs"],
                           "cta": best["cta_launches"], "grid": best["grid_launches"]}), flush=True)
     eng.close()
