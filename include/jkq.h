@@ -121,6 +121,10 @@ typedef struct {
   double q0;
 } jkq_snode;
 
+/* layout version of the structs in this header; a binding compares it with the value it was written against */
+#define JKQ_ABI_VERSION 3u
+uint32_t jkq_abi_version(void);
+
 int jkq_create(jkq_handle **out, const jkq_config *cfg);              /* replaces QMDDinit, QMDDpackage.cpp:1248 */
 void jkq_destroy(jkq_handle *h);
 const char *jkq_last_error(const jkq_handle *h);

@@ -7,7 +7,7 @@
  * exactly like the reference's 200-bit values are.  Each function cites the reference lines it
  * restates.  PARITY PINNING: this restatement is validated against the UNMODIFIED reference
  * engine compiled from /root/reference/src (oracle/build_ref.sh -> oracle/_ref/jku_ref) on
- * per-gate per-level node counts and final amplitudes (tests/test_oracle_vs_reference.py,
+ * per-gate per-level node counts and final amplitudes (tests/test_oracle.py,
  * golden outputs of the reference committed under tests/golden/).
  *
  * Differences from the reference that are deliberate and documented:
@@ -37,6 +37,9 @@ typedef uint64_t cw;
 
 static double Ctol = 1e-10; /* QMDDcomplexD.cpp:336 */
 static int tie_rule = 0;    /* --tie-tol: NOT the reference's rule (see normalize) */
+static long lossy_snaps_now = 0; /* Clookup hits of the current gate that identified two values more than 1e-13 apart */
+static long near_ties_now = 0; /* normalisations of the current gate that met two DIFFERENT magnitudes closer than the
+                                * snapping error (the reference decides those by 200-bit rounding noise, :565) */
 static double *cval;        /* index -> value          (Ctable)  */
 static uint8_t *calive;     /* erased by cleanCtable?            */
 static uint32_t Ctentries, ccap;
@@ -82,7 +85,13 @@ static uint32_t real_lookup(double x) {
   int64_t k = (int64_t)floor(x / Ctol);
   uint32_t idx;
   for (int d = -1; d <= 1; d++)
-    if (vtab_get(k + d, &idx) && fabs(cval[idx] - x) <= Ctol) return idx;
+    if (vtab_get(k + d, &idx) && fabs(cval[idx] - x) <= Ctol) {
+      /* a DIFFERENT value (further away than any FP64 rounding of the same quantity) identified with an entry: from
+       * here on the diagram depends on which values happened to be inserted first, i.e. on the exact sequence of
+       * intermediate results of the reference's recursion */
+      if (fabs(cval[idx] - x) > 1e-13 * (x > 1.0 ? x : 1.0)) lossy_snaps_now++;
+      return idx;
+    }
   if (Ctentries == ccap) {
     ccap *= 2;
     cval = (double *)realloc(cval, ccap * sizeof(double));
@@ -281,7 +290,9 @@ static Edge normalize(Edge e) {
     /* strict >, first index wins ties (:565).  With --tie-tol (study instrument, off by default) two
      * magnitudes closer than the snapping error of their canonical parts count as a tie, which is
      * what the CUDA engine does (DESIGN.md "normalisation ties"). */
-    double slack = tie_rule ? 4.0 * Ctol * sqrt(m > best ? m : best) : 0.0;
+    double near = 4.0 * Ctol * sqrt(m > best ? m : best);
+    double slack = tie_rule ? near : 0.0;
+    if (max != -1 && m != best && fabs(m - best) <= near) near_ties_now++;
     if (max == -1 || m > best + slack) { best = m; max = i; }
   }
   if (max == -1) { e.w = C_ZERO; return e; }
@@ -779,6 +790,18 @@ static int hent_cmp(const void *a, const void *b) {
   return x < y ? -1 : x > y;
 }
 
+/* debugging aid: the live nodes of one level of the final state, on stderr */
+static int dump_level = -1;
+static void dump_nodes(Edge e, uint8_t *seen) {
+  if (e.p == NULLP || e.p == TNODE || seen[e.p]) return;
+  seen[e.p] = 1;
+  Node *nd = &nodes[e.p];
+  if (nd->v == dump_level)
+    fprintf(stderr, "node %d: e0 -> %d w=(%.17g, %.17g)  e2 -> %d w=(%.17g, %.17g)\n", e.p, nd->e[0].p, c_re(nd->e[0].w), c_im(nd->e[0].w),
+            nd->e[2].p, c_re(nd->e[2].w), c_im(nd->e[2].w));
+  for (int i = 0; i < 4; i++) dump_nodes(nd->e[i], seen);
+}
+
 int main(int argc, char **argv) {
   const char *circuit = NULL;
   long shots = 0, amp_limit = 0, shot_offset = 0;
@@ -797,6 +820,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--slab-ascending")) slab_descending = 0;
     else if (!strcmp(argv[i], "--dump-ctable")) dump_ctable = 1;
     else if (!strcmp(argv[i], "--tie-tol")) tie_rule = 1;
+    else if (!strcmp(argv[i], "--dump-level") && i + 1 < argc) dump_level = atoi(argv[++i]);
   }
   FILE *f = circuit ? fopen(circuit, "r") : NULL;
   if (!f) { fprintf(stderr, "usage: qmdd_oracle --circuit FILE [--shots N] [--seed S] [--levels] [--amps] [--rng rand|philox]\n"); return 2; }
@@ -805,8 +829,9 @@ int main(int argc, char **argv) {
   int n = 0, line[MAXN];
   for (int i = 0; i < MAXN; i++) line[i] = -1;
   char w[64], a1[64], a2[64], a3[64];
-  size_t applies = 0, lvcap = 0, lvn = 0;
+  size_t applies = 0, lvcap = 0, lvn = 0, ntcap = 0;
   int *lv = NULL;
+  long *nt = NULL, *ls = NULL;
   int peak_active = 0;
   struct timespec t0, t1;
   double t_apply = 0;
@@ -854,8 +879,20 @@ int main(int argc, char **argv) {
     Edge g = QMDDmvlgate(m, n, line);
     for (int i = 0; i < nctl; i++) line[n - 1 - ctl[i]] = -1;
     line[n - 1 - target] = -1;
+    near_ties_now = 0;
+    if (!is_u) lossy_snaps_now = 0;  /* (a U gate's matrix entries were looked up above: they count for this gate) */
     ApplyGate(g);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (levels) {
+      if (applies + 1 > ntcap) {
+        ntcap = ntcap * 2 + 4096;
+        nt = (long *)realloc(nt, ntcap * sizeof(long));
+        ls = (long *)realloc(ls, ntcap * sizeof(long));
+      }
+      nt[applies] = near_ties_now;
+      ls[applies] = lossy_snaps_now;
+    }
+    lossy_snaps_now = 0;
     t_apply += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     applies++;
     if (ActiveNodeCount > peak_active) peak_active = ActiveNodeCount;
@@ -865,6 +902,12 @@ int main(int argc, char **argv) {
     }
   }
   fclose(f);
+  if (dump_level >= 0) {
+    uint8_t *seen = (uint8_t *)calloc(nalloc, 1);
+    fprintf(stderr, "root weight (%.17g, %.17g)\n", c_re(circ_e.w), c_im(circ_e.w));
+    dump_nodes(circ_e, seen);
+    free(seen);
+  }
   printf("{\n \"n\": %d,\n \"applies\": %zu,\n \"t_apply_s\": %.9g,\n", n, applies, t_apply);
   printf(" \"nodes_created\": %ld,\n \"ut_lookups\": %ld,\n", (long)(UTlookups - UTmatch), (long)UTlookups);
   printf(" \"ct_look_mult\": %ld, \"ct_hit_mult\": %ld, \"ct_look_add\": %ld, \"ct_hit_add\": %ld,\n",
@@ -882,6 +925,12 @@ int main(int argc, char **argv) {
       for (int v = 0; v < n; v++) printf("%s%d", v ? "," : "", lv[g * n + v]);
       printf("]");
     }
+    printf("]");
+    printf(",\n \"near_ties_per_gate\": [");
+    for (size_t g = 0; g < applies; g++) printf("%s%ld", g ? "," : "", nt[g]);
+    printf("]");
+    printf(",\n \"lossy_snaps_per_gate\": [");
+    for (size_t g = 0; g < applies; g++) printf("%s%ld", g ? "," : "", ls[g]);
     printf("]");
   }
   if (amps) {

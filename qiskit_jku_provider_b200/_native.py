@@ -7,6 +7,7 @@ import os
 from ._build import LIB, build_native, stale
 
 _lib = None
+ABI_VERSION = 3  # include/jkq.h JKQ_ABI_VERSION: bumped whenever a struct of the C ABI changes layout
 
 
 class JkqConfig(C.Structure):
@@ -42,6 +43,7 @@ class JkqSNode(C.Structure):
 # every symbol include/jkq.h declares: (name, restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = [
+    ("jkq_abi_version", C.c_uint32, []),
     ("jkq_create", C.c_int, [C.POINTER(_H), C.POINTER(JkqConfig)]),
     ("jkq_destroy", None, [_H]),
     ("jkq_last_error", C.c_char_p, [_H]),
@@ -90,13 +92,22 @@ def load():
         return _lib
     if stale():  # sources newer than the library (or no library yet): rebuild when nvcc is around
         try:
-            build_native()
+            from ._build import nvcc_path
+            nvcc_path()
+            have_nvcc = True
         except Exception:
-            pass
+            have_nvcc = False
+        if have_nvcc:
+            build_native()  # a failed rebuild must not leave Python bound to a stale binary with other struct layouts
     if not os.path.exists(LIB):
         raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the engine is CUDA only, there is no CPU fallback)" % LIB)
     lib = C.CDLL(LIB)
+    lib.jkq_abi_version.restype = C.c_uint32
+    got = lib.jkq_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError("%s has ABI version %d, this package binds version %d: rebuild the library "
+                          "(python -c 'import __graft_entry__ as g; g.build()')" % (LIB, got, ABI_VERSION))
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)
         fn.restype = res

@@ -952,9 +952,15 @@ JD bool cta_norms(Ctx &c, ShotScratch *X) {
           }
       }
     block_sync();
+    // every thread takes the SAME snapshot of the list: the counter and the failure flag are read between two
+    // barriers, before any warp starts appending the next level (a slower warp would otherwise see entries of the
+    // level after next as part of this one)
+    const uint32_t cnt_now = X->cnt;
+    const int fail_now = X->fail;
+    block_sync();
     b = e;
-    e = X->cnt < 1024u ? X->cnt : 1024u;
-    if (X->fail) return false;
+    e = cnt_now < 1024u ? cnt_now : 1024u;
+    if (fail_now) return false;
   }
   // level L occupies [lvl_b[L], lvl_b[L - 1]) (level 0 ends at cnt); bottom-up like build_sampling
   for (int L = 0; L < n; L++) {

@@ -408,6 +408,7 @@ static const char *status_text(int s) {
   }
 }
 
+extern "C" uint32_t jkq_abi_version(void) { return JKQ_ABI_VERSION; }
 extern "C" const char *jkq_last_error(const jkq_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
 static void free_hist(jkq_handle *h) {

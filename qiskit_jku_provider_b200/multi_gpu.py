@@ -142,7 +142,9 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None, 
             engine.dd_import(n, nodes, root, mm)
     lo, hi = shard(total_shots, rank, world)
     engine.sample(hi - lo, seed=seed, shot_offset=lo)
-    n_bits = int(sum(1 for b in mm if b < 64))
+    # histogram keys are indexed by classical-bit POSITION: the width is the highest position + 1, not the number of
+    # measured qubits (a sparse map such as {0: 5} has one measured qubit and keys up to 32)
+    n_bits = max([int(b) for b in mm if b < 64] + [0]) + 1
     if world > 1 and sparse == "owner" and n_bits > DENSE_MAX_BITS and dist.get_backend() == "nccl":
         owned, total, sent, _ = merge_counts_by_owner(dist, engine)
         return {"owned": owned, "distinct_total": total, "pairs_sent": sent}, engine.stats()
@@ -168,5 +170,9 @@ def run_shots_sharded(dist, runner, n_qubits, ops, total_shots, seed, measure_se
     uniq, cnt = np.unique(good, return_counts=True) if len(good) else (np.zeros(0, np.uint64), np.zeros(0, np.int64))
     failed = [lo + int(i) for i in np.nonzero(np.asarray(status))[0]]
     if world > 1:
-        return merge_counts(dist, uniq.astype(np.uint64), cnt.astype(np.uint64), n_bits if n_bits is not None else int(n_qubits)), failed, ms
+        if n_bits is None:  # widest classical bit any MEASURE / MEASURE_ONE op writes (+ 1), not the qubit count
+            n_bits = max([int(o["arg"]) + 1 for o in ops if int(o["kind"]) in (2, 4)] + [1]) if hasattr(ops, "__iter__") and len(ops) and isinstance(ops[0], dict) else 64
+        if len(uniq) and int(uniq.max()) >= (1 << min(int(n_bits), 63)):
+            n_bits = 64  # a key outside the declared width: take the sparse merge
+        return merge_counts(dist, uniq.astype(np.uint64), cnt.astype(np.uint64), int(n_bits)), failed, ms
     return {int(k): int(v) for k, v in zip(uniq, cnt)}, failed, ms

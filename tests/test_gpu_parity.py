@@ -50,8 +50,8 @@ def test_golden_reference_parity(eng, oracle_mod, name, mode):
     ref = np.array([complex(*a) for a in g["amps"]])
     assert np.abs(amps - ref).max() < AMP_TOL
     lg = eng.level_log(len(circ))
-    level_parity(g["level_counts_per_gate"], lg, name)       # vs the unmodified reference
     o = oracle_mod.run_oracle(circ, shots=2048, seed=5, levels=True, extra=TIE)
+    level_parity(g["level_counts_per_gate"], lg, name, o)  # vs the unmodified reference
     assert lg == o["level_counts_per_gate"]                    # vs the oracle, every gate, every level
     assert eng.level_counts() == o["level_counts"]
     assert eng.counts_bitstrings() == o["counts"]              # same Philox stream -> identical counts
