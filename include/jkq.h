@@ -113,6 +113,8 @@ typedef struct {
   double norm;               /* squared norm of the final state                                */
   uint64_t distinct_outcomes;
   uint64_t thin_gates;       /* gates applied below the cursor edges without work items (thin_gate) */
+  uint64_t h2d_bytes;        /* bytes this handle copied host -> device since jkq_create (every copy is counted) */
+  uint64_t d2h_bytes;        /* ... device -> host                                                               */
 } jkq_stats;
 
 /* sampling record exported for multi-GPU shot sharding (16 bytes) */
@@ -122,7 +124,7 @@ typedef struct {
 } jkq_snode;
 
 /* layout version of the structs in this header; a binding compares it with the value it was written against */
-#define JKQ_ABI_VERSION 3u
+#define JKQ_ABI_VERSION 5u
 uint32_t jkq_abi_version(void);
 
 int jkq_create(jkq_handle **out, const jkq_config *cfg);              /* replaces QMDDinit, QMDDpackage.cpp:1248 */
@@ -141,6 +143,8 @@ int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offse
 int jkq_run(jkq_handle *h, uint64_t shots, uint64_t seed);
 
 int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, size_t cap, size_t *n);
+/* give the histogram's device memory back (a 1e9-shot histogram of QFT-32 holds 34 GB); the next jkq_sample allocates anew */
+int jkq_release_histogram(jkq_handle *h);
 int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, size_t cap_amplitudes);
 int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count, double *re_im); /* GetElementOfVector */
 int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n);              /* Active[v] */
@@ -158,6 +162,31 @@ int jkq_dd_export(jkq_handle *h, jkq_snode *host_nodes, size_t cap, uint32_t *n_
 int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *host_nodes, uint32_t n_nodes, uint32_t root,
                   const uint8_t *clbit_of_level);
 int jkq_get_measure_map(jkq_handle *h, uint8_t *clbit_of_level, size_t n);
+/* the same export / import with DEVICE buffers of the caller (any device of this process): both ends of an NCCL
+ * broadcast of the sampling DD, no host staging */
+int jkq_dd_export_device(jkq_handle *h, void *dev_nodes, size_t cap, uint32_t *n_nodes, uint32_t *root);
+int jkq_dd_import_device(jkq_handle *h, uint32_t n_qubits, const void *dev_nodes, uint32_t n_nodes, uint32_t root,
+                         const uint8_t *clbit_of_level);
+
+/* Shot sampling over several GPUs of ONE process (the reference draws its shots one after the other on one
+ * core, QASMsimulator.cpp:487-500).  `h` holds the state (jkq_apply or jkq_dd_import); devices[0..n) are CUDA ordinals,
+ * h's own device among them or not.  The sampling DD goes to a helper engine per other device by peer copy
+ * (cudaMemcpyPeerAsync over NVLink), device i draws shots [i S / n, (i + 1) S / n) of the Philox stream `seed` -- the
+ * very shots a one-GPU jkq_sample(h, S, seed, 0, 0) draws -- and the histograms are merged on the device into h's,
+ * which jkq_get_counts returns.  An outcome space too large for one GPU stays distributed: st->merged = 0 and
+ * st->distinct_total is the sum over the devices. */
+typedef struct {
+  uint32_t n_devices, merged;
+  uint64_t distinct_total;
+  uint64_t dd_bytes;              /* bytes of sampling DD copied to every other device                 */
+  double broadcast_ms;            /* peer copies, host clock                                           */
+  double sample_wall_ms;          /* all devices sampling side by side, host clock                     */
+  double sample_kernel_ms_max;    /* CUDA-event time of the sampling kernel, max over the devices      */
+  double merge_ms;                /* compaction + peer copies + device merge, host clock               */
+  double wall_ms;                 /* the whole call                                                    */
+} jkq_multi_stats;
+int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint32_t n_devices, uint64_t shots, uint64_t seed,
+                         jkq_multi_stats *st);
 
 /* Sparse histogram exchange between GPUs: every outcome key has an owner rank (a hash of the key).
  * jkq_counts_partition sorts this handle's (key, count) pairs by owner into DEVICE buffers of the caller (`cap` entries

@@ -7,7 +7,7 @@ import os
 from ._build import LIB, build_native, stale
 
 _lib = None
-ABI_VERSION = 3  # include/jkq.h JKQ_ABI_VERSION: bumped whenever a struct of the C ABI changes layout
+ABI_VERSION = 5  # include/jkq.h JKQ_ABI_VERSION: bumped whenever a struct of the C ABI changes layout
 
 
 class JkqConfig(C.Structure):
@@ -27,7 +27,7 @@ class JkqStats(C.Structure):
         "gates", "items", "nodes_created", "value_inserts", "gc_runs", "gc_nodes_copied", "retry_rounds",
         "max_frontier", "live_nodes", "live_values", "cta_launches", "grid_launches", "sample_launches")] + [
         ("apply_ms", C.c_double), ("sample_ms", C.c_double), ("sample_kernel_ms", C.c_double), ("norm", C.c_double),
-        ("distinct_outcomes", C.c_uint64), ("thin_gates", C.c_uint64)]
+        ("distinct_outcomes", C.c_uint64), ("thin_gates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class JkqProgramInfo(C.Structure):
@@ -38,6 +38,12 @@ class JkqProgramInfo(C.Structure):
 
 class JkqSNode(C.Structure):
     _fields_ = [("c0", C.c_uint32), ("c1", C.c_uint32), ("q0", C.c_double)]
+
+
+class JkqMultiStats(C.Structure):
+    _fields_ = [("n_devices", C.c_uint32), ("merged", C.c_uint32), ("distinct_total", C.c_uint64), ("dd_bytes", C.c_uint64),
+                ("broadcast_ms", C.c_double), ("sample_wall_ms", C.c_double), ("sample_kernel_ms_max", C.c_double),
+                ("merge_ms", C.c_double), ("wall_ms", C.c_double)]
 
 
 # every symbol include/jkq.h declares: (name, restype, argtypes)
@@ -53,6 +59,7 @@ SYMBOLS = [
     ("jkq_sample", C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
     ("jkq_run", C.c_int, [_H, C.c_uint64, C.c_uint64]),
     ("jkq_get_counts", C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("jkq_release_histogram", C.c_int, [_H]),
     ("jkq_get_statevector", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.c_size_t]),
     ("jkq_get_amplitudes", C.c_int, [_H, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
     ("jkq_get_level_counts", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t]),
@@ -64,6 +71,9 @@ SYMBOLS = [
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("jkq_dd_import", C.c_int, [_H, C.c_uint32, C.POINTER(JkqSNode), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     ("jkq_get_measure_map", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_size_t]),
+    ("jkq_dd_export_device", C.c_int, [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("jkq_dd_import_device", C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
+    ("jkq_sample_multi_gpu", C.c_int, [_H, C.POINTER(C.c_int32), C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(JkqMultiStats)]),
     ("jkq_counts_partition", C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     ("jkq_counts_merge", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     ("jkq_batch_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.POINTER(JkqConfig)]),

@@ -514,6 +514,23 @@ JD uint32_t block_scan_flag(Ctx &c, bool flag, uint32_t *total) {
 #endif
 
 // Out of line, context by value (the caller's stays in registers): gc_call() below takes over the ring index.
+// collector / table rebuild: node `id` (not in the table yet, nobody looks anything up meanwhile) into the HBM table
+JD void ut_put_hbm(JEng *E, unsigned long long gen, const JNode &nn, uint32_t id) {
+  uint32_t h = ut_hash(nn) & E->utab_mask;
+  for (;;) {
+    unsigned long long sv = ld_r<MODE_GRID>(E->utab + h);
+    if ((sv >> 32) != (gen >> 32) && jatomic_cas(E->utab + h, sv, gen | id) == sv) return;
+    h = (h + 1) & E->utab_mask;
+  }
+}
+// The part of the HBM value table in use.  Sizing it to the reals that survive a sweep (16 slots each) cut the clears
+// to a few MB, but a single gate of a blown-up circuit can add more reals than the whole previous state held
+// (random n=20, 200 ops: "value table full" at gate 601) and an open-addressing table cannot grow in the middle of
+// a phase -- so the part in use is the whole allocation, cleared only by a sweep of the reals (a handful per run:
+// the limit doubles, Simulator.cpp:495-497), not by every collection.  Generation tags as in the unique table do not
+// work here: a claimed slot takes atomicMin proposals and would have to be reset first.
+JD uint32_t vt_mask_for(const JEng *E, uint32_t) { return E->vtab_mask; }
+
 template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   JEng *E = c.E;
   const int n = (int)E->n;
@@ -528,15 +545,13 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   if (MODE == MODE_CTA && vlimit > (c.sh->val_hard / 4) * 3) vlimit = (c.sh->val_hard / 4) * 3;
   const bool clean_vals = force_vals || old_vals > vlimit;
   for (uint32_t i = c.tid; i < old_count; i += c.nth) E->fwd[i] = 0;
-  if (MODE == MODE_GRID)
-    for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
-  else
+  // The HBM unique table is NOT cleared: it starts a new generation (below).  The value table is cleared only when the
+  // reals are swept.  (Clearing both on every collection wrote 6.4 GB of zeros on random n=18 / 160 ops, ncu r1:
+  // dram__bytes_write 11x the algorithmic traffic.)
+  if (MODE != MODE_GRID)
     for (uint32_t i = c.ltid; i < JKQ_SUT_SLOTS; i += c.lnth) c.sh->utab[i] = 0;
-  if (clean_vals) {
+  if (clean_vals)
     for (uint32_t i = c.tid; i < old_vals; i += c.nth) E->vfwd[i] = 0;
-    if (MODE == MODE_GRID)
-      for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
-  }
   if (MODE == MODE_CTA)  // node ids are about to change: memoised chain rebuilds are void
     for (uint32_t i = c.ltid; i < JKQ_SCMEMO; i += c.lnth) c.sh->cmemo[i] = 0;
   if (MODE == MODE_CTA && (clean_vals || reload)) {
@@ -625,7 +640,9 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
       E->val_epoch++;  // ids renumbered: cached gate-matrix ids are void
       if (E->val_gc_limit < 2 * nv) E->val_gc_limit *= 2;  // Simulator.cpp:495-497
       if (E->val_gc_limit > E->val_cap / 2) E->val_gc_limit = E->val_cap / 2;
+      if (MODE == MODE_GRID) E->vt_cur = vt_mask_for(E, nv);
     }
+    if (MODE == MODE_GRID) E->ut_gen++;  // every older unique-table entry now reads as empty
     E->root = 1;
     if (MODE == MODE_CTA) { c.sh->root = 1; c.sh->rootw = E->rootw; c.sh->flushed_nodes = live + 1; c.sh->flushed_vals = *cnt_vals<MODE>(c); }
     *cnt_nodes<MODE>(c) = live + 1;
@@ -645,6 +662,12 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   sync_or<MODE>(c, 0);  // (a JF_GRID raised here is picked up below through sh->want_grid)
   const uint32_t nv = rd_vals<MODE>(c);
   const bool fits = MODE != MODE_CTA || !c.sh->want_grid;
+  const unsigned long long ugen = MODE == MODE_GRID ? (unsigned long long)ld_s<MODE_GRID>(&E->ut_gen) << 32 : 0ull;
+  if (MODE == MODE_GRID && clean_vals) {  // the part of the value table about to be filled
+    const uint32_t vm = ld_s<MODE_GRID>(&E->vt_cur);
+    for (uint32_t i = c.tid; i <= vm; i += c.nth) vt_clear_slot(E->vtab + i);
+    sync_or<MODE>(c, 0);
+  }
   if (MODE == MODE_CTA && !fits && c.ltid == 0) c.sh->nofit = 1;
   // copy back with remapped weights, rebuild the unique table
   for (uint32_t i = c.tid; i < live; i += c.nth) {
@@ -656,10 +679,8 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
       nn.w = ((uint64_t)hr << 32) | hi;
     }
     E->nodes[i + 1] = nn;
-    if (MODE == MODE_GRID) {
-      uint32_t h = ut_hash(nn) & E->utab_mask;
-      while (jatomic_cas(E->utab + h, 0u, i + 1) != 0) h = (h + 1) & E->utab_mask;
-    } else if (fits) {
+    if (MODE == MODE_GRID) ut_put_hbm(E, ugen, nn, i + 1);
+    else if (fits) {
       c.sh->nodes[i + 1] = nn;
       uint32_t h = ut_hash(nn) & (JKQ_SUT_SLOTS - 1);
       while (jatomic_cas(&c.sh->utab[h], 0u, i + 1) != 0) h = (h + 1) & (JKQ_SUT_SLOTS - 1);
@@ -769,14 +790,16 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       // No root to collect from (the state is a saved cursor): hash every arena node and every real as
       // they are.  Ids stay what they are; slots that lost an insertion race carry a tombstone.
       const uint32_t nn = ld_s<MODE>(&E->node_count), nv = ld_s<MODE>(&E->val_count);
-      for (uint32_t i = c.tid; i <= E->utab_mask; i += c.nth) E->utab[i] = 0;
-      for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
+      if (c.block0 && c.ltid == 0) { E->ut_gen++; E->vt_cur = vt_mask_for(E, nv); }
+      sync_or<MODE>(c, 0);
+      const unsigned long long ugen = (unsigned long long)ld_s<MODE>(&E->ut_gen) << 32;
+      const uint32_t vm = ld_s<MODE>(&E->vt_cur);
+      for (uint32_t i = c.tid; i <= vm; i += c.nth) vt_clear_slot(E->vtab + i);
       sync_or<MODE>(c, 0);
       for (uint32_t i = 1 + c.tid; i < nn; i += c.nth) {
         const JNode nd = ld_s<MODE>(E->nodes + i);
         if (nd.c1 == JN_TOMB) continue;
-        uint32_t h = ut_hash(nd) & E->utab_mask;
-        while (jatomic_cas(E->utab + h, 0u, i) != 0) h = (h + 1) & E->utab_mask;
+        ut_put_hbm(E, ugen, nd, i);
       }
       for (uint32_t i = 1 + c.tid; i < nv; i += c.nth) vt_put<MODE>(c.E, c.sh, i, ld_s<MODE>(E->vals + i));
     } else if (gc_call<MODE>(c, false, true) & JF_ERROR) return JF_ERROR;

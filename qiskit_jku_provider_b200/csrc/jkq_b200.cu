@@ -9,6 +9,8 @@
 #include <cstring>
 #include <array>
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -178,20 +180,24 @@ struct SampleParams {
 #define JH_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define JH_SMEM 2048
 
-// (the all-ones outcome of a 64-bit register collides with the empty marker: it is counted in the extra word
-// hc[slots] behind the table)
-__device__ __forceinline__ void hist_global_add(unsigned long long *hk, unsigned long long *hc, uint32_t hmask, uint64_t key,
-                                                unsigned long long cnt, int *overflow) {
-  if (key == JH_EMPTY) { atomicAdd(hc + (size_t)hmask + 1, cnt); return; }
+// Count histogram in HBM: open addressing over FUSED 16-byte slots (key, count) -- the probe that finds (or claims)
+// the key and the add that counts the shot touch the same 32-byte sector, where separate key / count arrays cost two
+// to three sectors per shot.  The all-ones outcome of a 64-bit register collides with the empty
+// marker: it is counted in the extra slot hs[slots] behind the table.
+struct __align__(16) JHSlot {
+  unsigned long long key, cnt;
+};
+__device__ __forceinline__ void hist_global_add(JHSlot *hs, uint32_t hmask, uint64_t key, unsigned long long cnt, int *overflow) {
+  if (key == JH_EMPTY) { atomicAdd(&hs[(size_t)hmask + 1].cnt, cnt); return; }
   uint32_t h = (uint32_t)jmix(key) & hmask;
   for (uint32_t probes = 0; probes <= hmask; probes++) {
-    unsigned long long old = hk[h];
+    unsigned long long old = hs[h].key;
     if (old != key) {
       if (old != JH_EMPTY) { h = (h + 1) & hmask; continue; }
-      old = atomicCAS(hk + h, JH_EMPTY, (unsigned long long)key);
+      old = atomicCAS(&hs[h].key, JH_EMPTY, (unsigned long long)key);
       if (old != JH_EMPTY && old != key) { h = (h + 1) & hmask; continue; }
     }
-    atomicAdd(hc + h, cnt);
+    atomicAdd(&hs[h].cnt, cnt);
     return;
   }
   *overflow = 1;
@@ -201,8 +207,7 @@ __device__ __forceinline__ void hist_global_add(unsigned long long *hk, unsigned
 // dependent 16-byte loads through L1/L2, equal outcomes merged inside the warp (__match_any_sync),
 // then in a shared-memory hash, then in the HBM hash histogram.
 __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, uint32_t root, int n, SampleParams sp, uint64_t seed,
-                                               uint64_t shot0, uint64_t nshots, unsigned long long *hk, unsigned long long *hc,
-                                               uint32_t hmask, int *overflow) {
+                                               uint64_t shot0, uint64_t nshots, JHSlot *hs, uint32_t hmask, int *overflow) {
   __shared__ unsigned long long skeys[JH_SMEM];
   __shared__ unsigned int scnts[JH_SMEM];
   for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x) { skeys[i] = JH_EMPTY; scnts[i] = 0; }
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
     uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
     if (!active || lane != (uint32_t)(__ffs(peers) - 1)) continue;
     uint32_t cnt = __popc(peers);
-    if (key == JH_EMPTY) { hist_global_add(hk, hc, hmask, key, cnt, overflow); continue; }
+    if (key == JH_EMPTY) { hist_global_add(hs, hmask, key, cnt, overflow); continue; }
     uint32_t h = (uint32_t)jmix(key) & (JH_SMEM - 1);
     bool done = false;
     for (int p = 0; p < 8 && !done; p++) {
@@ -228,32 +233,31 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
       atomicAdd(&scnts[h], cnt);
       done = true;
     }
-    if (!done) hist_global_add(hk, hc, hmask, key, cnt, overflow);
+    if (!done) hist_global_add(hs, hmask, key, cnt, overflow);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x)
-    if (skeys[i] != JH_EMPTY && scnts[i]) hist_global_add(hk, hc, hmask, skeys[i], scnts[i], overflow);
+    if (skeys[i] != JH_EMPTY && scnts[i]) hist_global_add(hs, hmask, skeys[i], scnts[i], overflow);
 }
 
-__global__ void k_hist_fill(unsigned long long *hk, unsigned long long *hc, uint64_t slots) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-    hk[i] = JH_EMPTY;
-    hc[i] = 0;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) hc[slots] = 0;
+__global__ void k_hist_fill(JHSlot *hs, uint64_t slots) {
+  JHSlot e;
+  e.key = JH_EMPTY; e.cnt = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= slots; i += (uint64_t)gridDim.x * blockDim.x) hs[i] = e;
 }
 
-__global__ void k_hist_compact(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, unsigned long long *ok,
-                               unsigned long long *oc, unsigned long long *n_out, uint64_t cap) {
+__global__ void k_hist_compact(const JHSlot *hs, uint64_t slots, unsigned long long *ok, unsigned long long *oc, unsigned long long *n_out,
+                               uint64_t cap) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (hk[i] != JH_EMPTY) {
+    const JHSlot e = hs[i];
+    if (e.key != JH_EMPTY) {
       unsigned long long p = atomicAdd(n_out, 1ull);
-      if (p < cap) { ok[p] = hk[i]; oc[p] = hc[i]; }
+      if (p < cap) { ok[p] = e.key; oc[p] = e.cnt; }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hs[slots].cnt) {
     unsigned long long p = atomicAdd(n_out, 1ull);
-    if (p < cap) { ok[p] = JH_EMPTY; oc[p] = hc[slots]; }
+    if (p < cap) { ok[p] = JH_EMPTY; oc[p] = hs[slots].cnt; }
   }
 }
 
@@ -264,26 +268,28 @@ __global__ void k_hist_compact(const unsigned long long *hk, const unsigned long
 // it received into its histogram with the same insert the sampler uses.
 __device__ __forceinline__ uint32_t hist_owner(uint64_t key, uint32_t world) { return (uint32_t)((jmix(key ^ 0x5851F42D4C957F2Dull) >> 32) % world); }
 
-__global__ void __launch_bounds__(256) k_hist_owner_count(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, uint32_t world,
-                                                          unsigned long long *per_owner) {
+__global__ void __launch_bounds__(256) k_hist_owner_count(const JHSlot *hs, uint64_t slots, uint32_t world, unsigned long long *per_owner) {
   __shared__ unsigned int s_cnt[64];
   for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x)
-    if (hk[i] != JH_EMPTY) atomicAdd(&s_cnt[hist_owner(hk[i], world)], 1u);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) atomicAdd(&s_cnt[hist_owner(JH_EMPTY, world)], 1u);
+    if (hs[i].key != JH_EMPTY) atomicAdd(&s_cnt[hist_owner(hs[i].key, world)], 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hs[slots].cnt) atomicAdd(&s_cnt[hist_owner(JH_EMPTY, world)], 1u);
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
     if (s_cnt[i]) atomicAdd(per_owner + i, (unsigned long long)s_cnt[i]);
 }
 
-__global__ void __launch_bounds__(256) k_hist_owner_scatter(const unsigned long long *hk, const unsigned long long *hc, uint64_t slots, uint32_t world,
-                                                            unsigned long long *cursor, unsigned long long *out_keys, unsigned long long *out_counts) {
+__global__ void __launch_bounds__(256) k_hist_owner_scatter(const JHSlot *hs, uint64_t slots, uint32_t world, unsigned long long *cursor,
+                                                            unsigned long long *out_keys, unsigned long long *out_counts) {
   // one atomic per (warp, owner) instead of one per pair: the `world` cursors are the only contended words
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, rounded = (slots + 31) & ~31ull;
   const uint32_t lane = threadIdx.x & 31;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-    const unsigned long long key = i < slots ? hk[i] : JH_EMPTY;
+    JHSlot e;
+    e.key = JH_EMPTY; e.cnt = 0;
+    if (i < slots) e = hs[i];
+    const unsigned long long key = e.key;
     const bool live = key != JH_EMPTY;
     const uint32_t owner = live ? hist_owner(key, world) : 0xFFFFFFFFu;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, owner);
@@ -293,18 +299,18 @@ __global__ void __launch_bounds__(256) k_hist_owner_scatter(const unsigned long 
     if (lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const unsigned long long p = base + __popc(peers & ((1u << lane) - 1u));
-    out_keys[p] = key; out_counts[p] = hc[i];
+    out_keys[p] = key; out_counts[p] = e.cnt;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hc[slots]) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hs[slots].cnt) {
     const unsigned long long p = atomicAdd(cursor + hist_owner(JH_EMPTY, world), 1ull);
-    out_keys[p] = JH_EMPTY; out_counts[p] = hc[slots];
+    out_keys[p] = JH_EMPTY; out_counts[p] = hs[slots].cnt;
   }
 }
 
-__global__ void __launch_bounds__(256) k_hist_merge(unsigned long long *hk, unsigned long long *hc, uint32_t hmask, const unsigned long long *in_keys,
-                                                    const unsigned long long *in_counts, uint64_t n, int *overflow) {
+__global__ void __launch_bounds__(256) k_hist_merge(JHSlot *hs, uint32_t hmask, const unsigned long long *in_keys, const unsigned long long *in_counts,
+                                                    uint64_t n, int *overflow) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    if (in_counts[i]) hist_global_add(hk, hc, hmask, in_keys[i], in_counts[i], overflow);
+    if (in_counts[i]) hist_global_add(hs, hmask, in_keys[i], in_counts[i], overflow);
 }
 
 // Roofline denominators measured on the device in use: uniform random 32-byte sector reads
@@ -356,6 +362,7 @@ struct jkq_handle {
   double *scalar_dev = nullptr;
   uint32_t n = 0;
   bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied by this handle since it was created (jcopy)
   bool wide_now = false;            // the single-CTA kernel of this circuit is launched with cfg.cta_threads (it asked for them)
   SampleParams sp;
   uint32_t dd_root = 0, dd_nodes = 0;
@@ -365,13 +372,22 @@ struct jkq_handle {
   uint64_t placeholder_gates = 0;   // projector / X slots of MEASURE_ONE and RESET applied by the last jkq_apply
   bool debug_stop_at_handover = false;  // testing aid: jkq_apply returns where the single-CTA path would hand over
   // histogram
-  unsigned long long *hk = nullptr, *hc = nullptr, *ok = nullptr, *oc = nullptr, *n_out = nullptr;
+  JHSlot *hs = nullptr;             // hslots + 1 fused (key, count) slots
+  unsigned long long *ok = nullptr, *oc = nullptr, *n_out = nullptr;
   int *overflow = nullptr;
   uint64_t hslots = 0, out_cap = 0;
   bool hist_valid = false;
   jkq_stats stats;
   int grid_blocks = 0;
 };
+
+// every host <-> device copy of a handle goes through here: the bytes are counted (jkq_stats.h2d_bytes / d2h_bytes,
+// what bench.py reports as the measured copies of a call)
+static cudaError_t jcopy(jkq_handle *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  if (kind == cudaMemcpyHostToDevice) h->h2d_bytes += bytes;
+  else if (kind == cudaMemcpyDeviceToHost) h->d2h_bytes += bytes;
+  return cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+}
 
 static int fail(jkq_handle *h, int code, const char *fmt, ...) {
   char buf[512];
@@ -412,8 +428,9 @@ extern "C" uint32_t jkq_abi_version(void) { return JKQ_ABI_VERSION; }
 extern "C" const char *jkq_last_error(const jkq_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
 static void free_hist(jkq_handle *h) {
-  cudaFree(h->hk); cudaFree(h->hc); cudaFree(h->ok); cudaFree(h->oc);
-  h->hk = h->hc = h->ok = h->oc = nullptr;
+  cudaFree(h->hs); cudaFree(h->ok); cudaFree(h->oc);
+  h->hs = nullptr;
+  h->ok = h->oc = nullptr;
   h->hslots = 0; h->out_cap = 0; h->hist_valid = false;
 }
 static void free_snapshots(jkq_handle *h) {
@@ -423,7 +440,9 @@ static void free_snapshots(jkq_handle *h) {
   h->prob_slots.clear();
 }
 
+static void multi_free(jkq_handle *src);
 extern "C" void jkq_destroy(jkq_handle *h) {
+  if (h) multi_free(h);
   if (!h) return;
   cudaSetDevice(h->device);
   JEng &E = h->host;
@@ -487,7 +506,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
     struct Part { void **ptr; size_t bytes; };
     const Part parts[] = {
         {(void **)&E.nodes, (size_t)E.node_cap * sizeof(JNode)}, {(void **)&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)},
-        {(void **)&E.utab, ((size_t)E.utab_mask + 1) * 4}, {(void **)&E.vals, (size_t)E.val_cap * 8}, {(void **)&E.vals_alt, (size_t)E.val_cap * 8},
+        {(void **)&E.utab, ((size_t)E.utab_mask + 1) * 8}, {(void **)&E.vals, (size_t)E.val_cap * 8}, {(void **)&E.vals_alt, (size_t)E.val_cap * 8},
         {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.pend, (size_t)E.pend_cap * 4},
         {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
         {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
@@ -500,6 +519,8 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
     for (const Part &p : parts) { *p.ptr = (char *)h->slab + off; off += (p.bytes + 255) & ~(size_t)255; }
   }
   // generation-tagged de-dup tables: zeroed once, never cleared again (the generation counts across circuits)
+  CU(cudaMemsetAsync(E.utab, 0, ((size_t)E.utab_mask + 1) * 8, h->stream));  // (generation 0 = never written)
+  E.ut_gen = 1; E.vt_cur = E.vtab_mask;
   CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
   CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
   CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
@@ -685,14 +706,14 @@ extern "C" int jkq_load_circuit(jkq_handle *h, uint32_t n_qubits, const jkq_op *
   if (!h->gates.empty()) {
     // (the previous circuit's copy has completed: every path synchronises the stream before a new load)
     memcpy(h->gates_pin, h->gates.data(), h->gates.size() * sizeof(JGate));
-    CU(cudaMemcpyAsync(h->gates_dev, h->gates_pin, h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+    CU(jcopy(h, h->gates_dev, h->gates_pin, h->gates.size() * sizeof(JGate), cudaMemcpyHostToDevice));
   }
   h->loaded = true; h->applied = false; h->sampling_ready = false; h->imported = false; h->hist_valid = false;
   return JKQ_E_OK;
 }
 
 static int pull_state(jkq_handle *h) {
-  CU(cudaMemcpyAsync(&h->host, h->dev, sizeof(JEng), cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, &h->host, h->dev, sizeof(JEng), cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }
@@ -751,8 +772,8 @@ static int run_segment(jkq_handle *h, int upto) {
     if (h->host.want_grid && h->host.want_wide && !h->host.cursor_saved && !grid && !h->wide_now) {
       h->wide_now = true;
       h->host.want_grid = 0; h->host.want_wide = 0;
-      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-      CU(cudaMemcpyAsync(&h->dev->want_wide, &h->host.want_wide, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+      CU(jcopy(h, &h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice));
+      CU(jcopy(h, &h->dev->want_wide, &h->host.want_wide, sizeof(uint32_t), cudaMemcpyHostToDevice));
       continue;
     }
     if ((h->host.want_grid || h->host.cursor_saved) && !grid) {
@@ -764,7 +785,7 @@ static int run_segment(jkq_handle *h, int upto) {
       if (h->cfg.force_mode == 1) return fail(h, JKQ_E_ITEM_FULL, "gate %d: state or frontier exceeds the single-CTA path and force_mode=1", h->host.next_gate);
       grid = true;
       h->host.want_grid = 0;
-      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      CU(jcopy(h, &h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice));
       continue;
     }
     return fail(h, JKQ_E_INTERNAL, "gate kernel stopped at gate %d of %d without a reason", h->host.next_gate, upto);
@@ -794,7 +815,7 @@ static int qubit_probability(jkq_handle *h, uint32_t qubit, double *p0) {
   if (rc) return rc;
   k_marginal<<<1, 256, 0, h->stream>>>(h->dev, h->snodes, h->prob, (int)(h->n - 1 - qubit), h->scalar_dev);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(p0, h->scalar_dev, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, p0, h->scalar_dev, 8, cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   h->sampling_ready = false;  // (k_marginal used the probability array as scratch)
   return JKQ_E_OK;
@@ -844,7 +865,7 @@ static int measure_collapse(jkq_handle *h, size_t i) {
     }
   }
   h->placeholder_gates += (uint64_t)n_slots;
-  CU(cudaMemcpyAsync(h->gates_dev + g0, &h->gates[g0], n_slots * sizeof(JGate), cudaMemcpyHostToDevice, h->stream));
+  CU(jcopy(h, h->gates_dev + g0, &h->gates[g0], n_slots * sizeof(JGate), cudaMemcpyHostToDevice));
   CU(cudaStreamSynchronize(h->stream));  // (the host copies of the gates are pageable)
   return run_segment(h, g0 + n_slots);
 }
@@ -909,7 +930,7 @@ extern "C" int jkq_apply(jkq_handle *h) {
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));
-  CU(cudaMemcpyAsync(h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice, h->stream));
+  CU(jcopy(h, h->dev, &E, sizeof(JEng), cudaMemcpyHostToDevice));
   k_init<MODE_GRID><<<1, 32, 0, h->stream>>>(h->dev);
   CU(cudaGetLastError());
   const uint64_t cta0 = h->stats.cta_launches, grid0 = h->stats.grid_launches;
@@ -959,7 +980,7 @@ extern "C" int jkq_apply(jkq_handle *h) {
       if (rc) return rc;
       // skip the guarded ops: their gate slots are stepped over
       h->host.next_gate = i + 1 + cnt < h->ops.size() ? h->gate_of_op[i + 1 + cnt] : (int)h->gates.size();
-      CU(cudaMemcpyAsync(&h->dev->next_gate, &h->host.next_gate, sizeof(h->host.next_gate), cudaMemcpyHostToDevice, h->stream));
+      CU(jcopy(h, &h->dev->next_gate, &h->host.next_gate, sizeof(h->host.next_gate), cudaMemcpyHostToDevice));
       CU(cudaStreamSynchronize(h->stream));
       i += 1 + cnt;
     } else {
@@ -1009,7 +1030,7 @@ static int build_sampling_now(jkq_handle *h) {
       if (h->cfg.force_mode == 1) return fail(h, JKQ_E_NODE_FULL, "state does not fit the single-CTA path and force_mode=1");
       grid = true;
       h->host.want_grid = 0;
-      CU(cudaMemcpyAsync(&h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      CU(jcopy(h, &h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice));
       continue;
     }
     break;
@@ -1022,7 +1043,12 @@ static int build_sampling_now(jkq_handle *h) {
   return JKQ_E_OK;
 }
 
+static int sample_impl(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offset, int accumulate, uint64_t expect_shots);
 extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offset, int accumulate) {
+  return sample_impl(h, shots, seed, shot_offset, accumulate, shots);
+}
+// expect_shots: what the histogram is sized for (>= shots: the shots other GPUs will merge into this one)
+static int sample_impl(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t shot_offset, int accumulate, uint64_t expect_shots) {
   if (!h) return JKQ_E_ARGUMENT;
   CU(cudaSetDevice(h->device));
   CU(cudaEventRecord(h->ev2, h->stream));
@@ -1035,18 +1061,18 @@ extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t
             h->stats.norm);
   int measured = 0;
   for (uint32_t L = 0; L < h->n; L++) measured += h->sp.bitpos[L] < 64;
-  uint64_t need = shots < (1ull << 40) ? shots : (1ull << 40);
+  if (expect_shots < shots) expect_shots = shots;
+  uint64_t need = expect_shots < (1ull << 40) ? expect_shots : (1ull << 40);
   if (measured < 40 && (1ull << measured) < need) need = 1ull << measured;
   uint64_t slots = pow2_at_least(need * 2, 1u << 12);
   if (!accumulate || !h->hist_valid || slots > h->hslots) {
     if (accumulate && h->hist_valid) return fail(h, JKQ_E_STATE, "accumulating histogram would need to grow; sample the largest batch first");
     if (slots > h->hslots) {
       free_hist(h);
-      CU(cudaMalloc(&h->hk, slots * 8));
-      CU(cudaMalloc(&h->hc, (slots + 1) * 8));
+      CU(cudaMalloc(&h->hs, (slots + 1) * sizeof(JHSlot)));
       h->hslots = slots;
     }
-    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots);
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
     h->hist_valid = true;
@@ -1055,14 +1081,14 @@ extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t
     uint64_t want = (shots + 255) / 256;
     int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
     CU(cudaEventRecord(h->ev3, h->stream));
-    k_sample<<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hk, h->hc,
+    k_sample<<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hs,
                                             (uint32_t)(h->hslots - 1), h->overflow);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     h->stats.sample_launches++;
   }
   int ovf = 0;
-  CU(cudaMemcpyAsync(&ovf, h->overflow, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, &ovf, h->overflow, 4, cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   if (ovf) return fail(h, JKQ_E_CAPACITY, "count histogram overflow");
   if (shots) {
@@ -1072,6 +1098,14 @@ extern "C" int jkq_sample(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t
     CU(cudaEventElapsedTime(&ms, h->ev2, h->ev1));
     h->stats.sample_ms = ms;
   }
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_release_histogram(jkq_handle *h) {
+  if (!h) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  free_hist(h);
   return JKQ_E_OK;
 }
 
@@ -1094,17 +1128,17 @@ extern "C" int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, s
     h->out_cap = want;
   }
   CU(cudaMemsetAsync(h->n_out, 0, 8, h->stream));
-  k_hist_compact<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, h->ok, h->oc, h->n_out, cap);
+  k_hist_compact<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots, h->ok, h->oc, h->n_out, cap);
   CU(cudaGetLastError());
   unsigned long long cnt = 0;
-  CU(cudaMemcpyAsync(&cnt, h->n_out, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, &cnt, h->n_out, 8, cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   *n = (size_t)cnt;
   h->stats.distinct_outcomes = cnt;
   if (cnt > cap) return keys ? fail(h, JKQ_E_CAPACITY, "%llu distinct outcomes, buffer holds %zu", cnt, cap) : JKQ_E_OK;
   if (cnt && keys && counts) {
-    CU(cudaMemcpyAsync(keys, h->ok, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(counts, h->oc, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(jcopy(h, keys, h->ok, cnt * 8, cudaMemcpyDeviceToHost));
+    CU(jcopy(h, counts, h->oc, cnt * 8, cudaMemcpyDeviceToHost));
     CU(cudaStreamSynchronize(h->stream));
   }
   return JKQ_E_OK;
@@ -1118,9 +1152,9 @@ extern "C" int jkq_counts_partition(jkq_handle *h, uint32_t world, uint64_t *dev
   unsigned long long *cnt = nullptr;
   CU(cudaMalloc(&cnt, 64 * 8));
   CU(cudaMemsetAsync(cnt, 0, 64 * 8, h->stream));
-  k_hist_owner_count<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, world, cnt);
+  k_hist_owner_count<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots, world, cnt);
   unsigned long long host_cnt[64];
-  cudaError_t e = cudaMemcpyAsync(host_cnt, cnt, 64 * 8, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = jcopy(h, host_cnt, cnt, 64 * 8, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { cudaFree(cnt); return fail(h, JKQ_E_CUDA, "jkq_counts_partition: %s", cudaGetErrorString(e)); }
   uint64_t total = 0;
@@ -1129,9 +1163,9 @@ extern "C" int jkq_counts_partition(jkq_handle *h, uint32_t world, uint64_t *dev
   h->stats.distinct_outcomes = total;
   if (!dev_keys || !dev_counts) { cudaFree(cnt); return JKQ_E_OK; }  // size query
   if (cap < total) { cudaFree(cnt); return fail(h, JKQ_E_CAPACITY, "%llu distinct outcomes, buffers hold %zu", (unsigned long long)total, cap); }
-  e = cudaMemcpyAsync(cnt, offs, world * 8, cudaMemcpyHostToDevice, h->stream);
+  e = jcopy(h, cnt, offs, world * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    k_hist_owner_scatter<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots, world, cnt, (unsigned long long *)dev_keys,
+    k_hist_owner_scatter<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots, world, cnt, (unsigned long long *)dev_keys,
                                                                   (unsigned long long *)dev_counts);
     e = cudaStreamSynchronize(h->stream);
   }
@@ -1148,11 +1182,10 @@ extern "C" int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const u
     const uint64_t slots = pow2_at_least((uint64_t)(expect > n ? expect : n) * 2, 1u << 12);
     if (slots > h->hslots) {
       free_hist(h);
-      CU(cudaMalloc(&h->hk, slots * 8));
-      CU(cudaMalloc(&h->hc, (slots + 1) * 8));
+      CU(cudaMalloc(&h->hs, (slots + 1) * sizeof(JHSlot)));
       h->hslots = slots;
     }
-    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hk, h->hc, h->hslots);
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
     h->hist_valid = true;
@@ -1160,12 +1193,12 @@ extern "C" int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const u
   if (n) {
     uint64_t want = (n + 255) / 256;
     int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
-    k_hist_merge<<<blocks, 256, 0, h->stream>>>(h->hk, h->hc, (uint32_t)(h->hslots - 1), (const unsigned long long *)dev_keys,
+    k_hist_merge<<<blocks, 256, 0, h->stream>>>(h->hs, (uint32_t)(h->hslots - 1), (const unsigned long long *)dev_keys,
                                                 (const unsigned long long *)dev_counts, n, h->overflow);
     CU(cudaGetLastError());
   }
   int ovf = 0;
-  CU(cudaMemcpyAsync(&ovf, h->overflow, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, &ovf, h->overflow, 4, cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   if (ovf) return fail(h, JKQ_E_CAPACITY, "count histogram overflow while merging (raise `expect`)");
   return JKQ_E_OK;
@@ -1183,7 +1216,7 @@ extern "C" int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count,
   if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
   k_amplitudes<<<blocks, 256, 0, h->stream>>>(h->dev, first, count, buf);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(re_im, buf, count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = jcopy(h, re_im, buf, count * sizeof(double2), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(buf);
   if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "amplitudes: %s", cudaGetErrorString(e));
@@ -1199,7 +1232,7 @@ extern "C" int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, 
   auto it = h->snapshots.find(slot);
   if (it == h->snapshots.end()) return fail(h, JKQ_E_ARGUMENT, "no snapshot in slot %u", slot);
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(re_im, it->second, len * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, re_im, it->second, len * sizeof(double2), cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }
@@ -1213,7 +1246,7 @@ extern "C" int jkq_get_probabilities(jkq_handle *h, uint32_t slot, double *out, 
   if (!out) return JKQ_E_OK;
   if (cap < len) return fail(h, JKQ_E_CAPACITY, "need room for %zu probabilities", len);
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(out, it->second.first, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, out, it->second.first, len * sizeof(double), cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }
@@ -1236,7 +1269,7 @@ extern "C" int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_
   if (!out) { *n_written = total; return JKQ_E_OK; }  // size query
   if (cap < total) return fail(h, JKQ_E_CAPACITY, "need %zu entries", total);
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(out, h->lvl_log, total * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, out, h->lvl_log, total * 4, cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   *n_written = total;
   return JKQ_E_OK;
@@ -1277,6 +1310,7 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   h->stats.gates = E.st[JST_GATES] - h->placeholder_gates; h->stats.items = E.st[JST_ITEMS]; h->stats.nodes_created = E.st[JST_NODES];
   h->stats.value_inserts = E.st[JST_VALS]; h->stats.gc_runs = E.st[JST_GC_RUNS]; h->stats.gc_nodes_copied = E.st[JST_GC_COPIED];
   h->stats.retry_rounds = E.st[JST_RETRY]; h->stats.max_frontier = E.st[JST_MAXF]; h->stats.thin_gates = E.st[JST_THIN];
+  h->stats.h2d_bytes = h->h2d_bytes; h->stats.d2h_bytes = h->d2h_bytes;
   h->stats.live_nodes = E.node_count ? E.node_count - 1 : 0; h->stats.live_values = E.val_count;
   *out = h->stats;
   return JKQ_E_OK;
@@ -1307,7 +1341,7 @@ extern "C" int jkq_dd_export(jkq_handle *h, jkq_snode *host_nodes, size_t cap, u
   *root = h->dd_root;
   if (!host_nodes) return JKQ_E_OK;
   if (cap < h->dd_nodes) return fail(h, JKQ_E_CAPACITY, "need room for %u nodes", h->dd_nodes);
-  CU(cudaMemcpyAsync(host_nodes, h->snodes, (size_t)h->dd_nodes * sizeof(JSNode), cudaMemcpyDeviceToHost, h->stream));
+  CU(jcopy(h, host_nodes, h->snodes, (size_t)h->dd_nodes * sizeof(JSNode), cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }
@@ -1317,13 +1351,212 @@ extern "C" int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *
   if (!h || !host_nodes || !clbit_of_level) return JKQ_E_ARGUMENT;
   if (n_qubits < 1 || n_qubits > JKQ_MAXQ || n_nodes > h->host.node_cap || root >= n_nodes) return fail(h, JKQ_E_ARGUMENT, "bad DD");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->snodes, host_nodes, (size_t)n_nodes * sizeof(JSNode), cudaMemcpyHostToDevice, h->stream));
+  CU(jcopy(h, h->snodes, host_nodes, (size_t)n_nodes * sizeof(JSNode), cudaMemcpyHostToDevice));
   CU(cudaStreamSynchronize(h->stream));
   h->n = n_qubits; h->dd_root = root; h->dd_nodes = n_nodes;
   memcpy(h->sp.bitpos, clbit_of_level, n_qubits);
   for (uint32_t L = n_qubits; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
   h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false;
   h->stats.norm = 1.0;
+  return JKQ_E_OK;
+}
+
+// the same two calls with DEVICE buffers of the caller (any device of this process): what an NCCL broadcast of the
+// sampling DD uses on both ends -- no host staging
+extern "C" int jkq_dd_export_device(jkq_handle *h, void *dev_nodes, size_t cap, uint32_t *n_nodes, uint32_t *root) {
+  if (!h || !n_nodes || !root) return JKQ_E_ARGUMENT;
+  CU(cudaSetDevice(h->device));
+  if (!h->imported) {
+    int rc = ensure_sampling(h);
+    if (rc) return rc;
+  }
+  *n_nodes = h->dd_nodes;
+  *root = h->dd_root;
+  if (!dev_nodes) return JKQ_E_OK;
+  if (cap < h->dd_nodes) return fail(h, JKQ_E_CAPACITY, "need room for %u nodes", h->dd_nodes);
+  CU(cudaMemcpyAsync(dev_nodes, h->snodes, (size_t)h->dd_nodes * sizeof(JSNode), cudaMemcpyDefault, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
+extern "C" int jkq_dd_import_device(jkq_handle *h, uint32_t n_qubits, const void *dev_nodes, uint32_t n_nodes, uint32_t root,
+                                    const uint8_t *clbit_of_level) {
+  if (!h || !dev_nodes || !clbit_of_level) return JKQ_E_ARGUMENT;
+  if (n_qubits < 1 || n_qubits > JKQ_MAXQ || n_nodes > h->host.node_cap || root >= n_nodes) return fail(h, JKQ_E_ARGUMENT, "bad DD");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->snodes, dev_nodes, (size_t)n_nodes * sizeof(JSNode), cudaMemcpyDefault, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n = n_qubits; h->dd_root = root; h->dd_nodes = n_nodes;
+  memcpy(h->sp.bitpos, clbit_of_level, n_qubits);
+  for (uint32_t L = n_qubits; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
+  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false;
+  h->stats.norm = 1.0;
+  return JKQ_E_OK;
+}
+
+// ---- shot sampling over the GPUs of ONE process ------------------------------------------------
+// The handle that holds the state applies nothing here: its level-ordered sampling DD (16 bytes per node) goes to one
+// helper handle per other device by peer copy over NVLink (cudaMemcpyPeerAsync, no host staging), device i draws the
+// shots [i S / G, (i + 1) S / G) of the one Philox stream on its own stream and host thread, and the helpers'
+// histograms come back compacted to (key, count) pairs, peer-copied and merged on the device (k_hist_merge) into the
+// histogram of `src` -- which jkq_get_counts then returns, identical to a one-GPU run of the same seed.  An outcome
+// space too large for one GPU stays distributed (st->merged = 0, distinct_total = the sum).
+struct MultiPeer { int device = -1; jkq_handle *h = nullptr; };
+static std::map<jkq_handle *, std::vector<MultiPeer>> g_multi_peers;  // helper handles, kept for the life of `src`
+
+static void multi_free(jkq_handle *src) {
+  auto it = g_multi_peers.find(src);
+  if (it == g_multi_peers.end()) return;
+  for (MultiPeer &p : it->second) if (p.h) jkq_destroy(p.h);
+  g_multi_peers.erase(it);
+}
+
+extern "C" int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint32_t n_devices, uint64_t shots, uint64_t seed,
+                                    jkq_multi_stats *st) {
+  if (!h || !devices || n_devices < 1 || n_devices > 64) return JKQ_E_ARGUMENT;
+  jkq_handle *const src = h;
+  const auto t_begin = std::chrono::steady_clock::now();
+  CU(cudaSetDevice(src->device));
+  if (!src->imported) {
+    int rc = ensure_sampling(src);
+    if (rc) return rc;
+  }
+  // helper handles: small pools, room for the DD
+  std::vector<MultiPeer> &peers = g_multi_peers[src];
+  std::vector<jkq_handle *> hs(n_devices, nullptr);
+  for (uint32_t i = 0; i < n_devices; i++) {
+    if (devices[i] == src->device && hs[i] == nullptr) {
+      bool taken = false;
+      for (uint32_t j = 0; j < i; j++) taken |= hs[j] == src;
+      if (!taken) { hs[i] = src; continue; }
+    }
+    MultiPeer *found = nullptr;
+    for (MultiPeer &p : peers) {
+      bool used = false;
+      for (uint32_t j = 0; j < i; j++) used |= hs[j] == p.h;
+      if (p.device == devices[i] && !used && p.h->host.node_cap >= src->dd_nodes) { found = &p; break; }
+    }
+    if (!found) {
+      jkq_config cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.device = devices[i];
+      cfg.node_capacity = pow2_at_least((uint64_t)src->dd_nodes + 1, 1u << 12);
+      cfg.value_capacity = 1u << 10; cfg.item_capacity = 1u << 10;
+      jkq_handle *nh = nullptr;
+      int rc = jkq_create(&nh, &cfg);
+      if (rc) {
+        std::string msg = nh ? nh->err : "out of memory";
+        if (nh) jkq_destroy(nh);
+        return fail(src, rc, "helper engine on device %d: %s", devices[i], msg.c_str());
+      }
+      MultiPeer mp; mp.device = devices[i]; mp.h = nh;
+      peers.push_back(mp);
+      found = &peers.back();
+      int can = 0;  // direct NVLink path when the topology offers it (errors: already enabled / not supported -- copies still work)
+      if (cudaDeviceCanAccessPeer(&can, devices[i], src->device) == cudaSuccess && can) { cudaSetDevice(devices[i]); cudaDeviceEnablePeerAccess(src->device, 0); }
+      if (cudaDeviceCanAccessPeer(&can, src->device, devices[i]) == cudaSuccess && can) { cudaSetDevice(src->device); cudaDeviceEnablePeerAccess(devices[i], 0); }
+      cudaGetLastError();
+    }
+    hs[i] = found->h;
+  }
+  // broadcast of the sampling DD: device to device
+  const auto t_bc0 = std::chrono::steady_clock::now();
+  CU(cudaSetDevice(src->device));
+  CU(cudaStreamSynchronize(src->stream));
+  for (uint32_t i = 0; i < n_devices; i++) {
+    jkq_handle *ph = hs[i];
+    if (ph == src) continue;
+    cudaSetDevice(ph->device);
+    cudaError_t e = cudaMemcpyPeerAsync(ph->snodes, ph->device, src->snodes, src->device, (size_t)src->dd_nodes * sizeof(JSNode), ph->stream);
+    if (e != cudaSuccess) return fail(src, JKQ_E_CUDA, "peer copy to device %d: %s", ph->device, cudaGetErrorString(e));
+    ph->n = src->n; ph->dd_root = src->dd_root; ph->dd_nodes = src->dd_nodes; ph->sp = src->sp;
+    ph->imported = true; ph->applied = false; ph->sampling_ready = false; ph->hist_valid = false; ph->stats.norm = 1.0;
+  }
+  for (uint32_t i = 0; i < n_devices; i++)
+    if (hs[i] != src) { cudaSetDevice(hs[i]->device); cudaStreamSynchronize(hs[i]->stream); }
+  const auto t_bc1 = std::chrono::steady_clock::now();
+  // can everything be merged on src?  (2 x 16 bytes per possible outcome against the free memory there)
+  int measured = 0;
+  for (uint32_t L = 0; L < src->n; L++) measured += src->sp.bitpos[L] < 64;
+  uint64_t outcomes = shots;
+  if (measured < 40 && (1ull << measured) < outcomes) outcomes = 1ull << measured;
+  size_t free_b = 0, total_b = 0;
+  cudaSetDevice(src->device);
+  cudaMemGetInfo(&free_b, &total_b);
+  // (beyond 2^26 possible outcomes the merged histogram is a result no caller reads back as a dictionary, and merging
+  // it on one device would serialise what the devices did side by side)
+  const bool merge = n_devices == 1 || (outcomes <= (1ull << 26) && outcomes * 2 * sizeof(JHSlot) + outcomes * 32 < free_b / 2);
+  // sample: one host thread per device (jkq_sample blocks on its stream)
+  std::vector<int> rcs(n_devices, 0);
+  std::vector<std::thread> th;
+  for (uint32_t i = 0; i < n_devices; i++) {
+    const uint64_t lo = shots / n_devices * i + (i < shots % n_devices ? i : shots % n_devices);
+    const uint64_t cnt = shots / n_devices + (i < shots % n_devices ? 1 : 0);
+    jkq_handle *ph = hs[i];
+    const uint64_t expect = (ph == src && merge) ? shots : cnt;
+    th.emplace_back([=, &rcs]() { rcs[i] = sample_impl(ph, cnt, seed, lo, 0, expect); });
+  }
+  for (std::thread &t : th) t.join();
+  for (uint32_t i = 0; i < n_devices; i++)
+    if (rcs[i]) return hs[i] == src ? rcs[i] : fail(src, rcs[i], "device %d: %s", hs[i]->device, hs[i]->err.c_str());
+  const auto t_s1 = std::chrono::steady_clock::now();
+  double k_ms = 0;
+  for (uint32_t i = 0; i < n_devices; i++) if (hs[i]->stats.sample_kernel_ms > k_ms) k_ms = hs[i]->stats.sample_kernel_ms;
+  // merge on the device: compact on the helper, peer copy, k_hist_merge on src
+  uint64_t distinct_total = 0;
+  if (merge) {
+    for (uint32_t i = 0; i < n_devices; i++) {
+      jkq_handle *ph = hs[i];
+      if (ph == src) continue;
+      size_t n = 0;
+      int rc = jkq_get_counts(ph, nullptr, nullptr, 0, &n);  // how many
+      if (rc) return fail(src, rc, "device %d: %s", ph->device, ph->err.c_str());
+      if (n == 0) continue;
+      rc = jkq_get_counts(ph, nullptr, nullptr, n, &n);  // compacts into ph->ok / ph->oc on its device (no host copy: keys == NULL)
+      if (rc) return fail(src, rc, "device %d: %s", ph->device, ph->err.c_str());
+      CU(cudaSetDevice(src->device));
+      if (n > src->out_cap) {
+        cudaFree(src->ok); cudaFree(src->oc);
+        src->ok = src->oc = nullptr;
+        CU(cudaMalloc(&src->ok, n * 8));
+        CU(cudaMalloc(&src->oc, n * 8));
+        src->out_cap = n;
+      }
+      CU(cudaMemcpyPeerAsync(src->ok, src->device, ph->ok, ph->device, n * 8, src->stream));
+      CU(cudaMemcpyPeerAsync(src->oc, src->device, ph->oc, ph->device, n * 8, src->stream));
+      int blocks = (int)((n + 255) / 256);
+      if (blocks > src->sm_count * 8) blocks = src->sm_count * 8;
+      k_hist_merge<<<blocks, 256, 0, src->stream>>>(src->hs, (uint32_t)(src->hslots - 1), src->ok, src->oc, n, src->overflow);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(src->stream));
+    }
+    int ovf = 0;
+    CU(cudaSetDevice(src->device));
+    CU(jcopy(src, &ovf, src->overflow, 4, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(src->stream));
+    if (ovf) return fail(src, JKQ_E_CAPACITY, "count histogram overflow in the merge");
+    size_t n = 0;
+    int rc = jkq_get_counts(src, nullptr, nullptr, 0, &n);
+    if (rc) return rc;
+    distinct_total = n;
+  } else {
+    for (uint32_t i = 0; i < n_devices; i++) {
+      size_t n = 0;
+      int rc = jkq_get_counts(hs[i], nullptr, nullptr, 0, &n);
+      if (rc) return fail(src, rc, "device %d: %s", hs[i]->device, hs[i]->err.c_str());
+      distinct_total += n;  // (an outcome drawn on two devices counts twice: an upper bound)
+    }
+  }
+  CU(cudaSetDevice(src->device));
+  const auto t_end = std::chrono::steady_clock::now();
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  if (st) {
+    st->n_devices = n_devices; st->merged = merge ? 1u : 0u; st->distinct_total = distinct_total;
+    st->broadcast_ms = ms(t_bc0, t_bc1); st->sample_wall_ms = ms(t_bc1, t_s1); st->sample_kernel_ms_max = k_ms;
+    st->merge_ms = ms(t_s1, t_end); st->wall_ms = ms(t_begin, t_end); st->dd_bytes = (uint64_t)src->dd_nodes * sizeof(JSNode);
+  }
   return JKQ_E_OK;
 }
 
@@ -1343,7 +1576,7 @@ struct JBatchEng {   // device-side view of one engine of the pool
   JEng *E;
   JSNode *sn;
   double *prob;
-  unsigned long long *hk, *hc;
+  JHSlot *hs;
 };
 struct JBatchCirc {
   uint32_t n, n_gates;
@@ -1406,8 +1639,8 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
     unsigned int nd = 0;
     if (!st) {
       // MeasureAll x shots (Simulator.cpp:148-224): this CTA's threads walk the shots of the circuit
-      for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x) { be.hk[k] = JH_EMPTY; be.hc[k] = 0; }
-      if (threadIdx.x == 0) { s_cnt = 0; s_ovf = 0; be.hc[hslots] = 0; }
+      for (uint32_t k = threadIdx.x; k <= hslots; k += blockDim.x) { be.hs[k].key = JH_EMPTY; be.hs[k].cnt = 0; }
+      if (threadIdx.x == 0) { s_cnt = 0; s_ovf = 0; }
       __syncthreads();
       const uint64_t rounded = (shots + 31) & ~31ull;
       const uint32_t lane = threadIdx.x & 31;
@@ -1415,17 +1648,17 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
         const bool active = s < shots;
         const uint64_t key = active ? sample_walk(be.sn, 1u, (int)cd.n, cd.sp.bitpos, cd.seed, s) : JH_EMPTY;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
-        if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hk, be.hc, hslots - 1, key, __popc(peers), &s_ovf);
+        if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hs, hslots - 1, key, __popc(peers), &s_ovf);
       }
       __syncthreads();
       for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x)
-        if (be.hk[k] != JH_EMPTY) {
+        if (be.hs[k].key != JH_EMPTY) {
           const unsigned int p = atomicAdd(&s_cnt, 1u);
-          if (p < cap) { keys[(size_t)i * cap + p] = be.hk[k]; counts[(size_t)i * cap + p] = be.hc[k]; }
+          if (p < cap) { keys[(size_t)i * cap + p] = be.hs[k].key; counts[(size_t)i * cap + p] = be.hs[k].cnt; }
         }
-      if (threadIdx.x == 0 && be.hc[hslots]) {
+      if (threadIdx.x == 0 && be.hs[hslots].cnt) {
         const unsigned int p = atomicAdd(&s_cnt, 1u);
-        if (p < cap) { keys[(size_t)i * cap + p] = JH_EMPTY; counts[(size_t)i * cap + p] = be.hc[hslots]; }
+        if (p < cap) { keys[(size_t)i * cap + p] = JH_EMPTY; counts[(size_t)i * cap + p] = be.hs[hslots].cnt; }
       }
       __syncthreads();
       nd = s_cnt;
@@ -1788,8 +2021,7 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
   if (hslots > b->hslots) {
     for (jkq_handle *h : b->eng) {
       free_hist(h);
-      CU(cudaMalloc(&h->hk, hslots * 8));
-      CU(cudaMalloc(&h->hc, (hslots + 1) * 8));
+      CU(cudaMalloc(&h->hs, (hslots + 1) * sizeof(JHSlot)));
       h->hslots = hslots;
     }
     b->hslots = hslots;
@@ -1797,7 +2029,7 @@ extern "C" int jkq_batch_run(jkq_batch *b, size_t n_circuits, const uint32_t *n_
     std::vector<JBatchEng> be(b->eng.size());
     for (size_t e = 0; e < b->eng.size(); e++) {
       jkq_handle *h = b->eng[e];
-      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hk = h->hk; be[e].hc = h->hc;
+      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hs = h->hs;
     }
     BCU(cudaMemcpy(b->engs_dev, be.data(), be.size() * sizeof(JBatchEng), cudaMemcpyHostToDevice));
   }
@@ -1938,7 +2170,7 @@ extern "C" int jkq_batch_run_shots(jkq_batch *b, uint32_t n_qubits, const jkq_op
     std::vector<JBatchEng> be(b->eng.size());
     for (size_t e = 0; e < b->eng.size(); e++) {
       jkq_handle *h = b->eng[e];
-      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hk = h->hk; be[e].hc = h->hc;
+      be[e].E = h->dev; be[e].sn = h->snodes; be[e].prob = h->prob; be[e].hs = h->hs;
     }
     BCU(cudaMemcpy(b->engs_dev, be.data(), be.size() * sizeof(JBatchEng), cudaMemcpyHostToDevice));
     b->engs_uploaded = true;

@@ -354,7 +354,9 @@ JD uint64_t jneg(uint64_t a) {  // Cnegative, QMDDcomplexD.cpp:483-496
   return (r << 32) | i;
 }
 
-template <int MODE> JD uint32_t vt_mask2(const JEng *E) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : E->vtab_mask; }
+template <int MODE> JD uint32_t vt_mask2(const JEng *E) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : ld_s<MODE>(&E->vt_cur); }
+// the HBM value table has four slots per real of the value array
+JD bool vt_room(const JEng *E, uint32_t idx) { return idx < E->val_cap && (uint64_t)idx * 2 < (uint64_t)ld_s<MODE_GRID>(&E->vt_cur); }
 template <int MODE> JD JVSlot *vt_tab2(JEng *E, CtaState *S) { return MODE == MODE_CTA ? S->vtab : E->vtab; }
 JD long long vt_bucket(double x, double inv_tol) { return (long long)floor(JKQ_DMUL(x, inv_tol)); }
 // eight consecutive buckets share one 128-byte line (8 x 16-byte slots): the three probes of a lookup
@@ -470,7 +472,7 @@ template <int MODE> JNI void vals_commit(JEng *E, CtaState *S, uint32_t par, uin
         if (idx >= S->val_limit) jwant_grid(S);  // the shared table is full: grid path
         else { S->vals[idx] = v; id1 = idx + 1; jstat<MODE>(E, S, JST_VALS, 1u); }  // (copied to HBM by cta_flush)
       } else {
-        if (idx >= E->val_cap || (uint64_t)idx * 2 >= E->vtab_mask) jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+        if (!vt_room(E, idx)) jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
         else { E->vals[idx] = v; id1 = idx + 1; jstat<MODE>(E, S, JST_VALS, 1u); }
       }
     }
@@ -488,7 +490,7 @@ template <int MODE> JNI uint32_t real_insert_direct(JEng *E, CtaState *S, double
     S->vals[idx] = x;  // (copied to HBM by cta_flush)
     jstat<MODE>(E, S, JST_VALS, 1u);
   } else {
-    if (E->val_count >= E->val_cap || (uint64_t)E->val_count * 2 >= E->vtab_mask) { jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL); return 0; }
+    if (!vt_room(E, E->val_count)) { jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL); return 0; }
     idx = E->val_count++;
     E->vals[idx] = x;
     jstat<MODE>(E, S, JST_VALS, 1u);
@@ -705,18 +707,24 @@ template <int MODE> JD uint32_t ut_find_or_insert(JEng *E, CtaState *S, uint32_t
     jwant_grid(S);
     return 0;
   }
+  // HBM table: 64-bit slots, generation << 32 | node id.  An entry of an older generation reads as empty (the
+  // collector starts a new generation instead of clearing the table) and is claimed by CAS from whatever it holds.
   uint32_t h = ut_hash3(c0, c1, w) & E->utab_mask, mine = 0;
+  const unsigned long long gen = (unsigned long long)ld_s<MODE>(&E->ut_gen) << 32;
   for (uint32_t probes = 0; probes <= E->utab_mask; probes++) {
-    uint32_t s = ld_r<MODE>(E->utab + h);
-    if (s == 0) {
+    unsigned long long sv = ld_r<MODE>(E->utab + h);
+    uint32_t s = (sv >> 32) == (gen >> 32) ? (uint32_t)sv : 0u;
+    while (s == 0) {
       if (mine == 0) {
         mine = jagg_inc(&E->node_count);
         if (mine >= E->node_cap) { jset_error<MODE>(E, S, JKQ_ERR_NODE_FULL); return 0; }
         E->nodes[mine] = rec;
         jfence<MODE>();
       }
-      s = jatomic_cas(E->utab + h, 0u, mine);
-      if (s == 0) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
+      const unsigned long long old = jatomic_cas(E->utab + h, sv, gen | mine);
+      if (old == sv) { jstat<MODE>(E, S, JST_NODES, 1u); return mine; }
+      sv = old;
+      s = (sv >> 32) == (gen >> 32) ? (uint32_t)sv : 0u;
     }
     JNode o = ld_r<MODE>(E->nodes + s);
     if (o.c0 == c0 && o.c1 == c1 && o.w == w) {

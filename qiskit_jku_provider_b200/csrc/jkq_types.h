@@ -122,7 +122,7 @@ typedef struct {
   double inv_tol;
   // ---- arrays ----
   JNode *nodes, *nodes_alt;
-  uint32_t *utab;
+  unsigned long long *utab;  // generation << 32 | node id: a collection starts a new generation instead of clearing
   double *vals, *vals_alt;
   JVSlot *vtab;
   uint32_t *pend;     // value-table slots claimed in the current phase
@@ -150,6 +150,8 @@ typedef struct {
   uint32_t gc_count;   // collector cursor
   uint32_t val_gc_limit;  // sweep the reals only above this many (reference complex_limit)
   uint32_t val_epoch;     // bumped whenever a sweep renumbers the reals
+  uint32_t ut_gen;        // generation of the unique-table entries that count (older ones read as empty)
+  uint32_t vt_cur;        // mask of the part of the value table in use (= vtab_mask: see vt_mask_for, jkq_apply.cuh)
   double norm;        // squared norm of the state at the last finalisation
   uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L], lvl_off[L] + lvl_cnt[L])
   uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection

@@ -163,6 +163,9 @@ class Engine:
                                              v.ctypes.data_as(C.POINTER(C.c_uint64)), k.size, C.byref(n)))
         return k[:n.value], v[:n.value]
 
+    def free_histogram(self):
+        self._check(self._lib.jkq_release_histogram(self._h))
+
     def distinct_outcomes(self):
         """number of distinct outcomes in the histogram (no copy)"""
         n = C.c_size_t(0)
@@ -246,6 +249,33 @@ class Engine:
         self._check(self._lib.jkq_dd_import(self._h, int(n_qubits), nodes.ctypes.data_as(C.POINTER(_native.JkqSNode)),
                                             nodes.size, int(root), m.ctypes.data_as(C.POINTER(C.c_uint8))))
         self.n = int(n_qubits)
+
+    def dd_size(self):
+        """(nodes, root) of the sampling DD (builds it if need be)"""
+        n, root = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.jkq_dd_export_device(self._h, None, 0, C.byref(n), C.byref(root)))
+        return int(n.value), int(root.value)
+
+    def dd_export_device(self, dev_ptr, cap_nodes):
+        """Copy the sampling DD (16 bytes per node) into a DEVICE buffer of the caller (raw pointer): (nodes, root)."""
+        n, root = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.jkq_dd_export_device(self._h, C.c_void_p(dev_ptr), int(cap_nodes), C.byref(n), C.byref(root)))
+        return int(n.value), int(root.value)
+
+    def dd_import_device(self, n_qubits, dev_ptr, n_nodes, root, clbit_of_level):
+        m = np.ascontiguousarray(clbit_of_level, dtype=np.uint8)
+        self._check(self._lib.jkq_dd_import_device(self._h, int(n_qubits), C.c_void_p(dev_ptr), int(n_nodes), int(root),
+                                                   m.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self.n = int(n_qubits)
+
+    def sample_multi(self, devices, shots, seed=1):
+        """jkq_sample_multi_gpu: the shots of the current state split over ``devices`` (CUDA ordinals of this process),
+        sampling DD broadcast by peer copy, histograms merged on the device; ``counts()`` afterwards as after ``sample``.
+        Returns the call's statistics."""
+        dv = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        st = _native.JkqMultiStats()
+        self._check(self._lib.jkq_sample_multi_gpu(self._h, dv, len(devices), int(shots), int(seed), C.byref(st)))
+        return {name: getattr(st, name) for name, _ in st._fields_}
 
     def counts_partition(self, world, dev_keys=0, dev_counts=0, cap=0):
         """Sort the histogram by owner rank into device buffers (raw pointers; 0 = only count): per-owner sizes."""

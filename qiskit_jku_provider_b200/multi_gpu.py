@@ -50,6 +50,36 @@ def broadcast_dd(dist, nodes, root, n_qubits, measure_map, src=0):
     return out, root, n_qubits, mm
 
 
+def broadcast_dd_device(dist, engine, src=0):
+    """NCCL path: the sampling DD travels device to device -- ``jkq_dd_export_device`` into a torch tensor on rank
+    ``src``, one NCCL broadcast over NVLink, ``jkq_dd_import_device`` everywhere else.  No host staging of the node
+    array (the 3 + 64 header words are the only thing a rank reads back).  Returns (n_qubits, measure map)."""
+    import torch
+    dev = _dev(dist)
+    rank = dist.get_rank()
+    hdr = torch.zeros(3 + 64, dtype=torch.int64, device=dev)
+    n_nodes = root = 0
+    if rank == src:
+        n_nodes, root = engine.dd_size()
+        mm = engine.measure_map()
+        h = np.zeros(3 + 64, dtype=np.int64)
+        h[0], h[1], h[2] = n_nodes, root, engine.n
+        h[3:3 + engine.n] = mm
+        hdr.copy_(torch.from_numpy(h))
+    dist.broadcast(hdr, src=src)
+    hh = hdr.cpu().numpy()
+    n_nodes, root, n_qubits = int(hh[0]), int(hh[1]), int(hh[2])
+    mm = hh[3:3 + n_qubits].astype(np.uint8)
+    buf = torch.empty(n_nodes * 2, dtype=torch.int64, device=dev)  # 16 bytes per node
+    if rank == src:
+        engine.dd_export_device(buf.data_ptr(), n_nodes)
+    dist.broadcast(buf, src=src)
+    if rank != src:
+        torch.cuda.current_stream().synchronize()  # the library copies on its own stream
+        engine.dd_import_device(n_qubits, buf.data_ptr(), n_nodes, root, mm)
+    return n_qubits, mm
+
+
 def merge_counts(dist, keys, counts, n_bits):
     """All-reduce per-rank (keys, counts) into the global histogram, returned as a dict on every rank."""
     import torch
@@ -134,9 +164,12 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None, 
     if rank == 0:
         engine.load(circuit, measure=measure)
         engine.apply()
-        nodes, root = engine.dd_export()
         n, mm = engine.n, engine.measure_map()
-    if world > 1:
+    if world > 1 and dist.get_backend() == "nccl":
+        n, mm = broadcast_dd_device(dist, engine, src=0)  # device to device over NVLink
+    elif world > 1:
+        if rank == 0:
+            nodes, root = engine.dd_export()
         nodes, root, n, mm = broadcast_dd(dist, nodes, root, n, mm, src=0)
         if rank != 0:
             engine.dd_import(n, nodes, root, mm)

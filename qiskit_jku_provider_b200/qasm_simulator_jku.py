@@ -34,6 +34,7 @@ logger = logging.getLogger(__name__)
 # (``:116-120,138``).  Above this many qubits the final state vector is only produced on request
 # (experiment.config.data contains 'statevector').
 STATEVECTOR_AUTO_MAX_QUBITS = 20
+MULTI_GPU_MIN_SHOTS = 1 << 22  # from here on the shots of one experiment are split over the backend's devices
 
 
 _TEMPLATES = {}
@@ -63,8 +64,9 @@ def _gate_template(name, n_qubits, params):
 class JKUSimulatorWrapper:
     """Converter between Qobj experiments and the engine."""
 
-    def __init__(self, engine=None, silent=False, physical_reset=False, shots_runner=None):
+    def __init__(self, engine=None, silent=False, physical_reset=False, shots_runner=None, devices=None):
         self.physical_reset = bool(physical_reset)
+        self.devices = list(devices) if devices else None  # CUDA ordinals the shots of one experiment may be split over
         self.shots_runner = shots_runner  # batch.BatchRunner for per-shot re-simulation, or None: sequential
         self.seed = 0
         self.shots = 1
@@ -196,7 +198,12 @@ class JKUSimulatorWrapper:
                 eng.apply()
             output_data = self.collect_output(eng, measurement_data, slots, want_sv, counts_override=merged)
         else:
-            eng.run(self.shots, self.seed)
+            if self.devices and len(self.devices) > 1 and int(self.shots) >= MULTI_GPU_MIN_SHOTS:
+                # the shots of one state over several GPUs (jkq_sample_multi_gpu): same counts as on one
+                eng.apply()
+                self.multi_gpu_stats = eng.sample_multi(self.devices, self.shots, self.seed)
+            else:
+                eng.run(self.shots, self.seed)
             output_data = self.collect_output(eng, measurement_data, slots, want_sv)
         self.end_time = time.time()
         stats = eng.stats()
@@ -273,11 +280,17 @@ class QasmSimulator(BaseBackend):
         ]
     }
 
-    def __init__(self, configuration=None, provider=None, silent=False, device=0, physical_reset=False, **engine_options):
+    def __init__(self, configuration=None, provider=None, silent=False, device=0, physical_reset=False, devices=None, **engine_options):
         """
         Args:
             configuration (dict): backend configuration
             device (int): CUDA ordinal the engine runs on
+            devices (list of int): CUDA ordinals of ONE process to spread work over (default: ``[device]``).  The
+                                   experiments of a Qobj go round-robin to one engine per device and run side by side
+                                   (the reference runs them one after the other, ``:340-359``); the shots of a single
+                                   experiment are split over all of them once there are at least 2^22
+                                   (``jkq_sample_multi_gpu``: peer copy of the sampling DD, device-side merge).
+                                   Counts do not depend on the number of devices.
             physical_reset (bool): ``reset`` = measure and flip back (per-shot re-simulation) instead of the
                                    reference's projection on |0> (Simulator.cpp:291-339)
             engine_options: forwarded to ``jkq_config`` (node_capacity, tolerance, ...)
@@ -292,15 +305,21 @@ class QasmSimulator(BaseBackend):
         _native.load()  # fail early and loudly, like the reference's executable check
         self.silent = silent
         self.physical_reset = physical_reset
-        self._device = device
+        self._devices = [int(d) for d in devices] if devices else [int(device)]
+        self._device = self._devices[0]
         self._engine_options = engine_options
         self._engine = None
+        self._more_engines = {}   # device ordinal -> Engine, for the experiments of a Qobj that run side by side
         self._shots_runner = None
 
-    def _get_engine(self):
-        if self._engine is None:  # lazy: creating the CUDA context is deferred to the first job
-            self._engine = Engine(device=self._device, **self._engine_options)
-        return self._engine
+    def _get_engine(self, device=None):
+        if device is None or device == self._device:
+            if self._engine is None:  # lazy: creating the CUDA context is deferred to the first job
+                self._engine = Engine(device=self._device, **self._engine_options)
+            return self._engine
+        if device not in self._more_engines:
+            self._more_engines[device] = Engine(device=device, **self._engine_options)
+        return self._more_engines[device]
 
     def _get_shots_runner(self):
         if self._shots_runner is None:  # pool of small engines, one per SM, for per-shot re-simulation
@@ -319,12 +338,31 @@ class QasmSimulator(BaseBackend):
         """Run circuits in q_job"""
         result_list = []
         self._validate(qobj)
-        s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset,
-                                shots_runner=self._get_shots_runner() if self.physical_reset else None)
-        s.shots = qobj.config.shots
         start = time.time()
-        for experiment in qobj.experiments:
-            result_list.append(s.run_experiment(qobj.config, experiment))
+        n_dev = len(self._devices)
+        if n_dev > 1 and len(qobj.experiments) > 1:
+            # one engine per device, experiment i on device i % n_dev, every device in its own host thread (ctypes
+            # releases the GIL inside the library)
+            from concurrent.futures import ThreadPoolExecutor
+
+            def lane(k):
+                w = JKUSimulatorWrapper(self._get_engine(self._devices[k]), silent=self.silent, physical_reset=self.physical_reset,
+                                        shots_runner=None)
+                w.shots = qobj.config.shots
+                return [(i, w.run_experiment(qobj.config, qobj.experiments[i])) for i in range(k, len(qobj.experiments), n_dev)]
+
+            for k in range(n_dev):
+                self._get_engine(self._devices[k])  # (created here: one CUDA context after the other)
+            with ThreadPoolExecutor(n_dev) as ex:
+                done = dict(p for part in ex.map(lane, range(n_dev)) for p in part)
+            result_list = [done[i] for i in range(len(qobj.experiments))]
+        else:
+            s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset,
+                                    shots_runner=self._get_shots_runner() if self.physical_reset else None,
+                                    devices=self._devices)
+            s.shots = qobj.config.shots
+            for experiment in qobj.experiments:
+                result_list.append(s.run_experiment(qobj.config, experiment))
         end = time.time()
         result = {'backend_name': self._configuration.backend_name,
                   'backend_version': VERSION,

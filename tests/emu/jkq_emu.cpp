@@ -145,7 +145,8 @@ int main(int argc, char **argv) {
   E->cta_no_reserve = cta_no_reserve;
   E->nodes = (JNode *)calloc(E->node_cap, sizeof(JNode));
   E->nodes_alt = (JNode *)calloc(E->node_cap, sizeof(JNode));
-  E->utab = (uint32_t *)calloc((size_t)E->utab_mask + 1, 4);
+  E->utab = (unsigned long long *)calloc((size_t)E->utab_mask + 1, 8);
+  E->ut_gen = 1; E->vt_cur = E->vtab_mask;
   E->vals = (double *)calloc(E->val_cap, 8);
   E->vals_alt = (double *)calloc(E->val_cap, 8);
   E->vtab = (JVSlot *)calloc((size_t)E->vtab_mask + 1, sizeof(JVSlot));

@@ -76,3 +76,41 @@ def test_two_gpus_under_torchrun():
                           "--master-port", "29533", os.path.join(ROOT, "scripts", "multi_gpu_check.py")],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-3000:]
+
+
+def test_sample_multi_gpu_single_process_equals_one_gpu():
+    """jkq_sample_multi_gpu (C ABI): the sampling DD goes to helper engines by peer copy, the shots are split, the
+    histograms merged on the device.  Here both "devices" are GPU 0 (two engines side by side), which runs the whole
+    path on a one-GPU box; scripts/multi_gpu_check.py repeats it over real peers."""
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import Engine
+    for circ, shots in ((C.ghz(24), 1 << 20), (C.qft(12), 300000), (C.random_circuit(10, 40, 3), 100001)):
+        with Engine(device=0, node_capacity=1 << 18) as a, Engine(device=0, node_capacity=1 << 18) as b:
+            a.load(circ)
+            a.run(shots, 9)
+            want = a.counts()
+            b.load(circ)
+            b.apply()
+            for devs in ([0], [0, 0], [0, 0, 0]):
+                st = b.sample_multi(devs, shots, 9)
+                assert st["n_devices"] == len(devs) and st["merged"] == 1
+                assert b.counts() == want, (circ.name, devs)
+                assert st["distinct_total"] == len(want)
+
+
+def test_dd_broadcast_through_device_buffers():
+    """jkq_dd_export_device / jkq_dd_import_device: what the NCCL broadcast uses on both ends."""
+    import torch
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import Engine
+    circ = C.random_circuit(9, 50, 5)
+    with Engine(device=0, node_capacity=1 << 16) as a, Engine(device=0, node_capacity=1 << 16) as b:
+        a.load(circ)
+        a.run(50000, 3)
+        n_nodes, root = a.dd_size()
+        buf = torch.empty(2 * n_nodes, dtype=torch.int64, device="cuda:0")
+        assert a.dd_export_device(buf.data_ptr(), n_nodes) == (n_nodes, root)
+        torch.cuda.synchronize()
+        b.dd_import_device(circ.n, buf.data_ptr(), n_nodes, root, a.measure_map())
+        b.sample(50000, seed=3)
+        assert b.counts() == a.counts()
