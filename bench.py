@@ -132,12 +132,21 @@ def executable_legs(device):
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "jku_simulator")
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
+        # the same executable behind its resident server (`jku_simulator --serve`): the short-lived process forwards
+        # argv + program over a Unix socket, no CUDA start-up per invocation
+        env = dict(os.environ, JKU_SIMULATOR_SOCKET=os.path.join(tmp, "jku.sock"))
+        server = subprocess.Popen([_build.CLI, "--serve", "--idle=300", "--device=%d" % device], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for _ in range(400):
+            if os.path.exists(env["JKU_SIMULATOR_SOCKET"]):
+                break
+            time.sleep(0.05)
         for c, ref_runs in ((C.qft(32), 3), (C.random_circuit(18, 100, 1), 1)):
             path = os.path.join(tmp, c.name + ".qasm")
             with open(path, "w") as f:
                 f.write(c.qasm())
             leg = {"applies": len(c)}
-            for key, cmd, runs in (("b200", [_build.CLI, "--simulate_qasm=" + path, "--shots=1024", "--seed=1", "--device=%d" % device], 3),
+            for key, cmd, runs in (("b200", [_build.CLI, "--no_server", "--simulate_qasm=" + path, "--shots=1024", "--seed=1", "--device=%d" % device], 3),
+                                   ("b200_resident_server", [_build.CLI, "--simulate_qasm=" + path, "--shots=1024", "--seed=1", "--device=%d" % device], 4),
                                    ("reference_cpu", [ref_exe, "--simulate_qasm=" + path, "--shots=1024", "--seed=1"], ref_runs)):
                 if not os.path.exists(cmd[0]):
                     leg[key + "_wall_s"] = None
@@ -145,12 +154,17 @@ def executable_legs(device):
                 best = None
                 for _ in range(runs):
                     t0 = time.perf_counter()
-                    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+                    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=env if key == "b200_resident_server" else None)
                     dt = time.perf_counter() - t0
                     if r.returncode == 0 and (best is None or dt < best):
                         best = dt
                 leg[key + "_wall_s"] = best
             out[c.name] = leg
+        server.terminate()
+        try:
+            server.wait(timeout=10)
+        except Exception:
+            server.kill()
     return out
 
 

@@ -187,7 +187,10 @@ struct SampleParams {
 struct __align__(16) JHSlot {
   unsigned long long key, cnt;
 };
-__device__ __forceinline__ void hist_global_add(JHSlot *hs, uint32_t hmask, uint64_t key, unsigned long long cnt, int *overflow) {
+// `fresh`: a counter in shared memory that takes one for every slot this call claims (the number of distinct outcomes
+// then costs no pass over a 34 GB table: the kernels add their block's count to a device word at the end)
+__device__ __forceinline__ void hist_global_add(JHSlot *hs, uint32_t hmask, uint64_t key, unsigned long long cnt, int *overflow,
+                                                unsigned int *fresh) {
   if (key == JH_EMPTY) { atomicAdd(&hs[(size_t)hmask + 1].cnt, cnt); return; }
   uint32_t h = (uint32_t)jmix(key) & hmask;
   for (uint32_t probes = 0; probes <= hmask; probes++) {
@@ -196,6 +199,7 @@ __device__ __forceinline__ void hist_global_add(JHSlot *hs, uint32_t hmask, uint
       if (old != JH_EMPTY) { h = (h + 1) & hmask; continue; }
       old = atomicCAS(&hs[h].key, JH_EMPTY, (unsigned long long)key);
       if (old != JH_EMPTY && old != key) { h = (h + 1) & hmask; continue; }
+      if (old == JH_EMPTY) atomicAdd(fresh, 1u);
     }
     atomicAdd(&hs[h].cnt, cnt);
     return;
@@ -207,9 +211,12 @@ __device__ __forceinline__ void hist_global_add(JHSlot *hs, uint32_t hmask, uint
 // dependent 16-byte loads through L1/L2, equal outcomes merged inside the warp (__match_any_sync),
 // then in a shared-memory hash, then in the HBM hash histogram.
 __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, uint32_t root, int n, SampleParams sp, uint64_t seed,
-                                               uint64_t shot0, uint64_t nshots, JHSlot *hs, uint32_t hmask, int *overflow) {
+                                               uint64_t shot0, uint64_t nshots, JHSlot *hs, uint32_t hmask, int *overflow,
+                                               unsigned long long *n_distinct) {
   __shared__ unsigned long long skeys[JH_SMEM];
   __shared__ unsigned int scnts[JH_SMEM];
+  __shared__ unsigned int s_fresh;
+  if (threadIdx.x == 0) s_fresh = 0;
   for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x) { skeys[i] = JH_EMPTY; scnts[i] = 0; }
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
     uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
     if (!active || lane != (uint32_t)(__ffs(peers) - 1)) continue;
     uint32_t cnt = __popc(peers);
-    if (key == JH_EMPTY) { hist_global_add(hs, hmask, key, cnt, overflow); continue; }
+    if (key == JH_EMPTY) { hist_global_add(hs, hmask, key, cnt, overflow, &s_fresh); continue; }
     uint32_t h = (uint32_t)jmix(key) & (JH_SMEM - 1);
     bool done = false;
     for (int p = 0; p < 8 && !done; p++) {
@@ -233,16 +240,19 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
       atomicAdd(&scnts[h], cnt);
       done = true;
     }
-    if (!done) hist_global_add(hs, hmask, key, cnt, overflow);
+    if (!done) hist_global_add(hs, hmask, key, cnt, overflow, &s_fresh);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < JH_SMEM; i += blockDim.x)
-    if (skeys[i] != JH_EMPTY && scnts[i]) hist_global_add(hs, hmask, skeys[i], scnts[i], overflow);
+    if (skeys[i] != JH_EMPTY && scnts[i]) hist_global_add(hs, hmask, skeys[i], scnts[i], overflow, &s_fresh);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_fresh) atomicAdd(n_distinct, (unsigned long long)s_fresh);
 }
 
-__global__ void k_hist_fill(JHSlot *hs, uint64_t slots) {
+__global__ void k_hist_fill(JHSlot *hs, uint64_t slots, unsigned long long *n_distinct) {
   JHSlot e;
   e.key = JH_EMPTY; e.cnt = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_distinct = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= slots; i += (uint64_t)gridDim.x * blockDim.x) hs[i] = e;
 }
 
@@ -308,9 +318,14 @@ __global__ void __launch_bounds__(256) k_hist_owner_scatter(const JHSlot *hs, ui
 }
 
 __global__ void __launch_bounds__(256) k_hist_merge(JHSlot *hs, uint32_t hmask, const unsigned long long *in_keys, const unsigned long long *in_counts,
-                                                    uint64_t n, int *overflow) {
+                                                    uint64_t n, int *overflow, unsigned long long *n_distinct) {
+  __shared__ unsigned int s_fresh;
+  if (threadIdx.x == 0) s_fresh = 0;
+  __syncthreads();
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    if (in_counts[i]) hist_global_add(hs, hmask, in_keys[i], in_counts[i], overflow);
+    if (in_counts[i]) hist_global_add(hs, hmask, in_keys[i], in_counts[i], overflow, &s_fresh);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_fresh) atomicAdd(n_distinct, (unsigned long long)s_fresh);
 }
 
 // Roofline denominators measured on the device in use: uniform random 32-byte sector reads
@@ -374,6 +389,7 @@ struct jkq_handle {
   // histogram
   JHSlot *hs = nullptr;             // hslots + 1 fused (key, count) slots
   unsigned long long *ok = nullptr, *oc = nullptr, *n_out = nullptr;
+  unsigned long long *n_distinct = nullptr;  // slots claimed since the histogram was cleared (k_sample / k_hist_merge)
   int *overflow = nullptr;
   uint64_t hslots = 0, out_cap = 0;
   bool hist_valid = false;
@@ -511,7 +527,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
         {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
         {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
         {(void **)&E.vfwd, (size_t)E.val_cap * 4}, {(void **)&h->dev, sizeof(JEng)}, {(void **)&h->snodes, (size_t)E.node_cap * sizeof(JSNode)},
-        {(void **)&h->prob, (size_t)E.node_cap * 8}, {(void **)&h->n_out, 8}, {(void **)&h->overflow, 4}, {(void **)&h->scalar_dev, 8}};
+        {(void **)&h->prob, (size_t)E.node_cap * 8}, {(void **)&h->n_out, 8}, {(void **)&h->n_distinct, 8}, {(void **)&h->overflow, 4}, {(void **)&h->scalar_dev, 8}};
     size_t total = 0;
     for (const Part &p : parts) total += (p.bytes + 255) & ~(size_t)255;
     CU(cudaMalloc(&h->slab, total));
@@ -1072,7 +1088,7 @@ static int sample_impl(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t sh
       CU(cudaMalloc(&h->hs, (slots + 1) * sizeof(JHSlot)));
       h->hslots = slots;
     }
-    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots);
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots, h->n_distinct);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
     h->hist_valid = true;
@@ -1082,7 +1098,7 @@ static int sample_impl(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t sh
     int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
     CU(cudaEventRecord(h->ev3, h->stream));
     k_sample<<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hs,
-                                            (uint32_t)(h->hslots - 1), h->overflow);
+                                            (uint32_t)(h->hslots - 1), h->overflow, h->n_distinct);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     h->stats.sample_launches++;
@@ -1119,6 +1135,16 @@ extern "C" int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, s
   if (!h || !n) return JKQ_E_ARGUMENT;
   if (!h->hist_valid) return fail(h, JKQ_E_STATE, "no histogram: call jkq_sample first");
   CU(cudaSetDevice(h->device));
+  if (cap == 0 && !keys) {
+    // only the number of distinct outcomes: the kernels counted the slots they claimed
+    unsigned long long fresh = 0, all_ones = 0;
+    CU(jcopy(h, &fresh, h->n_distinct, 8, cudaMemcpyDeviceToHost));
+    CU(jcopy(h, &all_ones, &h->hs[h->hslots].cnt, 8, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    *n = (size_t)(fresh + (all_ones ? 1 : 0));
+    h->stats.distinct_outcomes = *n;
+    return JKQ_E_OK;
+  }
   uint64_t want = cap ? cap : 1;
   if (want > h->out_cap) {
     cudaFree(h->ok); cudaFree(h->oc);
@@ -1185,7 +1211,7 @@ extern "C" int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const u
       CU(cudaMalloc(&h->hs, (slots + 1) * sizeof(JHSlot)));
       h->hslots = slots;
     }
-    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots);
+    k_hist_fill<<<h->sm_count * 4, 256, 0, h->stream>>>(h->hs, h->hslots, h->n_distinct);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->overflow, 0, 4, h->stream));
     h->hist_valid = true;
@@ -1194,7 +1220,7 @@ extern "C" int jkq_counts_merge(jkq_handle *h, const uint64_t *dev_keys, const u
     uint64_t want = (n + 255) / 256;
     int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
     k_hist_merge<<<blocks, 256, 0, h->stream>>>(h->hs, (uint32_t)(h->hslots - 1), (const unsigned long long *)dev_keys,
-                                                (const unsigned long long *)dev_counts, n, h->overflow);
+                                                (const unsigned long long *)dev_counts, n, h->overflow, h->n_distinct);
     CU(cudaGetLastError());
   }
   int ovf = 0;
@@ -1526,7 +1552,7 @@ extern "C" int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint3
       CU(cudaMemcpyPeerAsync(src->oc, src->device, ph->oc, ph->device, n * 8, src->stream));
       int blocks = (int)((n + 255) / 256);
       if (blocks > src->sm_count * 8) blocks = src->sm_count * 8;
-      k_hist_merge<<<blocks, 256, 0, src->stream>>>(src->hs, (uint32_t)(src->hslots - 1), src->ok, src->oc, n, src->overflow);
+      k_hist_merge<<<blocks, 256, 0, src->stream>>>(src->hs, (uint32_t)(src->hslots - 1), src->ok, src->oc, n, src->overflow, src->n_distinct);
       CU(cudaGetLastError());
       CU(cudaStreamSynchronize(src->stream));
     }
@@ -1604,6 +1630,7 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
                                                  JBatchOut *out, unsigned long long *keys, unsigned long long *counts) {
   __shared__ unsigned int s_i, s_cnt;
   __shared__ int s_ovf;
+  __shared__ unsigned int s_fresh_unused;
   const JBatchEng be = engs[blockIdx.x];
   JEng *E = be.E;
   for (;;) {
@@ -1648,7 +1675,7 @@ __global__ void __launch_bounds__(256, 1) k_batch(const JBatchEng *engs, const J
         const bool active = s < shots;
         const uint64_t key = active ? sample_walk(be.sn, 1u, (int)cd.n, cd.sp.bitpos, cd.seed, s) : JH_EMPTY;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
-        if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hs, hslots - 1, key, __popc(peers), &s_ovf);
+        if (active && lane == (uint32_t)(__ffs(peers) - 1)) hist_global_add(be.hs, hslots - 1, key, __popc(peers), &s_ovf, &s_fresh_unused);
       }
       __syncthreads();
       for (uint32_t k = threadIdx.x; k < hslots; k += blockDim.x)

@@ -15,6 +15,7 @@ world size.
 import numpy as np
 
 DENSE_MAX_BITS = 20
+SMALL_HISTOGRAM = 1 << 16  # up to this many distinct outcomes per rank the (key, count) pairs are simply all-gathered
 
 
 def shard(total, rank, world):
@@ -179,8 +180,14 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None, 
     # measured qubits (a sparse map such as {0: 5} has one measured qubit and keys up to 32)
     n_bits = max([int(b) for b in mm if b < 64] + [0]) + 1
     if world > 1 and sparse == "owner" and n_bits > DENSE_MAX_BITS and dist.get_backend() == "nccl":
-        owned, total, sent, _ = merge_counts_by_owner(dist, engine)
-        return {"owned": owned, "distinct_total": total, "pairs_sent": sent}, engine.stats()
+        # how large is the largest local histogram?  (counted by the sampling kernel itself: no pass over the table)
+        import torch
+        d = torch.tensor([engine.distinct_outcomes()], dtype=torch.int64, device=_dev(dist))
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        if int(d[0]) > SMALL_HISTOGRAM:
+            owned, total, sent, _ = merge_counts_by_owner(dist, engine)
+            return {"owned": owned, "distinct_total": total, "pairs_sent": sent}, engine.stats()
+        n_bits = 64  # a handful of outcomes of a wide register (GHZ): the all-gather merge below
     keys, vals = engine.counts_arrays()
     if world > 1:
         return merge_counts(dist, keys, vals, n_bits), engine.stats()

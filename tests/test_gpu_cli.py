@@ -283,3 +283,45 @@ def test_if_op_needs_something_to_guard(eng):
     from qiskit_jku_provider_b200.jkusimulatorerror import JKUSimulatorError
     with pytest.raises(JKUSimulatorError):
         eng.load_ops(2, [simple_op(OP_IF, 0, 1)])
+
+
+def test_cli_guarded_first_measurement(cli):
+    """`if (c == 0) measure ...` as the first measurement: the prefix "before the first measurement" ends in
+    front of the guard instead of in a dangling IF op."""
+    qasm = HEADER + "qreg q[2];\ncreg c[2];\nh q[0];\ncx q[0],q[1];\nif(c==0) measure q[0] -> c[0];\nmeasure q[1] -> c[1];\n"
+    got, _, _ = run_cli(cli, qasm, 2000, 3, [])
+    assert set(got["counts"]) == {"00", "11"} and sum(got["counts"].values()) == 2000
+    assert abs(got["counts"]["00"] - 1000) < 150
+
+
+def test_cli_resident_server_prints_what_a_fresh_process_prints(cli, tmp_path):
+    """`jku_simulator --serve`: every ordinary invocation forwards to it (no CUDA start-up in the short-lived process)
+    and prints the very same stdout -- counts, snapshots, statistics -- with the same exit code, also for errors."""
+    import time
+    env = dict(os.environ, JKU_SIMULATOR_SOCKET=str(tmp_path / "jku.sock"))
+    server = subprocess.Popen([cli, "--serve", "--idle=120"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        for _ in range(200):
+            if os.path.exists(env["JKU_SIMULATOR_SOCKET"]):
+                break
+            time.sleep(0.05)
+        assert os.path.exists(env["JKU_SIMULATOR_SOCKET"])
+        for name in PROGRAMS[:4]:
+            qasm, rec, _ = load_case(name)
+            args = ["--simulate_qasm", "--shots=%d" % rec["shots"], "--seed=%d" % rec["seed"]] + list(rec["flags"])
+            fresh = subprocess.run([cli, "--no_server"] + args, input=qasm, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                   universal_newlines=True, timeout=600)
+            t0 = time.perf_counter()
+            served = subprocess.run([cli] + args, input=qasm, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                    universal_newlines=True, timeout=600)
+            dt = time.perf_counter() - t0
+            assert served.returncode == fresh.returncode == 0
+            assert served.stdout == fresh.stdout, name
+            assert dt < 2.0
+        bad = subprocess.run([cli, "--simulate_qasm", "--shots=1"], input="OPENQASM 2.0;\nqreg q[1];\nfoo q[0];\n", env=env,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=60)
+        assert bad.returncode == 1 and "ERROR" in bad.stderr
+        assert server.poll() is None  # a failed request does not end the server
+    finally:
+        server.terminate()
+        server.wait(timeout=10)
