@@ -298,6 +298,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
   // the whole gate by itself (solo), without a barrier
   JHand *hand = MODE == MODE_CTA ? &c.sh->hand[gi & 1] : &E->hand[gi & 1];
   if (thin_warp) {
+    if (MODE == MODE_CTA && c.ltid == 0) c.sh->solo_now = 1;  // (everybody else is at the gate barrier)
     if (MODE == MODE_CTA && c.sh->gen >= 0xFFF0u) {  // generation tags about to wrap: clear the de-dup tables (nobody else is using them)
       for (uint32_t i = c.ltid; i < JKQ_SNODES; i += JKQ_WARP) c.sh->mdir[i] = 0;
       for (uint32_t i = c.ltid; i < JKQ_SDT_SLOTS; i += JKQ_WARP) c.sh->dtab[i] = 0;
@@ -375,6 +376,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       JPROF_ADD(c, 14, sp3, sp4);
     }
     if (c.ltid == 0) {
+      if (MODE == MODE_CTA && wide_L >= 0) c.sh->solo_now = 0;  // every warp joins in: values go through propose / commit
       hand->lsw = (uint32_t)lsw; hand->blocked = blocked; hand->wide_L = wide_L; hand->wide_b = b; hand->wide_low = lowest;
       hand->collect = want_collect<MODE>(c, log);
       if (!f && wide_L < 0) {
@@ -770,7 +772,7 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       S->pend_n[0] = S->pend_n[1] = S->pend_n[2] = 0;
       S->bflags[0] = S->bflags[1] = S->bflags[2] = S->bflags[3] = 0;
       S->err = (uint32_t)E->status; S->want_grid = 0; S->nofit = 0;
-      S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw; S->chain_dirty = 1;
+      S->gen = 1; S->lsw = 0; S->root = E->root; S->rootw = E->rootw; S->chain_dirty = 1; S->solo_now = 0; S->val_lock = 0;
       S->flushed_nodes = S->node_count; S->flushed_vals = S->val_count;  // shared memory holds nothing yet
       S->next_gate = E->next_gate;
       for (int k = 0; k <= JST_N; k++) S->st[k] = 0;

@@ -99,7 +99,8 @@ JD uint32_t jffs(uint32_t x) { return (uint32_t)__ffs((int)x); }
 #define JKQ_SDEFER 8u        // items per level that were created for a level further down
 struct CtaState {
   uint32_t item_count, node_count, val_count, item_limit;
-  uint32_t node_limit, val_limit, chain_dirty, pad5;  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
+  uint32_t node_limit, val_limit, chain_dirty, solo_now;  // solo_now: the cursor warp is the only one at work (real_lookup)
+  uint32_t val_lock, pad_l[3];  // pool sizes the gate code may use (a reserve stays for cursor_to_root)
   uint32_t node_hard, val_hard, node_soft, val_soft;
   JHand hand[2];
   uint32_t pend_n[3], err;
@@ -409,6 +410,7 @@ template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, do
   else jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
 }
 
+template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x);
 // index of the entry within tol of x (x >= 0), or JV_MISS; with `propose` a miss leaves x as a candidate
 template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
   const double tol = jtol2<MODE>(E, S);
@@ -435,6 +437,9 @@ template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring,
       sl = ld_s<MODE>(tab + hh);
     }
   }
+#ifndef JKQ_NO_SOLO_INSERT
+  if (propose && MODE == MODE_CTA && S->solo_now) return real_insert_solo<MODE>(E, S, x);
+#endif
   if (propose) real_propose<MODE>(E, S, ring, x, k);
   return JV_MISS;
 }
@@ -513,9 +518,41 @@ template <int MODE> JNI uint32_t real_insert_direct(JEng *E, CtaState *S, double
   }
   JVSlot sl;
   sl.vbits = jd2u(x); sl.keylo = (uint32_t)k; sl.id1 = idx + 1;
+  jfence<MODE>();  // the real before the slot that names it (real_insert_solo: other lanes look things up meanwhile)
   tab[h] = sl;
   return idx;
 }
+// A miss while the cursor warp works alone (solo levels, thin gates, cursor moves: every gate of a narrow diagram).
+// Nobody but the lanes of this one warp touches the table, so the value goes in at once instead of through the
+// propose / commit round that exists for concurrent phases -- and the item that needed it is not run a second time
+// (Grover n=20 spent a fifth of its time in those second runs).  The lanes take turns under a lock in shared memory;
+// under it a lane looks again (another lane may just have inserted a value within tol: first come, first kept, as
+// in the reference, QMDDcomplexD.cpp:402-418) and appends only if the value is still missing.  JV_MISS only when the
+// shared pools are exhausted (sticky want_grid: the gate is abandoned).
+template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x) {
+  uint32_t r = JV_MISS;
+#ifdef JKQ_EMU
+  r = real_lookup<MODE>(E, S, 0, x, false);
+  if (r == JV_MISS) { r = real_insert_direct<MODE>(E, S, x); if (S->want_grid) r = JV_MISS; }
+#else
+  bool done = false;
+  while (!done) {
+    if (atomicCAS(&S->val_lock, 0u, 1u) == 0u) {
+      __threadfence_block();
+      r = real_lookup<MODE>(E, S, 0, x, false);
+      if (r == JV_MISS) {
+        r = real_insert_direct<MODE>(E, S, x);
+        if (*(volatile uint32_t *)&S->want_grid) r = JV_MISS;
+      }
+      __threadfence_block();
+      atomicExch(&S->val_lock, 0u);
+      done = true;
+    }
+  }
+#endif
+  return r;
+}
+
 // parallel hash-only insert of an existing real (collector / table reload): slot claimed by CAS on id1
 template <int MODE> JD void vt_put(JEng *E, CtaState *S, uint32_t idx, double x) {
   const long long k = vt_bucket(x, jinv_tol2<MODE>(E, S));
