@@ -114,3 +114,24 @@ def test_dd_broadcast_through_device_buffers():
         b.dd_import_device(circ.n, buf.data_ptr(), n_nodes, root, a.measure_map())
         b.sample(50000, seed=3)
         assert b.counts() == a.counts()
+
+
+def test_packed_and_fused_histograms_hold_the_same_counts():
+    """Registers of at most 32 classical bits are counted in packed 8-byte slots (key << 32 | count, one atomic per new
+    outcome), wider ones in fused 16-byte slots; the option ``histogram_fused`` forces the second format."""
+    from qiskit_jku_provider_b200 import circuits as C
+    from qiskit_jku_provider_b200.engine import Engine
+    for circ, shots in ((C.qft(20), 3000000), (C.random_circuit(12, 60, 2), 500000), (C.ghz(40), 100000)):
+        with Engine(device=0, node_capacity=1 << 16) as e:
+            e.load(circ)
+            e.run(shots, 11)
+            a = e.counts()
+            e.set_option("histogram_fused", 1)
+            e.run(shots, 11)
+            assert e.counts() == a and sum(a.values()) == shots
+            e.set_option("histogram_fused", 0)
+            # accumulate in two halves: the same histogram
+            e.apply()
+            e.sample(shots // 2, seed=11, shot_offset=0, accumulate=False)
+            e.sample(shots - shots // 2, seed=11, shot_offset=shots // 2, accumulate=True)
+            assert e.counts() == a
