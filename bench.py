@@ -449,6 +449,21 @@ def main():
             "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue (longest gate list first); circuits split "
                     "i % world == rank; kernel_ms = k_batch + the circuits that outgrew one SM, redone from gate 0 on up to 4 full engines side by side (that part by the host clock: an upper bound)"}
         if rank == 0:
+            # the CPU side of the batch: the unmodified reference, one process per circuit like its Python
+            # backend runs them, P processes side by side on the host cores; a bounded sample of the same batch
+            import oracle as _o
+            from concurrent.futures import ThreadPoolExecutor
+            if _o.have_reference():
+                sample_n = 64
+                for procs in sorted({1, min(16, os.cpu_count() or 1)}):
+                    t2 = time.perf_counter()
+                    with ThreadPoolExecutor(procs) as ex:
+                        list(ex.map(lambda c4: _o.run_reference(c4, shots=1024, seed=1), batch[:sample_n]))
+                    dt = time.perf_counter() - t2
+                    extra["batch_1024_random18_40"]["cpu_reference_%d_processes" % procs] = {
+                        "circuits_sampled": sample_n, "wall_s": dt, "circuits_per_s": sample_n / dt,
+                        "gate_applies_per_s": sum(len(c4) for c4 in batch[:sample_n]) / dt,
+                        "note": "oracle/_ref/jku_ref (unmodified reference), apply + 1024 shots per circuit, process start included"}
             for c3 in (C.ghz(24), C.grover(20, 20), C.random_circuit(18, 100, 1), C.random_circuit(18, 120, 1), C.random_circuit(18, 160, 1)):
                 eng.load(c3)
                 eng.apply()

@@ -1590,13 +1590,23 @@ extern "C" int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint3
   const bool merge = n_devices == 1 || (outcomes <= (1ull << 26) && outcomes * 2 * sizeof(JHSlot) + outcomes * 32 < free_b / 2);
   // sample: one host thread per device (jkq_sample blocks on its stream)
   std::vector<int> rcs(n_devices, 0);
+  std::vector<size_t> compacted(n_devices, 0);
   std::vector<std::thread> th;
   for (uint32_t i = 0; i < n_devices; i++) {
     const uint64_t lo = shots / n_devices * i + (i < shots % n_devices ? i : shots % n_devices);
     const uint64_t cnt = shots / n_devices + (i < shots % n_devices ? 1 : 0);
     jkq_handle *ph = hs[i];
     const uint64_t expect = (ph == src && merge) ? shots : cnt;
-    th.emplace_back([=, &rcs]() { rcs[i] = sample_impl(ph, cnt, seed, lo, 0, expect); });
+    // (a helper also compacts its histogram right away, in its own thread: the merge below only copies and adds)
+    th.emplace_back([=, &rcs, &compacted]() {
+      rcs[i] = sample_impl(ph, cnt, seed, lo, 0, expect);
+      if (!rcs[i] && merge && ph != src) {
+        size_t n = 0;
+        rcs[i] = jkq_get_counts(ph, nullptr, nullptr, 0, &n);
+        if (!rcs[i] && n) rcs[i] = jkq_get_counts(ph, nullptr, nullptr, n, &n);  // into ph->ok / ph->oc on its device (keys == NULL: no host copy)
+        compacted[i] = n;
+      }
+    });
   }
   for (std::thread &t : th) t.join();
   for (uint32_t i = 0; i < n_devices; i++)
@@ -1607,34 +1617,29 @@ extern "C" int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint3
   // merge on the device: compact on the helper, peer copy, k_hist_merge on src
   uint64_t distinct_total = 0;
   if (merge) {
+    CU(cudaSetDevice(src->device));
+    size_t most = 0;
+    for (uint32_t i = 0; i < n_devices; i++) if (compacted[i] > most) most = compacted[i];
+    if (most > src->out_cap) {
+      cudaFree(src->ok); cudaFree(src->oc);
+      src->ok = src->oc = nullptr;
+      CU(cudaMalloc(&src->ok, most * 8));
+      CU(cudaMalloc(&src->oc, most * 8));
+      src->out_cap = most;
+    }
     for (uint32_t i = 0; i < n_devices; i++) {
       jkq_handle *ph = hs[i];
-      if (ph == src) continue;
-      size_t n = 0;
-      int rc = jkq_get_counts(ph, nullptr, nullptr, 0, &n);  // how many
-      if (rc) return fail(src, rc, "device %d: %s", ph->device, ph->err.c_str());
-      if (n == 0) continue;
-      rc = jkq_get_counts(ph, nullptr, nullptr, n, &n);  // compacts into ph->ok / ph->oc on its device (no host copy: keys == NULL)
-      if (rc) return fail(src, rc, "device %d: %s", ph->device, ph->err.c_str());
-      CU(cudaSetDevice(src->device));
-      if (n > src->out_cap) {
-        cudaFree(src->ok); cudaFree(src->oc);
-        src->ok = src->oc = nullptr;
-        CU(cudaMalloc(&src->ok, n * 8));
-        CU(cudaMalloc(&src->oc, n * 8));
-        src->out_cap = n;
-      }
+      const size_t n = compacted[i];
+      if (ph == src || n == 0) continue;
       CU(cudaMemcpyPeerAsync(src->ok, src->device, ph->ok, ph->device, n * 8, src->stream));
       CU(cudaMemcpyPeerAsync(src->oc, src->device, ph->oc, ph->device, n * 8, src->stream));
       int blocks = (int)((n + 255) / 256);
       if (blocks > src->sm_count * 8) blocks = src->sm_count * 8;
       if (src->hist_packed) k_hist_merge<true><<<blocks, 256, 0, src->stream>>>(src->hs, (uint32_t)(src->hslots - 1), src->ok, src->oc, n, src->overflow, src->n_distinct);
       else k_hist_merge<false><<<blocks, 256, 0, src->stream>>>(src->hs, (uint32_t)(src->hslots - 1), src->ok, src->oc, n, src->overflow, src->n_distinct);
-      CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(src->stream));
+      CU(cudaGetLastError());  // (the next peer's pairs reuse src->ok / src->oc: same stream, in order)
     }
     int ovf = 0;
-    CU(cudaSetDevice(src->device));
     CU(jcopy(src, &ovf, src->overflow, 4, cudaMemcpyDeviceToHost));
     CU(cudaStreamSynchronize(src->stream));
     if (ovf) return fail(src, JKQ_E_CAPACITY, "count histogram overflow in the merge");

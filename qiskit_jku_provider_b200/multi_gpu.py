@@ -51,34 +51,78 @@ def broadcast_dd(dist, nodes, root, n_qubits, measure_map, src=0):
     return out, root, n_qubits, mm
 
 
+INLINE_DD_NODES = 4096  # a sampling DD of up to this many nodes travels in the same broadcast as its header
+
+
 def broadcast_dd_device(dist, engine, src=0):
     """NCCL path: the sampling DD travels device to device -- ``jkq_dd_export_device`` into a torch tensor on rank
-    ``src``, one NCCL broadcast over NVLink, ``jkq_dd_import_device`` everywhere else.  No host staging of the node
-    array (the 3 + 64 header words are the only thing a rank reads back).  Returns (n_qubits, measure map)."""
+    ``src``, NCCL broadcast over NVLink, ``jkq_dd_import_device`` everywhere else.  No host staging of the node
+    array (the 3 + 64 header words are the only thing a rank reads back).  A DD of at most INLINE_DD_NODES nodes (GHZ:
+    47, QFT-32: 32) rides in the header's broadcast: one collective.  Returns (n_qubits, measure map)."""
     import torch
     dev = _dev(dist)
     rank = dist.get_rank()
-    hdr = torch.zeros(3 + 64, dtype=torch.int64, device=dev)
+    H = 3 + 64
+    buf = torch.zeros(H + 2 * INLINE_DD_NODES, dtype=torch.int64, device=dev)
     n_nodes = root = 0
     if rank == src:
         n_nodes, root = engine.dd_size()
         mm = engine.measure_map()
-        h = np.zeros(3 + 64, dtype=np.int64)
+        h = np.zeros(H, dtype=np.int64)
         h[0], h[1], h[2] = n_nodes, root, engine.n
         h[3:3 + engine.n] = mm
-        hdr.copy_(torch.from_numpy(h))
-    dist.broadcast(hdr, src=src)
-    hh = hdr.cpu().numpy()
+        buf[:H].copy_(torch.from_numpy(h))
+        if n_nodes <= INLINE_DD_NODES:
+            engine.dd_export_device(buf.data_ptr() + 8 * H, n_nodes)
+    dist.broadcast(buf, src=src)
+    hh = buf[:H].cpu().numpy()
     n_nodes, root, n_qubits = int(hh[0]), int(hh[1]), int(hh[2])
     mm = hh[3:3 + n_qubits].astype(np.uint8)
-    buf = torch.empty(n_nodes * 2, dtype=torch.int64, device=dev)  # 16 bytes per node
+    if n_nodes <= INLINE_DD_NODES:
+        if rank != src:  # (.cpu() above synchronised the stream the broadcast ran on)
+            engine.dd_import_device(n_qubits, buf.data_ptr() + 8 * H, n_nodes, root, mm)
+        return n_qubits, mm
+    big = torch.empty(n_nodes * 2, dtype=torch.int64, device=dev)  # 16 bytes per node
     if rank == src:
-        engine.dd_export_device(buf.data_ptr(), n_nodes)
-    dist.broadcast(buf, src=src)
+        engine.dd_export_device(big.data_ptr(), n_nodes)
+    dist.broadcast(big, src=src)
     if rank != src:
         torch.cuda.current_stream().synchronize()  # the library copies on its own stream
-        engine.dd_import_device(n_qubits, buf.data_ptr(), n_nodes, root, mm)
+        engine.dd_import_device(n_qubits, big.data_ptr(), n_nodes, root, mm)
     return n_qubits, mm
+
+
+TINY_HISTOGRAM = 1024  # up to this many distinct outcomes per rank: one all-gather of fixed-size blocks merges them
+
+
+def merge_counts_tiny(dist, engine):
+    """A handful of outcomes per rank (GHZ: 2): every rank puts (n, keys, counts) into a fixed block, ONE all-gather,
+    merged on the host.  Returns the dict, or None when some rank holds more than TINY_HISTOGRAM outcomes."""
+    import torch
+    dev = _dev(dist)
+    world = dist.get_world_size()
+    K = TINY_HISTOGRAM
+    n = engine.distinct_outcomes()
+    blk = np.zeros(1 + 2 * K, dtype=np.int64)
+    if n <= K:
+        keys, vals = engine.counts_arrays()
+        blk[0] = len(keys)
+        blk[1:1 + len(keys)] = keys.view(np.int64)
+        blk[1 + K:1 + K + len(keys)] = vals.view(np.int64)
+    else:
+        blk[0] = -1
+    mine = torch.from_numpy(blk).to(dev)
+    allb = torch.empty(world * (1 + 2 * K), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allb, mine)
+    a = allb.cpu().numpy().reshape(world, 1 + 2 * K)
+    if (a[:, 0] < 0).any():
+        return None
+    merged = {}
+    for r in range(world):
+        m = int(a[r, 0])
+        for k, v in zip(a[r, 1:1 + m].view(np.uint64).tolist(), a[r, 1 + K:1 + K + m].tolist()):
+            merged[k] = merged.get(k, 0) + v
+    return merged
 
 
 def merge_counts(dist, keys, counts, n_bits):
@@ -179,6 +223,10 @@ def sample_sharded(dist, engine, total_shots, seed, circuit=None, measure=None, 
     # histogram keys are indexed by classical-bit POSITION: the width is the highest position + 1, not the number of
     # measured qubits (a sparse map such as {0: 5} has one measured qubit and keys up to 32)
     n_bits = max([int(b) for b in mm if b < 64] + [0]) + 1
+    if world > 1 and dist.get_backend() == "nccl":
+        tiny = merge_counts_tiny(dist, engine)
+        if tiny is not None:
+            return tiny, engine.stats()
     if world > 1 and sparse == "owner" and n_bits > DENSE_MAX_BITS and dist.get_backend() == "nccl":
         # how large is the largest local histogram?  (counted by the sampling kernel itself: no pass over the table)
         import torch
