@@ -34,6 +34,7 @@ enum {
   JKQ_E_ZERO_STATE = 8,  /* "numerical instabilities led to a 0-vector", Simulator.cpp:158-161 */
   JKQ_E_INTERNAL = 9,
   JKQ_E_RETRY_LIMIT = 10, /* watchdog: one level kept producing new values for 512 rounds */
+  JKQ_E_VALUE_RANGE = 11, /* a weight of magnitude >= 1e8 or NaN: numerical breakdown of the state, not a capacity problem */
   JKQ_E_CUDA = 100,      /* CUDA runtime error or no device */
   JKQ_E_ARGUMENT = 101,
   JKQ_E_STATE = 102,     /* call made in the wrong order */

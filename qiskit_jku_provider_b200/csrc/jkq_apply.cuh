@@ -533,6 +533,31 @@ JD void ut_put_hbm(JEng *E, unsigned long long gen, const JNode &nn, uint32_t id
 // work here: a claimed slot takes atomicMin proposals and would have to be reset first.
 JD uint32_t vt_mask_for(const JEng *E, uint32_t) { return E->vtab_mask; }
 
+// Clear the HBM value table before a sweep re-fills it: only the 128-byte lines in which a slot was claimed since the
+// last clear (JEng.vbm), found by a scan of the 1-bit-per-line map (4 MB for 2^28 slots) -- writes proportional to the
+// reals that were in the table, not to its allocation.  All threads of the grid; the caller puts a barrier behind it.
+template <int MODE> JD void vt_clear_used(Ctx &c) {
+  JEng *E = c.E;
+  if (ld_s<MODE>(&E->vt_dirty_all)) {  // first use of this allocation: everything
+    for (uint32_t i = c.tid; i <= E->vtab_mask; i += c.nth) vt_clear_slot(E->vtab + i);
+    for (uint32_t i = c.tid; i < ((E->vtab_mask + 1) >> 8) + 1; i += c.nth) E->vbm[i] = 0;
+    return;
+  }
+  const uint32_t nw = ((E->vtab_mask + 1) >> 8) + 1;
+  for (uint32_t i = c.tid; i < nw; i += c.nth) {
+    uint32_t w = ld_s<MODE>(E->vbm + i);
+    if (!w) continue;
+    E->vbm[i] = 0;
+    while (w) {
+      const uint32_t b = jffs(w) - 1u;
+      w &= w - 1u;
+      JVSlot *line = E->vtab + (((size_t)i * 32u + b) << 3);
+      JKQ_UNROLL
+      for (int k = 0; k < 8; k++) vt_clear_slot(line + k);
+    }
+  }
+}
+
 template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   JEng *E = c.E;
   const int n = (int)E->n;
@@ -665,10 +690,10 @@ template <int MODE> JNI uint32_t gc_run(Ctx c, bool reload, bool force_vals) {
   const uint32_t nv = rd_vals<MODE>(c);
   const bool fits = MODE != MODE_CTA || !c.sh->want_grid;
   const unsigned long long ugen = MODE == MODE_GRID ? (unsigned long long)ld_s<MODE_GRID>(&E->ut_gen) << 32 : 0ull;
-  if (MODE == MODE_GRID && clean_vals) {  // the part of the value table about to be filled
-    const uint32_t vm = ld_s<MODE_GRID>(&E->vt_cur);
-    for (uint32_t i = c.tid; i <= vm; i += c.nth) vt_clear_slot(E->vtab + i);
+  if (MODE == MODE_GRID && clean_vals) {  // the lines of the value table that hold something
+    vt_clear_used<MODE>(c);
     sync_or<MODE>(c, 0);
+    if (c.block0 && c.ltid == 0) E->vt_dirty_all = 0;
   }
   if (MODE == MODE_CTA && !fits && c.ltid == 0) c.sh->nofit = 1;
   // copy back with remapped weights, rebuild the unique table
@@ -795,9 +820,9 @@ template <int MODE> JD uint32_t mode_enter(Ctx &c) {
       if (c.block0 && c.ltid == 0) { E->ut_gen++; E->vt_cur = vt_mask_for(E, nv); }
       sync_or<MODE>(c, 0);
       const unsigned long long ugen = (unsigned long long)ld_s<MODE>(&E->ut_gen) << 32;
-      const uint32_t vm = ld_s<MODE>(&E->vt_cur);
-      for (uint32_t i = c.tid; i <= vm; i += c.nth) vt_clear_slot(E->vtab + i);
+      vt_clear_used<MODE>(c);
       sync_or<MODE>(c, 0);
+      if (c.block0 && c.ltid == 0) E->vt_dirty_all = 0;
       for (uint32_t i = 1 + c.tid; i < nn; i += c.nth) {
         const JNode nd = ld_s<MODE>(E->nodes + i);
         if (nd.c1 == JN_TOMB) continue;

@@ -54,7 +54,13 @@ template <int MODE> __global__ void __launch_bounds__(256) k_init(JEng *E) {
 }
 
 // Persistent circuit kernel: all gates of a segment in one launch, no host round trip per gate.
-template <int MODE> __global__ void __launch_bounds__(256, 1) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
+// The grid shape is bound by memory-level parallelism: every thread follows ONE dependent chain of random accesses, so
+// throughput = resident threads / latency.  Two CTAs per SM (128 registers per thread, the rest spills to L1-cached local
+// memory) instead of one doubles the accesses in flight (JKQ_GRID_MINB: A/B builds).
+#ifndef JKQ_GRID_MINB
+#define JKQ_GRID_MINB 1
+#endif
+template <int MODE> __global__ void __launch_bounds__(256, (MODE == MODE_GRID ? JKQ_GRID_MINB : 1)) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
   Ctx c = make_ctx<MODE>(E);
   run_gates<MODE>(c, gates, n_gates);
 }
@@ -490,6 +496,7 @@ static const char *status_text(int s) {
     case JKQ_ERR_BARRIER_TIMEOUT: return "grid barrier timeout";
     case JKQ_ERR_ZERO_STATE: return "numerical instabilities led to a 0-vector";
     case JKQ_ERR_RETRY_LIMIT: return "a level kept producing new values (retry limit of the value table reached)";
+    case JKQ_ERR_VAL_RANGE: return "a weight of absurd magnitude (>= 1e8) or NaN: numerical breakdown";
     default: return "internal error";
   }
 }
@@ -545,7 +552,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   cfg.cta_threads = (cfg.cta_threads + 31) & ~31u;
   if (!cfg.cta_item_limit || cfg.cta_item_limit > JKQ_SITEMS / 2) cfg.cta_item_limit = JKQ_SITEMS / 2;
   if (!cfg.gc_min) cfg.gc_min = 1u << 15;
-  if (!cfg.grid_blocks_per_sm) cfg.grid_blocks_per_sm = 2;
+  if (!cfg.grid_blocks_per_sm) cfg.grid_blocks_per_sm = JKQ_GRID_MINB;
   h->cfg = cfg;
   h->device = cfg.device;
   memset(&h->stats, 0, sizeof(h->stats));
@@ -578,7 +585,8 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
     const Part parts[] = {
         {(void **)&E.nodes, (size_t)E.node_cap * sizeof(JNode)}, {(void **)&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)},
         {(void **)&E.utab, ((size_t)E.utab_mask + 1) * 8}, {(void **)&E.vals, (size_t)E.val_cap * 8}, {(void **)&E.vals_alt, (size_t)E.val_cap * 8},
-        {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.pend, (size_t)E.pend_cap * 4},
+        {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.vbm, ((((size_t)E.vtab_mask + 1) >> 8) + 1) * 4},
+        {(void **)&E.pend, (size_t)E.pend_cap * 4},
         {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
         {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
         {(void **)&E.vfwd, (size_t)E.val_cap * 4}, {(void **)&h->dev, sizeof(JEng)}, {(void **)&h->snodes, (size_t)E.node_cap * sizeof(JSNode)},
@@ -591,7 +599,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   }
   // generation-tagged de-dup tables: zeroed once, never cleared again (the generation counts across circuits)
   CU(cudaMemsetAsync(E.utab, 0, ((size_t)E.utab_mask + 1) * 8, h->stream));  // (generation 0 = never written)
-  E.ut_gen = 1; E.vt_cur = E.vtab_mask;
+  E.ut_gen = 1; E.vt_cur = E.vtab_mask; E.vt_dirty_all = 1;
   CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
   CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
   CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));

@@ -371,6 +371,19 @@ JD uint32_t vt_next(uint32_t h, uint32_t mask) { return (h + 8u) & mask; }
 JD unsigned long long *vt_meta(JVSlot *s) { return reinterpret_cast<unsigned long long *>(&s->keylo); }
 JD unsigned long long vt_meta_of(uint32_t keylo, uint32_t id1) { return (unsigned long long)keylo | ((unsigned long long)id1 << 32); }
 
+// HBM table: remember that the line of slot h holds something (see JEng.vbm); a load first, the atomic only for the
+// first claim in a line
+template <int MODE> JD void vt_mark(JEng *E, uint32_t h) {
+  if (MODE != MODE_GRID) return;
+  const uint32_t line = h >> 3, bit = 1u << (line & 31u);
+  uint32_t *w = E->vbm + (line >> 5);
+#ifdef JKQ_EMU
+  *w |= bit;
+#else
+  if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+#endif
+}
+
 template <int MODE> JD void pend_push(JEng *E, CtaState *S, uint32_t ring, uint32_t slot) {
   uint32_t i = MODE == MODE_CTA ? jatomic_add(&S->pend_n[ring], 1u) : jagg_inc(&E->pend_n[ring]);
   if (MODE == MODE_CTA) {
@@ -393,7 +406,7 @@ template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, do
     unsigned long long meta = ld_r<MODE>(mp);
     if (meta == 0) {
       meta = jatomic_cas(mp, 0ull, claim);
-      if (meta == 0) { jatomic_min(&tab[h].vbits, xb); pend_push<MODE>(E, S, ring, h); return; }
+      if (meta == 0) { vt_mark<MODE>(E, h); jatomic_min(&tab[h].vbits, xb); pend_push<MODE>(E, S, ring, h); return; }
     }
     if ((uint32_t)meta == klo) {
       const uint32_t id1 = (uint32_t)(meta >> 32);
@@ -415,8 +428,8 @@ template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x
 template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
   const double tol = jtol2<MODE>(E, S);
   if (x <= tol) return 0;
-  if (!(x < JKQ_VAL_MAX)) {  // absurd magnitude
-    if (propose) jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
+  if (!(x < JKQ_VAL_MAX)) {  // absurd magnitude (or NaN)
+    if (propose) jset_error<MODE>(E, S, JKQ_ERR_VAL_RANGE);
     return JV_MISS;
   }
   const long long k = vt_bucket(x, jinv_tol2<MODE>(E, S));
@@ -520,6 +533,7 @@ template <int MODE> JNI uint32_t real_insert_direct(JEng *E, CtaState *S, double
   sl.vbits = jd2u(x); sl.keylo = (uint32_t)k; sl.id1 = idx + 1;
   jfence<MODE>();  // the real before the slot that names it (real_insert_solo: other lanes look things up meanwhile)
   tab[h] = sl;
+  vt_mark<MODE>(E, h);
   return idx;
 }
 // A miss while the cursor warp works alone (solo levels, thin gates, cursor moves: every gate of a narrow diagram).
@@ -568,6 +582,7 @@ template <int MODE> JD void vt_put(JEng *E, CtaState *S, uint32_t idx, double x)
   }
   tab[h].vbits = jd2u(x);
   tab[h].keylo = (uint32_t)k;
+  vt_mark<MODE>(E, h);
 }
 
 // Clookup for one complex value.  JW_MISS = at least one part is not in the table yet; the missing

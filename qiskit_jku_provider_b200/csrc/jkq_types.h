@@ -125,6 +125,8 @@ typedef struct {
   unsigned long long *utab;  // generation << 32 | node id: a collection starts a new generation instead of clearing
   double *vals, *vals_alt;
   JVSlot *vtab;
+  uint32_t *vbm;      // one bit per 128-byte line (8 slots) of the HBM value table: some slot of the line was claimed since
+                      // the last sweep -- a sweep clears those lines instead of the whole table (4.3 GB at 2^26 reals)
   uint32_t *pend;     // value-table slots claimed in the current phase
   JItem *items;
   unsigned long long *dtab;  // F/S item de-dup: generation << 32 | item index + 1
@@ -152,6 +154,7 @@ typedef struct {
   uint32_t val_epoch;     // bumped whenever a sweep renumbers the reals
   uint32_t ut_gen;        // generation of the unique-table entries that count (older ones read as empty)
   uint32_t vt_cur;        // mask of the part of the value table in use (= vtab_mask: see vt_mask_for, jkq_apply.cuh)
+  uint32_t vt_dirty_all;  // the value table has never been cleared by this engine: the next sweep clears all of it
   double norm;        // squared norm of the state at the last finalisation
   uint32_t lvl_off[JKQ_MAXQ + 2];  // after a collection: nodes of level L are [lvl_off[L], lvl_off[L] + lvl_cnt[L])
   uint32_t lvl_cnt[JKQ_MAXQ];      // live nodes per level at the last collection
@@ -198,6 +201,7 @@ typedef struct {
 #define JKQ_ERR_ZERO_STATE 8
 #define JKQ_ERR_INTERNAL 9
 #define JKQ_ERR_RETRY_LIMIT 10  // a level kept meeting new values for JKQ_RETRY_LIMIT rounds (watchdog)
+#define JKQ_ERR_VAL_RANGE 11  // a weight of absurd magnitude (>= 1e8) or NaN: numerical breakdown, not a capacity problem
 #define JKQ_RETRY_LIMIT 512u
 
 #endif

@@ -37,15 +37,41 @@ STATEVECTOR_AUTO_MAX_QUBITS = 20
 MULTI_GPU_MIN_SHOTS = 1 << 22  # from here on the shots of one experiment are split over the backend's devices
 
 
-_TEMPLATES = {}
+class _Templates:
+    """Registry of macro-expanded gates: (name, number of qubits, params) -> a run of primitives in flat tables
+    (target position, control positions / values, matrix index into a table of distinct 2x2 matrices), positions into
+    the instruction's qubit list.  ``circuits.expand`` restates qelib1 (reference ``:32-60``).  The tables are kept as
+    numpy arrays so that a whole experiment is stamped out with a handful of vector operations instead of a Python
+    loop over its primitives."""
 
+    def __init__(self):
+        self.ids = {}
+        self.start, self.count = [], []
+        self.p_kind, self.p_t, self.p_m, self.p_ctl = [], [], [], []   # per primitive; p_ctl: ((position, value), ...)
+        self.mats, self.mat_ids = [], {}
+        self._np = None
+        for kind in (OP_MEASURE, OP_SNAPSHOT, OP_BARRIER, OP_RESET):  # the non-gate instructions are one-slot templates
+            self._add(("#", kind), [(kind, 0 if kind in (OP_MEASURE, OP_RESET) else -1, (), (0.0,) * 8)])
 
-def _gate_template(name, n_qubits, params):
-    """(name, params) -> ((target position, ((control position, value), ...), 8 floats), ...), positions into the
-    instruction's qubit list.  Raises JKUSimulatorError for a gate qelib1 does not define."""
-    key = (name, n_qubits, params)
-    tpl = _TEMPLATES.get(key)
-    if tpl is None:
+    def _add(self, key, prims):
+        tid = len(self.start)
+        self.start.append(len(self.p_kind)); self.count.append(len(prims))
+        for kind, t_pos, ctl, flat in prims:
+            mi = self.mat_ids.get(flat)
+            if mi is None:
+                mi = self.mat_ids[flat] = len(self.mats)
+                self.mats.append(flat)
+            self.p_kind.append(kind); self.p_t.append(t_pos); self.p_ctl.append(ctl); self.p_m.append(mi)
+        self.ids[key] = tid
+        self._np = None
+        return tid
+
+    def special(self, kind):
+        return self.ids[("#", kind)]
+
+    def gate(self, key):
+        """key = (name, n_qubits, params).  Raises JKUSimulatorError for a gate qelib1 does not define."""
+        name, n_qubits, params = key
         try:
             prims = circuits.expand(name, list(range(n_qubits)), params)
         except (KeyError, IndexError, ValueError):
@@ -54,11 +80,32 @@ def _gate_template(name, n_qubits, params):
         for p in prims:
             m = p.matrix()
             flat = tuple(x for row in m for z in row for x in (complex(z).real, complex(z).imag))
-            out.append((p.target, tuple(p.controls), flat))
-        tpl = tuple(out)
-        if len(_TEMPLATES) < 65536:
-            _TEMPLATES[key] = tpl
-    return tpl
+            out.append((OP_GATE, p.target, tuple(p.controls), flat))
+        return self._add(key, out)
+
+    def tables(self):
+        if self._np is None:
+            width = max(1, max(len(c) for c in self.p_ctl))
+            cpos = np.full((len(self.p_ctl), width), -1, dtype=np.int64)
+            cval = np.zeros((len(self.p_ctl), width), dtype=bool)
+            for i, ctl in enumerate(self.p_ctl):
+                for k, (pos, val) in enumerate(ctl):
+                    cpos[i, k] = pos
+                    cval[i, k] = bool(val)
+            self._np = (np.array(self.start, dtype=np.int64), np.array(self.count, dtype=np.int64),
+                        np.array(self.p_kind, dtype=np.uint32), np.array(self.p_t, dtype=np.int64),
+                        np.array(self.p_m, dtype=np.int64), cpos, cval, np.array(self.mats, dtype=np.float64).reshape(-1, 8))
+        return self._np
+
+
+_TEMPLATES = None
+
+
+def _templates():
+    global _TEMPLATES
+    if _TEMPLATES is None:
+        _TEMPLATES = _Templates()
+    return _TEMPLATES
 
 
 class JKUSimulatorWrapper:
@@ -109,24 +156,27 @@ class JKUSimulatorWrapper:
         Each named gate is macro-expanded once per (name, params) into a template of primitives
         (``circuits.expand`` restates qelib1) and stamped onto the instruction's qubits; the result is one
         numpy structured array with the memory layout of ``jkq_op`` (include/jkq.h)."""
-        kinds, targets, cpos, cneg, mats, args = [], [], [], [], [], []
+        T = _templates()
+        if len(T.start) >= 65536:  # (circuits of all-different angles: start over rather than grow without bound)
+            T.__init__()
+        ids = T.ids
+        t_measure, t_snapshot, t_barrier, t_reset = (T.special(k) for k in (OP_MEASURE, OP_SNAPSHOT, OP_BARRIER, OP_RESET))
+        tids, args, qlens, flatq = [], [], [], []   # per instruction: template, argument, its qubit list (flattened)
         self.per_shot = False
         self.max_snapshot_index = 0
         snapshot_slots = []
-        zero_m = (0.0,) * 8
         for op in experiment.instructions:
             name = op.name
             if name == 'measure':
-                kinds.append(OP_MEASURE); targets.append(op.qubits[0]); cpos.append(0); cneg.append(0)
-                mats.append(zero_m); args.append(op.memory[0])
+                tids.append(t_measure); args.append(op.memory[0]); qlens.append(1); flatq.append(op.qubits[0])
             elif name == 'snapshot':
                 params = list(getattr(op, 'params', []) or [])
                 slot = int(params[0]) if params else int(getattr(op, 'label', 0))
                 self.max_snapshot_index = max(self.max_snapshot_index, slot)
                 snapshot_slots.append(slot)
-                kinds.append(OP_SNAPSHOT); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(slot)
+                tids.append(t_snapshot); args.append(slot); qlens.append(0)
             elif name == 'barrier':
-                kinds.append(OP_BARRIER); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
+                tids.append(t_barrier); args.append(0); qlens.append(0)
             elif name == 'reset':
                 # ResetQubit (Simulator.cpp:291-339) PROJECTS on |0> and rescales -- deterministic, so the shots are
                 # drawn from the one final state.  With ``physical_reset`` the qubit is measured and flipped back
@@ -134,32 +184,44 @@ class JKUSimulatorWrapper:
                 # when a state is not reusable (QASMsimulator.cpp:501-522).
                 if self.physical_reset:
                     self.per_shot = True
-                kinds.append(OP_RESET); targets.append(op.qubits[0]); cpos.append(0); cneg.append(0); mats.append(zero_m); args.append(0)
+                tids.append(t_reset); args.append(0); qlens.append(1); flatq.append(op.qubits[0])
             else:
-                params = tuple(getattr(op, 'params', None) or ())
+                params = getattr(op, 'params', None)
                 qubits = op.qubits
-                for t_pos, ctl, m in _gate_template(name, len(qubits), params):
-                    pos = neg = 0
-                    for c_pos, val in ctl:
-                        if val:
-                            pos |= 1 << qubits[c_pos]
-                        else:
-                            neg |= 1 << qubits[c_pos]
-                    kinds.append(OP_GATE); targets.append(qubits[t_pos]); cpos.append(pos); cneg.append(neg)
-                    mats.append(m); args.append(0)
+                key = (name, len(qubits), tuple(params) if params else ())
+                tid = ids.get(key)
+                if tid is None:
+                    tid = T.gate(key)
+                    ids = T.ids
+                tids.append(tid); args.append(0); qlens.append(len(qubits)); flatq.extend(qubits)
         self.max_snapshot_index += 1  # add_final_snapshot, :116-120
         if want_final_statevector:
-            kinds.append(OP_SNAPSHOT); targets.append(0); cpos.append(0); cneg.append(0); mats.append(zero_m)
-            args.append(self.max_snapshot_index)
+            tids.append(t_snapshot); args.append(self.max_snapshot_index); qlens.append(0)
             snapshot_slots.append(self.max_snapshot_index)
-        ops = np.zeros(len(kinds), dtype=OP_DTYPE)
-        if len(kinds):
-            ops['kind'] = kinds
-            ops['target'] = targets
-            ops['ctrl_pos'] = np.array(cpos, dtype=np.uint64)
-            ops['ctrl_neg'] = np.array(cneg, dtype=np.uint64)
-            ops['m'] = np.array(mats, dtype=np.float64)
-            ops['arg'] = args
+        if not tids:
+            return np.zeros(0, dtype=OP_DTYPE), snapshot_slots
+        # stamp the templates onto the instructions' qubits, all primitives of the experiment at once
+        t_start, t_count, p_kind, p_t, p_m, p_cpos, p_cval, mats = T.tables()
+        tids = np.array(tids, dtype=np.int64)
+        cnt = t_count[tids]
+        first = np.cumsum(cnt) - cnt                       # index of the instruction's first primitive in the output
+        inst = np.repeat(np.arange(len(tids)), cnt)        # primitive -> instruction
+        prim = t_start[tids][inst] + (np.arange(len(inst)) - first[inst])   # primitive -> row of the template tables
+        qlens = np.array(qlens, dtype=np.int64)
+        qoff = (np.cumsum(qlens) - qlens)[inst]            # where the instruction's qubits start in flatq
+        flatq = np.array(flatq + [0], dtype=np.int64)
+        ops = np.zeros(len(inst), dtype=OP_DTYPE)
+        ops['kind'] = p_kind[prim]
+        tp = p_t[prim]
+        ops['target'] = np.where(tp >= 0, flatq[np.minimum(qoff + np.maximum(tp, 0), len(flatq) - 1)], 0)
+        cp = p_cpos[prim]                                  # (primitives, widest control list), -1 = no control
+        bit = np.left_shift(np.uint64(1), flatq[np.minimum(qoff[:, None] + np.maximum(cp, 0), len(flatq) - 1)].astype(np.uint64))
+        has = cp >= 0
+        val = p_cval[prim]
+        ops['ctrl_pos'] = np.bitwise_or.reduce(np.where(has & val, bit, np.uint64(0)), axis=1)
+        ops['ctrl_neg'] = np.bitwise_or.reduce(np.where(has & ~val, bit, np.uint64(0)), axis=1)
+        ops['m'] = mats[p_m[prim]]
+        ops['arg'] = np.array(args, dtype=np.int64)[inst]
         return ops, snapshot_slots
 
     def run_experiment(self, config, experiment):

@@ -7,8 +7,11 @@ import sys
 sys.path.insert(0, ".")
 from qiskit_jku_provider_b200 import circuits as C
 from qiskit_jku_provider_b200.engine import Engine
-for name, circ in (("r120", C.random_circuit(18, 120, 1)), ("r160", C.random_circuit(18, 160, 1))):
-    eng = Engine(device=0, node_capacity=1 << 20)
+import os
+big = os.environ.get("BIG")
+cases = (("r22_200", C.random_circuit(22, 200, 1)),) if big else (("r120", C.random_circuit(18, 120, 1)), ("r160", C.random_circuit(18, 160, 1)))
+for name, circ in cases:
+    eng = Engine(device=0, node_capacity=1 << (25 if big else 20), value_capacity=1 << (26 if big else 20))
     eng.load(circ); eng.apply(); st = eng.stats()
     print(name, "apply_ms", st["apply_ms"], "items", st["items"], "gc", st["gc_runs"], "retry", st["retry_rounds"], "thin", st["thin_gates"], flush=True)
     eng.close()
