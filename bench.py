@@ -433,6 +433,41 @@ def main():
             b_wall = time.perf_counter() - t2
             fb = br.fallbacks
             b_kernel_only, b_fallback = br.last_kernel_ms, br.last_fallback_ms
+        # the same batch through the provider API: ONE Qobj of 1 024 experiments into QasmSimulator(statevector=False)
+        # .run(qobj).result() -- named gates in, counts out (rank 0, its own GPU; `devices=` spreads it inside one process)
+        api = None
+        if rank == 0:
+            import random as _random
+            from qiskit_jku_provider_b200 import QasmSimulator as _QS
+            from qiskit_jku_provider_b200.compat import ClassicalRegister as _CR, QuantumCircuit as _QC, QuantumRegister as _QR, assemble as _asm
+            names = [k for k in sorted(C.RANDOM_OPS) if C.RANDOM_OPS[k][0] <= 18]
+            qcs = []
+            for s_ in range(n_batch):  # the draws of circuits.random_circuit(18, 40, s_), kept as named instructions
+                rng = _random.Random(s_)
+                qr_, cr_ = _QR(18, "q"), _CR(18, "c")
+                qc_ = _QC(qr_, cr_, name="random18_40_s%d" % s_)
+                for _ in range(40):
+                    nm = rng.choice(names)
+                    nregs, nparams = C.RANDOM_OPS[nm]
+                    pr = [rng.random() for _ in range(nparams)]
+                    qc_.data.append((nm, pr, rng.sample(range(18), nregs), []))
+                qc_.measure(qr_, cr_)
+                qcs.append(qc_)
+            qobj_b = _asm(qcs, shots=1024, seed=1)
+            be = _QS(silent=True, device=local, statevector=False, node_capacity=1 << 20)
+            be.run(qobj_b).result()  # warm-up: engines, buffers
+            t3 = time.perf_counter()
+            res_b = be.run(qobj_b).result()
+            api_wall = time.perf_counter() - t3
+            # the same seed for every experiment (the backend's rule), so compare against the one-at-a-time engine on a few
+            ok = True
+            for s_ in (0, 17, 170, 1023):
+                eng.load(batch[s_])
+                eng.run(1024, 1)
+                ok = ok and res_b.to_dict()["results"][s_]["data"]["counts"] == {hex(k_): v_ for k_, v_ in eng.counts().items()}
+            api = {"call": "QasmSimulator(statevector=False).run(qobj of 1024 experiments).result()", "wall_s": api_wall,
+                   "circuits_per_s": n_batch / api_wall, "gate_applies_per_s": sum(len(c2) for c2 in batch) / api_wall,
+                   "counts_equal_one_at_a_time_engine": bool(ok), "metadata": res_b.to_dict()["results"][0]["metadata"]["batch"]}
         tt = torch.tensor([float(b_gates), b_ms], dtype=torch.float64, device="cuda")
         if dist is not None:
             g_all = tt.clone()
@@ -445,7 +480,7 @@ def main():
             "gate_applies_per_s_kernel": b_gates / (b_ms * 1e-3), "wall_s_host_ops_in_counts_out": b_wall,
             "gate_applies_per_s_wall": b_gates / b_wall, "circuits_per_s_wall": n_batch / b_wall, "engines_per_gpu": 148,
             "full_engine_fallbacks_rank0": fb,
-            "k_batch_ms_rank0": b_kernel_only, "fallback_apply_ms_rank0": b_fallback,
+            "k_batch_ms_rank0": b_kernel_only, "fallback_apply_ms_rank0": b_fallback, "through_the_provider_api": api,
             "note": "one persistent kernel per GPU, one CTA per SM pulling circuits from a queue (longest gate list first); circuits split "
                     "i % world == rank; kernel_ms = k_batch + the circuits that outgrew one SM, redone from gate 0 on up to 4 full engines side by side (that part by the host clock: an upper bound)"}
         if rank == 0:

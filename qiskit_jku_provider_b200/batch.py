@@ -54,12 +54,24 @@ class BatchRunner:
         mine = [i for i in range(len(circuits)) if i % world == rank]
         if not mine:
             return {}, 0, 0.0
-        arrs = [circuit_ops(circuits[i]) for i in mine]
+        return self.run_ops([(circuits[i].n, circuit_ops(circuits[i])) for i in mine], shots, [seed + i for i in mine], index=mine)
+
+    def run_ops(self, programs, shots, seeds, index=None):
+        """``programs``: sequence of (n_qubits, numpy array of OP_DTYPE) -- GATE / MEASURE / BARRIER ops, e.g. what
+        ``JKUSimulatorWrapper.convert_qobj_circuit_to_ops`` makes of a Qobj experiment; program j samples with
+        ``seeds[j]`` and is reported under key ``index[j]`` (default j).  Same return value as ``run``."""
+        mine = list(index) if index is not None else list(range(len(programs)))
+        if not mine:
+            return {}, 0, 0.0
+        arrs = [np.ascontiguousarray(a, dtype=OP_DTYPE) for _, a in programs]
         offs = np.zeros(len(mine) + 1, dtype=np.uint64)
         offs[1:] = np.cumsum([len(a) for a in arrs])
         ops = np.ascontiguousarray(np.concatenate(arrs) if len(arrs) > 1 else arrs[0], dtype=OP_DTYPE)
-        nq = np.array([circuits[i].n for i in mine], dtype=np.uint32)
-        seeds = np.array([seed + i for i in mine], dtype=np.uint64)
+        if len(ops) == 0:
+            ops = np.zeros(1, dtype=OP_DTYPE)  # (a valid pointer for a batch of empty programs)
+        nq = np.array([n for n, _ in programs], dtype=np.uint32)
+        seeds = np.array([int(x) for x in seeds], dtype=np.uint64)
+        n_of = {i: int(programs[j][0]) for j, i in enumerate(mine)}
         cap = int(max(1, min(shots, 1 << 16)))
         keys = np.zeros((len(mine), cap), dtype=np.uint64)
         cnts = np.zeros((len(mine), cap), dtype=np.uint64)
@@ -101,8 +113,8 @@ class BatchRunner:
             def work(w):
                 eng, res = self._bigs[w], []
                 for j, i in redo[w::want]:
-                    eng.load_ops(circuits[i].n, arrs[j])
-                    eng.run(shots, seed + i)
+                    eng.load_ops(n_of[i], arrs[j])
+                    eng.run(shots, int(seeds[j]))
                     st = eng.stats()
                     res.append((i, eng.counts(), st["gates"], st["apply_ms"]))
                 return res

@@ -34,6 +34,8 @@ logger = logging.getLogger(__name__)
 # (``:116-120,138``).  Above this many qubits the final state vector is only produced on request
 # (experiment.config.data contains 'statevector').
 STATEVECTOR_AUTO_MAX_QUBITS = 20
+BATCH_MIN_EXPERIMENTS = 4      # from here on the experiments of a Qobj that only ask for counts go through k_batch
+BATCH_MAX_SHOTS = 1 << 16      # (capacity of the per-circuit result block of jkq_batch_run)
 MULTI_GPU_MIN_SHOTS = 1 << 22  # from here on the shots of one experiment are split over the backend's devices
 
 
@@ -111,8 +113,9 @@ def _templates():
 class JKUSimulatorWrapper:
     """Converter between Qobj experiments and the engine."""
 
-    def __init__(self, engine=None, silent=False, physical_reset=False, shots_runner=None, devices=None):
+    def __init__(self, engine=None, silent=False, physical_reset=False, shots_runner=None, devices=None, statevector='auto'):
         self.physical_reset = bool(physical_reset)
+        self.statevector = statevector
         self.devices = list(devices) if devices else None  # CUDA ordinals the shots of one experiment may be split over
         self.shots_runner = shots_runner  # batch.BatchRunner for per-shot re-simulation, or None: sequential
         self.seed = 0
@@ -224,11 +227,16 @@ class JKUSimulatorWrapper:
         ops['arg'] = np.array(args, dtype=np.int64)[inst]
         return ops, snapshot_slots
 
+    def wants_statevector(self, n_qubits):
+        if 'statevector' in self.additional_output_data:
+            return True
+        return self.statevector == 'auto' and n_qubits <= STATEVECTOR_AUTO_MAX_QUBITS
+
     def run_experiment(self, config, experiment):
         self.set_config(config, experiment.config)
         measurement_data = self.compute_measurement_data(experiment)
         n = measurement_data['qubits_num']
-        want_sv = n <= STATEVECTOR_AUTO_MAX_QUBITS or 'statevector' in self.additional_output_data
+        want_sv = self.wants_statevector(n)
         self.start_time = time.time()
         ops, slots = self.convert_qobj_circuit_to_ops(experiment, want_sv)
         if not self.silent:
@@ -342,7 +350,8 @@ class QasmSimulator(BaseBackend):
         ]
     }
 
-    def __init__(self, configuration=None, provider=None, silent=False, device=0, physical_reset=False, devices=None, **engine_options):
+    def __init__(self, configuration=None, provider=None, silent=False, device=0, physical_reset=False, devices=None,
+                 statevector='auto', **engine_options):
         """
         Args:
             configuration (dict): backend configuration
@@ -353,6 +362,12 @@ class QasmSimulator(BaseBackend):
                                    experiment are split over all of them once there are at least 2^22
                                    (``jkq_sample_multi_gpu``: peer copy of the sampling DD, device-side merge).
                                    Counts do not depend on the number of devices.
+            statevector: 'auto' (default) -- every experiment of at most 20 qubits also returns its final state vector,
+                                   like the reference, which always appends a final snapshot (``:116-120``); False -- only
+                                   when the experiment asks for it (``config.data`` contains 'statevector').  A Qobj of
+                                   at least 4 experiments that return counts only runs as ONE batch: one persistent
+                                   kernel per device, one circuit per SM at a time (``jkq_batch_run``), instead of
+                                   one experiment after the other (``:340-359``) -- same counts either way.
             physical_reset (bool): ``reset`` = measure and flip back (per-shot re-simulation) instead of the
                                    reference's projection on |0> (Simulator.cpp:291-339)
             engine_options: forwarded to ``jkq_config`` (node_capacity, tolerance, ...)
@@ -367,6 +382,8 @@ class QasmSimulator(BaseBackend):
         _native.load()  # fail early and loudly, like the reference's executable check
         self.silent = silent
         self.physical_reset = physical_reset
+        self.statevector = statevector
+        self._batch_runners = {}  # device ordinal -> batch.BatchRunner (one engine per SM) for count-only Qobjs
         self._devices = [int(d) for d in devices] if devices else [int(device)]
         self._device = self._devices[0]
         self._engine_options = engine_options
@@ -402,14 +419,17 @@ class QasmSimulator(BaseBackend):
         self._validate(qobj)
         start = time.time()
         n_dev = len(self._devices)
-        if n_dev > 1 and len(qobj.experiments) > 1:
+        batch = self._batch_plan(qobj)
+        if batch is not None:
+            result_list = self._run_batch(qobj, batch)
+        elif n_dev > 1 and len(qobj.experiments) > 1:
             # one engine per device, experiment i on device i % n_dev, every device in its own host thread (ctypes
             # releases the GIL inside the library)
             from concurrent.futures import ThreadPoolExecutor
 
             def lane(k):
                 w = JKUSimulatorWrapper(self._get_engine(self._devices[k]), silent=self.silent, physical_reset=self.physical_reset,
-                                        shots_runner=None)
+                                        shots_runner=None, statevector=self.statevector)
                 w.shots = qobj.config.shots
                 return [(i, w.run_experiment(qobj.config, qobj.experiments[i])) for i in range(k, len(qobj.experiments), n_dev)]
 
@@ -421,7 +441,7 @@ class QasmSimulator(BaseBackend):
         else:
             s = JKUSimulatorWrapper(self._get_engine(), silent=self.silent, physical_reset=self.physical_reset,
                                     shots_runner=self._get_shots_runner() if self.physical_reset else None,
-                                    devices=self._devices)
+                                    devices=self._devices, statevector=self.statevector)
             s.shots = qobj.config.shots
             for experiment in qobj.experiments:
                 result_list.append(s.run_experiment(qobj.config, experiment))
@@ -435,6 +455,75 @@ class QasmSimulator(BaseBackend):
                   'success': True,
                   'time_taken': (end - start)}
         return Result.from_dict(result)
+
+    def _batch_plan(self, qobj):
+        """The converted experiments [(wrapper, n_qubits, ops, measurement data)] if the whole Qobj can go through the
+        batch kernel (counts only: no state vector, no snapshot, no per-shot re-simulation), else None."""
+        exps = qobj.experiments
+        if len(exps) < BATCH_MIN_EXPERIMENTS or int(qobj.config.shots) > BATCH_MAX_SHOTS:
+            return None
+        plan = []
+        for experiment in exps:
+            w = JKUSimulatorWrapper(None, silent=True, physical_reset=self.physical_reset, statevector=self.statevector)
+            w.shots = qobj.config.shots
+            w.set_config(qobj.config, experiment.config)
+            md = w.compute_measurement_data(experiment)
+            n = md['qubits_num']
+            if w.wants_statevector(n) or not md['mapping'] or md['clbits_num'] == 0 or n > 64:
+                return None
+            ops, slots = w.convert_qobj_circuit_to_ops(experiment, False)
+            if slots or w.per_shot or bool(np.any(ops['kind'] == OP_RESET)):
+                return None
+            plan.append((w, n, ops, md))
+        return plan
+
+    def _get_batch_runner(self, device):
+        if device not in self._batch_runners:
+            from .batch import BatchRunner
+            small = {"tolerance": self._engine_options["tolerance"]} if "tolerance" in self._engine_options else None
+            self._batch_runners[device] = BatchRunner(workers=1 << 16, device=device, small=small, big=dict(self._engine_options))
+        return self._batch_runners[device]
+
+    def _run_batch(self, qobj, plan):
+        """All experiments of the Qobj as one batch per device (experiment i on device i % n_dev, one host thread each);
+        experiment i samples with the seed ``run_experiment`` would use, so the counts are those of the sequential path."""
+        if not self.silent:
+            print(RUN_MESSAGE)
+        start = time.time()
+        n_dev = len(self._devices)
+        shots = int(qobj.config.shots)
+
+        def lane(k):
+            idx = list(range(k, len(plan), n_dev))
+            if not idx:
+                return {}, {}
+            br = self._get_batch_runner(self._devices[k])
+            out, _, _ = br.run_ops([(plan[i][1], plan[i][2]) for i in idx], shots, [plan[i][0].seed for i in idx], index=idx)
+            return out, {"fallbacks": br.fallbacks, "kernel_ms": br.last_kernel_ms, "fallback_ms": br.last_fallback_ms}
+
+        if n_dev == 1:
+            parts = [lane(0)]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            for k in range(n_dev):
+                self._get_batch_runner(self._devices[k])  # (created here: one CUDA context after the other)
+            with ThreadPoolExecutor(n_dev) as ex:
+                parts = list(ex.map(lane, range(n_dev)))
+        elapsed = time.time() - start
+        result_list = []
+        for i, (w, n, ops, md) in enumerate(plan):
+            k = i % n_dev
+            counts = parts[k][0][i]
+            experiment = qobj.experiments[i]
+            result_list.append({'header': {'name': experiment.header.name,
+                                           'memory_slots': experiment.config.memory_slots,
+                                           'creg_sizes': experiment.header.creg_sizes},
+                                'status': 'DONE', 'time_taken': elapsed / len(plan),
+                                'seed': w.seed, 'shots': shots,
+                                'data': {'counts': {hex(int(key)): int(v) for key, v in counts.items()}},
+                                'success': True,
+                                'metadata': {'batch': dict(parts[k][1], device=self._devices[k], experiments=len(plan))}})
+        return result_list
 
     def _validate(self, qobj):
         # no-op in the reference as well (:361-364)

@@ -237,3 +237,54 @@ def test_physical_reset_is_resimulated_per_shot():
         backend.physical_reset = False
     assert set(counts) <= {"00", "10"} and sum(counts.values()) == 300
     assert 100 <= counts.get("00", 0) <= 200
+
+
+def _random_qc(seed):
+    import random
+    rnd = random.Random(seed)
+    n = rnd.randint(3, 9)
+    qr, cr = QuantumRegister(n, "q"), ClassicalRegister(n, "c")
+    qc = QuantumCircuit(qr, cr, name="batch%d" % seed)
+    for _ in range(rnd.randint(10, 60)):
+        g = rnd.choice(["h", "x", "t", "s", "u3", "u1", "cx", "cz", "ccx", "cu1", "swap"])
+        q = rnd.sample(range(n), 3)
+        a = [rnd.uniform(-3, 3) for _ in range(3)]
+        if g in ("h", "x", "t", "s"):
+            getattr(qc, g)(qr[q[0]])
+        elif g == "u1":
+            qc.u1(a[0], qr[q[0]])
+        elif g == "u3":
+            qc.u3(a[0], a[1], a[2], qr[q[0]])
+        elif g in ("cx", "cz", "swap"):
+            getattr(qc, g)(qr[q[0]], qr[q[1]])
+        elif g == "ccx":
+            qc.ccx(qr[q[0]], qr[q[1]], qr[q[2]])
+        else:
+            qc.cu1(a[0], qr[q[0]], qr[q[1]])
+    if seed % 3 == 0:  # a partial, permuted measure map
+        for k in range(0, n, 2):
+            qc.measure(qr[k], cr[n - 1 - k])
+    else:
+        qc.measure(qr, cr)
+    return qc
+
+
+def test_count_only_qobj_runs_as_one_batch_with_the_counts_of_the_sequential_path():
+    """A Qobj of many experiments that return counts only (statevector=False) goes through jkq_batch_run -- one
+    persistent kernel, one circuit per SM -- where the reference loops over one process per experiment
+    (qasm_simulator_jku.py:340-359); the counts are those of the one-after-the-other path, experiment by experiment."""
+    from qiskit_jku_provider_b200 import QasmSimulator
+    qcs = [_random_qc(s) for s in range(40)]
+    qobj = assemble(qcs, shots=500, seed=11)
+    seq = QasmSimulator(silent=True, node_capacity=1 << 18)
+    bat = QasmSimulator(silent=True, node_capacity=1 << 18, statevector=False)
+    assert seq._batch_plan(qobj) is None and bat._batch_plan(qobj) is not None
+    r_seq, r_bat = seq.run(qobj).result(), bat.run(qobj).result()
+    for i, qc in enumerate(qcs):
+        assert r_bat.get_counts(qc.name) == r_seq.get_counts(qc.name), qc.name
+        assert 'statevector' not in r_bat.data(i) and 'statevector' in r_seq.data(i)
+    assert 'batch' in r_bat.to_dict()['results'][0]['metadata']
+    # an experiment that asks for its state vector takes the whole Qobj back to the sequential path
+    qobj_sv = assemble(qcs[:5], shots=100, seed=3, data=['statevector'])
+    assert bat._batch_plan(qobj_sv) is None
+    assert len(bat.run(qobj_sv).result().get_statevector(qcs[0].name)) == 1 << qcs[0].qregs[0].size
