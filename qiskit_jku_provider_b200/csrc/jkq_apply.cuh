@@ -117,15 +117,46 @@ template <int MODE> JD uint32_t level_item(const Ctx &c, int L, uint32_t b, uint
   return (lvl == 0 || lvl == (uint32_t)L + 1u) ? i : JI_FAIL;  // (an item of [b, e) parked for a lower level)
 }
 
+// thread index in which consecutive warps lie on different CTAs (the grid path: different SMs)
+template <int MODE> JD uint32_t spread_id(const Ctx &c) {
+#ifdef JKQ_EMU
+  return c.tid;
+#else
+  if (MODE == MODE_CTA) return c.ltid;
+  return ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * JKQ_WARP + (threadIdx.x & (JKQ_WARP - 1u));
+#endif
+}
+
 // One level of the generic path: run every item of [b, e), and while some item met a value that is
 // not in the table yet, commit the proposed values (vals_commit) and run those items again.
 template <int MODE, bool expand>
 JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
+#if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
+  struct WProf {  // level phases of the grid path by width class
+    Ctx &c; long long t0; uint32_t n, ph0;
+    __device__ WProf(Ctx &c_, uint32_t n_) : c(c_), t0(clock64()), n(n_), ph0(c_.phase) {}
+    __device__ ~WProf() {
+      if (MODE == MODE_GRID && c.tid == 0) {
+        int cls = 0;
+        for (uint32_t x = n; x > 4 && cls < 7; x >>= 2) cls++;
+        c.E->prof_w[cls] += (unsigned long long)(clock64() - t0); c.E->prof_w[8 + cls] += 1;
+        c.E->prof_w[16 + cls] += c.phase - ph0; c.E->prof_w[24 + cls] += n;
+      }
+    }
+  } wprof(c, e - b);
+#endif
   for (uint32_t round = 0;; round++) {
     uint32_t my = 0;
     JPROF_T(pt0);
     const uint32_t nwork = e - b + defer_count<MODE>(c, L);
-    for (uint32_t j = c.tid; j < nwork; j += c.nth) {
+    // Lanes of one warp that work on different items take different paths through expand_item / reduce_item and run one
+    // after the other (r160, profile build: a level of at most 64 items cost 48 k cycles with item j on thread j).  A
+    // level narrower than the grid is therefore spread out: one item per warp while there are enough warps, consecutive
+    // warps on different SMs.
+    uint32_t stride = 1;
+    while (stride < JKQ_WARP && nwork * stride * 2u <= c.nth) stride <<= 1;
+    const uint32_t sid = spread_id<MODE>(c);
+    for (uint32_t j = (sid & (stride - 1u)) ? nwork : sid / stride; j < nwork; j += c.nth / stride) {
       const uint32_t i = level_item<MODE>(c, L, b, e, j);
       if (i == JI_FAIL) continue;
       JItem *it = c.items + i;
@@ -753,6 +784,7 @@ template <int MODE> JD uint32_t init_state(Ctx &c) {
     E->gen += 2;
     for (int k = 0; k < 12; k++) E->st[k] = 0;
     for (int k = 0; k < 16; k++) E->prof[k] = 0;
+    for (int k = 0; k < 32; k++) E->prof_w[k] = 0;
     JNode t; t.c0 = 0; t.c1 = 0; t.w = 0;
     E->nodes[0] = t;
     // the reals 0, 1 and the reference's gate constants 1/2, FP64 sqrt(2)/2 in its insertion order

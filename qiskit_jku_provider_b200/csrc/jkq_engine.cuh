@@ -423,7 +423,15 @@ template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, do
   else jset_error<MODE>(E, S, JKQ_ERR_VAL_FULL);
 }
 
+// where a value that missed the table goes at once instead of through propose / commit (A/B builds: -DJKQ_INPLACE_CTA=0 ...)
+#ifndef JKQ_INPLACE_CTA
+#define JKQ_INPLACE_CTA 0
+#endif
+#ifndef JKQ_INPLACE_GRID
+#define JKQ_INPLACE_GRID 0
+#endif
 template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x);
+template <int MODE> JNI uint32_t real_insert_par(JEng *E, CtaState *S, double x, long long k);
 // index of the entry within tol of x (x >= 0), or JV_MISS; with `propose` a miss leaves x as a candidate
 template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring, double x, bool propose) {
   const double tol = jtol2<MODE>(E, S);
@@ -450,10 +458,12 @@ template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring,
       sl = ld_s<MODE>(tab + hh);
     }
   }
-#ifndef JKQ_NO_SOLO_INSERT
-  if (propose && MODE == MODE_CTA && S->solo_now) return real_insert_solo<MODE>(E, S, x);
-#endif
-  if (propose) real_propose<MODE>(E, S, ring, x, k);
+  if (propose) {
+    // in place (real_insert_par below: the item carries on) or as a candidate for the commit round behind the next barrier
+    const bool in_place = MODE == MODE_CTA ? (JKQ_INPLACE_CTA || S->solo_now) : JKQ_INPLACE_GRID;
+    if (in_place) return real_insert_par<MODE>(E, S, x, k);
+    real_propose<MODE>(E, S, ring, x, k);
+  }
   return JV_MISS;
 }
 
@@ -561,6 +571,85 @@ template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x
       __threadfence_block();
       atomicExch(&S->val_lock, 0u);
       done = true;
+    }
+  }
+#endif
+  return r;
+}
+
+// A miss during a phase that many threads run at once (levels wider than the cursor warp; every phase of the grid path).
+// Round 1 collected the misses of a phase as candidates and committed them behind a barrier (real_propose / vals_commit,
+// still there behind JKQ_PROPOSE_COMMIT): schedule-independent, but every level that met a new value -- on a random
+// circuit nearly every level -- cost two more barriers and a second run of its items (r160: 28 k of the 29 k cycles of a
+// level of four items).  Now the value goes in at once, first come, first kept like the reference
+// (QMDDcomplexD.cpp:402-418).  What keeps the entries pairwise more than tol apart is a lock over the buckets k-1 .. k+1:
+//   MODE_CTA   the one lock word of real_insert_solo (a critical section is ~300 cycles of shared memory);
+//   MODE_GRID  one lock BIT per 128-byte line of the HBM table (JEng.vlk): the home lines of the bucket groups of k-1
+//              and k+1 (k's own is one of the two).  Inserters into adjacent buckets share at least one of them; the
+//              lower line is taken first and given back if the second is busy, so nobody waits while holding.
+// Under the lock the thread looks again and appends only if the value is still missing.  Lookups take no lock: a slot is
+// claimed by CAS (PENDING reads as "no match, keep probing"), filled, and named by its id last.
+// Which of two values within tol of each other becomes the entry now depends on timing (they differ by rounding noise:
+// amplitudes agree to ~1e-16 between runs instead of bit for bit).
+#ifndef JKQ_EMU
+JD bool vt_try_lock(JEng *E, uint32_t line) {
+  const uint32_t bit = 1u << (line & 31u);
+  return (atomicOr(E->vlk + (line >> 5), bit) & bit) == 0u;
+}
+JD void vt_unlock(JEng *E, uint32_t line) { atomicAnd(E->vlk + (line >> 5), ~(1u << (line & 31u))); }
+#endif
+// the grid path's append: real into the array, slot claimed along the probe chain of bucket k, id published last
+JD uint32_t real_append_grid(JEng *E, double x, long long k) {
+  const uint32_t idx = jagg_inc(&E->val_count);
+  if (!vt_room(E, idx)) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); return JV_MISS; }
+  E->vals[idx] = x;
+  jstat<MODE_GRID>(E, nullptr, JST_VALS, 1u);
+  const uint32_t klo = (uint32_t)k, mask = vt_mask2<MODE_GRID>(E);
+  const unsigned long long claim = vt_meta_of(klo, JV_PENDING);
+  JVSlot *tab = E->vtab;
+  uint32_t h = vt_slot0(k, mask);
+  for (uint32_t probes = 0;; probes++) {
+    if (probes > (mask >> 3)) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); return JV_MISS; }
+    unsigned long long *mp = vt_meta(tab + h);
+    const unsigned long long meta = ld_r<MODE_GRID>(mp);
+    if (meta == 0 || ((uint32_t)meta == klo && (uint32_t)(meta >> 32) == JV_DROPPED)) {
+      if (jatomic_cas(mp, meta, claim) == meta) break;
+      continue;  // somebody else took it: look at the slot again
+    }
+    h = vt_next(h, mask);
+  }
+  tab[h].vbits = jd2u(x);
+  jfence<MODE_GRID>();  // the real and the value before the id that names them
+#ifdef JKQ_EMU
+  *vt_meta(tab + h) = vt_meta_of(klo, idx + 1);
+#else
+  *(volatile unsigned long long *)vt_meta(tab + h) = vt_meta_of(klo, idx + 1);
+#endif
+  vt_mark<MODE_GRID>(E, h);
+  return idx;
+}
+template <int MODE> JNI uint32_t real_insert_par(JEng *E, CtaState *S, double x, long long k) {
+  if (MODE == MODE_CTA) return real_insert_solo<MODE>(E, S, x);
+  uint32_t r = JV_MISS;
+#ifdef JKQ_EMU
+  r = real_lookup<MODE>(E, S, 0, x, false);
+  if (r == JV_MISS) r = real_append_grid(E, x, k);
+#else
+  const uint32_t mask = vt_mask2<MODE>(E);
+  uint32_t la = vt_slot0(k - 1, mask) >> 3, lb = vt_slot0(k + 1, mask) >> 3;
+  if (la > lb) { const uint32_t t = la; la = lb; lb = t; }
+  bool done = false;
+  while (!done) {
+    if (vt_try_lock(E, la)) {
+      if (lb == la || vt_try_lock(E, lb)) {
+        __threadfence();
+        r = real_lookup<MODE>(E, S, 0, x, false);
+        if (r == JV_MISS) r = real_append_grid(E, x, k);
+        __threadfence();
+        if (lb != la) vt_unlock(E, lb);
+        vt_unlock(E, la);
+        done = true;
+      } else vt_unlock(E, la);
     }
   }
 #endif

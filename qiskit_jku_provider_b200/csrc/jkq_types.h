@@ -127,6 +127,8 @@ typedef struct {
   JVSlot *vtab;
   uint32_t *vbm;      // one bit per 128-byte line (8 slots) of the HBM value table: some slot of the line was claimed since
                       // the last sweep -- a sweep clears those lines instead of the whole table (4.3 GB at 2^26 reals)
+  uint32_t *vlk;      // one lock bit per line of the HBM value table, held while a new real goes into the buckets around it
+                      // (real_insert_par, jkq_engine.cuh)
   uint32_t *pend;     // value-table slots claimed in the current phase
   JItem *items;
   unsigned long long *dtab;  // F/S item de-dup: generation << 32 | item index + 1
@@ -172,6 +174,7 @@ typedef struct {
   unsigned int bar_gen;
   unsigned int bar_flags[3];
   unsigned long long prof[16];  // JKQ_PROFILE builds: cycle counters, see jkq_b200.cu jkq_get_stats
+  unsigned long long prof_w[32];  // JKQ_PROFILE, grid path: level phases by width class (log4 of the item count): [c] cycles, [8+c] levels, [16+c] barriers, [24+c] items
   uint32_t gc_bsum[1024];  // collector: live reals per CTA chunk
   unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was
   unsigned int dbg_phase[1024];

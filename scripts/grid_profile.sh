@@ -1,7 +1,8 @@
 # cycle counters of the grid path (JKQ_PROFILE build in a scratch library): usage: bash scripts/grid_profile.sh
+# (build it where nvcc is: JKQ_LIB=ab/libjkq_prof.so JKQ_DEFINES=JKQ_PROFILE python -c "from qiskit_jku_provider_b200 import _build; _build.build_native(force=True)")
 set -e
-export JKQ_LIB=/tmp/libjkq_prof.so
-JKQ_DEFINES="JKQ_PROFILE" python -c "from qiskit_jku_provider_b200 import _build; _build.build_native(force=True)" > /dev/null 2>&1 || true
+export JKQ_LIB=${JKQ_LIB:-$PWD/ab/libjkq_prof.so}
+[ -f "$JKQ_LIB" ] || JKQ_DEFINES="JKQ_PROFILE" python -c "from qiskit_jku_provider_b200 import _build; _build.build_native(force=True)" > /dev/null 2>&1 || true
 python - <<'PY'
 import sys
 sys.path.insert(0, ".")
