@@ -106,6 +106,12 @@ def _format_counts(hex_counts, creg_sizes, memory_slots):
     """hex keys -> bit strings with a space between classical registers (what qiskit's
     Result.get_counts does; gives '01 10' / '100 100' in the reference's tests)."""
     out = {}
+    if not (creg_sizes and len(creg_sizes) > 1):  # one register: no spaces to put in
+        fmt = '0%db' % memory_slots
+        for key, val in hex_counts.items():
+            bits = format(int(key, 16), fmt)
+            out[bits] = out.get(bits, 0) + val
+        return out
     for key, val in hex_counts.items():
         bits = bin(int(key, 16))[2:].rjust(memory_slots, '0')
         if creg_sizes and len(creg_sizes) > 1:

@@ -345,6 +345,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     jsyncwarp();
     int lsw = 0, wide_L = -1;
     uint32_t icount = 0, blocked = 0;
+    const uint32_t solo_opt = ld_s<MODE>(&E->solo_max), solo_max = solo_opt && solo_opt < JKQ_WARP ? solo_opt : JKQ_WARP;
     JPROF_T(sp0);
     // Where the cursor goes for this gate: up to the gate's top level if it is below; down only as far as the next
     // few gates need it (JGate.park) when the gate is one thin_gate is bound to take (diagonal / anti-diagonal matrix):
@@ -371,7 +372,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
       jsyncwarp();
       for (int L = lsw; L >= 0 && (e > b || (MODE == MODE_CTA && ld_r<MODE>(&c.sh->min_def) <= L)); L--) {
         const uint32_t nwork = e - b + defer_count<MODE>(c, L);
-        if (nwork > JKQ_WARP) {
+        if (nwork > solo_max) {
           if (MODE == MODE_CTA && c.lnth <= JKQ_WARP && E->cta_wide_ok) {
             // launched with the cursor warp alone (all a narrow diagram ever needs): give the gate up like one that
             // does not fit, and let the host launch the wide shape from here

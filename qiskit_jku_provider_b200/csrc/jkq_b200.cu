@@ -622,6 +622,8 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "measure_seed")) { h->measure_seed = (uint64_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "physical_reset")) { h->physical_reset = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "solo_max")) { h->host.solo_max = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "cta_always_wide")) { h->cfg.reserved = value ? 1u : 0u; return JKQ_E_OK; }
   if (!strcmp(name, "cta_no_reserve")) { h->host.cta_no_reserve = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "histogram_fused")) { h->force_fused = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "thin_off")) { h->host.thin_off = (uint32_t)value; return JKQ_E_OK; }

@@ -117,6 +117,8 @@ typedef struct {
   uint32_t cta_val_limit;   // testing aid: the same for the shared-memory value table
   uint32_t cta_wide_ok;     // a one-warp single-CTA launch may ask for the wide one (want_wide) when a level outgrows the warp
   uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all
+  uint32_t solo_max;       // widest level the cursor warp runs by itself (one lane per item); 0 = JKQ_WARP.  Wider levels are shared out
+                           // over the warps of the CTA / grid (run_level)
   uint32_t cta_no_reserve; // testing aid: no reserve in the shared pools, so the root rebuild of an abandoned gate fails too (saved-cursor hand-over)
   double tol;
   double inv_tol;

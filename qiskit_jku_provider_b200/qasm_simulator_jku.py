@@ -301,7 +301,7 @@ class JKUSimulatorWrapper:
                     result['counts'] = {hex(int(k)): int(v) for k, v in counts_override.items()}
                 else:
                     keys, vals = eng.counts_arrays()
-                    result['counts'] = {hex(int(k)): int(v) for k, v in zip(keys, vals)}
+                    result['counts'] = dict(zip(map(hex, keys.tolist()), vals.tolist()))
             else:  # nothing measured: every shot reads all-zero classical bits
                 result['counts'] = {hex(0): int(self.shots)}
         else:
