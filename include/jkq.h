@@ -148,6 +148,16 @@ int jkq_get_counts(jkq_handle *h, uint64_t *keys, uint64_t *counts, size_t cap, 
 int jkq_release_histogram(jkq_handle *h);
 int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, size_t cap_amplitudes);
 int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count, double *re_im); /* GetElementOfVector */
+/* Amplitudes [first, first+count) of the state a SNAPSHOT op recorded in `slot` (0xFFFFFFFF = the current state).  Up to
+ * option "snapshot_dense_max" (26) qubits a snapshot is a dense vector on the device; above, it is a copy of the DIAGRAM
+ * (16 B per node) and every amplitude read is one walk through it (GetElementOfVector, Simulator.cpp:415-431) -- the
+ * state vector of QASMsimulator.cpp:1012-1030 for a register of any width, read range by range instead of at once. */
+int jkq_get_snapshot_amplitudes(jkq_handle *h, uint32_t slot, uint64_t first, uint64_t count, double *re_im);
+/* the same with bit b of the index (first + i) standing for qubit qubit_of_bit[b] (a permutation of the n qubits): the
+ * reference prints a snapshot's state vector with the first listed qubit as the most significant bit
+ * (QASMsimulator.cpp:1016-1028) */
+int jkq_get_snapshot_amplitudes_ordered(jkq_handle *h, uint32_t slot, const uint32_t *qubit_of_bit, uint64_t first, uint64_t count,
+                                        double *re_im);
 int jkq_get_level_counts(jkq_handle *h, uint32_t *per_level, size_t n);              /* Active[v] */
 int jkq_get_level_log(jkq_handle *h, uint32_t *out, size_t cap, size_t *n_written);
 int jkq_get_stats(jkq_handle *h, jkq_stats *out);
@@ -155,6 +165,8 @@ int jkq_get_stats(jkq_handle *h, jkq_stats *out);
 int jkq_get_qubit_probability(jkq_handle *h, uint32_t qubit, double *p0);
 /* the 2^k probabilities a PROBABILITIES op recorded in `slot`; *n = 2^k (also when out is NULL or cap too small) */
 int jkq_get_probabilities(jkq_handle *h, uint32_t slot, double *out, size_t cap, size_t *n);
+/* entries [first, first+count) of the same (streaming read-out of a wide register's probabilities) */
+int jkq_get_probabilities_range(jkq_handle *h, uint32_t slot, uint64_t first, uint64_t count, double *out);
 /* outcomes of the MEASURE_ONE ops of the last jkq_apply: bit c of *bits = classical bit c, *mask = bits written */
 int jkq_get_mid_measurements(jkq_handle *h, uint64_t *bits, uint64_t *mask);
 

@@ -62,10 +62,13 @@ SYMBOLS = [
     ("jkq_release_histogram", C.c_int, [_H]),
     ("jkq_get_statevector", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.c_size_t]),
     ("jkq_get_amplitudes", C.c_int, [_H, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
+    ("jkq_get_snapshot_amplitudes", C.c_int, [_H, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
+    ("jkq_get_snapshot_amplitudes_ordered", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
     ("jkq_get_level_counts", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t]),
     ("jkq_get_level_log", C.c_int, [_H, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
     ("jkq_get_stats", C.c_int, [_H, C.POINTER(JkqStats)]),
     ("jkq_get_probabilities", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("jkq_get_probabilities_range", C.c_int, [_H, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
     ("jkq_get_qubit_probability", C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double)]),
     ("jkq_get_mid_measurements", C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("jkq_dd_export", C.c_int, [_H, C.POINTER(JkqSNode), C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

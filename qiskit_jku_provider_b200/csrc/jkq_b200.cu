@@ -81,6 +81,24 @@ __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *o
   }
 }
 
+// the same in a caller-chosen bit order: bit b of the output index is qubit bp.q[b]; from the dense vector of a snapshot
+// when there is one, else by walking the diagram E names
+struct BitPerm { uint8_t q[JKQ_MAXQ]; };
+__global__ void k_amplitudes_ordered(JEng *E, const double2 *dense, BitPerm bp, int n, uint64_t first, uint64_t count, double2 *out) {
+  Ctx c;
+  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = nullptr; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
+  for (uint64_t i = c.tid; i < count; i += c.nth) {
+    const uint64_t idx = first + i;
+    uint64_t e = 0;
+    for (int b = 0; b < n; b++) e |= ((idx >> b) & 1ull) << bp.q[b];
+    if (dense) { out[i] = dense[e]; continue; }
+    double re, im;
+    amp_walk<MODE_GRID>(c, e, &re, &im);
+    out[i] = make_double2(re, im);
+  }
+}
+
 // Simulator::AssignProbsOne (Simulator.cpp:291-339): probability that the qubit on `level` reads 0.  The arena
 // is level-ordered and the sampling records hold every node's branch probability, so the path mass is pushed
 // down from the root one level at a time; at `level` the masses times q0 add up to P(0).  One CTA.
@@ -439,6 +457,12 @@ struct jkq_handle {
   SampleParams sp;
   uint32_t dd_root = 0, dd_nodes = 0;
   std::map<uint32_t, double2 *> snapshots;  // slot -> device buffer of 2^n amplitudes
+  // Above snapshot_dense_max qubits a snapshot keeps the DIAGRAM instead of 2^n amplitudes: a copy of the node arena and
+  // the reals as they are when the statement is reached (16 B per node, 8 B per real) plus a control block that names
+  // them; amplitudes are produced range by range when they are read (jkq_get_snapshot_amplitudes)
+  struct DDSnap { JNode *nodes = nullptr; double *vals = nullptr; JEng *eng = nullptr; uint32_t n_nodes = 0, n_vals = 0; };
+  std::map<uint32_t, DDSnap> dd_snapshots;
+  uint32_t snapshot_dense_max = 26;
   std::map<uint32_t, std::pair<double *, uint32_t>> prob_slots;  // slot -> (device buffer of 2^k probabilities, k)
   bool physical_reset = false;      // RESET = measure-then-X instead of the reference's projection
   uint64_t placeholder_gates = 0;   // projector / X slots of MEASURE_ONE and RESET applied by the last jkq_apply
@@ -516,6 +540,8 @@ static void free_snapshots(jkq_handle *h) {
   h->snapshots.clear();
   for (auto &kv : h->prob_slots) cudaFree(kv.second.first);
   h->prob_slots.clear();
+  for (auto &kv : h->dd_snapshots) { cudaFree(kv.second.nodes); cudaFree(kv.second.vals); cudaFree(kv.second.eng); }
+  h->dd_snapshots.clear();
 }
 
 static void multi_free(jkq_handle *src);
@@ -622,6 +648,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "measure_seed")) { h->measure_seed = (uint64_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "physical_reset")) { h->physical_reset = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_node_limit")) { h->host.cta_node_limit = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "snapshot_dense_max")) { h->snapshot_dense_max = value < 0 ? 0u : (value > 30 ? 30u : (uint32_t)value); return JKQ_E_OK; }
   if (!strcmp(name, "solo_max")) { h->host.solo_max = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "cta_always_wide")) { h->cfg.reserved = value ? 1u : 0u; return JKQ_E_OK; }
   if (!strcmp(name, "cta_no_reserve")) { h->host.cta_no_reserve = (uint32_t)value; return JKQ_E_OK; }
@@ -992,6 +1019,33 @@ static int record_probabilities(jkq_handle *h, const jkq_op &o) {
   return JKQ_E_OK;
 }
 
+// SNAPSHOT on a register too wide for a dense vector: copy the arena (nodes and reals up to their counters, root edge
+// in the control block) -- the state is a rooted DD here, run_segment has just returned
+static int snapshot_dd(jkq_handle *h, uint32_t slot) {
+  int rc = pull_state(h);
+  if (rc) return rc;
+  auto it = h->dd_snapshots.find(slot);
+  if (it != h->dd_snapshots.end()) {
+    cudaFree(it->second.nodes); cudaFree(it->second.vals); cudaFree(it->second.eng);
+    h->dd_snapshots.erase(it);
+  }
+  jkq_handle::DDSnap d;
+  d.n_nodes = h->host.node_count; d.n_vals = h->host.val_count;
+  CU(cudaMalloc((void **)&d.nodes, (size_t)d.n_nodes * sizeof(JNode)));
+  CU(cudaMalloc((void **)&d.vals, (size_t)d.n_vals * sizeof(double)));
+  CU(cudaMalloc((void **)&d.eng, sizeof(JEng)));
+  CU(cudaMemcpyAsync(d.nodes, h->host.nodes, (size_t)d.n_nodes * sizeof(JNode), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(d.vals, h->host.vals, (size_t)d.n_vals * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  JEng *clone = new JEng(h->host);
+  clone->nodes = d.nodes; clone->vals = d.vals;
+  cudaError_t e = cudaMemcpyAsync(d.eng, clone, sizeof(JEng), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  delete clone;
+  h->dd_snapshots[slot] = d;
+  if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "snapshot: %s", cudaGetErrorString(e));
+  return JKQ_E_OK;
+}
+
 extern "C" int jkq_apply(jkq_handle *h) {
   if (!h) return JKQ_E_ARGUMENT;
   if (!h->loaded) return fail(h, JKQ_E_STATE, "jkq_apply before jkq_load_circuit");
@@ -1034,7 +1088,12 @@ extern "C" int jkq_apply(jkq_handle *h) {
     } else if (kind == JKQ_OP_SNAPSHOT) {
       int rc0 = run_segment(h, h->gate_of_op[i]);
       if (rc0) return rc0;
-      if (h->n > 30) return fail(h, JKQ_E_CAPACITY, "state-vector snapshot needs 2^%u amplitudes", h->n);
+      if (h->n > h->snapshot_dense_max) {  // keep the diagram, not the vector
+        int rcs = snapshot_dd(h, h->ops[i].arg);
+        if (rcs) return rcs;
+        i++;
+        continue;
+      }
       double2 *buf = nullptr;
       uint64_t len = 1ull << h->n;
       CU(cudaMalloc(&buf, len * sizeof(double2)));
@@ -1336,16 +1395,102 @@ extern "C" int jkq_get_amplitudes(jkq_handle *h, uint64_t first, uint64_t count,
   return JKQ_E_OK;
 }
 
+// amplitudes [first, first + count) of the state a SNAPSHOT op recorded in `slot` (0xFFFFFFFF: the current state):
+// a slice of the dense vector, or -- for a snapshot kept as a diagram -- one walk per amplitude, so a register of any
+// width is read out range by range (the streaming read-out of QASMsimulator.cpp:1012-1030's state vectors)
+extern "C" int jkq_get_snapshot_amplitudes(jkq_handle *h, uint32_t slot, uint64_t first, uint64_t count, double *re_im) {
+  if (!h || (count && !re_im)) return JKQ_E_ARGUMENT;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  if (slot == 0xFFFFFFFFu) return jkq_get_amplitudes(h, first, count, re_im);
+  if (h->n < 64 && (first > (1ull << h->n) || count > (1ull << h->n) - first)) return fail(h, JKQ_E_ARGUMENT, "amplitude range exceeds 2^n");
+  if (!count) return JKQ_E_OK;
+  CU(cudaSetDevice(h->device));
+  auto it = h->snapshots.find(slot);
+  if (it != h->snapshots.end()) {
+    CU(jcopy(h, re_im, it->second + first, count * sizeof(double2), cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    return JKQ_E_OK;
+  }
+  auto dt = h->dd_snapshots.find(slot);
+  if (dt == h->dd_snapshots.end()) return fail(h, JKQ_E_ARGUMENT, "no snapshot in slot %u", slot);
+  double2 *buf = nullptr;
+  CU(cudaMalloc(&buf, count * sizeof(double2)));
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+  k_amplitudes<<<blocks, 256, 0, h->stream>>>(dt->second.eng, first, count, buf);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = jcopy(h, re_im, buf, count * sizeof(double2), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "snapshot amplitudes: %s", cudaGetErrorString(e));
+  return JKQ_E_OK;
+}
+
+// ... with the bits of the index in the caller's order: bit b of (first + i) is qubit qubit_of_bit[b] (n entries, a
+// permutation of 0..n-1).  The reference prints a snapshot's state vector with the FIRST listed qubit as the most
+// significant bit (QASMsimulator.cpp:1016-1028); the executable streams that order through this call.
+extern "C" int jkq_get_snapshot_amplitudes_ordered(jkq_handle *h, uint32_t slot, const uint32_t *qubit_of_bit, uint64_t first, uint64_t count,
+                                                   double *re_im) {
+  if (!h || !qubit_of_bit || (count && !re_im)) return JKQ_E_ARGUMENT;
+  if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  if (h->n < 64 && (first > (1ull << h->n) || count > (1ull << h->n) - first)) return fail(h, JKQ_E_ARGUMENT, "amplitude range exceeds 2^n");
+  BitPerm bp;
+  uint64_t seen = 0;
+  for (uint32_t b = 0; b < h->n; b++) {
+    if (qubit_of_bit[b] >= h->n || (seen >> qubit_of_bit[b] & 1)) return fail(h, JKQ_E_ARGUMENT, "qubit_of_bit is not a permutation of the %u qubits", h->n);
+    seen |= 1ull << qubit_of_bit[b];
+    bp.q[b] = (uint8_t)qubit_of_bit[b];
+  }
+  if (!count) return JKQ_E_OK;
+  JEng *eng = h->dev;
+  const double2 *dense = nullptr;
+  if (slot != 0xFFFFFFFFu) {
+    auto it = h->snapshots.find(slot);
+    auto dt = h->dd_snapshots.find(slot);
+    if (it != h->snapshots.end()) dense = it->second;
+    else if (dt != h->dd_snapshots.end()) eng = dt->second.eng;
+    else return fail(h, JKQ_E_ARGUMENT, "no snapshot in slot %u", slot);
+  }
+  CU(cudaSetDevice(h->device));
+  double2 *buf = nullptr;
+  CU(cudaMalloc(&buf, count * sizeof(double2)));
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+  k_amplitudes_ordered<<<blocks, 256, 0, h->stream>>>(eng, dense, bp, (int)h->n, first, count, buf);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = jcopy(h, re_im, buf, count * sizeof(double2), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(h, JKQ_E_CUDA, "snapshot amplitudes: %s", cudaGetErrorString(e));
+  return JKQ_E_OK;
+}
+
 extern "C" int jkq_get_statevector(jkq_handle *h, uint32_t slot, double *re_im, size_t cap_amplitudes) {
   if (!h || !re_im) return JKQ_E_ARGUMENT;
   if (!h->applied) return fail(h, JKQ_E_STATE, "no state: call jkq_apply first");
+  if (h->n >= 48) return fail(h, JKQ_E_CAPACITY, "2^%u amplitudes: read ranges with jkq_get_snapshot_amplitudes", h->n);
   uint64_t len = 1ull << h->n;
   if (cap_amplitudes < len) return fail(h, JKQ_E_CAPACITY, "need room for %llu amplitudes", (unsigned long long)len);
   if (slot == 0xFFFFFFFFu) return jkq_get_amplitudes(h, 0, len, re_im);
+  if (h->dd_snapshots.count(slot)) return jkq_get_snapshot_amplitudes(h, slot, 0, len, re_im);
   auto it = h->snapshots.find(slot);
   if (it == h->snapshots.end()) return fail(h, JKQ_E_ARGUMENT, "no snapshot in slot %u", slot);
   CU(cudaSetDevice(h->device));
   CU(jcopy(h, re_im, it->second, len * sizeof(double2), cudaMemcpyDeviceToHost));
+  CU(cudaStreamSynchronize(h->stream));
+  return JKQ_E_OK;
+}
+
+// entries [first, first + count) of the probabilities in `slot`
+extern "C" int jkq_get_probabilities_range(jkq_handle *h, uint32_t slot, uint64_t first, uint64_t count, double *out) {
+  if (!h || (count && !out)) return JKQ_E_ARGUMENT;
+  auto it = h->prob_slots.find(slot);
+  if (it == h->prob_slots.end()) return fail(h, JKQ_E_ARGUMENT, "no probabilities in slot %u", slot);
+  const uint64_t len = 1ull << it->second.second;
+  if (first > len || count > len - first) return fail(h, JKQ_E_ARGUMENT, "range exceeds the %llu probabilities of slot %u", (unsigned long long)len, slot);
+  if (!count) return JKQ_E_OK;
+  CU(cudaSetDevice(h->device));
+  CU(jcopy(h, out, it->second.first + first, count * sizeof(double), cudaMemcpyDeviceToHost));
   CU(cudaStreamSynchronize(h->stream));
   return JKQ_E_OK;
 }

@@ -112,7 +112,18 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
 struct SnapshotData {
   std::vector<double> probabilities;             // reference index order (first argument = MSB); empty = not recorded
   std::vector<std::string> statevector;          // empty = not recorded
+  // a register too wide to hold 2^n strings: the amplitudes are read from the engine range by range while they are printed
+  bool stream = false;
+  uint32_t slot = 0, k = 0;
+  std::vector<uint32_t> qubit_of_bit;            // bit b of the printed index = this qubit
 };
+// from here on a state vector is streamed (JKQ_STREAM_MIN_QUBITS: testing aid, puts small registers on the streaming path)
+static uint32_t stream_min_qubits() {
+  const char *e = getenv("JKQ_STREAM_MIN_QUBITS");
+  return e ? (uint32_t)atoi(e) : 21u;
+}
+#define STREAM_MIN_QUBITS stream_min_qubits()
+static const uint64_t STREAM_CHUNK = 1ull << 20;
 
 // Cprint (QMDDcomplexD.cpp:100-135): parts that snap to zero are left out, "0" when both do
 std::string format_amplitude(double re, double im, double tol) {
@@ -202,7 +213,14 @@ struct Runner {
           d.probabilities[i] = raw[e];
         }
       }
-      if (statevector && k == info.n_qubits) {
+      if (statevector && k == info.n_qubits && k >= STREAM_MIN_QUBITS) {
+        double probe[2];
+        d.qubit_of_bit.resize(k);
+        for (size_t a = 0; a < k; a++) d.qubit_of_bit[k - 1 - a] = qubits[a];  // first argument = most significant bit
+        if (jkq_get_snapshot_amplitudes_ordered(h, slot, d.qubit_of_bit.data(), 0, 1, probe) == 0) {  // (else: the statement lies behind n_ops)
+          d.stream = true; d.slot = slot; d.k = (uint32_t)k;
+        }
+      } else if (statevector && k == info.n_qubits) {
         const size_t len = (size_t)1 << k;
         std::vector<double> amps(2 * len);
         if (jkq_get_statevector(h, slot, amps.data(), len) == 0) {
@@ -427,6 +445,19 @@ static int run_request(const Options &opt, const std::string &text, const std::s
           first = false;
         }
         out << "}";
+      }
+      if (d.stream) {
+        if (!d.probabilities.empty()) out << "," << std::endl;
+        out << "      \"statevector\": [";
+        const uint64_t len = 1ull << d.k;
+        std::vector<double> amps(2 * STREAM_CHUNK);
+        for (uint64_t first = 0; first < len; first += STREAM_CHUNK) {
+          const uint64_t cnt = len - first < STREAM_CHUNK ? len - first : STREAM_CHUNK;
+          int rc = jkq_get_snapshot_amplitudes_ordered(r.h, d.slot, d.qubit_of_bit.data(), first, cnt, amps.data());
+          if (rc) r.die("jkq_get_snapshot_amplitudes_ordered", rc);
+          for (uint64_t i = 0; i < cnt; i++) out << (first + i ? ", \"" : "\"") << format_amplitude(amps[2 * i], amps[2 * i + 1], r.tol) << "\"";
+        }
+        out << "]";
       }
       if (!d.statevector.empty()) {
         if (!d.probabilities.empty()) out << "," << std::endl;

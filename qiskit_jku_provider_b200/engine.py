@@ -193,6 +193,22 @@ class Engine:
         self._check(self._lib.jkq_get_amplitudes(self._h, int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out.view(np.complex128)[:count]
 
+    def snapshot_amplitudes(self, slot, first, count):
+        """Amplitudes [first, first + count) of the state the SNAPSHOT op of ``slot`` recorded (``jkq_get_snapshot_amplitudes``):
+        a slice of the dense vector, or -- above ``snapshot_dense_max`` (26) qubits, where the snapshot is a copy of the
+        diagram -- one walk per amplitude.  Read a wide register range by range::
+
+            for first in range(0, 1 << n, 1 << 20):
+                chunk = eng.snapshot_amplitudes(slot, first, 1 << 20)"""
+        out = np.zeros(2 * max(1, count), dtype=np.float64)
+        self._check(self._lib.jkq_get_snapshot_amplitudes(self._h, int(slot), int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.view(np.complex128)[:count]
+
+    def probabilities_range(self, slot, first, count):
+        out = np.zeros(max(1, count), dtype=np.float64)
+        self._check(self._lib.jkq_get_probabilities_range(self._h, int(slot), int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[:count]
+
     def level_counts(self):
         out = np.zeros(self.n, dtype=np.uint32)
         self._check(self._lib.jkq_get_level_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), self.n))

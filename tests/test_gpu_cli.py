@@ -21,9 +21,10 @@ def cli():
     return _build.CLI
 
 
-def run_cli(cli, qasm, shots, seed, flags, cwd=None):
+def run_cli(cli, qasm, shots, seed, flags, cwd=None, env=None):
     out = subprocess.run([cli, "--simulate_qasm", "--shots=%d" % shots, "--seed=%d" % seed, "--ps"] + list(flags), input=qasm,
-                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=600, cwd=cwd)
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=600, cwd=cwd,
+                         env=dict(os.environ, **env) if env else None)
     assert out.returncode == 0, out.stderr
     text = out.stdout
     body = json.loads(text[text.index("{"):text.index("SIMULATION STATS")])
@@ -325,3 +326,28 @@ def test_cli_resident_server_prints_what_a_fresh_process_prints(cli, tmp_path):
     finally:
         server.terminate()
         server.wait(timeout=10)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_cli_streamed_statevector_equals_the_one_printed_at_once(cli, seed):
+    """A register of 21 qubits or more prints its state vector while reading it from the engine range by range
+    (jkq_get_snapshot_amplitudes_ordered; QASMsimulator.cpp:1012-1030 holds 2^n strings).  JKQ_STREAM_MIN_QUBITS puts the
+    small random programs of the test above on that path: same text, character for character."""
+    text = random_program(seed)
+    once, _, _ = run_cli(cli, text, 64, seed, ["--display_statevector"])
+    streamed, _, _ = run_cli(cli, text, 64, seed, ["--display_statevector"], env={"JKQ_STREAM_MIN_QUBITS": "1"})
+    assert streamed["snapshots"]["0"]["statevector"] == once["snapshots"]["0"]["statevector"]
+    assert streamed["counts"] == once["counts"]
+
+
+def test_cli_streams_the_statevector_of_a_22_qubit_register(cli):
+    """2^22 amplitudes through the streaming read-out: GHZ with a phase, every entry but the two ends prints as 0."""
+    n = 22
+    text = "OPENQASM 2.0;\ninclude \"qelib1.inc\";\nqreg q[%d];\ncreg c[%d];\nh q[0];\n" % (n, n)
+    text += "".join("cx q[%d],q[%d];\n" % (i, i + 1) for i in range(n - 1)) + "t q[%d];\nsnapshot(0) %s;\nmeasure q -> c;\n" % (n - 1, ",".join("q[%d]" % i for i in range(n)))
+    got, _, _ = run_cli(cli, text, 16, 3, ["--display_statevector"])
+    sv = got["snapshots"]["0"]["statevector"]
+    assert len(sv) == 1 << n
+    a0, a1 = parse_amplitude(sv[0]), parse_amplitude(sv[-1])   # (the U convention carries a global phase)
+    assert abs(abs(a0) ** 2 - 0.5) < 1e-5 and abs(abs(a1) ** 2 - 0.5) < 1e-5 and abs(a1 / a0 - np.exp(0.25j * np.pi)) < 1e-5
+    assert all(a == "0" for a in sv[1:-1])

@@ -328,3 +328,62 @@ def test_parity_sweep_subset():
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "parity_sweep.py"), "14", "6", "7", "28"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "parity sweep ok" in out.stdout
+
+
+def test_snapshot_kept_as_a_diagram_and_read_range_by_range(eng):
+    """Above `snapshot_dense_max` qubits a SNAPSHOT keeps a copy of the diagram instead of 2^n amplitudes, and
+    jkq_get_snapshot_amplitudes walks it range by range (the streaming read-out of SURVEY 8f rank 2).  (1) forced on a
+    10-qubit random circuit: bit for bit the dense snapshot, also in a permuted bit order; (2) a mid-circuit snapshot of a
+    40-qubit register survives the gates and the collections that follow it."""
+    import ctypes as Ct
+    from qiskit_jku_provider_b200.engine import OP_SNAPSHOT, circuit_ops, gate_op, simple_op
+    eng.set_option("force_mode", 0)
+    eng.set_option("level_log", 0)
+    circ = C.random_circuit(10, 60, 5)
+    base = circuit_ops(circ)
+    ops = np.zeros(len(base) + 1, dtype=base.dtype)
+    half = len(base) // 2
+    ops[:half] = base[:half]
+    ops[half]["kind"] = OP_SNAPSHOT
+    ops[half]["arg"] = 3
+    ops[half + 1:] = base[half:]
+    eng.load_ops(10, ops)
+    eng.apply()
+    dense = eng.statevector(3)
+    eng.set_option("snapshot_dense_max", 4)
+    try:
+        eng.load_ops(10, ops)
+        eng.apply()
+        walked = np.concatenate([eng.snapshot_amplitudes(3, f, 256) for f in range(0, 1024, 256)])
+        assert walked.tolist() == dense.tolist()
+        assert eng.statevector(3).tolist() == dense.tolist()
+        assert np.abs(dense - C.dense_statevector(C.Circuit(10, circ.ops[:half]))).max() < 1e-9
+        perm = np.array([3, 0, 9, 1, 8, 2, 7, 4, 6, 5], dtype=np.uint32)
+        out = np.zeros(2 * 1024)
+        rc = eng._lib.jkq_get_snapshot_amplitudes_ordered(eng._h, 3, perm.ctypes.data_as(Ct.POINTER(Ct.c_uint32)), 0, 1024,
+                                                          out.ctypes.data_as(Ct.POINTER(Ct.c_double)))
+        assert rc == 0
+        idx = np.arange(1024)
+        e = np.zeros(1024, dtype=np.int64)
+        for b in range(10):
+            e |= ((idx >> b) & 1) << int(perm[b])
+        assert out.view(np.complex128).tolist() == dense[e].tolist()
+    finally:
+        eng.set_option("snapshot_dense_max", 26)
+    n = 40
+    h, t = C.expand("h", [0])[0], C.expand("t", [n - 1])[0]
+    ops = [gate_op(0, h.matrix()), simple_op(OP_SNAPSHOT, 0, 1)]
+    for q in range(n - 1):
+        cx = C.expand("cx", [q, q + 1])[0]
+        ops.append(gate_op(cx.target, cx.matrix(), cx.controls))
+    ops += [gate_op(n - 1, t.matrix()), simple_op(OP_SNAPSHOT, 0, 2)]
+    eng.load_ops(n, ops)
+    eng.apply()
+    hm, tm = np.array(h.matrix(), dtype=complex), np.array(t.matrix(), dtype=complex)  # (the U convention carries a global phase)
+    first = eng.snapshot_amplitudes(1, 0, 4)          # H|0> on qubit 0, nothing else yet
+    assert np.abs(first - np.array([hm[0, 0], hm[1, 0], 0, 0])).max() < 1e-9
+    assert eng.snapshot_amplitudes(1, (1 << n) - 2, 2).tolist() == [0j, 0j]
+    last = eng.snapshot_amplitudes(2, (1 << n) - 2, 2)  # GHZ with the T phases on its two ends
+    assert last[0] == 0 and abs(last[1] - hm[1, 0] * tm[1, 1]) < 1e-9
+    assert abs(eng.snapshot_amplitudes(2, 0, 1)[0] - hm[0, 0] * tm[0, 0]) < 1e-9
+    assert eng.amplitudes((1 << n) - 1, 1)[0] == last[1]
