@@ -300,6 +300,10 @@ template <int MODE> JD uint32_t want_collect(const Ctx &c, bool log) {
   return nodes_now > ld_s<MODE>(&c.E->gc_limit);
 }
 
+// widest level the cursor warp runs by itself when the option "solo_max" is not set (see JEng.solo_max)
+#ifndef JKQ_SOLO_MAX_DEFAULT
+#define JKQ_SOLO_MAX_DEFAULT (JKQ_WARP < 8u ? JKQ_WARP : 8u)
+#endif
 template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n, bool log) {
   JEng *E = c.E;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
@@ -345,7 +349,7 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     jsyncwarp();
     int lsw = 0, wide_L = -1;
     uint32_t icount = 0, blocked = 0;
-    const uint32_t solo_opt = ld_s<MODE>(&E->solo_max), solo_max = solo_opt && solo_opt < JKQ_WARP ? solo_opt : JKQ_WARP;
+    const uint32_t solo_opt = ld_s<MODE>(&E->solo_max), solo_max = solo_opt && solo_opt < JKQ_WARP ? solo_opt : JKQ_SOLO_MAX_DEFAULT;
     JPROF_T(sp0);
     // Where the cursor goes for this gate: up to the gate's top level if it is below; down only as far as the next
     // few gates need it (JGate.park) when the gate is one thin_gate is bound to take (diagonal / anti-diagonal matrix):
