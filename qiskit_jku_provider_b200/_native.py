@@ -111,7 +111,15 @@ def load():
         except Exception:
             have_nvcc = False
         if have_nvcc:
-            build_native()  # a failed rebuild must not leave Python bound to a stale binary with other struct layouts
+            # (one builder at a time: the ranks of a torchrun launch all get here together)
+            import fcntl
+            with open(LIB + ".lock", "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    if stale():
+                        build_native()  # a failed rebuild must not leave Python bound to a stale binary with other struct layouts
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
     if not os.path.exists(LIB):
         raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the engine is CUDA only, there is no CPU fallback)" % LIB)
