@@ -170,6 +170,13 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
       if ((fl & 3u) == JS_RETRY) my |= JF_RETRY;
     }
     JPROF_T(pt1);
+#if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
+    if (MODE == MODE_GRID && (sid & (stride - 1u)) == 0 && sid / stride < nwork) {  // this thread had at least one item
+      const int slot = round > 0 ? 4 : (my ? 2 : 0);
+      atomicAdd(&c.E->prof_x[slot], (unsigned long long)(pt1 - pt0));
+      atomicAdd(&c.E->prof_x[slot + 1], 1ull);
+    }
+#endif
     uint32_t flags = sync_or<MODE>(c, my);
     JPROF_T(pt2);
     JPROF_ADD(c, expand ? 2 : 3, pt0, pt1);
@@ -790,6 +797,7 @@ template <int MODE> JD uint32_t init_state(Ctx &c) {
     for (int k = 0; k < 12; k++) E->st[k] = 0;
     for (int k = 0; k < 16; k++) E->prof[k] = 0;
     for (int k = 0; k < 32; k++) E->prof_w[k] = 0;
+    for (int k = 0; k < 8; k++) E->prof_x[k] = 0;
     JNode t; t.c0 = 0; t.c1 = 0; t.w = 0;
     E->nodes[0] = t;
     // the reals 0, 1 and the reference's gate constants 1/2, FP64 sqrt(2)/2 in its insertion order

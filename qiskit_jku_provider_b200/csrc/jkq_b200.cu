@@ -611,7 +611,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
     const Part parts[] = {
         {(void **)&E.nodes, (size_t)E.node_cap * sizeof(JNode)}, {(void **)&E.nodes_alt, (size_t)E.node_cap * sizeof(JNode)},
         {(void **)&E.utab, ((size_t)E.utab_mask + 1) * 8}, {(void **)&E.vals, (size_t)E.val_cap * 8}, {(void **)&E.vals_alt, (size_t)E.val_cap * 8},
-        {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.vbm, ((((size_t)E.vtab_mask + 1) >> 8) + 1) * 4}, {(void **)&E.vlk, ((((size_t)E.vtab_mask + 1) >> 8) + 1) * 4},
+        {(void **)&E.vtab, ((size_t)E.vtab_mask + 1) * sizeof(JVSlot)}, {(void **)&E.vbm, ((((size_t)E.vtab_mask + 1) >> 8) + 1) * 4},
         {(void **)&E.pend, (size_t)E.pend_cap * 4},
         {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
         {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
@@ -626,7 +626,6 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   // generation-tagged de-dup tables: zeroed once, never cleared again (the generation counts across circuits)
   CU(cudaMemsetAsync(E.utab, 0, ((size_t)E.utab_mask + 1) * 8, h->stream));  // (generation 0 = never written)
   E.ut_gen = 1; E.vt_cur = E.vtab_mask; E.vt_dirty_all = 1;
-  CU(cudaMemsetAsync(E.vlk, 0, ((((size_t)E.vtab_mask + 1) >> 8) + 1) * 4, h->stream));  // no line of the value table is locked
   CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
   CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
   CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
@@ -1545,6 +1544,10 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
   if (E.prof[6])
     fprintf(stderr, "  per gate: cursor_prepare %llu  solo expand %llu  solo reduce %llu  cursor_finish %llu | solo levels/gate %.2f  wide gates %llu\n",
             E.prof[11] / E.prof[6], E.prof[12] / E.prof[6], E.prof[13] / E.prof[6], E.prof[14] / E.prof[6], (double)E.prof[15] / E.prof[6], E.prof[10]);
+  if (E.prof_x[1] + E.prof_x[3])
+    fprintf(stderr, "  grid item loops (cycles per thread and phase): first run without a miss %.0f (%llu), first run with a value miss %.0f (%llu), rerun %.0f (%llu)\n",
+            E.prof_x[1] ? (double)E.prof_x[0] / E.prof_x[1] : 0.0, E.prof_x[1], E.prof_x[3] ? (double)E.prof_x[2] / E.prof_x[3] : 0.0, E.prof_x[3],
+            E.prof_x[5] ? (double)E.prof_x[4] / E.prof_x[5] : 0.0, E.prof_x[5]);
   for (int k = 0; k < 8; k++)
     if (E.prof_w[8 + k])
       fprintf(stderr, "  grid level phases of up to %d items: %llu levels, %llu items, %llu barriers, %.1f Mcycles (%.0f cycles per level)\n", 4 << (2 * k),

@@ -371,8 +371,7 @@ JD uint32_t vt_next(uint32_t h, uint32_t mask) { return (h + 8u) & mask; }
 JD unsigned long long *vt_meta(JVSlot *s) { return reinterpret_cast<unsigned long long *>(&s->keylo); }
 JD unsigned long long vt_meta_of(uint32_t keylo, uint32_t id1) { return (unsigned long long)keylo | ((unsigned long long)id1 << 32); }
 
-// HBM table: remember that the line of slot h holds something (see JEng.vbm); a load first, the atomic only for the
-// first claim in a line
+// HBM table: remember that the line of slot h holds something (see JEng.vbm)
 template <int MODE> JD void vt_mark(JEng *E, uint32_t h) {
   if (MODE != MODE_GRID) return;
   const uint32_t line = h >> 3, bit = 1u << (line & 31u);
@@ -380,7 +379,7 @@ template <int MODE> JD void vt_mark(JEng *E, uint32_t h) {
 #ifdef JKQ_EMU
   *w |= bit;
 #else
-  if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+  atomicOr(w, bit);  // (result unused: a RED, nobody waits for it)
 #endif
 }
 
@@ -428,7 +427,7 @@ template <int MODE> JD void real_propose(JEng *E, CtaState *S, uint32_t ring, do
 #define JKQ_INPLACE_CTA 0
 #endif
 #ifndef JKQ_INPLACE_GRID
-#define JKQ_INPLACE_GRID 0
+#define JKQ_INPLACE_GRID 1
 #endif
 template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x);
 template <int MODE> JNI uint32_t real_insert_par(JEng *E, CtaState *S, double x, long long k);
@@ -453,7 +452,7 @@ template <int MODE> JD uint32_t real_lookup(JEng *E, CtaState *S, uint32_t ring,
     uint32_t hh = h[d];
     JVSlot sl = s[d];
     for (uint32_t probes = 0; sl.id1 != 0 && probes <= (mask >> 3); probes++) {
-      if (sl.keylo == klo && sl.id1 < JV_DROPPED && fabs(JKQ_DSUB(ju2d(sl.vbits), x)) <= tol) return sl.id1 - 1;
+      if (sl.keylo == klo && sl.id1 < JV_WAITING && fabs(JKQ_DSUB(ju2d(sl.vbits), x)) <= tol) return sl.id1 - 1;
       hh = vt_next(hh, mask);
       sl = ld_s<MODE>(tab + hh);
     }
@@ -578,82 +577,141 @@ template <int MODE> JNI uint32_t real_insert_solo(JEng *E, CtaState *S, double x
 }
 
 // A miss during a phase that many threads run at once (levels wider than the cursor warp; every phase of the grid path).
-// Round 1 collected the misses of a phase as candidates and committed them behind a barrier (real_propose / vals_commit,
-// still there behind JKQ_PROPOSE_COMMIT): schedule-independent, but every level that met a new value -- on a random
-// circuit nearly every level -- cost two more barriers and a second run of its items (r160: 28 k of the 29 k cycles of a
-// level of four items).  Now the value goes in at once, first come, first kept like the reference
-// (QMDDcomplexD.cpp:402-418).  What keeps the entries pairwise more than tol apart is a lock over the buckets k-1 .. k+1:
-//   MODE_CTA   the one lock word of real_insert_solo (a critical section is ~300 cycles of shared memory);
-//   MODE_GRID  one lock BIT per 128-byte line of the HBM table (JEng.vlk): the home lines of the bucket groups of k-1
-//              and k+1 (k's own is one of the two).  Inserters into adjacent buckets share at least one of them; the
-//              lower line is taken first and given back if the second is busy, so nobody waits while holding.
-// Under the lock the thread looks again and appends only if the value is still missing.  Lookups take no lock: a slot is
-// claimed by CAS (PENDING reads as "no match, keep probing"), filled, and named by its id last.
-// Which of two values within tol of each other becomes the entry now depends on timing (they differ by rounding noise:
-// amplitudes agree to ~1e-16 between runs instead of bit for bit).
+// Round 1 collected the misses of a phase as candidates and committed them behind a barrier (real_propose / vals_commit):
+// schedule-independent, but an item that met a new value was run again after the commit round -- and again for every
+// value that depended on the one before (r160, profile build: 2.4 reruns per item with a miss; the reruns were 47 % of
+// all item time, and the first run of such an item took 3.7 times as long as one without a miss).  With JKQ_INPLACE_GRID
+// the value goes in at once, first come, first kept like the reference (QMDDcomplexD.cpp:402-418), without locks:
+//   1. the thread claims the slot of bucket k by CAS (PENDING).  One slot per bucket: whoever loses waits for the owner's
+//      id (same bucket = within tol) or, if the owner gives the slot up, looks the value up again;
+//   2. the owner writes its value into the slot and looks at the buckets k-1 and k+1 (it could only issue these loads
+//      after its CAS came back, so of two owners of adjacent buckets at least one sees the other).  A committed entry
+//      within tol: the owner gives its slot up (DROPPED) and returns that entry.  An owner of k-1 still at work: this
+//      one marks itself WAITING and waits for it; an owner of k+1 still PENDING: wait until it is WAITING (it defers) or
+//      done.  Waits only go to the bucket below or to a transient state of the one above: no cycle;
+//   3. the real is appended, and the id published last (fence in between).
+// Lookups take no lock: PENDING / WAITING read as "no match, keep probing".  Which of two values within tol of each other
+// becomes the entry depends on timing (they differ by rounding noise: amplitudes agree to ~1e-16 between runs, not
+// bit for bit).
 #ifndef JKQ_EMU
-JD bool vt_try_lock(JEng *E, uint32_t line) {
-  const uint32_t bit = 1u << (line & 31u);
-  return (atomicOr(E->vlk + (line >> 5), bit) & bit) == 0u;
-}
-JD void vt_unlock(JEng *E, uint32_t line) { atomicAnd(E->vlk + (line >> 5), ~(1u << (line & 31u))); }
+#define JKQ_SPIN_LIMIT 4000000u
 #endif
-// the grid path's append: real into the array, slot claimed along the probe chain of bucket k, id published last
-JD uint32_t real_append_grid(JEng *E, double x, long long k) {
-  const uint32_t idx = jagg_inc(&E->val_count);
-  if (!vt_room(E, idx)) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); return JV_MISS; }
-  E->vals[idx] = x;
-  jstat<MODE_GRID>(E, nullptr, JST_VALS, 1u);
-  const uint32_t klo = (uint32_t)k, mask = vt_mask2<MODE_GRID>(E);
-  const unsigned long long claim = vt_meta_of(klo, JV_PENDING);
-  JVSlot *tab = E->vtab;
-  uint32_t h = vt_slot0(k, mask);
-  for (uint32_t probes = 0;; probes++) {
-    if (probes > (mask >> 3)) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); return JV_MISS; }
-    unsigned long long *mp = vt_meta(tab + h);
-    const unsigned long long meta = ld_r<MODE_GRID>(mp);
-    if (meta == 0 || ((uint32_t)meta == klo && (uint32_t)(meta >> 32) == JV_DROPPED)) {
-      if (jatomic_cas(mp, meta, claim) == meta) break;
-      continue;  // somebody else took it: look at the slot again
-    }
+// state of bucket kb's slot as seen now: returns its meta (0 = no slot), *hp = where (in: its first slot, whose meta the
+// caller has loaded already)
+JD unsigned long long vt_find_bucket(JEng *E, long long kb, uint32_t mask, uint32_t *hp, unsigned long long meta) {
+  const uint32_t klo = (uint32_t)kb;
+  uint32_t h = *hp;
+  for (uint32_t probes = 0; probes <= (mask >> 3); probes++) {
+    if (meta == 0) return 0;
+    if ((uint32_t)meta == klo) { *hp = h; return meta; }
     h = vt_next(h, mask);
+    meta = ld_r<MODE_GRID>(vt_meta(E->vtab + h));
   }
-  tab[h].vbits = jd2u(x);
-  jfence<MODE_GRID>();  // the real and the value before the id that names them
-#ifdef JKQ_EMU
-  *vt_meta(tab + h) = vt_meta_of(klo, idx + 1);
-#else
-  *(volatile unsigned long long *)vt_meta(tab + h) = vt_meta_of(klo, idx + 1);
+  return 0;
+}
+// wait until the slot at h (bucket key klo) leaves the states in `while_mask` (bit 0: PENDING, bit 1: WAITING)
+JD unsigned long long vt_wait(JEng *E, uint32_t h, uint32_t while_mask) {
+  unsigned long long meta = ld_r<MODE_GRID>(vt_meta(E->vtab + h));
+#ifndef JKQ_EMU
+  for (uint32_t spins = 0;; spins++) {
+    const uint32_t id1 = (uint32_t)(meta >> 32);
+    const bool busy = (id1 == JV_PENDING && (while_mask & 1u)) || (id1 == JV_WAITING && (while_mask & 2u));
+    if (!busy) break;
+    if (spins > JKQ_SPIN_LIMIT) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_INTERNAL); break; }
+    __nanosleep(40);
+    meta = ld_r<MODE_GRID>(vt_meta(E->vtab + h));
+  }
 #endif
-  vt_mark<MODE_GRID>(E, h);
-  return idx;
+  return meta;
 }
 template <int MODE> JNI uint32_t real_insert_par(JEng *E, CtaState *S, double x, long long k) {
   if (MODE == MODE_CTA) return real_insert_solo<MODE>(E, S, x);
-  uint32_t r = JV_MISS;
-#ifdef JKQ_EMU
-  r = real_lookup<MODE>(E, S, 0, x, false);
-  if (r == JV_MISS) r = real_append_grid(E, x, k);
-#else
-  const uint32_t mask = vt_mask2<MODE>(E);
-  uint32_t la = vt_slot0(k - 1, mask) >> 3, lb = vt_slot0(k + 1, mask) >> 3;
-  if (la > lb) { const uint32_t t = la; la = lb; lb = t; }
-  bool done = false;
-  while (!done) {
-    if (vt_try_lock(E, la)) {
-      if (lb == la || vt_try_lock(E, lb)) {
-        __threadfence();
-        r = real_lookup<MODE>(E, S, 0, x, false);
-        if (r == JV_MISS) r = real_append_grid(E, x, k);
-        __threadfence();
-        if (lb != la) vt_unlock(E, lb);
-        vt_unlock(E, la);
-        done = true;
-      } else vt_unlock(E, la);
+  const uint32_t klo = (uint32_t)k, mask = vt_mask2<MODE_GRID>(E);
+  const double tol = E->tol;
+  JVSlot *tab = E->vtab;
+  for (uint32_t attempt = 0; attempt < 64u; attempt++) {
+    if (attempt) {  // the owner of my bucket gave its slot up: the neighbourhood has changed, look again
+      const uint32_t r = real_lookup<MODE>(E, S, 0, x, false);
+      if (r != JV_MISS) return r;
     }
-  }
+    // ---- 1. the slot of bucket k: mine, or somebody else's
+    uint32_t h = vt_slot0(k, mask);
+    bool mine = false, again = false;
+    for (uint32_t probes = 0; probes <= (mask >> 3);) {
+      unsigned long long *mp = vt_meta(tab + h);
+      unsigned long long meta = ld_r<MODE_GRID>(mp);
+      if (meta == 0 || ((uint32_t)meta == klo && (uint32_t)(meta >> 32) == JV_DROPPED)) {
+        const unsigned long long old = jatomic_cas(mp, meta, vt_meta_of(klo, JV_PENDING));
+        if (old == meta) { mine = true; break; }
+        meta = old;
+      }
+      if ((uint32_t)meta == klo) {
+        meta = vt_wait(E, h, 3u);
+        const uint32_t id1 = (uint32_t)(meta >> 32);
+        if (id1 < JV_WAITING && id1 != 0) return id1 - 1;  // same bucket: within tol by construction
+        again = true;                                      // given up (or an error): start over
+        break;
+      }
+      h = vt_next(h, mask);
+      probes++;
+    }
+    if (again) continue;
+    if (!mine) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); return JV_MISS; }
+    // ---- 2. I own bucket k.  My value first (an owner next door compares against it once I am done), then the neighbours
+    unsigned long long *my_meta = vt_meta(tab + h);
+    tab[h].vbits = jd2u(x);
+    uint32_t found = JV_MISS;
+    uint32_t hl = vt_slot0(k - 1, mask), hu = vt_slot0(k + 1, mask);
+    unsigned long long ml = ld_r<MODE_GRID>(vt_meta(tab + hl)), mu = ld_r<MODE_GRID>(vt_meta(tab + hu));  // both in flight ...
+    uint32_t idx = jagg_inc(&E->val_count);  // ... and so is the allocation (an index is lost if the slot is given up)
+    ml = vt_find_bucket(E, k - 1, mask, &hl, ml);
+    mu = vt_find_bucket(E, k + 1, mask, &hu, mu);
+    if (ml != 0) {
+      uint32_t id1 = (uint32_t)(ml >> 32);
+      if (id1 == JV_PENDING || id1 == JV_WAITING) {  // the owner below is at work: it goes first
+#ifdef JKQ_EMU
+        *my_meta = vt_meta_of(klo, JV_WAITING);
+#else
+        *(volatile unsigned long long *)my_meta = vt_meta_of(klo, JV_WAITING);
 #endif
-  return r;
+        ml = vt_wait(E, hl, 3u);
+        id1 = (uint32_t)(ml >> 32);
+      }
+      if (id1 < JV_WAITING && id1 != 0 && fabs(JKQ_DSUB(ju2d(ld_r<MODE_GRID>(&tab[hl].vbits)), x)) <= tol) found = id1 - 1;
+    }
+    if (found == JV_MISS && mu != 0) {
+      uint32_t id1 = (uint32_t)(mu >> 32);
+      if (id1 == JV_PENDING) {  // the owner above has not looked at me yet, or is about to: wait until it defers or is done
+        mu = vt_wait(E, hu, 1u);
+        id1 = (uint32_t)(mu >> 32);
+      }
+      if (id1 < JV_WAITING && id1 != 0 && fabs(JKQ_DSUB(ju2d(ld_r<MODE_GRID>(&tab[hu].vbits)), x)) <= tol) found = id1 - 1;
+    }
+    if (found == JV_MISS && !vt_room(E, idx)) { jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_VAL_FULL); found = 0; idx = 0xFFFFFFFFu; }
+    if (found != JV_MISS) {  // somebody within tol got there first (or the array is full): give the slot up
+      tab[h].vbits = JV_INF;
+      jfence<MODE_GRID>();
+#ifdef JKQ_EMU
+      *my_meta = vt_meta_of(klo, JV_DROPPED);
+#else
+      *(volatile unsigned long long *)my_meta = vt_meta_of(klo, JV_DROPPED);
+#endif
+      return idx == 0xFFFFFFFFu ? JV_MISS : found;
+    }
+    // ---- 3. append, publish
+    E->vals[idx] = x;
+    jstat<MODE_GRID>(E, nullptr, JST_VALS, 1u);
+    jfence<MODE_GRID>();  // the real and the value before the id that names them
+#ifdef JKQ_EMU
+    *my_meta = vt_meta_of(klo, idx + 1);
+#else
+    *(volatile unsigned long long *)my_meta = vt_meta_of(klo, idx + 1);
+#endif
+    vt_mark<MODE_GRID>(E, h);
+    return idx;
+  }
+  jset_error<MODE_GRID>(E, nullptr, JKQ_ERR_INTERNAL);
+  return JV_MISS;
 }
 
 // parallel hash-only insert of an existing real (collector / table reload): slot claimed by CAS on id1

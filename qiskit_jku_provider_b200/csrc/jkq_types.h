@@ -34,11 +34,12 @@ typedef struct __attribute__((aligned(16))) {
 // atomicMin proposals while the slot is pending.
 #define JV_PENDING 0xFFFFFFFFu  // claimed in the current phase, value = min of the proposals so far
 #define JV_DROPPED 0xFFFFFFFEu  // claimed once, no entry (the candidate joined a lower neighbour)
+#define JV_WAITING 0xFFFFFFFDu  // in-place insertion (real_insert_par): claimed, waits for the owner of the bucket below to finish
 #define JV_INF 0x7FF0000000000000ull
 typedef struct __attribute__((aligned(16))) {
   unsigned long long vbits;  // non-negative real as raw bits; JV_INF = none
   uint32_t keylo;            // low 32 bits of the bucket number floor(value / tol)
-  uint32_t id1;              // 0 = empty, JV_PENDING, JV_DROPPED, else value index + 1
+  uint32_t id1;              // 0 = empty, JV_PENDING, JV_DROPPED, JV_WAITING, else (< JV_WAITING) value index + 1
 } JVSlot;
 
 // work-item kinds
@@ -129,8 +130,6 @@ typedef struct {
   JVSlot *vtab;
   uint32_t *vbm;      // one bit per 128-byte line (8 slots) of the HBM value table: some slot of the line was claimed since
                       // the last sweep -- a sweep clears those lines instead of the whole table (4.3 GB at 2^26 reals)
-  uint32_t *vlk;      // one lock bit per line of the HBM value table, held while a new real goes into the buckets around it
-                      // (real_insert_par, jkq_engine.cuh)
   uint32_t *pend;     // value-table slots claimed in the current phase
   JItem *items;
   unsigned long long *dtab;  // F/S item de-dup: generation << 32 | item index + 1
@@ -176,6 +175,7 @@ typedef struct {
   unsigned int bar_gen;
   unsigned int bar_flags[3];
   unsigned long long prof[16];  // JKQ_PROFILE builds: cycle counters, see jkq_b200.cu jkq_get_stats
+  unsigned long long prof_x[8];   // JKQ_PROFILE, grid path: cycles / count of item loops: [0,1] first run, no miss  [2,3] first run with a value miss  [4,5] reruns
   unsigned long long prof_w[32];  // JKQ_PROFILE, grid path: level phases by width class (log4 of the item count): [c] cycles, [8+c] levels, [16+c] barriers, [24+c] items
   uint32_t gc_bsum[1024];  // collector: live reals per CTA chunk
   unsigned int dbg_timeout_block;   // debugging aid: who timed out at a grid barrier, and where everyone was

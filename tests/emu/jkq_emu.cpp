@@ -148,7 +148,6 @@ int main(int argc, char **argv) {
   E->utab = (unsigned long long *)calloc((size_t)E->utab_mask + 1, 8);
   E->ut_gen = 1; E->vt_cur = E->vtab_mask; E->vt_dirty_all = 1;
   E->vbm = (uint32_t *)calloc((((size_t)E->vtab_mask + 1) >> 8) + 1, 4);
-  E->vlk = (uint32_t *)calloc((((size_t)E->vtab_mask + 1) >> 8) + 1, 4);
   E->vals = (double *)calloc(E->val_cap, 8);
   E->vals_alt = (double *)calloc(E->val_cap, 8);
   E->vtab = (JVSlot *)calloc((size_t)E->vtab_mask + 1, sizeof(JVSlot));
