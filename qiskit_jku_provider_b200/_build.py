@@ -10,7 +10,7 @@ LIB = os.environ.get("JKQ_LIB") or os.path.join(HERE, "libjkq_b200.so")  # (JKQ_
 SOURCES = ["jkq_b200.cu", "jkq_qasm.cpp"]
 CLI = os.path.join(HERE, "jku_simulator")  # the executable interface of the reference (src/main.cpp) on this engine
 CLI_SOURCES = ["jku_simulator.cpp"]
-HEADERS = ["jkq_types.h", "jkq_engine.cuh", "jkq_thin.cuh", "jkq_apply.cuh", "jkq_sample.cuh", os.path.join("..", "..", "include", "jkq.h")]
+HEADERS = ["jkq_types.h", "jkq_engine.cuh", "jkq_thin.cuh", "jkq_grid.cuh", "jkq_apply.cuh", "jkq_sample.cuh", os.path.join("..", "..", "include", "jkq.h")]
 
 
 def nvcc_path():

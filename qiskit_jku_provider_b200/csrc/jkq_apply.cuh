@@ -7,6 +7,7 @@
 
 #include "jkq_engine.cuh"
 #include "jkq_thin.cuh"
+#include "jkq_grid.cuh"
 
 #if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
 #define JPROF_T(var) long long var = clock64()
@@ -156,7 +157,37 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
     uint32_t stride = 1;
     while (stride < JKQ_WARP && nwork * stride * 2u <= c.nth) stride <<= 1;
     const uint32_t sid = spread_id<MODE>(c);
-    for (uint32_t j = (sid & (stride - 1u)) ? nwork : sid / stride; j < nwork; j += c.nth / stride) {
+    // more warps than items: a whole warp per item (jkq_grid.cuh: the parts of the item's arithmetic and its two de-dup
+    // inserts on different lanes) -- a narrow level costs the instruction chain of one item, which this cuts
+    const bool wmode = MODE == MODE_GRID && JKQ_GRID_ILP && JKQ_GRID_WARP && JKQ_WARP > 1u && stride == JKQ_WARP;
+    JGP_SET(c, MODE == MODE_GRID && nwork <= 32u && (!wmode || (sid & (JKQ_WARP - 1u)) == 0));
+    for (uint32_t j = (!wmode && (sid & (stride - 1u))) ? nwork : sid / stride; j < nwork; j += c.nth / stride) {
+      if (MODE == MODE_GRID && JKQ_GRID_ILP) {  // jkq_grid.cuh: the item's first quad in one load, the staged item steps
+        JItem *it = c.items + b + j;
+        JGP_T(gp0);
+        const JQuad q0 = ldq(it);  // a, b, tag, flags
+        const uint32_t lvl = (q0.z >> 8) & 0xFFu;
+        if (lvl != 0 && lvl != (uint32_t)L + 1u) continue;  // (parked for a lower level)
+        uint32_t fl = q0.w;
+        const uint32_t st = fl & 3u;
+        if (st == JS_DEAD) continue;
+        if (round > 0 && st != JS_RETRY) continue;
+        JGP_T(gp1);
+        JGP_ADD(c, 0, gp0, gp1);
+#ifndef JKQ_EMU
+        if (wmode) {
+          if (expand) fl = expand_item_g<true>(c, g, b + j, L, q0.x, q0.y, q0.z);
+          else fl = (fl & ~3u) | (reduce_item_g<true>(c, b + j, fl) ? JS_DONE : JS_RETRY);
+        } else
+#endif
+        if (expand) fl = expand_item_g<false>(c, g, b + j, L, q0.x, q0.y, q0.z);
+        else fl = (fl & ~3u) | (reduce_item_g<false>(c, b + j, fl) ? JS_DONE : JS_RETRY);
+        JGP_T(gp2);
+        JGP_ADD(c, expand ? 1 : 2, gp1, gp2);
+        if (!wmode || (sid & (JKQ_WARP - 1u)) == 0) it->flags = fl;
+        if ((fl & 3u) == JS_RETRY) my |= JF_RETRY;
+        continue;
+      }
       const uint32_t i = level_item<MODE>(c, L, b, e, j);
       if (i == JI_FAIL) continue;
       JItem *it = c.items + i;
@@ -179,6 +210,13 @@ JD uint32_t run_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
 #endif
     uint32_t flags = sync_or<MODE>(c, my);
     JPROF_T(pt2);
+#if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
+    if (MODE == MODE_GRID && c.gprof) {
+      if ((sid & (stride - 1u)) == 0 && sid / stride < nwork) { JGP_ADD(c, 3, pt1, pt2); JGP_ADD(c, 5, pt0, pt1); }  // (lane 0 of a warp in wmode: c.gprof)
+      if (c.tid == 0) { JGP_ADD(c, 4, pt1, pt2); JGP_ADD(c, 6, pt0, pt2); }
+    }
+#endif
+    JGP_SET(c, 0);
     JPROF_ADD(c, expand ? 2 : 3, pt0, pt1);
     JPROF_ADD(c, 4, pt1, pt2);
     JPROF_INC(c, 7);
@@ -238,7 +276,32 @@ template <int MODE, bool expand>
 JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   const uint32_t nwork = e - b + defer_count<MODE>(c, L);
 #if !defined(JKQ_EMU) && !defined(JKQ_NO_PAIRS)
-  if (expand && nwork <= JKQ_WARP / 2) return solo_expand_pairs<MODE>(c, g, b, e, L, nwork);
+  if (expand && nwork <= JKQ_WARP / 2 && !(MODE == MODE_GRID && JKQ_GRID_ILP)) return solo_expand_pairs<MODE>(c, g, b, e, L, nwork);
+#endif
+#ifndef JKQ_EMU
+  if (MODE == MODE_GRID && JKQ_GRID_ILP && JKQ_GRID_WARP) {
+    // the cursor warp alone on the grid path: the items one after the other, all lanes on each (jkq_grid.cuh)
+    for (uint32_t j = 0; j < nwork; j++) {
+      const uint32_t i = level_item<MODE>(c, L, b, e, j);
+      if (i == JI_FAIL) continue;
+      JItem *it = c.items + i;
+      const JQuad q0 = ldq(it);
+      uint32_t fl = q0.w;
+      if ((fl & 3u) == JS_DEAD) continue;
+      for (uint32_t rounds = 0;; rounds++) {
+        if (expand) fl = expand_item_g<true>(c, g, i, L, q0.x, q0.y, q0.z);
+        else fl = (fl & ~3u) | (reduce_item_g<true>(c, i, fl) ? JS_DONE : JS_RETRY);
+        if (c.ltid == 0) it->flags = fl;
+        jsyncwarp();
+        const uint32_t tr = thin_trouble<MODE>(c);  // pools exhausted / errors are sticky words
+        if (tr) return tr;
+        if ((fl & 3u) != JS_RETRY) break;
+        if (rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);  // (seen by thin_trouble next round)
+        thin_commit<MODE>(c);
+      }
+    }
+    return 0;
+  }
 #endif
   const uint32_t i = c.ltid < nwork ? level_item<MODE>(c, L, b, e, c.ltid) : JI_FAIL;
   JItem *it = c.items + (i == JI_FAIL ? 0 : i);
@@ -248,6 +311,10 @@ JD uint32_t solo_level(Ctx &c, const JGate &g, uint32_t b, uint32_t e, int L) {
   uint32_t rounds = 0;
   for (;;) {
     if (need) {
+      if (MODE == MODE_GRID && JKQ_GRID_ILP) {
+        if (expand) { const JQuad q0 = ldq(it); fl = expand_item_g<false>(c, g, i, L, q0.x, q0.y, q0.z); }
+        else fl = (fl & ~3u) | (reduce_item_g<false>(c, i, fl) ? JS_DONE : JS_RETRY);
+      } else
       if (expand) fl = expand_item<MODE>(c, g, i, L);
       else fl = (fl & ~3u) | (reduce_item<MODE>(c, i, fl) ? JS_DONE : JS_RETRY);
       it->flags = fl;
@@ -311,6 +378,11 @@ template <int MODE> JD uint32_t want_collect(const Ctx &c, bool log) {
 #ifndef JKQ_SOLO_MAX_DEFAULT
 #define JKQ_SOLO_MAX_DEFAULT (JKQ_WARP < 8u ? JKQ_WARP : 8u)
 #endif
+// ... on the grid path, where the warp takes the items of such a level one after the other (solo_level) and a level handed to
+// the grid costs one barrier
+#ifndef JKQ_SOLO_MAX_GRID
+#define JKQ_SOLO_MAX_GRID (JKQ_WARP < 2u ? JKQ_WARP : 2u)
+#endif
 template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n, bool log) {
   JEng *E = c.E;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
@@ -356,7 +428,8 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     jsyncwarp();
     int lsw = 0, wide_L = -1;
     uint32_t icount = 0, blocked = 0;
-    const uint32_t solo_opt = ld_s<MODE>(&E->solo_max), solo_max = solo_opt && solo_opt < JKQ_WARP ? solo_opt : JKQ_SOLO_MAX_DEFAULT;
+    const uint32_t solo_opt = ld_s<MODE>(&E->solo_max);
+    const uint32_t solo_max = solo_opt && solo_opt < JKQ_WARP ? solo_opt : (MODE == MODE_GRID && JKQ_GRID_ILP && JKQ_GRID_WARP ? JKQ_SOLO_MAX_GRID : JKQ_SOLO_MAX_DEFAULT);
     JPROF_T(sp0);
     // Where the cursor goes for this gate: up to the gate's top level if it is below; down only as far as the next
     // few gates need it (JGate.park) when the gate is one thin_gate is bound to take (diagonal / anti-diagonal matrix):

@@ -40,7 +40,7 @@ template <int MODE> __device__ __forceinline__ Ctx make_ctx(JEng *E) {
     c.T = reinterpret_cast<ThinState *>(jkq_dyn_smem);  // the cursor runs in warp 0 of block 0 (k_run_gates only)
   }
   c.items = MODE == MODE_CTA ? c.sh->items : E->items;
-  c.phase = 0; c.ring = 0;
+  c.phase = 0; c.ring = 0; c.gprof = 0;
   c.ltid = threadIdx.x;
   c.lnth = blockDim.x;
   if (MODE == MODE_CTA) { c.tid = threadIdx.x; c.nth = blockDim.x; c.block0 = 1; }
@@ -72,7 +72,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k_build_sampling(JEng
 
 __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *out) {
   Ctx c;
-  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = E->items; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = E->items; c.gprof = 0; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
   c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
   for (uint64_t i = c.tid; i < count; i += c.nth) {
     double re, im;
@@ -86,7 +86,7 @@ __global__ void k_amplitudes(JEng *E, uint64_t first, uint64_t count, double2 *o
 struct BitPerm { uint8_t q[JKQ_MAXQ]; };
 __global__ void k_amplitudes_ordered(JEng *E, const double2 *dense, BitPerm bp, int n, uint64_t first, uint64_t count, double2 *out) {
   Ctx c;
-  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = nullptr; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
+  c.E = E; c.sh = nullptr; c.T = nullptr; c.items = nullptr; c.gprof = 0; c.phase = 0; c.ring = 0; c.block0 = 0; c.ltid = threadIdx.x; c.lnth = blockDim.x;
   c.tid = blockIdx.x * blockDim.x + threadIdx.x; c.nth = gridDim.x * blockDim.x;
   for (uint64_t i = c.tid; i < count; i += c.nth) {
     const uint64_t idx = first + i;
@@ -1552,6 +1552,18 @@ extern "C" int jkq_get_stats(jkq_handle *h, jkq_stats *out) {
     if (E.prof_w[8 + k])
       fprintf(stderr, "  grid level phases of up to %d items: %llu levels, %llu items, %llu barriers, %.1f Mcycles (%.0f cycles per level)\n", 4 << (2 * k),
               E.prof_w[8 + k], E.prof_w[24 + k], E.prof_w[16 + k], E.prof_w[k] * 1e-6, (double)E.prof_w[k] / E.prof_w[8 + k]);
+#endif
+#ifdef JKQ_PROFILE
+  {
+    unsigned long long p[64], z[64] = {0};
+    cudaMemcpyFromSymbol(p, g_gprof, sizeof(p));
+    cudaMemcpyToSymbol(g_gprof, z, sizeof(z));
+    static const char *nm[32] = {"item quad load", "expand_item_g", "reduce_item_g", "barrier wait (item thread)", "barrier wait (tid 0)", "item loop (item thread)", "phase loop+barrier (tid 0)", "",
+                                 "expand: header loads", "expand: batch 1 (products)", "expand: magnitudes", "expand: batch 2 (div/add)", "expand: de-dup x2", "expand: M above target", "", "",
+                                 "reduce: header loads", "reduce: arithmetic", "reduce: unique table", "", "batch: operands+compute", "batch: probes", "batch: value insert", "", "", "", "", "", "", "", "", ""};
+    for (int k = 0; k < 32; k++)
+      if (p[32 + k]) fprintf(stderr, "  narrow grid phases: %-30s %10llu x %8.0f cycles\n", nm[k], p[32 + k], (double)p[k] / p[32 + k]);
+  }
 #endif
 #ifdef JKQ_PROFILE2
   {

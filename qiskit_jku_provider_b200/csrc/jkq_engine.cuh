@@ -66,8 +66,15 @@ static inline uint32_t jffs(uint32_t x) { return (uint32_t)__builtin_ffs((int)x)
 template <class T> JD T jatomic_add(T *p, T v) { return atomicAdd(p, v); }
 template <class T> JD T jatomic_cas(T *p, T cmp, T v) { return atomicCAS(p, cmp, v); }
 JD void jatomic_min(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+// (the grid path only ever publishes with it: record, fence, CAS / store of the word that names the record.  A/B builds:
+// -DJKQ_FENCE_ACQREL=1 issues fence.acq_rel.gpu, which orders exactly that, instead of the sequentially consistent
+// membar.gl of __threadfence())
+#ifndef JKQ_FENCE_ACQREL
+#define JKQ_FENCE_ACQREL 0
+#endif
 template <int MODE> JD void jfence() {
   if (MODE == MODE_CTA) __threadfence_block();
+  else if (JKQ_FENCE_ACQREL) asm volatile("fence.acq_rel.gpu;" ::: "memory");
   else __threadfence();
 }
 JD unsigned long long jd2u(double x) { return (unsigned long long)__double_as_longlong(x); }
@@ -172,7 +179,20 @@ struct Ctx {
   uint32_t ring;        // phase % 3
   uint32_t block0;      // 1 if this thread belongs to the CTA that runs the serial sections
   uint32_t ltid, lnth;
+  uint32_t gprof;       // JKQ_PROFILE builds: this phase is narrow enough for the per-stage cycle counters (g_gprof)
 };
+
+// JKQ_PROFILE builds, grid path: where the cycles of a NARROW level phase go (per-thread clock64 deltas, summed; slot + 32 = count)
+#if defined(JKQ_PROFILE) && !defined(JKQ_EMU)
+__device__ unsigned long long g_gprof[64];
+#define JGP_T(v) long long v = clock64()
+#define JGP_ADD(c, slot, a, b) do { if ((c).gprof) { atomicAdd(&g_gprof[slot], (unsigned long long)((b) - (a))); atomicAdd(&g_gprof[32 + (slot)], 1ull); } } while (0)
+#define JGP_SET(c, v) (c).gprof = (v)
+#else
+#define JGP_T(v) do {} while (0)
+#define JGP_ADD(c, slot, a, b) do {} while (0)
+#define JGP_SET(c, v) do {} while (0)
+#endif
 
 // Warp-aggregated increment of a counter that every lane of the warp may be bumping at this point: ONE atomic
 // per warp instead of up to 32 on the same address (the bump allocators and statistics of the grid path are
@@ -355,9 +375,10 @@ JD uint64_t jneg(uint64_t a) {  // Cnegative, QMDDcomplexD.cpp:483-496
   return (r << 32) | i;
 }
 
-template <int MODE> JD uint32_t vt_mask2(const JEng *E) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : ld_s<MODE>(&E->vt_cur); }
+// (JEng.vt_cur == vtab_mask from jkq_create on: a plain cached load -- ld.cg here put an L2 round trip in front of every probe)
+template <int MODE> JD uint32_t vt_mask2(const JEng *E) { return MODE == MODE_CTA ? JKQ_SVT_SLOTS - 1 : E->vtab_mask; }
 // the HBM value table has four slots per real of the value array
-JD bool vt_room(const JEng *E, uint32_t idx) { return idx < E->val_cap && (uint64_t)idx * 2 < (uint64_t)ld_s<MODE_GRID>(&E->vt_cur); }
+JD bool vt_room(const JEng *E, uint32_t idx) { return idx < E->val_cap && (uint64_t)idx * 2 < (uint64_t)E->vtab_mask; }
 template <int MODE> JD JVSlot *vt_tab2(JEng *E, CtaState *S) { return MODE == MODE_CTA ? S->vtab : E->vtab; }
 JD long long vt_bucket(double x, double inv_tol) { return (long long)floor(JKQ_DMUL(x, inv_tol)); }
 // eight consecutive buckets share one 128-byte line (8 x 16-byte slots): the three probes of a lookup
@@ -753,6 +774,289 @@ static_assert(JKQ_SNODES <= 2048u, "the chain-rebuild memo holds 11-bit node ids
 // weight id <-> 22 bits (value indices below 1024: single-CTA path)
 JD uint64_t jpack22(uint64_t w) { return ((w >> 63) << 21) | (((w >> 32) & 0x3FFull) << 11) | (((w >> 31) & 1ull) << 10) | (w & 0x3FFull); }
 JD uint64_t junpack22(uint64_t p) { return ((p >> 21) << 63) | (((p >> 11) & 0x3FFull) << 32) | (((p >> 10) & 1ull) << 31) | (p & 0x3FFull); }
+// MODE_GRID experiments of round 2, measured WITHOUT gain and therefore off (scripts/grid_ab.py
+// times builds side by side): -DJKQ_GRID_ILP=1 stages an item so that its independent loads are in flight together
+// (jkq_grid.cuh), and with it -DJKQ_GRID_WARP=1 puts a whole warp on one item while there are more warps than items
+// (cx_batch_w: one real part per lane).  random n=18/160: 76.0 ms as built, 78.6 ms staged, 74.8 ms staged + warp;
+// random n=22/200: 423 / 537 / 516 ms.
+#ifndef JKQ_GRID_ILP
+#define JKQ_GRID_ILP 0
+#endif
+#ifndef JKQ_GRID_WARP
+#define JKQ_GRID_WARP 1
+#endif
+// ------------------------------------------------------------------------------------ batched complex arithmetic
+// one Cmul / Cadd / Cdiv with the id short-cuts of QMDDcomplexD.cpp:498-777 taken at once; what needs arithmetic
+// stays pending until the batch runs
+struct QOp {
+  uint64_t a, b, r;
+  uint32_t op, pend;
+};
+JD void q_set(QOp &o, uint64_t r) { o.r = r; o.pend = 0; }
+JD void q_mul(QOp &o, uint64_t a, uint64_t b) {
+  o.pend = 0;
+  if (a == JW_ONE) o.r = b;
+  else if (b == JW_ONE) o.r = a;
+  else if (a == 0 || b == 0) o.r = 0;
+  else if (a == JW_MONE) o.r = jneg(b);
+  else if (b == JW_MONE) o.r = jneg(a);
+  else { o.op = JOP_MUL; o.a = a; o.b = b; o.pend = 1; }
+}
+JD void q_add(QOp &o, uint64_t a, uint64_t b) {
+  o.pend = 0;
+  if (a == 0) o.r = b;
+  else if (b == 0) o.r = a;
+  else if (a == jneg(b)) o.r = 0;
+  else { o.op = JOP_ADD; o.a = a; o.b = b; o.pend = 1; }
+}
+JD void q_div(QOp &o, uint64_t a, uint64_t b) {
+  o.pend = 0;
+  if (a == b) o.r = JW_ONE;
+  else if (a == 0) o.r = 0;
+  else if (b == JW_ONE) o.r = a;
+  else if (b == JW_MONE) o.r = jneg(a);
+  else if (a == jneg(b)) o.r = JW_MONE;
+  else { o.op = JOP_DIV; o.a = a; o.b = b; o.pend = 1; }
+}
+
+#define JQ_PARTS 6  // real lookups whose probes are in flight together (three 16-byte slots each)
+
+// Runs the pending operations of q[0..N): false if a value could not be entered (error raised, or -- builds without
+// in-place insertion -- proposed for the commit round: the item is run again).
+template <int N> JNI bool cx_batch(Ctx &c, QOp *q) {
+  uint32_t any = 0;
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) any |= q[i].pend;
+  if (!any) return true;
+  JEng *E = c.E;
+  JGP_T(b0);
+  const double *vals = E->vals;
+  double ar[N], ai[N], br[N], bi[N];
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) {
+    if (q[i].pend) {  // all operand loads first
+      ar[i] = ld_s<MODE_GRID>(vals + ((uint32_t)(q[i].a >> 32) & 0x7FFFFFFFu)); ai[i] = ld_s<MODE_GRID>(vals + ((uint32_t)q[i].a & 0x7FFFFFFFu));
+      br[i] = ld_s<MODE_GRID>(vals + ((uint32_t)(q[i].b >> 32) & 0x7FFFFFFFu)); bi[i] = ld_s<MODE_GRID>(vals + ((uint32_t)q[i].b & 0x7FFFFFFFu));
+    }
+  }
+  const double tol = E->tol, inv_tol = E->inv_tol;
+  double lx[2 * N];       // parts that need the table (indexed at run time: local memory, by intent)
+  uint32_t lslot[2 * N];
+  uint32_t res[2 * N];
+  uint32_t sgn = 0;
+  int np = 0;
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) {
+    if (!q[i].pend) continue;
+    const uint64_t a = q[i].a, b = q[i].b;
+    double xr = ar[i], xi = ai[i], yr = br[i], yi = bi[i];
+    if (a >> 63) xr = -xr;
+    if ((a >> 31) & 1) xi = -xi;
+    if (b >> 63) yr = -yr;
+    if ((b >> 31) & 1) yi = -yi;
+    double re, im;  // (same expressions as cx_arith)
+    if (q[i].op == JOP_MUL) {
+      re = JKQ_DSUB(JKQ_DMUL(xr, yr), JKQ_DMUL(xi, yi));
+      im = JKQ_DADD(JKQ_DMUL(xr, yi), JKQ_DMUL(xi, yr));
+    } else if (q[i].op == JOP_ADD) {
+      re = JKQ_DADD(xr, yr);
+      im = JKQ_DADD(xi, yi);
+    } else if ((b & 0x7FFFFFFFull) == 0) {
+      re = JKQ_DDIV(xr, yr);
+      im = JKQ_DDIV(xi, yr);
+    } else {
+      const double d = JKQ_DADD(JKQ_DMUL(yr, yr), JKQ_DMUL(yi, yi));
+      re = JKQ_DDIV(JKQ_DADD(JKQ_DMUL(xr, yr), JKQ_DMUL(xi, yi)), d);
+      im = JKQ_DDIV(JKQ_DSUB(JKQ_DMUL(xi, yr), JKQ_DMUL(xr, yi)), d);
+    }
+    if (re < 0.0) sgn |= 1u << (2 * i);
+    if (im < 0.0) sgn |= 1u << (2 * i + 1);
+    JKQ_UNROLL
+    for (int p = 0; p < 2; p++) {
+      const double x = fabs(p ? im : re);
+      if (x <= tol) res[2 * i + p] = 0;
+      else if (!(x < JKQ_VAL_MAX)) { jset_error<MODE_GRID>(E, c.sh, JKQ_ERR_VAL_RANGE); res[2 * i + p] = JV_MISS; }
+      else { lx[np] = x; lslot[np] = (uint32_t)(2 * i + p); np++; }
+    }
+  }
+  const uint32_t mask = vt_mask2<MODE_GRID>(E);
+  const JVSlot *tab = E->vtab;
+  JGP_T(b1);
+  JGP_ADD(c, 20, b0, b1);
+  for (int base = 0; base < np; base += JQ_PARTS) {
+    double x[JQ_PARTS];
+    long long k[JQ_PARTS];
+    JVSlot s[JQ_PARTS][3];
+    JKQ_UNROLL
+    for (int p = 0; p < JQ_PARTS; p++) {
+      if (base + p < np) {
+        x[p] = lx[base + p];
+        k[p] = vt_bucket(x[p], inv_tol);
+        JKQ_UNROLL
+        for (int d = 0; d < 3; d++) s[p][d] = ld_s<MODE_GRID>(tab + vt_slot0(k[p] - 1 + d, mask));
+      }
+    }
+    JKQ_UNROLL
+    for (int p = 0; p < JQ_PARTS; p++) {
+      if (base + p < np) {
+        uint32_t r = JV_MISS;
+        JKQ_UNROLL
+        for (int d = 0; d < 3; d++) {
+          if (r == JV_MISS) {
+            const uint32_t klo = (uint32_t)(k[p] - 1 + d);
+            JVSlot sl = s[p][d];
+            if (sl.id1 != 0) {
+              uint32_t hh = vt_slot0(k[p] - 1 + d, mask);
+              for (uint32_t probes = 0; sl.id1 != 0 && probes <= (mask >> 3); probes++) {
+                if (sl.keylo == klo && sl.id1 < JV_WAITING && fabs(JKQ_DSUB(ju2d(sl.vbits), x[p])) <= tol) { r = sl.id1 - 1; break; }
+                hh = vt_next(hh, mask);
+                sl = ld_s<MODE_GRID>(tab + hh);
+              }
+            }
+          }
+        }
+        if (r == JV_MISS) {
+          JGP_T(i0);
+          if (JKQ_INPLACE_GRID) r = real_insert_par<MODE_GRID>(E, c.sh, x[p], k[p]);
+          else real_propose<MODE_GRID>(E, c.sh, c.ring, x[p], k[p]);
+          JGP_T(i1);
+          JGP_ADD(c, 22, i0, i1);
+        }
+        res[lslot[base + p]] = r;
+      }
+    }
+  }
+  JGP_T(b2);
+  JGP_ADD(c, 21, b1, b2);
+  bool ok = true;
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) {
+    if (!q[i].pend) continue;
+    uint32_t r = res[2 * i], im = res[2 * i + 1];
+    if (r == JV_MISS || im == JV_MISS) { q[i].r = JW_MISS; ok = false; continue; }
+    if (((sgn >> (2 * i)) & 1u) && r) r |= 0x80000000u;
+    if (((sgn >> (2 * i + 1)) & 1u) && im) im |= 0x80000000u;
+    q[i].r = ((uint64_t)r << 32) | (uint64_t)im;
+    q[i].pend = 0;
+  }
+  return ok;
+}
+
+// The same batch run by ALL 32 lanes of a warp that works on one item together (narrow levels: there are more warps than
+// items).  Every lane holds the same q[]; lane p < 2N takes ONE real part of one operation -- operand loads, arithmetic,
+// the three bucket probes, the insertion of a missing value -- and the results come back by shuffle, so the dependent
+// instruction chain of a batch is that of one part instead of 2N of them (one thread runs ~7 cycles per instruction on
+// this path: narrow level phases are bound by the instructions of one item, not by its memory round trips).  Lanes
+// that computed the very same value elect one to do the table work.  Called convergently by the whole warp.
+#ifndef JKQ_EMU
+template <int N> JNI bool cx_batch_w(Ctx &c, QOp *q) {
+  static_assert(2 * N <= 32, "one lane per real part");
+  uint32_t any = 0;
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) any |= q[i].pend;
+  if (!any) return true;
+  JEng *E = c.E;
+  JGP_T(b0);
+  const uint32_t lane = threadIdx.x & 31u, oi = lane >> 1, part = lane & 1u;
+  const bool act = lane < 2u * N && q[oi < (uint32_t)N ? oi : 0u].pend != 0;
+  uint32_t r = 0;
+  bool neg = false, look = false;
+  double x = 0.0;
+  if (act) {
+    const uint64_t a = q[oi].a, b = q[oi].b;
+    const uint32_t op = q[oi].op;
+    const double *vals = E->vals;
+    double xr = ld_s<MODE_GRID>(vals + ((uint32_t)(a >> 32) & 0x7FFFFFFFu)), xi = ld_s<MODE_GRID>(vals + ((uint32_t)a & 0x7FFFFFFFu));
+    double yr = ld_s<MODE_GRID>(vals + ((uint32_t)(b >> 32) & 0x7FFFFFFFu)), yi = ld_s<MODE_GRID>(vals + ((uint32_t)b & 0x7FFFFFFFu));
+    if (a >> 63) xr = -xr;
+    if ((a >> 31) & 1) xi = -xi;
+    if (b >> 63) yr = -yr;
+    if ((b >> 31) & 1) yi = -yi;
+    double v;  // (same expressions as cx_arith, one part per lane)
+    if (op == JOP_MUL) v = part ? JKQ_DADD(JKQ_DMUL(xr, yi), JKQ_DMUL(xi, yr)) : JKQ_DSUB(JKQ_DMUL(xr, yr), JKQ_DMUL(xi, yi));
+    else if (op == JOP_ADD) v = part ? JKQ_DADD(xi, yi) : JKQ_DADD(xr, yr);
+    else if ((b & 0x7FFFFFFFull) == 0) v = part ? JKQ_DDIV(xi, yr) : JKQ_DDIV(xr, yr);
+    else {
+      const double d = JKQ_DADD(JKQ_DMUL(yr, yr), JKQ_DMUL(yi, yi));
+      v = part ? JKQ_DDIV(JKQ_DSUB(JKQ_DMUL(xi, yr), JKQ_DMUL(xr, yi)), d) : JKQ_DDIV(JKQ_DADD(JKQ_DMUL(xr, yr), JKQ_DMUL(xi, yi)), d);
+    }
+    neg = v < 0.0;
+    x = fabs(v);
+    if (x <= E->tol) r = 0;
+    else if (!(x < JKQ_VAL_MAX)) { jset_error<MODE_GRID>(E, c.sh, JKQ_ERR_VAL_RANGE); r = JV_MISS; }
+    else look = true;
+  }
+  JGP_T(b1);
+  JGP_ADD(c, 20, b0, b1);
+  // one lane per distinct value does the table work
+  const unsigned long long xkey = look ? jd2u(x) : 0xFFF8000000000000ull;  // (match.any costs a round per distinct key: the idle lanes share one)
+  const unsigned same = __match_any_sync(0xFFFFFFFFu, xkey);
+  const int leader = __ffs(same) - 1;
+  if (look && (int)lane == leader) {
+    const double tol = E->tol;
+    const uint32_t mask = vt_mask2<MODE_GRID>(E);
+    const JVSlot *tab = E->vtab;
+    const long long k = vt_bucket(x, E->inv_tol);
+    JVSlot s[3];
+    JKQ_UNROLL
+    for (int d = 0; d < 3; d++) s[d] = ld_s<MODE_GRID>(tab + vt_slot0(k - 1 + d, mask));
+    r = JV_MISS;
+    JKQ_UNROLL
+    for (int d = 0; d < 3; d++) {
+      if (r == JV_MISS) {
+        const uint32_t klo = (uint32_t)(k - 1 + d);
+        JVSlot sl = s[d];
+        if (sl.id1 != 0) {
+          uint32_t hh = vt_slot0(k - 1 + d, mask);
+          for (uint32_t probes = 0; sl.id1 != 0 && probes <= (mask >> 3); probes++) {
+            if (sl.keylo == klo && sl.id1 < JV_WAITING && fabs(JKQ_DSUB(ju2d(sl.vbits), x)) <= tol) { r = sl.id1 - 1; break; }
+            hh = vt_next(hh, mask);
+            sl = ld_s<MODE_GRID>(tab + hh);
+          }
+        }
+      }
+    }
+    if (r == JV_MISS) {
+      JGP_T(i0);
+      if (JKQ_INPLACE_GRID) r = real_insert_par<MODE_GRID>(E, c.sh, x, k);
+      else real_propose<MODE_GRID>(E, c.sh, c.ring, x, k);
+      JGP_T(i1);
+      JGP_ADD(c, 22, i0, i1);
+    }
+  }
+  __syncwarp();
+  const uint32_t rl = __shfl_sync(0xFFFFFFFFu, r, leader);
+  if (look) r = rl;
+  const unsigned negm = __ballot_sync(0xFFFFFFFFu, neg);
+  JGP_T(b2);
+  JGP_ADD(c, 21, b1, b2);
+  bool ok = true;
+  JKQ_UNROLL
+  for (int i = 0; i < N; i++) {
+    uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, 2 * i), im = __shfl_sync(0xFFFFFFFFu, r, 2 * i + 1);
+    if (!q[i].pend) continue;
+    if (rr == JV_MISS || im == JV_MISS) { q[i].r = JW_MISS; ok = false; continue; }
+    if (((negm >> (2 * i)) & 1u) && rr) rr |= 0x80000000u;
+    if (((negm >> (2 * i + 1)) & 1u) && im) im |= 0x80000000u;
+    q[i].r = ((uint64_t)rr << 32) | (uint64_t)im;
+    q[i].pend = 0;
+  }
+  return ok;
+}
+#endif
+// W: the whole warp works on the item (cx_batch_w); else one thread
+template <int N, bool W> JD bool cx_run(Ctx &c, QOp *q) {
+#ifndef JKQ_EMU
+  if (W) return cx_batch_w<N>(c, q);
+#endif
+  return cx_batch<N>(c, q);
+}
+
+JD double jmag2_g(const double *vals, uint64_t w) {
+  const double r = ld_s<MODE_GRID>(vals + ((uint32_t)(w >> 32) & 0x7FFFFFFFu)), i = ld_s<MODE_GRID>(vals + ((uint32_t)w & 0x7FFFFFFFu));
+  return JKQ_DADD(JKQ_DMUL(r, r), JKQ_DMUL(i, i));
+}
+
 #ifdef JKQ_EMU_MEMOSTAT
 #include <unordered_map>
 #include <string>
@@ -760,6 +1064,14 @@ struct JMemoStat { std::unordered_map<std::string, int> seen; unsigned long long
 inline JMemoStat &jmemostat() { static JMemoStat m; return m; }
 #endif
 template <int MODE> JNI uint64_t cx_arith(JEng *E, CtaState *S, uint32_t ring, uint32_t op, uint64_t a, uint64_t b) {
+  if (MODE == MODE_GRID && JKQ_GRID_ILP) {  // operand loads together, then the probes of both parts together
+    Ctx c;
+    c.E = E; c.sh = S; c.ring = ring; c.gprof = 0;
+    QOp q;
+    q.op = op; q.a = a; q.b = b; q.r = JW_MISS; q.pend = 1;
+    cx_batch<1>(c, &q);
+    return q.r;
+  }
 #ifdef JKQ_EMU_MEMOSTAT
   {
     JMemoStat &m = jmemostat();

@@ -37,16 +37,27 @@ JD JSNode ld_snode(const JSNode *p) {
 JD uint64_t sample_walk(const JSNode *sn, uint32_t root, int n, const uint8_t *bitpos, uint64_t seed, uint64_t shot) {
   uint32_t cur = root, c[4] = {0, 0, 0, 0};
   uint64_t key = 0;
+  int have = -1;  // Philox block held in c[]
   for (int step = 0; step < n; step++) {
-    if ((step & 3) == 0) {
-      c[0] = (uint32_t)shot; c[1] = (uint32_t)(shot >> 32); c[2] = (uint32_t)(step >> 2); c[3] = 0;
-      philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const JSNode s = ld_snode(sn + cur);
+    // A branch that is certain needs no random number: u lies strictly between 0 and 1, so u < q0 is decided by q0
+    // alone when q0 >= 1 (child 0) or q0 <= 0 (child 1).  The stream is counter-based -- word j of block b belongs to
+    // step 4b + j whether or not the steps before it drew theirs -- so a block is only computed when one of its four
+    // steps has a real choice to make: same outcomes bit for bit, one Philox block per GHZ shot instead of n / 4.
+    uint32_t bit;
+    if (s.q0 >= 1.0) bit = 0;
+    else if (!(s.q0 > 0.0)) bit = 1;
+    else {
+      if (have != (step >> 2)) {
+        have = step >> 2;
+        c[0] = (uint32_t)shot; c[1] = (uint32_t)(shot >> 32); c[2] = (uint32_t)have; c[3] = 0;
+        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      }
+      const uint32_t word = (step & 3) == 0 ? c[0] : (step & 3) == 1 ? c[1] : (step & 3) == 2 ? c[2] : c[3];
+      const double u = JKQ_DMUL(JKQ_DADD((double)word, 0.5), 1.0 / 4294967296.0);
+      bit = !(u < s.q0);
     }
-    uint32_t word = (step & 3) == 0 ? c[0] : (step & 3) == 1 ? c[1] : (step & 3) == 2 ? c[2] : c[3];
-    double u = JKQ_DMUL(JKQ_DADD((double)word, 0.5), 1.0 / 4294967296.0);
-    JSNode s = ld_snode(sn + cur);
-    uint32_t bit = !(u < s.q0);
-    uint32_t bp = bitpos[n - 1 - step];
+    const uint32_t bp = bitpos[n - 1 - step];
     if (bit && bp < 64) key |= 1ull << bp;
     cur = bit ? s.c1 : s.c0;
   }

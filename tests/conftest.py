@@ -40,7 +40,7 @@ def emu_bin():
     src = os.path.join(ROOT, "tests", "emu", "jkq_emu.cpp")
     out = os.path.join(ROOT, "tests", "emu", "jkq_emu")
     deps = [src] + [os.path.join(ROOT, "qiskit_jku_provider_b200", "csrc", f)
-                    for f in ("jkq_types.h", "jkq_engine.cuh", "jkq_thin.cuh", "jkq_apply.cuh", "jkq_sample.cuh")]
+                    for f in ("jkq_types.h", "jkq_engine.cuh", "jkq_thin.cuh", "jkq_grid.cuh", "jkq_apply.cuh", "jkq_sample.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-w", "-o", out, src])
     return out
