@@ -397,6 +397,99 @@ JD bool thin_reduce(Ctx &c, uint32_t node, const JNode &nd, uint32_t rn[2], cons
   return reduce_core<MODE>(c, rn, f, a, hint, out_node, out_w);
 }
 
+// ------------------------------------------------------------------------------------ linear sums
+// al * [A] + be * [B] for two DIFFERENT sub-diagrams on level m, as one lane's loop instead of work items -- for the case
+// where QMDDadd (QMDDpackage.cpp:1319-1414) stays a chain: on every level at most ONE of the two children is again a sum
+// of two different nodes, the other one is a zero edge, an edge of one operand only, or the same node on both sides (the
+// weights are added).  That is H on the node that carries the marked path of a Grover state: |marked> + b |uniform rest>
+// shares everything but one path.  The steps are those of the generic path, in its order along the chain -- combine_sum
+// (operand order by magnitude, ratio = the (1, y.w / x.w) key normalisation of :1354-1359), the S item's two children
+// (expand_child), reduce_core on the way up -- so the values that reach the value table and the nodes that reach the
+// unique table are the same; what is gone are the items, their de-dup inserts and two level phases per level.
+// Records of the levels passed on the way down live in the cursor's scratch rows (T->ent[level][slot], free below the
+// cursor while thin_probe runs).  Result: the edge (rn, f * a) as the parent's reduce_core wants it.  false: not a
+// chain, or some value / node could not be entered (sticky words raised) -- nothing of consequence has been written
+// (nodes and values that nobody refers to).
+#define TL_REF1 (1u << 31)  // ThinEnt.pk of a chain record: index of the child that is the sum further down; pad = node of the other
+template <int MODE>
+JD bool lin_child(Ctx &c, int mc, uint64_t aw, uint32_t ac, uint64_t bew, uint32_t bc, uint32_t *kind, uint32_t *node, uint64_t *w) {
+  // combine_sum up to the point where it would create an item: JC_ZERO / JC_PASS (node, w) / JC_REF
+  if (mc < 0 || ac == bc) {
+    uint64_t s;
+    if (aw == 0) s = bew;
+    else if (bew == 0) s = aw;
+    else if (!cadd<MODE>(c, aw, bew, &s)) return false;
+    *node = (aw == 0) ? bc : ac; *w = s; *kind = s ? JC_PASS : JC_ZERO;
+    return true;
+  }
+  if (aw == 0) { *node = bc; *w = bew; *kind = bew ? JC_PASS : JC_ZERO; return true; }
+  if (bew == 0) { *node = ac; *w = aw; *kind = JC_PASS; return true; }
+  *kind = JC_REF;
+  return true;
+}
+template <int MODE>
+JD bool lin_add(Ctx &c, uint32_t slot, int m, uint64_t al, uint32_t A, uint64_t be, uint32_t B, uint32_t *out_rn, uint64_t *out_f, uint64_t *out_a,
+                uint32_t *levels) {
+  ThinState *T = c.T;
+  const int m_top = m;
+  uint32_t rnode = 0;
+  uint64_t rw = 0, factor = 0;
+  for (;;) {  // ---- down: (al, A, be, B) is a sum of two different nodes with both weights non-zero, on level m >= 0
+    bool swap = A > B;  // operand order of the memo key, as in combine_sum
+    if (al != be && al != jneg(be)) {
+      const double ma = jmag2<MODE>(c, al), mb = jmag2<MODE>(c, be);
+      if (ma != mb) swap = mb > ma;
+    }
+    if (swap) { const uint32_t tn = A; A = B; B = tn; const uint64_t tw = al; al = be; be = tw; }
+    uint64_t r;
+    if (!cdiv<MODE>(c, be, al, &r)) return false;
+    // the S item (A, B, 1, r) on level m; its edge carries the factor al
+    const JNode na = node_load<MODE>(c, A), nb = node_load<MODE>(c, B);
+    uint32_t kd[2], nd[2] = {0, 0};
+    uint64_t wd[2] = {0, 0}, bew[2];
+    JKQ_UNROLL
+    for (int i = 0; i < 2; i++) {
+      if (!cmul<MODE>(c, r, i ? nd_w1(nb) : nd_w0(nb), &bew[i])) return false;
+      if (!lin_child<MODE>(c, m - 1, i ? nd_w1(na) : nd_w0(na), i ? na.c1 : nd_c0(na), bew[i], i ? nb.c1 : nd_c0(nb), &kd[i], &nd[i], &wd[i])) return false;
+    }
+    if (kd[0] == JC_REF && kd[1] == JC_REF) return false;  // the sum branches: work items
+    if (kd[0] != JC_REF && kd[1] != JC_REF) {  // the chain ends here: this item's reduction
+      uint32_t rn[2] = {kd[0] == JC_ZERO ? 0u : nd[0], kd[1] == JC_ZERO ? 0u : nd[1]};
+      const uint64_t f[2] = {JW_ONE, JW_ONE}, a[2] = {kd[0] == JC_ZERO ? 0ull : wd[0], kd[1] == JC_ZERO ? 0ull : wd[1]};
+      if (!reduce_core<MODE>(c, rn, f, a, 0, &rnode, &rw)) return false;
+      if (rw != 0 && rnode == 0 && m >= 0) return false;  // a pool ran out
+      factor = al;
+      break;
+    }
+    const uint32_t ri = kd[1] == JC_REF ? 1u : 0u, oi = 1u - ri;
+    ThinEnt e;
+    e.pk = (ri ? TL_REF1 : 0u) | (kd[oi] == JC_ZERO ? 0u : 1u);
+    e.pad = kd[oi] == JC_ZERO ? 0u : nd[oi];
+    e.w = kd[oi] == JC_ZERO ? 0ull : wd[oi];
+    e.f = al;
+    T->ent[m][slot] = e;
+    // the child that is a sum again, one level down
+    const uint64_t naw = ri ? nd_w1(na) : nd_w0(na);
+    const uint32_t nac = ri ? na.c1 : nd_c0(na), nbc = ri ? nb.c1 : nd_c0(nb);
+    al = naw; A = nac; be = bew[ri]; B = nbc;
+    m--;
+  }
+  *levels = (uint32_t)(m_top - m + 1);
+  for (int L = m + 1; L <= m_top; L++) {  // ---- up: the item of level L over the result of level L - 1
+    const ThinEnt e = T->ent[L][slot];
+    const uint32_t ri = (e.pk & TL_REF1) ? 1u : 0u, oi = 1u - ri;
+    uint32_t rn[2];
+    uint64_t f[2], a[2];
+    f[ri] = rw; a[ri] = rw ? factor : 0ull; rn[ri] = a[ri] ? rnode : 0u;  // (reduce_item: the child item's result times the slot's factor)
+    f[oi] = JW_ONE; a[oi] = e.w; rn[oi] = e.w ? e.pad : 0u;
+    if (!reduce_core<MODE>(c, rn, f, a, 0, &rnode, &rw)) return false;
+    if (rw != 0 && rnode == 0) return false;  // a pool ran out
+    factor = e.f;
+  }
+  *out_rn = rw ? rnode : 0u; *out_f = rw; *out_a = rw ? factor : 0ull;
+  return true;
+}
+
 // thin_probe: the cases of thin_gate that need no records at all, every cursor edge in its own lane with nothing
 // exchanged between lanes:
 //   * no control above the target, and from the cursor edge down to the target only nodes whose non-zero edges lead
@@ -437,7 +530,10 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
   const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
   uint32_t rn[2] = {0, 0}, rounds = 0;
   uint64_t p[2] = {0, 0}, a[2] = {0, 0};
-  const uint64_t f[2] = {JW_ONE, JW_ONE};
+  uint64_t f[2] = {JW_ONE, JW_ONE};
+  bool sum[2] = {false, false};  // row i is a sum of two different sub-diagrams: sal[i] * [c0] + sbe[i] * [c1] (lin_add)
+  uint64_t sal[2] = {0, 0}, sbe[2] = {0, 0};
+  const bool sums_ok = low == tgt && tgt > 0 && !(T->thin_off & 64u) && (JKQ_WARP == 1u || cnt <= JKQ_WARP / 2);
   for (;;) {  // the target node's two rows
     bool ok = true;
     if (act) {
@@ -446,7 +542,11 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
         uint64_t al, be;
         const bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), w0, &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), w1, &be);
         if (!(o1 && o2)) { ok = false; continue; }
-        if (al != 0 && be != 0 && c0 != c1) { fail = true; continue; }  // a sum of two different sub-diagrams
+        if (al != 0 && be != 0 && c0 != c1) {  // a sum of two different sub-diagrams: a chain (lin_add below), or work items
+          if (!sums_ok) fail = true;
+          else { sum[i] = true; sal[i] = al; sbe[i] = be; }
+          continue;
+        }
         if (!cadd<MODE>(c, al, be, &p[i])) { ok = false; continue; }
         rn[i] = al != 0 ? c0 : c1;  // the child p sits on
       }
@@ -457,6 +557,44 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
     if (fl) return fl;
     if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
     thin_commit<MODE>(c);
+  }
+  uint32_t sum_levels = 0;
+  if (jballot(fail)) return 0;
+  if (jballot(act && (sum[0] || sum[1]))) {
+    // the sums: one lane per (cursor edge, row) -- lane l + 16 takes row 1 of edge l -- each walking its chain by itself
+    // (values go in under the lock of real_insert_solo, nodes through the lock-free unique table)
+    bool sok = true;
+#ifdef JKQ_EMU
+    for (int i = 0; i < 2; i++)
+      if (act && !fail && sum[i]) {
+        uint32_t lv = 0;
+        if (!lin_add<MODE>(c, lane, tgt - 1, sal[i], c0, sbe[i], c1, &rn[i], &f[i], &p[i], &lv)) sok = false;
+        sum_levels += lv;
+      }
+#else
+    {
+      const uint32_t src = lane & (JKQ_WARP / 2 - 1u), row = lane / (JKQ_WARP / 2);
+      const bool go0 = act && !fail && sum[0], go1 = act && !fail && sum[1];
+      const uint32_t g0 = jshfl(go0 ? 1u : 0u, src), g1 = jshfl(go1 ? 1u : 0u, src);
+      const unsigned long long xa0 = jshfl64(sal[0], src), xa1 = jshfl64(sal[1], src), xb0 = jshfl64(sbe[0], src), xb1 = jshfl64(sbe[1], src);
+      const uint32_t xc0 = jshfl(c0, src), xc1 = jshfl(c1, src);
+      uint32_t res_rn = 0, lv = 0;
+      uint64_t res_f = 0, res_a = 0;
+      bool mine_ok = true;
+      if (row ? g1 != 0 : g0 != 0) mine_ok = lin_add<MODE>(c, lane, tgt - 1, row ? xa1 : xa0, xc0, row ? xb1 : xb0, xc1, &res_rn, &res_f, &res_a, &lv);
+      jsyncwarp();
+      const uint32_t up = (lane & (JKQ_WARP / 2 - 1u)) + JKQ_WARP / 2;  // the lane that ran my row 1
+      const uint32_t rn1 = jshfl(res_rn, up), ok1 = jshfl(mine_ok ? 1u : 0u, up), lv1 = jshfl(lv, up);
+      const unsigned long long f1 = jshfl64(res_f, up), a1 = jshfl64(res_a, up);
+      if (lane < JKQ_WARP / 2) {
+        if (go0) { rn[0] = res_rn; f[0] = res_f; p[0] = res_a; sok = mine_ok; sum_levels += lv; }
+        if (go1) { rn[1] = rn1; f[1] = f1; p[1] = a1; sok = sok && ok1 != 0; sum_levels += lv1; }
+      }
+    }
+#endif
+    const uint32_t fl = thin_trouble<MODE>(c);  // a pool ran out inside a chain: the gate is abandoned as usual
+    if (fl) return fl;
+    if (!sok) fail = true;
   }
   if (act && !fail) {
     if (low == tgt) { a[0] = p[0]; a[1] = p[1]; }
@@ -502,7 +640,8 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
   for (;;) {
     bool ok = true;
     if (act && !fail) {
-      ok = thin_reduce<MODE>(c, node, nd, rn, f, a, &rnode, &rw);
+      if (sum[0] || sum[1]) ok = reduce_core<MODE>(c, rn, f, a, 0, &rnode, &rw);  // (the M item's reduction: no hint)
+      else ok = thin_reduce<MODE>(c, node, nd, rn, f, a, &rnode, &rw);
       if (ok && rw != 0) {
         if (rnode == 0) {}  // (a pool ran out: seen below)
         else if (start > tgt && rnode != node) fail = true;
@@ -527,6 +666,11 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
   }
   jsyncwarp();
   *handled = 1; *entries = jpopc(jballot(act)) * (uint32_t)(start - low + 1);
+#ifndef JKQ_EMU
+  *entries += __reduce_add_sync(0xFFFFFFFFu, sum_levels);
+#else
+  *entries += sum_levels;
+#endif
   return 0;
 }
 
