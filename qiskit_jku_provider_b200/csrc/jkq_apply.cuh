@@ -383,7 +383,10 @@ template <int MODE> JD uint32_t want_collect(const Ctx &c, bool log) {
 #ifndef JKQ_SOLO_MAX_GRID
 #define JKQ_SOLO_MAX_GRID (JKQ_WARP < 2u ? JKQ_WARP : 2u)
 #endif
-template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n, bool log) {
+// SUMS: the kernel carries thin_probe_sums.  The circuits whose cost is the latency of one warp are sensitive to the mere
+// size of the code around their path (QFT-32: +3 to +6 % with it), so the single-CTA kernel exists without it as well; that
+// one stops once it keeps meeting gates that want it (JEng.sums_ask / want_sums) and the host launches the other.
+template <int MODE, bool SUMS> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, int n_gates, int n, bool log) {
   JEng *E = c.E;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
   JPROF_T(gt0);
@@ -445,6 +448,24 @@ template <int MODE> JD uint32_t apply_gate(Ctx &c, const JGate *gates, int gi, i
     uint32_t thin_done = 0, thin_entries = 0;
 #ifndef JKQ_NO_THIN_GATES
     if (!f && !blocked) f = thin_probe<MODE>(c, g, &thin_done, &thin_entries);  // single-child paths, controls on basis-like nodes: no records
+    if (!f && thin_done == 2) {  // a row of the target node is a sum of two different sub-diagrams (Grover's H)
+      if (SUMS) f = thin_probe_sums<MODE>(c, g, &thin_done, &thin_entries);
+      else {
+        thin_done = 0;
+        // sums_ask counts down: a circuit with a few such gates lets the work items have them (a relaunch costs ~0.15 ms);
+        // one that keeps meeting them (Grover: 40 per iteration) gives this gate up, untouched, and the host launches
+        // the kernel that has the code
+        const uint32_t ask = MODE == MODE_CTA ? ld_r<MODE>(&E->sums_ask) : 0u;
+        if (ask == 1u) {
+          if (c.ltid == 0) { E->want_sums = 1; jwant_grid(c.sh); }
+          jsyncwarp();
+          f = JF_GRID;
+        } else if (ask > 1u) {
+          jsyncwarp();
+          if (c.ltid == 0) E->sums_ask = ask - 1u;
+        }
+      }
+    }
     if (!f && !blocked && !thin_done) f = thin_gate<MODE>(c, g, &thin_done, &thin_entries);  // the whole gate below the cursor edges, if it is local
 #endif
     if (!f && !thin_done && !blocked && goal > g.top) f = cursor_prepare<MODE>(c, g.top, &lsw, &icount, &blocked);  // the item phases start at the top level
@@ -978,7 +999,7 @@ template <int MODE> JD void mode_leave(Ctx &c) {
 // gate when a level log was requested (parity tests: reference Active[v], QMDDpackage.h:199-201).
 // MODE_CTA, enter = false: the state of the previous call is still in this CTA's shared memory (same kernel, same
 // CTA, left with leave = false) -- no reload, no collection; leave = false: nothing is written back to the arena.
-template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, bool enter = true, bool leave = true) {
+template <int MODE, bool SUMS = false> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, bool enter = true, bool leave = true) {
   JEng *E = c.E;
   const int n = (int)E->n;
   const bool thin_warp = c.block0 && c.ltid < JKQ_WARP;
@@ -1024,7 +1045,7 @@ template <int MODE> JD void run_gates(Ctx &c, const JGate *gates, int n_gates, b
     }
   }
   for (; !f && g < n_gates; g++) {
-    f = apply_gate<MODE>(c, gates, g, n_gates, n, log);
+    f = apply_gate<MODE, SUMS>(c, gates, g, n_gates, n, log);
     if (f) break;
     // Gate g is applied from here on, whatever happens to the collection below: if the rebuild up to the root runs out
     // of the shared pools (JF_GRID), the grid path must continue AFTER this gate (it used to redo it: gate applied twice).

@@ -60,9 +60,9 @@ template <int MODE> __global__ void __launch_bounds__(256) k_init(JEng *E) {
 #ifndef JKQ_GRID_MINB
 #define JKQ_GRID_MINB 1
 #endif
-template <int MODE> __global__ void __launch_bounds__(256, (MODE == MODE_GRID ? JKQ_GRID_MINB : 1)) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
+template <int MODE, bool SUMS> __global__ void __launch_bounds__(256, (MODE == MODE_GRID ? JKQ_GRID_MINB : 1)) k_run_gates(JEng *E, const JGate *gates, int n_gates) {
   Ctx c = make_ctx<MODE>(E);
-  run_gates<MODE>(c, gates, n_gates);
+  run_gates<MODE, SUMS>(c, gates, n_gates);
 }
 
 template <int MODE> __global__ void __launch_bounds__(256) k_build_sampling(JEng *E, JSNode *sn, double *prob) {
@@ -274,7 +274,18 @@ template <bool PK> __device__ __forceinline__ unsigned long long hist_all_ones(c
 // MeasureAll x shots (Simulator.cpp:148-224, QASMsimulator.cpp:487-500): one thread per shot, n
 // dependent 16-byte loads through L1/L2, equal outcomes merged inside the warp (__match_any_sync),
 // then in a shared-memory hash, then in the HBM hash histogram.
-template <bool PK>
+// nodes of the sampling diagram with a real choice (0 < q0 < 1): decides whether k_sample draws its random numbers lazily
+__global__ void k_sn_choice(const JSNode *__restrict__ sn, uint32_t n_nodes, unsigned int *out) {
+  unsigned int mine = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n_nodes; i += gridDim.x * blockDim.x) {  // (record 0 is the terminal)
+    const double q0 = sn[i].q0;
+    mine += (q0 > 0.0 && q0 < 1.0) ? 1u : 0u;
+  }
+  mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
+template <bool PK, bool LAZY>
 __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, uint32_t root, int n, SampleParams sp, uint64_t seed,
                                                uint64_t shot0, uint64_t nshots, void *hs, uint32_t hmask, int *overflow,
                                                unsigned long long *n_distinct) {
@@ -289,7 +300,7 @@ __global__ void __launch_bounds__(256) k_sample(const JSNode *__restrict__ sn, u
   const uint32_t lane = threadIdx.x & 31;
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < rounded; s += stride) {
     const bool active = s < nshots;
-    uint64_t key = active ? sample_walk(sn, root, n, sp.bitpos, seed, shot0 + s) : JH_EMPTY;
+    uint64_t key = active ? sample_walk<LAZY>(sn, root, n, sp.bitpos, seed, shot0 + s) : JH_EMPTY;
     uint32_t peers = __match_any_sync(0xFFFFFFFFu, key) & __ballot_sync(0xFFFFFFFFu, active);
     if (!active || lane != (uint32_t)(__ffs(peers) - 1)) continue;
     uint32_t cnt = __popc(peers);
@@ -453,6 +464,7 @@ struct jkq_handle {
   uint32_t n = 0;
   bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied by this handle since it was created (jcopy)
+  bool sums_now = false;            // ... and it is the build with thin_probe_sums (it asked for it: want_sums)
   bool wide_now = false;            // the single-CTA kernel of this circuit is launched with cfg.cta_threads (it asked for them)
   SampleParams sp;
   uint32_t dd_root = 0, dd_nodes = 0;
@@ -475,6 +487,9 @@ struct jkq_handle {
   unsigned long long *ok = nullptr, *oc = nullptr, *n_out = nullptr;
   unsigned long long *n_distinct = nullptr;  // slots claimed since the histogram was cleared (k_sample / k_hist_merge)
   int *overflow = nullptr;
+  unsigned int *choice_dev = nullptr;  // k_sn_choice's counter
+  uint64_t sn_epoch = 1, sn_choice_epoch = 0;  // the sampling records changed / were last looked at by k_sn_choice
+  bool sn_lazy = false;
   uint64_t hslots = 0, out_cap = 0;
   bool hist_valid = false;
   jkq_stats stats;
@@ -616,7 +631,7 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
         {(void **)&E.items, (size_t)E.item_cap * sizeof(JItem)}, {(void **)&E.dtab, ((size_t)E.dtab_mask + 1) * 8},
         {(void **)&E.mdir, (size_t)E.node_cap * 8}, {(void **)&E.thin_spill, sizeof(ThinState)}, {(void **)&E.fwd, (size_t)E.node_cap * 4},
         {(void **)&E.vfwd, (size_t)E.val_cap * 4}, {(void **)&h->dev, sizeof(JEng)}, {(void **)&h->snodes, (size_t)E.node_cap * sizeof(JSNode)},
-        {(void **)&h->prob, (size_t)E.node_cap * 8}, {(void **)&h->n_out, 8}, {(void **)&h->n_distinct, 8}, {(void **)&h->overflow, 4}, {(void **)&h->scalar_dev, 8}};
+        {(void **)&h->prob, (size_t)E.node_cap * 8}, {(void **)&h->n_out, 8}, {(void **)&h->n_distinct, 8}, {(void **)&h->overflow, 4}, {(void **)&h->choice_dev, 4}, {(void **)&h->scalar_dev, 8}};
     size_t total = 0;
     for (const Part &p : parts) total += (p.bytes + 255) & ~(size_t)255;
     CU(cudaMalloc(&h->slab, total));
@@ -628,12 +643,13 @@ extern "C" int jkq_create(jkq_handle **out, const jkq_config *cfg_in) {
   E.ut_gen = 1; E.vt_cur = E.vtab_mask; E.vt_dirty_all = 1;
   CU(cudaMemsetAsync(E.dtab, 0, ((size_t)E.dtab_mask + 1) * 8, h->stream));
   CU(cudaMemsetAsync(E.mdir, 0, (size_t)E.node_cap * 8, h->stream));
-  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   CU(cudaFuncSetAttribute(k_build_sampling<MODE_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem)));
   // cooperative grid size: every CTA must be resident
   int per_sm = 0;
-  CU(cudaFuncSetAttribute(k_run_gates<MODE_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThinState)));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID>, 256, sizeof(ThinState)));
+  CU(cudaFuncSetAttribute(k_run_gates<MODE_GRID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThinState)));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_gates<MODE_GRID, true>, 256, sizeof(ThinState)));
   if (per_sm < 1) return fail(h, JKQ_E_CUDA, "grid kernel does not fit on an SM");
   if ((uint32_t)per_sm > cfg.grid_blocks_per_sm) per_sm = (int)cfg.grid_blocks_per_sm;
   h->grid_blocks = per_sm * h->sm_count;
@@ -842,13 +858,14 @@ static int launch_gates(jkq_handle *h, bool grid, int upto) {
     JEng *E = h->dev;
     const JGate *g = h->gates_dev;
     void *args[] = {&E, &g, &upto};
-    CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID>, dim3(h->grid_blocks), dim3(256), args, sizeof(ThinState), h->stream));
+    CU(cudaLaunchCooperativeKernel((void *)k_run_gates<MODE_GRID, true>, dim3(h->grid_blocks), dim3(256), args, sizeof(ThinState), h->stream));
     h->stats.grid_launches++;
   } else {
     // one warp while every level of every gate fits it (QFT, GHZ, Grover ...: the other warps would only wait at the
     // gate barrier); the wide shape once the kernel asked for it (want_wide)
     const unsigned threads = (h->wide_now || h->cfg.reserved == 1) ? h->cfg.cta_threads : 32u;
-    k_run_gates<MODE_CTA><<<1, threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
+    if (h->sums_now) k_run_gates<MODE_CTA, true><<<1, threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
+    else k_run_gates<MODE_CTA, false><<<1, threads, sizeof(CtaSmem), h->stream>>>(h->dev, h->gates_dev, upto);
     CU(cudaGetLastError());
     h->stats.cta_launches++;
   }
@@ -878,6 +895,13 @@ static int run_segment(jkq_handle *h, int upto) {
     }
     if (h->host.status) return fail(h, h->host.status, "gate %d: %s", h->host.next_gate, status_text(h->host.status));
     if (h->host.next_gate >= upto && !h->host.cursor_saved) return JKQ_E_OK;
+    if (h->host.want_grid && h->host.want_sums && !h->host.cursor_saved && !grid && !h->sums_now) {
+      h->sums_now = true;
+      h->host.want_grid = 0; h->host.want_sums = 0;
+      CU(jcopy(h, &h->dev->want_grid, &h->host.want_grid, sizeof(int32_t), cudaMemcpyHostToDevice));
+      CU(jcopy(h, &h->dev->want_sums, &h->host.want_sums, sizeof(uint32_t), cudaMemcpyHostToDevice));
+      continue;
+    }
     if (h->host.want_grid && h->host.want_wide && !h->host.cursor_saved && !grid && !h->wide_now) {
       h->wide_now = true;
       h->host.want_grid = 0; h->host.want_wide = 0;
@@ -1060,9 +1084,10 @@ extern "C" int jkq_apply(jkq_handle *h) {
   }
   E.lvl_log = h->lvl_log;
   E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
-  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0; E.want_wide = 0;
+  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0; E.want_wide = 0; E.want_sums = 0; E.sums_ask = 8;
   E.cta_wide_ok = (h->cfg.cta_threads > 32 && h->cfg.reserved != 1) ? 1u : 0u;
   h->wide_now = false;
+  h->sums_now = false;
   E.bar_count = 0; E.bar_gen = 0; E.bar_flags[0] = E.bar_flags[1] = E.bar_flags[2] = 0;
   E.pend_n[0] = E.pend_n[1] = E.pend_n[2] = 0;
   CU(cudaEventRecord(h->ev0, h->stream));
@@ -1181,6 +1206,7 @@ static int build_sampling_now(jkq_handle *h) {
   h->dd_nodes = h->host.node_count;
   h->stats.norm = h->host.norm;
   h->sampling_ready = true;
+  h->sn_epoch++;
   return JKQ_E_OK;
 }
 
@@ -1227,16 +1253,28 @@ static int sample_impl(jkq_handle *h, uint64_t shots, uint64_t seed, uint64_t sh
   if (h->hist_packed && (!narrow || h->hist_shots + shots >= 0xFFFFFFFEull))
     return fail(h, JKQ_E_STATE, "accumulating into a packed histogram beyond 2^32 shots or 32 classical bits; sample the largest batch first");
   h->hist_shots += shots;
+  // Random numbers on demand pay when most nodes leave no choice (GHZ: one node of 47; 19.7 -> 29 G shots/s) and cost
+  // ~15 % when every node has one (QFT-32): counted once per sampling diagram.
+  if (shots && h->sn_choice_epoch != h->sn_epoch) {
+    CU(cudaMemsetAsync(h->choice_dev, 0, 4, h->stream));
+    k_sn_choice<<<h->sm_count, 256, 0, h->stream>>>(h->snodes, h->dd_nodes, h->choice_dev);
+    CU(cudaGetLastError());
+    unsigned int n_choice = 0;
+    CU(jcopy(h, &n_choice, h->choice_dev, 4, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    h->sn_lazy = (uint64_t)n_choice * 2 < (uint64_t)h->dd_nodes;
+    h->sn_choice_epoch = h->sn_epoch;
+  }
+  const bool lazy = h->sn_lazy;
   if (shots) {
     uint64_t want = (shots + 255) / 256;
     int blocks = (int)(want < (uint64_t)h->sm_count * 8 ? want : (uint64_t)h->sm_count * 8);
     CU(cudaEventRecord(h->ev3, h->stream));
-    if (h->hist_packed)
-      k_sample<true><<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hs,
-                                                    (uint32_t)(h->hslots - 1), h->overflow, h->n_distinct);
-    else
-      k_sample<false><<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, h->hs,
-                                                     (uint32_t)(h->hslots - 1), h->overflow, h->n_distinct);
+#define JKQ_LAUNCH_SAMPLE(PK, LZ) k_sample<PK, LZ><<<blocks, 256, 0, h->stream>>>(h->snodes, h->dd_root, (int)h->n, h->sp, seed, shot_offset, shots, \
+                                                                                   h->hs, (uint32_t)(h->hslots - 1), h->overflow, h->n_distinct)
+    if (h->hist_packed) { if (lazy) JKQ_LAUNCH_SAMPLE(true, true); else JKQ_LAUNCH_SAMPLE(true, false); }
+    else { if (lazy) JKQ_LAUNCH_SAMPLE(false, true); else JKQ_LAUNCH_SAMPLE(false, false); }
+#undef JKQ_LAUNCH_SAMPLE
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     h->stats.sample_launches++;
@@ -1633,7 +1671,7 @@ extern "C" int jkq_dd_import(jkq_handle *h, uint32_t n_qubits, const jkq_snode *
   h->n = n_qubits; h->dd_root = root; h->dd_nodes = n_nodes;
   memcpy(h->sp.bitpos, clbit_of_level, n_qubits);
   for (uint32_t L = n_qubits; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
-  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false;
+  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false; h->sn_epoch++;
   h->stats.norm = 1.0;
   return JKQ_E_OK;
 }
@@ -1666,7 +1704,7 @@ extern "C" int jkq_dd_import_device(jkq_handle *h, uint32_t n_qubits, const void
   h->n = n_qubits; h->dd_root = root; h->dd_nodes = n_nodes;
   memcpy(h->sp.bitpos, clbit_of_level, n_qubits);
   for (uint32_t L = n_qubits; L < JKQ_MAXQ; L++) h->sp.bitpos[L] = 255;
-  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false;
+  h->imported = true; h->applied = false; h->sampling_ready = false; h->hist_valid = false; h->sn_epoch++;
   h->stats.norm = 1.0;
   return JKQ_E_OK;
 }
@@ -1747,7 +1785,7 @@ extern "C" int jkq_sample_multi_gpu(jkq_handle *h, const int32_t *devices, uint3
     cudaError_t e = cudaMemcpyPeerAsync(ph->snodes, ph->device, src->snodes, src->device, (size_t)src->dd_nodes * sizeof(JSNode), ph->stream);
     if (e != cudaSuccess) return fail(src, JKQ_E_CUDA, "peer copy to device %d: %s", ph->device, cudaGetErrorString(e));
     ph->n = src->n; ph->dd_root = src->dd_root; ph->dd_nodes = src->dd_nodes; ph->sp = src->sp;
-    ph->imported = true; ph->applied = false; ph->sampling_ready = false; ph->hist_valid = false; ph->stats.norm = 1.0;
+    ph->imported = true; ph->applied = false; ph->sampling_ready = false; ph->hist_valid = false; ph->stats.norm = 1.0; ph->sn_epoch++;
   }
   for (uint32_t i = 0; i < n_devices; i++)
     if (hs[i] != src) { cudaSetDevice(hs[i]->device); cudaStreamSynchronize(hs[i]->stream); }

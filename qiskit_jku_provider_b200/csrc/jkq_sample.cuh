@@ -34,6 +34,7 @@ JD JSNode ld_snode(const JSNode *p) {
 }
 #endif
 
+template <bool LAZY = false>
 JD uint64_t sample_walk(const JSNode *sn, uint32_t root, int n, const uint8_t *bitpos, uint64_t seed, uint64_t shot) {
   uint32_t cur = root, c[4] = {0, 0, 0, 0};
   uint64_t key = 0;
@@ -44,11 +45,13 @@ JD uint64_t sample_walk(const JSNode *sn, uint32_t root, int n, const uint8_t *b
     // alone when q0 >= 1 (child 0) or q0 <= 0 (child 1).  The stream is counter-based -- word j of block b belongs to
     // step 4b + j whether or not the steps before it drew theirs -- so a block is only computed when one of its four
     // steps has a real choice to make: same outcomes bit for bit, one Philox block per GHZ shot instead of n / 4.
+    // LAZY is chosen per diagram (jkq_b200.cu sample_impl: fewer than half of its nodes have a real choice); a diagram
+    // like QFT's, where every node has one, draws each block when it starts, with the node load in flight.
     uint32_t bit;
-    if (s.q0 >= 1.0) bit = 0;
-    else if (!(s.q0 > 0.0)) bit = 1;
+    if (LAZY && s.q0 >= 1.0) bit = 0;
+    else if (LAZY && !(s.q0 > 0.0)) bit = 1;
     else {
-      if (have != (step >> 2)) {
+      if (LAZY ? have != (step >> 2) : (step & 3) == 0) {
         have = step >> 2;
         c[0] = (uint32_t)shot; c[1] = (uint32_t)(shot >> 32); c[2] = (uint32_t)have; c[3] = 0;
         philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));

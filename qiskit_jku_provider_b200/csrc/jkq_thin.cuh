@@ -410,6 +410,12 @@ JD bool thin_reduce(Ctx &c, uint32_t node, const JNode &nd, uint32_t rn[2], cons
 // cursor while thin_probe runs).  Result: the edge (rn, f * a) as the parent's reduce_core wants it.  false: not a
 // chain, or some value / node could not be entered (sticky words raised) -- nothing of consequence has been written
 // (nodes and values that nobody refers to).
+#ifndef JKQ_SUMS_ATTR
+#define JKQ_SUMS_ATTR JD
+#endif
+#ifndef JKQ_LIN_ATTR
+#define JKQ_LIN_ATTR JD
+#endif
 #define TL_REF1 (1u << 31)  // ThinEnt.pk of a chain record: index of the child that is the sum further down; pad = node of the other
 template <int MODE>
 JD bool lin_child(Ctx &c, int mc, uint64_t aw, uint32_t ac, uint64_t bew, uint32_t bc, uint32_t *kind, uint32_t *node, uint64_t *w) {
@@ -428,7 +434,7 @@ JD bool lin_child(Ctx &c, int mc, uint64_t aw, uint32_t ac, uint64_t bew, uint32
   return true;
 }
 template <int MODE>
-JD bool lin_add(Ctx &c, uint32_t slot, int m, uint64_t al, uint32_t A, uint64_t be, uint32_t B, uint32_t *out_rn, uint64_t *out_f, uint64_t *out_a,
+JKQ_LIN_ATTR bool lin_add(Ctx &c, uint32_t slot, int m, uint64_t al, uint32_t A, uint64_t be, uint32_t B, uint32_t *out_rn, uint64_t *out_f, uint64_t *out_a,
                 uint32_t *levels) {
   ThinState *T = c.T;
   const int m_top = m;
@@ -490,6 +496,112 @@ JD bool lin_add(Ctx &c, uint32_t slot, int m, uint64_t al, uint32_t A, uint64_t 
   return true;
 }
 
+// thin_probe's tail when a row of the target node is such a sum (no control below the target, the cursor on the target
+// level: act lanes hold the target nodes).  Out of line: the gates of QFT / GHZ never get here, and their path keeps its
+// constant factors and its registers.  Called by the whole warp.
+template <int MODE> JKQ_SUMS_ATTR uint32_t thin_probe_sums(Ctx &c, const JGate &g, uint32_t *handled, uint32_t *entries) {
+  ThinState *T = c.T;
+  const uint32_t lane = c.ltid;
+  const int tgt = g.target, start = tgt;  // (thin_probe asks for this only with the cursor on the target level)
+  *handled = 0; *entries = 0;
+  if (T->M != tgt) return 0;
+  ThinRes edge;
+  edge.rw = 0; edge.rnode = 0; edge.pad = 0;
+  if (lane < T->cnt[start]) edge = T->res[start & 1][lane];
+  const bool act = edge.rw != 0;
+  JNode nd;
+  nd.c0 = 0; nd.c1 = 0; nd.w = 0;
+  if (act) nd = node_load<MODE>(c, edge.rnode);
+  struct { bool sum[2]; uint64_t sal[2], sbe[2]; uint32_t c0, c1; } ps;
+  ps.c0 = nd_c0(nd); ps.c1 = nd.c1;
+  uint32_t rn[2] = {0, 0}, sum_levels = 0;
+  uint64_t f[2] = {JW_ONE, JW_ONE}, a[2] = {0, 0};
+  bool ok_rows = true;
+  JKQ_UNROLL
+  for (int i = 0; i < 2; i++) {  // the target node's two rows, as in thin_probe
+    ps.sum[i] = false; ps.sal[i] = 0; ps.sbe[i] = 0;
+    if (!act) continue;
+    uint64_t al, be;
+    const bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), nd_w0(nd), &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), nd_w1(nd), &be);
+    if (!(o1 && o2)) { ok_rows = false; continue; }
+    if (al != 0 && be != 0 && ps.c0 != ps.c1) { ps.sum[i] = true; ps.sal[i] = al; ps.sbe[i] = be; continue; }
+    if (!cadd<MODE>(c, al, be, &a[i])) { ok_rows = false; continue; }
+    rn[i] = al != 0 ? ps.c0 : ps.c1;
+  }
+  if (jballot(!ok_rows)) return 0;
+  bool sok = true;
+  // one lane per (cursor edge, row) -- lane l + 16 takes row 1 of edge l -- each walking its chain by itself (values go
+  // in under the lock of real_insert_solo, nodes through the lock-free unique table)
+#ifdef JKQ_EMU
+  for (int i = 0; i < 2; i++)
+    if (act && ps.sum[i]) {
+      uint32_t lv = 0;
+      if (!lin_add<MODE>(c, lane, tgt - 1, ps.sal[i], ps.c0, ps.sbe[i], ps.c1, &rn[i], &f[i], &a[i], &lv)) sok = false;
+      sum_levels += lv;
+    }
+#else
+  {
+    const uint32_t src = lane & (JKQ_WARP / 2 - 1u), row = lane / (JKQ_WARP / 2);
+    const bool go0 = act && ps.sum[0], go1 = act && ps.sum[1];
+    const uint32_t g0 = jshfl(go0 ? 1u : 0u, src), g1 = jshfl(go1 ? 1u : 0u, src);
+    const unsigned long long xa0 = jshfl64(ps.sal[0], src), xa1 = jshfl64(ps.sal[1], src), xb0 = jshfl64(ps.sbe[0], src), xb1 = jshfl64(ps.sbe[1], src);
+    const uint32_t xc0 = jshfl(ps.c0, src), xc1 = jshfl(ps.c1, src);
+    uint32_t res_rn = 0, lv = 0;
+    uint64_t res_f = 0, res_a = 0;
+    bool mine_ok = true;
+    if (row ? g1 != 0 : g0 != 0) mine_ok = lin_add<MODE>(c, lane, tgt - 1, row ? xa1 : xa0, xc0, row ? xb1 : xb0, xc1, &res_rn, &res_f, &res_a, &lv);
+    jsyncwarp();
+    const uint32_t up = src + JKQ_WARP / 2;  // the lane that ran my row 1
+    const uint32_t rn1 = jshfl(res_rn, up), ok1 = jshfl(mine_ok ? 1u : 0u, up), lv1 = jshfl(lv, up);
+    const unsigned long long f1 = jshfl64(res_f, up), a1 = jshfl64(res_a, up);
+    if (lane < JKQ_WARP / 2) {
+      if (go0) { rn[0] = res_rn; f[0] = res_f; a[0] = res_a; sok = mine_ok; sum_levels += lv; }
+      if (go1) { rn[1] = rn1; f[1] = f1; a[1] = a1; sok = sok && ok1 != 0; sum_levels += lv1; }
+    }
+  }
+#endif
+  {
+    const uint32_t fl = thin_trouble<MODE>(c);  // a pool ran out inside a chain: the gate is abandoned as usual
+    if (fl) return fl;
+  }
+  if (jballot(!sok)) return 0;  // not a chain after all: work items
+  if (a[0] == 0) rn[0] = 0;
+  if (a[1] == 0) rn[1] = 0;
+  uint32_t rnode = 0;
+  uint64_t rw = 0;
+  bool fail = false, ok = true;
+  if (act) {
+    const bool lane_sum = ps.sum[0] || ps.sum[1];
+    if (lane_sum) ok = reduce_core<MODE>(c, rn, f, a, 0, &rnode, &rw);  // (the M item's reduction: no hint)
+    else {
+      ok = thin_reduce<MODE>(c, edge.rnode, nd, rn, f, a, &rnode, &rw);  // (a lane without a sum next to one with)
+    }
+    if (ok && !fail && rw != 0) {
+      if (rnode == 0) {}  // (a pool ran out: seen below)
+      else ok = cmul<MODE>(c, edge.rw, rw, &rw);
+    }
+  }
+  {
+    const uint32_t fl = thin_trouble<MODE>(c);
+    if (fl) return fl;
+  }
+  if (jballot(!ok || fail)) return 0;  // (a value that is neither there nor entered at once: builds without in-place insertion)
+  if (act) {
+    ThinRes r;
+    r.rw = rw; r.pad = 0;
+    r.rnode = rw == 0 ? 0u : rnode;
+    T->res[start & 1][lane] = r;
+  }
+  jsyncwarp();
+  *handled = 1;
+#ifndef JKQ_EMU
+  *entries = jpopc(jballot(act)) + __reduce_add_sync(0xFFFFFFFFu, sum_levels);
+#else
+  *entries = (act ? 1u : 0u) + sum_levels;
+#endif
+  return 0;
+}
+
 // thin_probe: the cases of thin_gate that need no records at all, every cursor edge in its own lane with nothing
 // exchanged between lanes:
 //   * no control above the target, and from the cursor edge down to the target only nodes whose non-zero edges lead
@@ -530,10 +642,8 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
   const uint32_t c0 = nd_c0(nd), c1 = nd.c1;
   uint32_t rn[2] = {0, 0}, rounds = 0;
   uint64_t p[2] = {0, 0}, a[2] = {0, 0};
-  uint64_t f[2] = {JW_ONE, JW_ONE};
-  bool sum[2] = {false, false};  // row i is a sum of two different sub-diagrams: sal[i] * [c0] + sbe[i] * [c1] (lin_add)
-  uint64_t sal[2] = {0, 0}, sbe[2] = {0, 0};
-  const bool sums_ok = low == tgt && tgt > 0 && !(T->thin_off & 64u) && (JKQ_WARP == 1u || cnt <= JKQ_WARP / 2);
+  const uint64_t f[2] = {JW_ONE, JW_ONE};
+  bool sumfail = false;  // why a lane failed: a row is a sum of two different sub-diagrams (looked at on the way out only)
   for (;;) {  // the target node's two rows
     bool ok = true;
     if (act) {
@@ -542,11 +652,7 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
         uint64_t al, be;
         const bool o1 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i), w0, &al), o2 = cmul<MODE>(c, gate_u<MODE>(c, 2 * i + 1), w1, &be);
         if (!(o1 && o2)) { ok = false; continue; }
-        if (al != 0 && be != 0 && c0 != c1) {  // a sum of two different sub-diagrams: a chain (lin_add below), or work items
-          if (!sums_ok) fail = true;
-          else { sum[i] = true; sal[i] = al; sbe[i] = be; }
-          continue;
-        }
+        if (al != 0 && be != 0 && c0 != c1) { fail = true; sumfail = true; continue; }  // a sum of two different sub-diagrams
         if (!cadd<MODE>(c, al, be, &p[i])) { ok = false; continue; }
         rn[i] = al != 0 ? c0 : c1;  // the child p sits on
       }
@@ -557,44 +663,6 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
     if (fl) return fl;
     if (++rounds > JKQ_RETRY_LIMIT) jset_error<MODE>(c.E, c.sh, JKQ_ERR_RETRY_LIMIT);
     thin_commit<MODE>(c);
-  }
-  uint32_t sum_levels = 0;
-  if (jballot(fail)) return 0;
-  if (jballot(act && (sum[0] || sum[1]))) {
-    // the sums: one lane per (cursor edge, row) -- lane l + 16 takes row 1 of edge l -- each walking its chain by itself
-    // (values go in under the lock of real_insert_solo, nodes through the lock-free unique table)
-    bool sok = true;
-#ifdef JKQ_EMU
-    for (int i = 0; i < 2; i++)
-      if (act && !fail && sum[i]) {
-        uint32_t lv = 0;
-        if (!lin_add<MODE>(c, lane, tgt - 1, sal[i], c0, sbe[i], c1, &rn[i], &f[i], &p[i], &lv)) sok = false;
-        sum_levels += lv;
-      }
-#else
-    {
-      const uint32_t src = lane & (JKQ_WARP / 2 - 1u), row = lane / (JKQ_WARP / 2);
-      const bool go0 = act && !fail && sum[0], go1 = act && !fail && sum[1];
-      const uint32_t g0 = jshfl(go0 ? 1u : 0u, src), g1 = jshfl(go1 ? 1u : 0u, src);
-      const unsigned long long xa0 = jshfl64(sal[0], src), xa1 = jshfl64(sal[1], src), xb0 = jshfl64(sbe[0], src), xb1 = jshfl64(sbe[1], src);
-      const uint32_t xc0 = jshfl(c0, src), xc1 = jshfl(c1, src);
-      uint32_t res_rn = 0, lv = 0;
-      uint64_t res_f = 0, res_a = 0;
-      bool mine_ok = true;
-      if (row ? g1 != 0 : g0 != 0) mine_ok = lin_add<MODE>(c, lane, tgt - 1, row ? xa1 : xa0, xc0, row ? xb1 : xb0, xc1, &res_rn, &res_f, &res_a, &lv);
-      jsyncwarp();
-      const uint32_t up = (lane & (JKQ_WARP / 2 - 1u)) + JKQ_WARP / 2;  // the lane that ran my row 1
-      const uint32_t rn1 = jshfl(res_rn, up), ok1 = jshfl(mine_ok ? 1u : 0u, up), lv1 = jshfl(lv, up);
-      const unsigned long long f1 = jshfl64(res_f, up), a1 = jshfl64(res_a, up);
-      if (lane < JKQ_WARP / 2) {
-        if (go0) { rn[0] = res_rn; f[0] = res_f; p[0] = res_a; sok = mine_ok; sum_levels += lv; }
-        if (go1) { rn[1] = rn1; f[1] = f1; p[1] = a1; sok = sok && ok1 != 0; sum_levels += lv1; }
-      }
-    }
-#endif
-    const uint32_t fl = thin_trouble<MODE>(c);  // a pool ran out inside a chain: the gate is abandoned as usual
-    if (fl) return fl;
-    if (!sok) fail = true;
   }
   if (act && !fail) {
     if (low == tgt) { a[0] = p[0]; a[1] = p[1]; }
@@ -633,15 +701,20 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
     if (a[0] == 0) rn[0] = 0;
     if (a[1] == 0) rn[1] = 0;
   }
-  if (jballot(fail)) return 0;
+  if (jballot(fail)) {
+    // Not a gate for this function.  If the reason is a sum of two different sub-diagrams with nothing else in the way (no
+    // control below the target, the cursor on the target level, a lane to spare per row), thin_probe_sums can try it as a
+    // chain: *handled = 2 tells the caller.  Decided out here so that the gates that do pass carry nothing for it.
+    if (low == tgt && start == tgt && tgt > 0 && !(T->thin_off & 64u) && (JKQ_WARP == 1u || cnt <= JKQ_WARP / 2) && jballot(sumfail) != 0) *handled = 2;
+    return 0;
+  }
   uint32_t rnode = 0;
   uint64_t rw = 0;
   rounds = 0;
   for (;;) {
     bool ok = true;
     if (act && !fail) {
-      if (sum[0] || sum[1]) ok = reduce_core<MODE>(c, rn, f, a, 0, &rnode, &rw);  // (the M item's reduction: no hint)
-      else ok = thin_reduce<MODE>(c, node, nd, rn, f, a, &rnode, &rw);
+      ok = thin_reduce<MODE>(c, node, nd, rn, f, a, &rnode, &rw);
       if (ok && rw != 0) {
         if (rnode == 0) {}  // (a pool ran out: seen below)
         else if (start > tgt && rnode != node) fail = true;
@@ -666,11 +739,6 @@ template <int MODE> JD uint32_t thin_probe(Ctx &c, const JGate &g, uint32_t *han
   }
   jsyncwarp();
   *handled = 1; *entries = jpopc(jballot(act)) * (uint32_t)(start - low + 1);
-#ifndef JKQ_EMU
-  *entries += __reduce_add_sync(0xFFFFFFFFu, sum_levels);
-#else
-  *entries += sum_levels;
-#endif
   return 0;
 }
 

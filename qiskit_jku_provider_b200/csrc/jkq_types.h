@@ -120,6 +120,8 @@ typedef struct {
   uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all
   uint32_t solo_max;       // widest level the cursor warp runs by itself (one lane per item); 0 = JKQ_WARP.  Wider levels are shared out
                            // over the warps of the CTA / grid (run_level)
+  uint32_t sums_ask;       // the single-CTA kernel without thin_probe_sums counts the gates that would have used it down from here;
+                           // at 1 it stops and asks for the kernel that has it (want_sums).  0: such gates take the work items
   uint32_t cta_no_reserve; // testing aid: no reserve in the shared pools, so the root rebuild of an abandoned gate fails too (saved-cursor hand-over)
   double tol;
   double inv_tol;
@@ -167,6 +169,7 @@ typedef struct {
   int32_t want_grid;    // CTA mode asked for the grid path
   uint32_t tables_valid;  // HBM unique / value hash tables match the arena (MODE_CTA lets them go stale)
   uint32_t cursor_saved;  // thin_spill holds the state; root / rootw are stale; only the grid path may continue
+  uint32_t want_sums;     // raised together with want_grid: relaunch the single-CTA kernel that has thin_probe_sums
   uint32_t want_wide;     // raised together with want_grid by a one-warp launch: the wide single-CTA launch is enough
   // ---- counters ----
   unsigned long long st[12];  // JST_* below

@@ -175,8 +175,8 @@ int main(int argc, char **argv) {
   // same escalation as the host driver (run_segment in jkq_b200.cu): CTA path until it does not fit
   while (!E->status && (E->next_gate < (int)gates.size() || E->cursor_saved)) {
     E->want_grid = 0;
-    if (grid) run_gates<MODE_GRID>(gctx, gates.data(), (int)gates.size());
-    else run_gates<MODE_CTA>(c, gates.data(), (int)gates.size());
+    if (grid) run_gates<MODE_GRID, true>(gctx, gates.data(), (int)gates.size());
+    else run_gates<MODE_CTA, true>(c, gates.data(), (int)gates.size());
     if ((E->want_grid || E->cursor_saved) && !grid) { grid = true; grid_switches++; }
     else if (E->next_gate < (int)gates.size() && !E->status) { fprintf(stderr, "stopped without reason\n"); return 3; }
   }

@@ -387,3 +387,33 @@ def test_snapshot_kept_as_a_diagram_and_read_range_by_range(eng):
     assert last[0] == 0 and abs(last[1] - hm[1, 0] * tm[1, 1]) < 1e-9
     assert abs(eng.snapshot_amplitudes(2, 0, 1)[0] - hm[0, 0] * tm[0, 0]) < 1e-9
     assert eng.amplitudes((1 << n) - 1, 1)[0] == last[1]
+
+
+def test_sums_that_stay_a_chain_take_no_work_items(eng, oracle_mod):
+    """H on the node that carries the marked path of a Grover state is a sum of two different sub-diagrams that shares
+    everything but one path: thin_probe_sums walks it as a chain (jkq_thin.cuh lin_add) instead of through work items.
+    The single-CTA kernel without that code asks for the one with it after a few such gates (JEng.sums_ask), so every
+    later gate of the circuit is a thin gate; switched off (thin_off bit 6) the same circuit goes through the item phases
+    and ends in the same diagram, gate by gate."""
+    circ = C.grover(16, 12, marked=0xA5A5)
+    eng.set_option("thin_off", 0)
+    run(eng, circ, 4096, 4, 0, levels=False)
+    st = eng.stats()
+    assert st["thin_gates"] >= len(circ) - 16, (st["thin_gates"], len(circ))  # all but the gates before the relaunch
+    a1, lc1, counts1 = eng.amplitudes(0, 1 << 12), eng.level_counts(), eng.counts()
+    o = oracle_mod.run_oracle(circ, shots=4096, seed=4, levels=True, amps=True, extra=["--amp-limit", str(1 << 12)] + TIE)
+    assert np.abs(a1 - np.array([complex(*x) for x in o["amps"]])).max() < AMP_TOL
+    assert lc1 == o["level_counts"]
+    try:
+        eng.set_option("thin_off", 64)
+        run(eng, circ, 4096, 4, 0, levels=False)
+        assert eng.stats()["thin_gates"] < st["thin_gates"]
+        assert np.abs(eng.amplitudes(0, 1 << 12) - a1).max() < 1e-12
+        assert eng.level_counts() == lc1 and eng.counts() == counts1
+        # per-gate level counts, both ways, against the oracle (the level log rebuilds to the root after every gate)
+        for off in (0, 64):
+            eng.set_option("thin_off", off)
+            run(eng, circ, 16, 4, 0, levels=True)
+            assert eng.level_log(len(circ)) == o["level_counts_per_gate"], off
+    finally:
+        eng.set_option("thin_off", 0)
