@@ -117,7 +117,8 @@ typedef struct {
   uint32_t cta_node_limit;  // testing aid: cap on the shared-memory node pool of the CTA path (0 = its real size)
   uint32_t cta_val_limit;   // testing aid: the same for the shared-memory value table
   uint32_t cta_wide_ok;     // a one-warp single-CTA launch may ask for the wide one (want_wide) when a level outgrows the warp
-  uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all
+  uint32_t thin_off;        // testing aid: bit 0 no thin gates with controls above the target, 1 none with controls below, 2 none wider than one lane, 3 none at all,
+                            // 4 no parked cursor, 5 no thin_probe, 6 no chain sums (thin_probe_sums)
   uint32_t solo_max;       // widest level the cursor warp runs by itself (one lane per item); 0 = JKQ_WARP.  Wider levels are shared out
                            // over the warps of the CTA / grid (run_level)
   uint32_t sums_ask;       // the single-CTA kernel without thin_probe_sums counts the gates that would have used it down from here;

@@ -1,5 +1,5 @@
 """Workloads for the round-2 ncu captures (one kernel family per mode).
-usage: profile_r2.py sample_ghz | sample_qft | batch | shots | grid160 | qft32"""
+usage: profile_r2.py sample_ghz | sample_qft | batch | shots | grid160 | qft32 | grover"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from qiskit_jku_provider_b200 import circuits as C
@@ -27,8 +27,8 @@ elif mode == "shots":
     with BatchRunner(workers=1 << 16, device=0) as br:
         keys, _, status, _, ms = br.run_shots(prog.n_qubits, prog.ops, 50000, seed=1)
         print("shots kernel_ms", ms, "failed", int(status.sum()))
-elif mode in ("grid160", "qft32"):
-    circ = C.random_circuit(18, 160, 1) if mode == "grid160" else C.qft(32)
+elif mode in ("grid160", "qft32", "grover"):
+    circ = C.random_circuit(18, 160, 1) if mode == "grid160" else (C.qft(32) if mode == "qft32" else C.grover(20, 20))
     with Engine(device=0, node_capacity=1 << 20) as eng:  # bench.py's engine configuration
         eng.load(circ)
         eng.apply()
