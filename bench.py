@@ -518,6 +518,25 @@ def main():
                                       "algorithmic_bytes": "%d frontier items x %d B" % (g3["items"], ALGO_BYTES_PER_ITEM),
                                       "peak_source": "jkq_random_sector_bench on this GPU, this run",
                                       "traffic": "profiles/ (ncu --set full of this kernel)"}
+            # ... and the same kernel where the frontiers are wide enough to occupy the grid: random n=22, 200 ops (47 M frontier
+            # pairs, 42 M nodes created; its own engine: 2^25 nodes, 2^26 reals)
+            try:
+                from qiskit_jku_provider_b200.engine import Engine as _Engine
+                c5 = C.random_circuit(22, 200, 1)
+                with _Engine(device=local, node_capacity=1 << 25, value_capacity=1 << 26) as big:
+                    big.load(c5)
+                    big.apply()
+                    s5 = big.stats()
+                ach5 = s5["items"] * ALGO_BYTES_PER_ITEM / (s5["apply_ms"] * 1e-3) / 1e9
+                extra["roofline_grid_wide"] = {"workload": "random n=22, 200 ops, seed 1: k_run_gates<MODE_GRID>", "applies": len(c5),
+                                               "apply_ms": s5["apply_ms"], "items": s5["items"], "items_per_s": s5["items"] / (s5["apply_ms"] * 1e-3),
+                                               "nodes_created": s5["nodes_created"], "nodes_created_per_s": s5["nodes_created"] / (s5["apply_ms"] * 1e-3),
+                                               "gc_runs": s5["gc_runs"], "bound": "hbm (random 32-byte sectors)", "achieved": ach5, "peak": sect,
+                                               "unit": "GB/s", "frac": ach5 / sect,
+                                               "algorithmic_bytes": "%d frontier items x %d B" % (s5["items"], ALGO_BYTES_PER_ITEM),
+                                               "peak_source": "jkq_random_sector_bench on this GPU, this run"}
+            except Exception as e:  # (a secondary figure: never the reason for a bench without its headline)
+                extra["roofline_grid_wide"] = {"error": str(e)[:200]}
 
         # per-shot re-simulation of a circuit with gates behind measurements: every shot is an
         # instance of the circuit on its own SM (k_batch_shots), shots split over the ranks
