@@ -464,6 +464,7 @@ struct jkq_handle {
   uint32_t n = 0;
   bool loaded = false, applied = false, sampling_ready = false, imported = false, level_log = false;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied by this handle since it was created (jcopy)
+  uint32_t sums_ask = 8;            // gates that would have used thin_probe_sums before the kernel that has it is launched (option sums_ask)
   bool sums_now = false;            // ... and it is the build with thin_probe_sums (it asked for it: want_sums)
   bool wide_now = false;            // the single-CTA kernel of this circuit is launched with cfg.cta_threads (it asked for them)
   SampleParams sp;
@@ -669,6 +670,7 @@ extern "C" int jkq_set_option(jkq_handle *h, const char *name, int64_t value) {
   if (!strcmp(name, "cta_no_reserve")) { h->host.cta_no_reserve = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "histogram_fused")) { h->force_fused = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "thin_off")) { h->host.thin_off = (uint32_t)value; return JKQ_E_OK; }
+  if (!strcmp(name, "sums_ask")) { h->sums_ask = (uint32_t)value; return JKQ_E_OK; }  // testing aid: JEng.sums_ask at the start of a run (0: never)
   if (!strcmp(name, "cta_val_limit")) { h->host.cta_val_limit = (uint32_t)value; return JKQ_E_OK; }
   if (!strcmp(name, "debug_stop_at_handover")) { h->debug_stop_at_handover = value != 0; return JKQ_E_OK; }
   if (!strcmp(name, "cta_item_limit")) {
@@ -1084,7 +1086,7 @@ extern "C" int jkq_apply(jkq_handle *h) {
   }
   E.lvl_log = h->lvl_log;
   E.mat_u = h->mat_u; E.mat_epoch = h->mat_epoch;
-  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0; E.want_wide = 0; E.want_sums = 0; E.sums_ask = 8;
+  E.status = 0; E.next_gate = 0; E.want_grid = 0; E.cursor_saved = 0; E.want_wide = 0; E.want_sums = 0; E.sums_ask = h->sums_ask;
   E.cta_wide_ok = (h->cfg.cta_threads > 32 && h->cfg.reserved != 1) ? 1u : 0u;
   h->wide_now = false;
   h->sums_now = false;
